@@ -1,0 +1,82 @@
+// lst_device.h -- structures and launchers shared by the CUDA kernels (lst_kernels.cu) and the
+// runtime (lst_runtime.cu).  Internal; the public boundary is include/lst_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lst_math.h"
+
+namespace lst {
+
+// One (frame, template) search window resident in the per-pass device scratch.
+struct DevTask {
+    int32_t frame;        // index into the pass's frame-pointer table
+    int32_t tpl;          // template slot (0..4; match_single uses slot 5)
+    int32_t x0, y0;       // window origin in the frame (already clipped to the frame)
+    int32_t w, h;         // window size
+    int32_t pitch;        // row pitch of the 8-bit window in scratch (bytes, multiple of 16)
+    int32_t rw, rh;       // result-map size: w - tw + 1, h - th + 1
+    int32_t s_used;       // search area used by the accept test (searchWidth = 2*s_used)
+    int32_t pad0, pad1;
+    uint64_t win_off;     // byte offset of the 8-bit window in the win8 scratch
+    uint64_t sum_off;     // element offset of this task's rw*rh maps (wsum, wsq, scores)
+};
+
+struct DevResult {
+    double x, y, score;   // coord_res of doMatch_coord_res (LST4:2502)
+    int32_t ix, iy;
+    int32_t accepted;
+    int32_t peak_check;   // 1 if the epilogue's recomputed peak score equals the argmax score
+    float nb[9];          // 3x3 neighbourhood of the peak (diagnostic)
+    float pad;
+};
+
+static const int kMaxTpl = 6;   // five tracked templates + one scratch slot for lst_match_single
+
+// Per-context template table as the kernels see it.
+struct DevTemplates {
+    TplConst c[kMaxTpl];
+    const uint32_t *shifted[kMaxTpl];   // [th][k4][4] words, see build_shifted_template
+    const uint8_t *raw[kMaxTpl];        // [th][tw] bytes
+};
+
+struct PreprocParams {
+    int pixel_type;        // LST_PIX_*
+    int frame_w, frame_h;  // slice size in pixels
+    int range_per_task;    // 1: lo/hi from the per-task min/max keys, 0: fixed lo/hi below
+    float lo, hi;
+    int quant_mode;        // LST_QUANT_*
+    int tile_w, tile_h;    // blur tile (output) size
+};
+
+struct MatchParams {
+    int band_rows;         // result rows per CTA
+    int tiles_per_cta;     // 32-wide result tiles per CTA
+    int smem_pitch;        // window tile pitch in shared memory (odd multiple of 16 bytes)
+    int sub_pixel;
+    int templ_size;
+    double thresh;
+};
+
+// launchers (all asynchronous on `stream`); each returns the number of kernels it launched or <0
+int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, cudaStream_t stream);
+int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const void *const *frames, const PreprocParams &pp,
+                  uint32_t *mm_keys, cudaStream_t stream);
+int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const void *const *frames,
+                      const PreprocParams &pp, const uint32_t *mm_keys, uint8_t *win8, cudaStream_t stream);
+int launch_box_sums(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
+                    const DevTemplates *tpls, const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream);
+int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
+                     const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
+                     unsigned long long *best, float *score_map, const MatchParams &mp, cudaStream_t stream);
+int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls, const uint8_t *win8,
+                    const uint32_t *wsum, const uint32_t *wsq, const unsigned long long *best, DevResult *results,
+                    const MatchParams &mp, cudaStream_t stream);
+int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_dist, const double *spot0,
+                 double *out5, cudaStream_t stream);
+int set_blur_kernel(const float kern[7], const float ksum[7]);
+// picks band/tile split and the shared-memory pitch for lst_ncc_match
+void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes);
+int measure_alu_peaks(double ms_per_test, double out[2]);
+
+}  // namespace lst

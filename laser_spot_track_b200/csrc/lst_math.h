@@ -1,0 +1,141 @@
+// lst_math.h -- arithmetic shared bit-for-bit by the host code and the CUDA kernels.
+//
+// Everything here must round exactly like Java / OpenCV double and float arithmetic: one IEEE
+// rounding per operation, no fused multiply-add.  The .cu files are compiled with -fmad=false
+// and the host files with -ffp-contract=off, so plain C++ expressions are safe in both.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LST_HD __host__ __device__ __forceinline__
+#else
+#define LST_HD inline
+#endif
+
+namespace lst {
+
+// Constants of cv::matchTemplate's normalisation for one template (OpenCV imgproc
+// templmatch.cpp common_matchTemplate, reached from LST4:2560), 1 channel, TM_CCOEFF_NORMED.
+struct TplConst {
+    double inv_area;    // 1/(tw*th)
+    double mean;        // templMean[0]
+    double norm;        // sqrt(templSdv^2)/sqrt(invArea)
+    int32_t flat;       // templSdv^2 < DBL_EPSILON  => whole result is 1
+    int32_t tw, th;
+    int32_t k4;         // 32-bit words per shifted template row (see build_shifted_template)
+    uint32_t tsum, tsq_lo;
+    double mideal;      // doMatch_test of the template (LST4:2724-2767)
+};
+
+// One position of common_matchTemplate for TM_CCOEFF_NORMED with an exact integer numerator:
+//   corr = sum I*T, wsum = sum I, wsq = sum I^2 over the template footprint.
+// Operation order follows templmatch.cpp; the result is what OpenCV stores: (float)num.
+LST_HD float ncc_score(double corr, double wsum, double wsq, double inv_area, double mean, double norm, int flat)
+{
+    if (flat) return 1.0f;
+    double t = wsum;
+    double wnd_mean2 = (t * t) * inv_area;
+    double num = corr - t * mean;
+    double diff2 = wsq - wnd_mean2;
+    if (diff2 < 0.0) diff2 = 0.0;
+    double thr = 10.0 * 1.1920928955078125e-07 * wsq;   // 10 * FLT_EPSILON * wndSum2
+    if (thr > 0.5) thr = 0.5;
+    double tt = (diff2 <= thr) ? 0.0 : sqrt(diff2) * norm;
+    double a = fabs(num);
+    double r;
+    if (a < tt) r = num / tt;
+    else if (a < tt * 1.125) r = num > 0.0 ? 1.0 : -1.0;
+    else r = 0.0;
+    return (float)r;
+}
+
+// 3x3 quadratic sub-pixel fit, LST4:2681-2717.  nb = 3x3 neighbourhood (row-major, centre nb[4])
+// read as float32 and computed in double.  border != 0 => peak on the map border => (0,0).
+LST_HD void subpixel_fit(const float *nb, int border, double *dx, double *dy)
+{
+    *dx = 0.0;
+    *dy = 0.0;
+    if (border) return;
+    double c = (double)nb[4];
+    double fxx = (double)nb[3] - 2.0 * c + (double)nb[5];
+    double fyy = (double)nb[1] - 2.0 * c + (double)nb[7];
+    double fxy = ((double)nb[8] + (double)nb[0] - (double)nb[2] - (double)nb[6]) / 4.0;
+    double fx = ((double)nb[5] - (double)nb[3]) / 2.0;
+    double fy = ((double)nb[7] - (double)nb[1]) / 2.0;
+    double denom = fxy * fxy - fxx * fyy;
+    if (denom == 0.0) return;
+    double ddx = (fyy * fx - fxy * fy) / denom;
+    double ddy = (fxx * fy - fxy * fx) / denom;
+    if (fabs(ddx) > 1.0 || fabs(ddy) > 1.0) return;
+    *dx = ddx;
+    *dy = ddy;
+}
+
+// testMatchResult for method 5, LST4:1225-1255.
+LST_HD int test_match_result(double result, double ref, double thresh, double x, double y, int search_width, int tpl_size)
+{
+    int ok = 1;
+    double d1 = 0.05 * tpl_size, d2 = 0.05 * search_width;
+    double dist = d1 < d2 ? d1 : d2;
+    if (fabs(result - ref) > thresh) ok = 0;
+    if (search_width != 0 && ((x < dist) || (y < dist) || (x > search_width - dist) || (y > search_width - dist))) ok = 0;
+    return ok;
+}
+
+// calcDisplacement, LST4:2318-2365.  ref = refX/refY (Java floats) of spot, mark1..4;
+// dis = disX/disY of spot, mark1..4.  have_spot0 == 0 reproduces the firstPoint latch.
+// out = dX_pix, dY_pix, x_abs, y_abs, dL.  spot0_io is updated when latching.
+LST_HD void calc_displacement(const float *ref, const double *dis, double mark_dist, int have_spot0,
+                              double *spot0_io, double *out)
+{
+    double dX_pix = dis[0] - dis[2];
+    double dY_pix = dis[1] - dis[3];
+    double m1x = (double)ref[2] + dis[2], m1y = (double)ref[3] + dis[3];
+    double m2x = (double)ref[4] + dis[4], m2y = (double)ref[5] + dis[5];
+    double m3x = (double)ref[6] + dis[6], m3y = (double)ref[7] + dis[7];
+    double m4x = (double)ref[8] + dis[8], m4y = (double)ref[9] + dis[9];
+    double a1x = m4x - m1x, a1y = m4y - m1y;
+    double b1x = m2x - m1x, b1y = m2y - m1y;
+    double a2x = m3x - m2x, a2y = m3y - m2y;
+    double b2x = m3x - m4x, b2y = m3y - m4y;
+    double rx = (double)ref[0] + dis[0] - m1x, ry = (double)ref[1] + dis[1] - m1y;
+    double AX = a1x * (b1y - b2y) + a1y * (b2x - b1x);
+    double BX = -a1x * b1y + a1y * b1x - rx * (b1y - b2y) - ry * (b2x - b1x);
+    double CX = -rx * b1y + ry * b1x;
+    double AY = b1x * (a1y - a2y) + b1y * (a2x - a1x);
+    double BY = -b1x * a1y + b1y * a1x - rx * (a1y - a2y) - ry * (a2x - a1x);
+    double CY = -rx * a1y + ry * a1x;
+    double x_abs, y_abs;
+    if (AX == 0.0) {
+        x_abs = CX / BX * mark_dist;
+        y_abs = CY / BY * mark_dist;
+    } else {
+        double DX = sqrt(BX * BX + 4.0 * AX * CX);
+        double DY = sqrt(BY * BY + 4.0 * AY * CY);
+        x_abs = (DX - BX) / AX / 2.0 * mark_dist;
+        y_abs = (-DY - BY) / AY / 2.0 * mark_dist;
+    }
+    if (!have_spot0) {
+        spot0_io[0] = x_abs;
+        spot0_io[1] = y_abs;
+    }
+    double dX = x_abs - spot0_io[0];
+    double dY = y_abs - spot0_io[1];
+    out[0] = dX_pix;
+    out[1] = dY_pix;
+    out[2] = x_abs;
+    out[3] = y_abs;
+    out[4] = sqrt(dX * dX + dY * dY);
+}
+
+// Java (int) cast of a double (LST4:1327): truncation toward zero, saturating, NaN -> 0.
+LST_HD int jint(double v)
+{
+    if (!(v == v)) return 0;
+    if (v >= 2147483647.0) return 2147483647;
+    if (v <= -2147483648.0) return (int)(-2147483647 - 1);
+    return (int)v;
+}
+
+}  // namespace lst

@@ -1,0 +1,899 @@
+// lst_runtime.cu -- device context, the CUDA executor behind the recurrence resolver, frame
+// ingest (double-buffered cudaMemcpyAsync ring) and the C ABI of include/lst_b200.h.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/lst_b200.h"
+#include "lst_device.h"
+#include "lst_host.h"
+
+using namespace lst;
+
+static thread_local std::string g_create_error;
+
+struct TimedLaunch {
+    cudaEvent_t e0, e1;
+    double macs;
+};
+
+struct lst_ctx : public Executor {
+    lst_params p;
+    int device = 0;
+    std::string err;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    // reference / templates
+    bool have_ref = false;
+    Rect rect[5];
+    float ref_xy[10];
+    double spot0[2] = {0, 0};
+    double dis[10] = {0};
+    DevTemplates h_tpls;
+    DevTemplates *d_tpls = nullptr;
+    uint32_t *d_shifted[kMaxTpl] = {nullptr};
+    uint8_t *d_raw[kMaxTpl] = {nullptr};
+    size_t shifted_cap[kMaxTpl] = {0}, raw_cap[kMaxTpl] = {0};
+    // per-pass scratch
+    int task_cap = 0;
+    DevTask *d_tasks = nullptr, *h_tasks = nullptr;
+    uint32_t *d_mm = nullptr;
+    unsigned long long *d_best = nullptr;
+    DevResult *d_results = nullptr, *h_results = nullptr;
+    uint8_t *d_win8 = nullptr;
+    size_t win8_cap = 0;
+    uint32_t *d_wsum = nullptr, *d_wsq = nullptr;
+    size_t sum_cap = 0;
+    float *d_map = nullptr;
+    size_t map_cap = 0;
+    // frame table + ring
+    int frame_cap = 0;
+    const void **d_frames = nullptr, **h_frames = nullptr;
+    uint8_t *d_ring[2] = {nullptr, nullptr};
+    size_t ring_cap = 0;   // bytes per half
+    // solve buffers
+    int solve_cap = 0;
+    double *d_dis10 = nullptr, *d_out5 = nullptr, *h_dis10 = nullptr, *h_out5 = nullptr;
+    // stats
+    lst_stats stats;
+    bool timing = false;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    size_t scratch_limit = (size_t)6 << 30;
+
+    size_t bpp() const { return p.pixel_type == LST_PIX_U8 ? 1 : (p.pixel_type == LST_PIX_U16 ? 2 : 4); }
+    size_t frame_bytes() const { return (size_t)p.width * p.height * bpp(); }
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char *what) { return fail(LST_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
+
+    int compute(const lst_task *tasks, int n, lst_task_result *results) override;
+    int solve(const double *dis10, int n, double *out5) override;
+    int run_group(const lst_task *tasks, int n, lst_task_result *results, bool preprocess_only, bool have_win8,
+                  int tpl_override, float *map_out_host);
+    int ensure_tasks(int n);
+    int ensure_frames(int n);
+    int ensure_scratch(size_t win_bytes, size_t sum_elems, size_t map_elems);
+    int upload_template(int slot, const uint8_t *tpl8, int tw, int th);
+    void preproc_params(PreprocParams *pp, int max_w) const;
+    void drain_timers();
+};
+
+#define CU(call)                                             \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+    } while (0)
+#define CUC(ctx, call)                                              \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return (ctx)->cuda_fail(e_, #call);  \
+    } while (0)
+
+template <typename T>
+static cudaError_t regrow(T **p, size_t count)
+{
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc((void **)p, count * sizeof(T));
+}
+template <typename T>
+static cudaError_t regrow_host(T **p, size_t count)
+{
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    return cudaMallocHost((void **)p, count * sizeof(T));
+}
+
+int lst_ctx::ensure_tasks(int n)
+{
+    if (n <= task_cap) return LST_OK;
+    CU(cudaStreamSynchronize(s_compute));
+    int cap = std::max(n, task_cap * 2);
+    CU(regrow(&d_tasks, cap));
+    CU(regrow(&d_mm, (size_t)cap * 2));
+    CU(regrow(&d_best, cap));
+    CU(regrow(&d_results, cap));
+    CU(regrow_host(&h_tasks, cap));
+    CU(regrow_host(&h_results, cap));
+    task_cap = cap;
+    return LST_OK;
+}
+
+int lst_ctx::ensure_frames(int n)
+{
+    if (n <= frame_cap) return LST_OK;
+    CU(cudaStreamSynchronize(s_compute));
+    int cap = std::max(n, frame_cap * 2);
+    CU(regrow(&d_frames, cap));
+    CU(regrow_host(&h_frames, cap));
+    frame_cap = cap;
+    return LST_OK;
+}
+
+int lst_ctx::ensure_scratch(size_t win_bytes, size_t sum_elems, size_t map_elems)
+{
+    if (win_bytes > win8_cap) {
+        CU(cudaStreamSynchronize(s_compute));
+        size_t cap = std::max(win_bytes, win8_cap + win8_cap / 2);
+        CU(regrow(&d_win8, cap));
+        win8_cap = cap;
+    }
+    if (sum_elems > sum_cap) {
+        CU(cudaStreamSynchronize(s_compute));
+        size_t cap = std::max(sum_elems, sum_cap + sum_cap / 2);
+        CU(regrow(&d_wsum, cap));
+        CU(regrow(&d_wsq, cap));
+        sum_cap = cap;
+    }
+    if (map_elems > map_cap) {
+        CU(cudaStreamSynchronize(s_compute));
+        CU(regrow(&d_map, map_elems));
+        map_cap = map_elems;
+    }
+    return LST_OK;
+}
+
+void lst_ctx::preproc_params(PreprocParams *pp, int max_w) const
+{
+    memset(pp, 0, sizeof(*pp));
+    pp->pixel_type = p.pixel_type;
+    pp->frame_w = p.width;
+    pp->frame_h = p.height;
+    pp->quant_mode = p.quant_mode;
+    if (p.pixel_type == LST_PIX_U8 && !p.match_intensity) {
+        // ByteProcessor blur rounds back with (int)(v+0.5f), clamped: == ROUND255 on [0,255]
+        pp->range_per_task = 0;
+        pp->lo = 0.0f;
+        pp->hi = 255.0f;
+        pp->quant_mode = LST_QUANT_ROUND255;
+    } else if (p.range_mode == LST_RANGE_FIXED) {
+        pp->range_per_task = 0;
+        pp->lo = (float)p.range_lo;
+        pp->hi = (float)p.range_hi;
+    } else if (p.range_mode == LST_RANGE_DISPLAY && p.pixel_type == LST_PIX_U8) {
+        pp->range_per_task = 0;
+        pp->lo = 0.0f;
+        pp->hi = 255.0f;
+    } else {
+        pp->range_per_task = 1;
+    }
+    int tw = (max_w + 7) & ~7;
+    pp->tile_w = tw < 128 ? tw : 128;
+    pp->tile_h = 32;
+}
+
+int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th)
+{
+    TplConst c = template_consts(tpl8, tw, th);
+    std::vector<uint32_t> sh;
+    build_shifted_template(tpl8, tw, th, &sh);
+    if (sh.size() > shifted_cap[slot]) {
+        CU(regrow(&d_shifted[slot], sh.size()));
+        shifted_cap[slot] = sh.size();
+    }
+    if ((size_t)tw * th > raw_cap[slot]) {
+        CU(regrow(&d_raw[slot], (size_t)tw * th));
+        raw_cap[slot] = (size_t)tw * th;
+    }
+    CU(cudaMemcpyAsync(d_shifted[slot], sh.data(), sh.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s_compute));
+    CU(cudaMemcpyAsync(d_raw[slot], tpl8, (size_t)tw * th, cudaMemcpyHostToDevice, s_compute));
+    h_tpls.c[slot] = c;
+    h_tpls.shifted[slot] = d_shifted[slot];
+    h_tpls.raw[slot] = d_raw[slot];
+    CU(cudaMemcpyAsync(d_tpls, &h_tpls, sizeof(DevTemplates), cudaMemcpyHostToDevice, s_compute));
+    CU(cudaStreamSynchronize(s_compute));   // sh / h_tpls are pageable: finish before they go away
+    stats.h2d_bytes += (int64_t)(sh.size() * 4 + (size_t)tw * th + sizeof(DevTemplates));
+    return LST_OK;
+}
+
+void lst_ctx::drain_timers()
+{
+    for (TimedLaunch &t : timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+            stats.ncc_kernel_ms += ms;
+            stats.ncc_kernel_launches += 1;
+            stats.ncc_algorithmic_macs += t.macs;
+        }
+        event_pool.push_back(t.e0);
+        event_pool.push_back(t.e1);
+    }
+    timed.clear();
+}
+
+// One device pass over a group of windows that fits the scratch.
+//   preprocess_only: stop after the 8-bit windows (template extraction, lst_preprocess)
+//   have_win8:       the 8-bit windows are already in scratch (lst_match_single)
+int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, bool preprocess_only, bool have_win8,
+                       int tpl_override, float *map_out_host)
+{
+    int rc = ensure_tasks(n);
+    if (rc != LST_OK) return rc;
+    size_t win_off = 0, sum_off = 0;
+    int max_w = 0, max_h = 0, max_rw = 0, max_rh = 0, max_tw = 0, max_th = 0;
+    double macs = 0;
+    for (int i = 0; i < n; i++) {
+        const lst_task &t = tasks[i];
+        DevTask &d = h_tasks[i];
+        memset(&d, 0, sizeof(d));
+        Rect c = have_win8 ? Rect{0, 0, t.ww, t.wh} : clip_rect(t.wx, t.wy, t.ww, t.wh, p.width, p.height);
+        d.frame = t.frame;
+        d.tpl = tpl_override >= 0 ? tpl_override : t.tpl;
+        d.x0 = c.x;
+        d.y0 = c.y;
+        d.w = c.w;
+        d.h = c.h;
+        d.pitch = (c.w + 15) & ~15;
+        d.s_used = t.s_used;
+        if (c.w < 2 * kBlurRadius || c.h < 2 * kBlurRadius)
+            if (!have_win8) return fail(LST_ERR_UNSUPPORTED, "window %dx%d smaller than the blur support", c.w, c.h);
+        if (!preprocess_only) {
+            const TplConst &tc = h_tpls.c[d.tpl];
+            d.rw = c.w - tc.tw + 1;
+            d.rh = c.h - tc.th + 1;
+            if (d.rw < 1 || d.rh < 1) return fail(LST_ERR_INVALID, "window %dx%d smaller than the template", c.w, c.h);
+            max_rw = std::max(max_rw, d.rw);
+            max_rh = std::max(max_rh, d.rh);
+            max_tw = std::max(max_tw, tc.tw);
+            max_th = std::max(max_th, tc.th);
+            macs += (double)d.rw * d.rh * tc.tw * tc.th;
+        }
+        d.win_off = win_off;
+        d.sum_off = sum_off;
+        win_off += ((size_t)d.pitch * d.h + 255) & ~(size_t)255;
+        sum_off += ((size_t)d.rw * d.rh + 31) & ~(size_t)31;
+        max_w = std::max(max_w, d.w);
+        max_h = std::max(max_h, d.h);
+    }
+    rc = ensure_scratch(win_off + 64, sum_off + 32, map_out_host ? sum_off + 32 : 0);
+    if (rc != LST_OK) return rc;
+    CU(cudaMemcpyAsync(d_tasks, h_tasks, sizeof(DevTask) * n, cudaMemcpyHostToDevice, s_compute));
+    stats.h2d_bytes += (int64_t)sizeof(DevTask) * n;
+    int launches = 0;
+    launches += launch_init_pass(n, d_mm, d_best, s_compute);
+    if (!have_win8) {
+        PreprocParams pp;
+        preproc_params(&pp, max_w);
+        if (pp.range_per_task) launches += launch_minmax(d_tasks, n, max_h, d_frames, pp, d_mm, s_compute);
+        launches += launch_preprocess(d_tasks, n, max_w, max_h, d_frames, pp, d_mm, d_win8, s_compute);
+    }
+    if (!preprocess_only) {
+        MatchParams mp;
+        size_t smem = 0;
+        plan_match(max_rw, max_rh, max_tw, max_th, n, &mp, &smem);
+        mp.sub_pixel = p.sub_pixel;
+        mp.templ_size = p.templ_size;
+        mp.thresh = p.match_threshold;
+        if (smem > 200 * 1024) return fail(LST_ERR_UNSUPPORTED, "match tile needs %zu bytes of shared memory", smem);
+        launches += launch_box_sums(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, s_compute);
+        TimedLaunch tl;
+        if (timing) {
+            for (cudaEvent_t *e : {&tl.e0, &tl.e1}) {
+                if (!event_pool.empty()) {
+                    *e = event_pool.back();
+                    event_pool.pop_back();
+                } else {
+                    CU(cudaEventCreate(e));
+                }
+            }
+            tl.macs = macs;
+            CU(cudaEventRecord(tl.e0, s_compute));
+        }
+        launches += launch_ncc_match(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, d_best,
+                                     map_out_host ? d_map : nullptr, mp, s_compute);
+        if (timing) {
+            CU(cudaEventRecord(tl.e1, s_compute));
+            timed.push_back(tl);
+        }
+        launches += launch_epilogue(d_tasks, n, d_tpls, d_win8, d_wsum, d_wsq, d_best, d_results, mp, s_compute);
+        CU(cudaMemcpyAsync(h_results, d_results, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s_compute));
+        stats.d2h_bytes += (int64_t)sizeof(DevResult) * n;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s_compute));
+    stats.kernel_launches += launches;
+    if (timing) drain_timers();
+    if (!preprocess_only && results) {
+        for (int i = 0; i < n; i++) {
+            const DevResult &r = h_results[i];
+            if (!r.peak_check)
+                return fail(LST_ERR_CUDA, "internal: epilogue peak score differs from the argmax score (task %d)", i);
+            results[i].x = r.x;
+            results[i].y = r.y;
+            results[i].score = r.score;
+            results[i].ix = r.ix;
+            results[i].iy = r.iy;
+            results[i].accepted = r.accepted;
+            results[i].reserved = 0;
+        }
+    }
+    if (map_out_host && !preprocess_only) {
+        // single task: the map starts at sum_off 0
+        CU(cudaMemcpy(map_out_host, d_map, sizeof(float) * (size_t)h_tasks[0].rw * h_tasks[0].rh, cudaMemcpyDeviceToHost));
+    }
+    return LST_OK;
+}
+
+int lst_ctx::compute(const lst_task *tasks, int n, lst_task_result *results)
+{
+    // split into groups whose scratch fits the limit
+    int i = 0;
+    while (i < n) {
+        size_t bytes = 0;
+        int j = i;
+        while (j < n) {
+            const lst_task &t = tasks[j];
+            size_t pitch = (t.ww + 15) & ~15;
+            size_t need = pitch * t.wh + 256 + 2 * sizeof(uint32_t) * ((size_t)t.ww * t.wh + 32);
+            if (j > i && bytes + need > scratch_limit) break;
+            bytes += need;
+            j++;
+        }
+        int rc = run_group(tasks + i, j - i, results + i, false, false, -1, nullptr);
+        if (rc != LST_OK) return rc;
+        i = j;
+    }
+    return LST_OK;
+}
+
+int lst_ctx::solve(const double *dis10, int n, double *out5)
+{
+    if (n > solve_cap) {
+        CU(cudaStreamSynchronize(s_compute));
+        int cap = std::max(n, solve_cap * 2);
+        CU(regrow(&d_dis10, (size_t)cap * 10));
+        CU(regrow(&d_out5, (size_t)cap * 5));
+        CU(regrow_host(&h_dis10, (size_t)cap * 10));
+        CU(regrow_host(&h_out5, (size_t)cap * 5));
+        solve_cap = cap;
+    }
+    memcpy(h_dis10, dis10, sizeof(double) * 10 * n);
+    CU(cudaMemcpyAsync(d_dis10, h_dis10, sizeof(double) * 10 * n, cudaMemcpyHostToDevice, s_compute));
+    stats.kernel_launches += launch_solve(d_dis10, n, ref_xy, p.mark_dist, spot0, d_out5, s_compute);
+    CU(cudaMemcpyAsync(h_out5, d_out5, sizeof(double) * 5 * n, cudaMemcpyDeviceToHost, s_compute));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s_compute));
+    memcpy(out5, h_out5, sizeof(double) * 5 * n);
+    stats.h2d_bytes += (int64_t)sizeof(double) * 10 * n;
+    stats.d2h_bytes += (int64_t)sizeof(double) * 5 * n;
+    return LST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int lst_abi_version(void) { return LST_ABI_VERSION; }
+
+int lst_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *lst_last_error(const lst_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int lst_create(const lst_params *params, int device, lst_ctx **out)
+{
+    if (!params || !out) {
+        g_create_error = "null argument";
+        return LST_ERR_INVALID;
+    }
+    *out = nullptr;
+    std::string e;
+    int rc = validate_params(*params, &e);
+    if (rc != LST_OK) {
+        g_create_error = e;
+        return rc;
+    }
+    int n = lst_device_count();
+    if (n <= 0) {
+        g_create_error = "no CUDA device: this library has no CPU fallback";
+        return LST_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        g_create_error = "bad device index";
+        return LST_ERR_INVALID;
+    }
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) {
+        g_create_error = cudaGetErrorString(ce);
+        return LST_ERR_CUDA;
+    }
+    lst_ctx *c = new lst_ctx();
+    c->p = *params;
+    if (c->p.max_batch == 0) c->p.max_batch = 512;
+    if (c->p.match_threshold == 0.0) c->p.match_threshold = 0.2;
+    c->device = device;
+    memset(&c->stats, 0, sizeof(c->stats));
+    memset(&c->h_tpls, 0, sizeof(c->h_tpls));
+    auto bail = [&](cudaError_t err2, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err2);
+        lst_destroy(c);
+        return LST_ERR_CUDA;
+    };
+    if ((ce = cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "stream");
+    if ((ce = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "stream");
+    for (int i = 0; i < 2; i++)
+        if ((ce = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
+    if ((ce = cudaMalloc((void **)&c->d_tpls, sizeof(DevTemplates))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    float kern[7], ksum[7];
+    make_gaussian_kernel(kern, ksum);
+    if (set_blur_kernel(kern, ksum) != 0) return bail(cudaGetLastError(), "blur kernel upload");
+    *out = c;
+    return LST_OK;
+}
+
+void lst_destroy(lst_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->s_compute) cudaStreamSynchronize(c->s_compute);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    for (int i = 0; i < kMaxTpl; i++) {
+        cudaFree(c->d_shifted[i]);
+        cudaFree(c->d_raw[i]);
+    }
+    cudaFree(c->d_tpls);
+    cudaFree(c->d_tasks);
+    cudaFree(c->d_mm);
+    cudaFree(c->d_best);
+    cudaFree(c->d_results);
+    cudaFree(c->d_win8);
+    cudaFree(c->d_wsum);
+    cudaFree(c->d_wsq);
+    cudaFree(c->d_map);
+    cudaFree(c->d_frames);
+    cudaFree(c->d_ring[0]);
+    cudaFree(c->d_ring[1]);
+    cudaFree(c->d_dis10);
+    cudaFree(c->d_out5);
+    cudaFreeHost(c->h_tasks);
+    cudaFreeHost(c->h_results);
+    cudaFreeHost(c->h_frames);
+    cudaFreeHost(c->h_dis10);
+    cudaFreeHost(c->h_out5);
+    for (TimedLaunch &t : c->timed) {
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++)
+        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    delete c;
+}
+
+static int ensure_ring(lst_ctx *c, size_t bytes_per_half)
+{
+    if (bytes_per_half <= c->ring_cap) return LST_OK;
+    CUC(c, cudaStreamSynchronize(c->s_compute));
+    CUC(c, cudaStreamSynchronize(c->s_copy));
+    for (int i = 0; i < 2; i++) CUC(c, regrow(&c->d_ring[i], bytes_per_half));
+    c->ring_cap = bytes_per_half;
+    return LST_OK;
+}
+
+int lst_set_reference(lst_ctx *c, const void *ref_frame, const float ref_xy[10], lst_reference_info *out)
+{
+    if (!c || !ref_frame || !ref_xy) return LST_ERR_INVALID;
+    CUC(c, cudaSetDevice(c->device));
+    int rc = ensure_ring(c, c->frame_bytes());
+    if (rc != LST_OK) return rc;
+    rc = c->ensure_frames(1);
+    if (rc != LST_OK) return rc;
+    CUC(c, cudaMemcpyAsync(c->d_ring[0], ref_frame, c->frame_bytes(), cudaMemcpyHostToDevice, c->s_compute));
+    c->stats.h2d_bytes += (int64_t)c->frame_bytes();
+    c->h_frames[0] = c->d_ring[0];
+    CUC(c, cudaMemcpyAsync(c->d_frames, c->h_frames, sizeof(void *), cudaMemcpyHostToDevice, c->s_compute));
+    lst_task tasks[5];
+    Rect crop[5];
+    for (int k = 0; k < 5; k++) {
+        c->ref_xy[2 * k] = ref_xy[2 * k];
+        c->ref_xy[2 * k + 1] = ref_xy[2 * k + 1];
+        c->rect[k] = template_rect(c->p, ref_xy[2 * k], ref_xy[2 * k + 1]);   // Roi.getBounds(): unclipped
+        crop[k] = clip_rect(c->rect[k].x, c->rect[k].y, c->rect[k].w, c->rect[k].h, c->p.width, c->p.height);
+        if (crop[k].w < 2 * kBlurRadius || crop[k].h < 2 * kBlurRadius)
+            return c->fail(LST_ERR_INVALID, "template %d falls outside the slice", k);
+        memset(&tasks[k], 0, sizeof(lst_task));
+        tasks[k].frame = 0;
+        tasks[k].tpl = k;
+        tasks[k].wx = crop[k].x;
+        tasks[k].wy = crop[k].y;
+        tasks[k].ww = crop[k].w;
+        tasks[k].wh = crop[k].h;
+    }
+    rc = c->run_group(tasks, 5, nullptr, true, false, -1, nullptr);
+    if (rc != LST_OK) return rc;
+    for (int k = 0; k < 5; k++) {
+        std::vector<uint8_t> t8((size_t)crop[k].w * crop[k].h);
+        const DevTask &d = c->h_tasks[k];
+        CUC(c, cudaMemcpy2D(t8.data(), crop[k].w, c->d_win8 + d.win_off, d.pitch, crop[k].w, crop[k].h, cudaMemcpyDeviceToHost));
+        c->stats.d2h_bytes += (int64_t)t8.size();
+        rc = c->upload_template(k, t8.data(), crop[k].w, crop[k].h);
+        if (rc != LST_OK) return rc;
+    }
+    for (int i = 0; i < 10; i++) c->dis[i] = 0.0;
+    double o5[5];
+    calc_displacement(c->ref_xy, c->dis, c->p.mark_dist, 0, c->spot0, o5);   // LST4:702: latches spotX0/spotY0
+    c->have_ref = true;
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        for (int k = 0; k < 5; k++) {
+            out->rect[k][0] = c->rect[k].x;
+            out->rect[k][1] = c->rect[k].y;
+            out->rect[k][2] = c->rect[k].w;
+            out->rect[k][3] = c->rect[k].h;
+            out->mideal[k] = c->h_tpls.c[k].mideal;
+        }
+        out->ref_record.frame = -1;
+        out->ref_record.status = LST_STATUS_OK;
+        out->ref_record.reject = -1;
+        out->ref_record.dX_pix = o5[0];
+        out->ref_record.dY_pix = o5[1];
+        out->ref_record.x_abs = o5[2];
+        out->ref_record.y_abs = o5[3];
+        out->ref_record.dL = o5[4];
+    }
+    return LST_OK;
+}
+
+static void fill_resolve_input(const lst_ctx *c, ResolveInput *in)
+{
+    in->p = c->p;
+    for (int k = 0; k < 5; k++) in->rect[k] = c->rect[k];
+    memcpy(in->ref_xy, c->ref_xy, sizeof(in->ref_xy));
+    in->spot0[0] = c->spot0[0];
+    in->spot0[1] = c->spot0[1];
+}
+
+// frames_of(i) -> host pointer of frame i, or device pointer when on_device
+static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *const *ptrs, bool on_device,
+                      int64_t first_index, int32_t n_frames, lst_record *out)
+{
+    if (!c || !out || n_frames < 0 || (!base && !ptrs)) return LST_ERR_INVALID;
+    if (!c->have_ref) return c->fail(LST_ERR_STATE, "lst_set_reference must be called before tracking");
+    CUC(c, cudaSetDevice(c->device));
+    if (n_frames == 0) return LST_OK;
+    const size_t fb = c->frame_bytes();
+    if (stride == 0) stride = fb;
+    const int B = c->p.max_batch;
+    ResolveInput in;
+    fill_resolve_input(c, &in);
+    int rc = c->ensure_frames(B);
+    if (rc != LST_OK) return rc;
+    if (!on_device) {
+        rc = ensure_ring(c, (size_t)std::min<int64_t>(B, n_frames) * fb);
+        if (rc != LST_OK) return rc;
+    }
+    auto src_of = [&](int64_t i) -> const void * { return ptrs ? ptrs[i] : (const uint8_t *)base + (size_t)i * stride; };
+    auto enqueue_copy = [&](int b) -> int {
+        int64_t f0 = (int64_t)b * B;
+        int nb = (int)std::min<int64_t>(B, n_frames - f0);
+        uint8_t *dst = c->d_ring[b & 1];
+        if (!ptrs && stride == fb) {
+            CUC(c, cudaMemcpyAsync(dst, src_of(f0), (size_t)nb * fb, cudaMemcpyHostToDevice, c->s_copy));
+        } else {
+            for (int i = 0; i < nb; i++)
+                CUC(c, cudaMemcpyAsync(dst + (size_t)i * fb, src_of(f0 + i), fb, cudaMemcpyHostToDevice, c->s_copy));
+        }
+        CUC(c, cudaEventRecord(c->ev_copy[b & 1], c->s_copy));
+        c->stats.h2d_bytes += (int64_t)nb * (int64_t)fb;
+        return LST_OK;
+    };
+    const int nbatches = (int)((n_frames + B - 1) / B);
+    if (!on_device) {
+        rc = enqueue_copy(0);
+        if (rc != LST_OK) return rc;
+    }
+    for (int b = 0; b < nbatches; b++) {
+        int64_t f0 = (int64_t)b * B;
+        int nb = (int)std::min<int64_t>(B, n_frames - f0);
+        if (!on_device) {
+            if (b + 1 < nbatches) {   // double buffering: next batch's copy overlaps this batch's kernels
+                rc = enqueue_copy(b + 1);
+                if (rc != LST_OK) return rc;
+            }
+            CUC(c, cudaStreamWaitEvent(c->s_compute, c->ev_copy[b & 1], 0));
+            for (int i = 0; i < nb; i++) c->h_frames[i] = c->d_ring[b & 1] + (size_t)i * fb;
+        } else {
+            for (int i = 0; i < nb; i++) c->h_frames[i] = src_of(f0 + i);
+        }
+        CUC(c, cudaMemcpyAsync(c->d_frames, c->h_frames, sizeof(void *) * nb, cudaMemcpyHostToDevice, c->s_compute));
+        c->stats.h2d_bytes += (int64_t)sizeof(void *) * nb;
+        rc = resolve_batch(in, c->dis, first_index + f0, nb, *c, out + f0, &c->stats);
+        if (rc != LST_OK) {
+            if (c->err.empty()) c->fail(rc, "resolver failed (%d)", rc);
+            return rc;
+        }
+    }
+    return LST_OK;
+}
+
+int lst_track(lst_ctx *c, const void *frames, size_t frame_stride_bytes, int64_t first_frame_index, int32_t n_frames,
+              lst_record *out)
+{
+    return track_impl(c, frames, frame_stride_bytes, nullptr, false, first_frame_index, n_frames, out);
+}
+int lst_track_ptrs(lst_ctx *c, const void *const *frame_ptrs, int64_t first_frame_index, int32_t n_frames, lst_record *out)
+{
+    return track_impl(c, nullptr, 0, frame_ptrs, false, first_frame_index, n_frames, out);
+}
+int lst_track_device(lst_ctx *c, const void *dev_frames, size_t frame_stride_bytes, int64_t first_frame_index,
+                     int32_t n_frames, lst_record *out)
+{
+    return track_impl(c, dev_frames, frame_stride_bytes, nullptr, true, first_frame_index, n_frames, out);
+}
+
+int lst_get_state(const lst_ctx *c, double dis[10])
+{
+    if (!c || !dis) return LST_ERR_INVALID;
+    memcpy(dis, c->dis, sizeof(double) * 10);
+    return LST_OK;
+}
+int lst_set_state(lst_ctx *c, const double dis[10])
+{
+    if (!c || !dis) return LST_ERR_INVALID;
+    memcpy(c->dis, dis, sizeof(double) * 10);
+    return LST_OK;
+}
+
+int lst_match_single(lst_ctx *c, const uint8_t *src8, int32_t sw, int32_t sh, const uint8_t *tpl8, int32_t tw,
+                     int32_t th, int32_t sub_pix, double out[3], float *score_map)
+{
+    if (!c || !src8 || !tpl8 || !out) return LST_ERR_INVALID;
+    if (tw < 1 || th < 1 || tw > 256 || th > 256 || sw < tw || sh < th) return c->fail(LST_ERR_INVALID, "bad sizes");
+    CUC(c, cudaSetDevice(c->device));
+    int rc = c->upload_template(kMaxTpl - 1, tpl8, tw, th);
+    if (rc != LST_OK) return rc;
+    size_t pitch = (sw + 15) & ~15;
+    rc = c->ensure_scratch(pitch * sh + 512, (size_t)sw * sh + 64, score_map ? (size_t)sw * sh + 64 : 0);
+    if (rc != LST_OK) return rc;
+    CUC(c, cudaMemsetAsync(c->d_win8, 0, pitch * sh, c->s_compute));
+    CUC(c, cudaMemcpy2DAsync(c->d_win8, pitch, src8, sw, sw, sh, cudaMemcpyHostToDevice, c->s_compute));
+    c->stats.h2d_bytes += (int64_t)sw * sh;
+    lst_task t;
+    memset(&t, 0, sizeof(t));
+    t.ww = sw;
+    t.wh = sh;
+    lst_task_result r;
+    int save_sub = c->p.sub_pixel;
+    c->p.sub_pixel = sub_pix;
+    rc = c->run_group(&t, 1, &r, false, true, kMaxTpl - 1, score_map);
+    c->p.sub_pixel = save_sub;
+    if (rc != LST_OK) return rc;
+    out[0] = r.x;
+    out[1] = r.y;
+    out[2] = r.score;
+    return LST_OK;
+}
+
+int lst_match_test(lst_ctx *c, const uint8_t *src8, int32_t sw, int32_t sh, double *out)
+{
+    double o[3];
+    int rc = lst_match_single(c, src8, sw, sh, src8, sw, sh, 0, o, nullptr);
+    if (rc == LST_OK && out) *out = o[2];
+    return rc;
+}
+
+int lst_preprocess(lst_ctx *c, const void *frame, int32_t x0, int32_t y0, int32_t w, int32_t h, uint8_t *out8)
+{
+    if (!c || !frame || !out8) return LST_ERR_INVALID;
+    CUC(c, cudaSetDevice(c->device));
+    Rect r = clip_rect(x0, y0, w, h, c->p.width, c->p.height);
+    if (r.w != w || r.h != h) return c->fail(LST_ERR_INVALID, "rectangle outside the slice");
+    int rc = ensure_ring(c, c->frame_bytes());
+    if (rc != LST_OK) return rc;
+    rc = c->ensure_frames(1);
+    if (rc != LST_OK) return rc;
+    CUC(c, cudaMemcpyAsync(c->d_ring[1], frame, c->frame_bytes(), cudaMemcpyHostToDevice, c->s_compute));
+    c->h_frames[0] = c->d_ring[1];
+    CUC(c, cudaMemcpyAsync(c->d_frames, c->h_frames, sizeof(void *), cudaMemcpyHostToDevice, c->s_compute));
+    lst_task t;
+    memset(&t, 0, sizeof(t));
+    t.wx = x0;
+    t.wy = y0;
+    t.ww = w;
+    t.wh = h;
+    rc = c->run_group(&t, 1, nullptr, true, false, -1, nullptr);
+    if (rc != LST_OK) return rc;
+    CUC(c, cudaMemcpy2D(out8, w, c->d_win8 + c->h_tasks[0].win_off, c->h_tasks[0].pitch, w, h, cudaMemcpyDeviceToHost));
+    return LST_OK;
+}
+
+int lst_calc_displacement(const float ref_xy[10], const double dis[10], double mark_dist, const double spot0[2],
+                          double out5[5])
+{
+    if (!ref_xy || !dis || !out5) return LST_ERR_INVALID;
+    double s0[2] = {spot0 ? spot0[0] : 0.0, spot0 ? spot0[1] : 0.0};
+    calc_displacement(ref_xy, dis, mark_dist, spot0 != nullptr, s0, out5);
+    return LST_OK;
+}
+
+int lst_alloc_pinned(size_t bytes, void **out)
+{
+    if (!out) return LST_ERR_INVALID;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? LST_OK : LST_ERR_NOMEM;
+}
+int lst_free_pinned(void *p) { return cudaFreeHost(p) == cudaSuccess ? LST_OK : LST_ERR_CUDA; }
+int lst_host_register(void *p, size_t bytes)
+{
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? LST_OK : LST_ERR_CUDA;
+}
+int lst_host_unregister(void *p) { return cudaHostUnregister(p) == cudaSuccess ? LST_OK : LST_ERR_CUDA; }
+
+int lst_device_alloc(lst_ctx *c, size_t bytes, void **out)
+{
+    if (!c || !out) return LST_ERR_INVALID;
+    CUC(c, cudaSetDevice(c->device));
+    CUC(c, cudaMalloc(out, bytes));
+    return LST_OK;
+}
+int lst_device_free(lst_ctx *c, void *p)
+{
+    if (!c) return LST_ERR_INVALID;
+    CUC(c, cudaSetDevice(c->device));
+    CUC(c, cudaFree(p));
+    return LST_OK;
+}
+int lst_device_upload(lst_ctx *c, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (!c) return LST_ERR_INVALID;
+    CUC(c, cudaSetDevice(c->device));
+    CUC(c, cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+    return LST_OK;
+}
+
+int lst_get_stats(const lst_ctx *c, lst_stats *out)
+{
+    if (!c || !out) return LST_ERR_INVALID;
+    *out = c->stats;
+    return LST_OK;
+}
+int lst_reset_stats(lst_ctx *c)
+{
+    if (!c) return LST_ERR_INVALID;
+    memset(&c->stats, 0, sizeof(c->stats));
+    return LST_OK;
+}
+int lst_set_kernel_timing(lst_ctx *c, int32_t on)
+{
+    if (!c) return LST_ERR_INVALID;
+    c->timing = on != 0;
+    return LST_OK;
+}
+
+int lst_measure_alu_peaks(int device, double ms_per_test, double out[2])
+{
+    if (!out) return LST_ERR_INVALID;
+    if (lst_device_count() <= device || device < 0) return LST_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return LST_ERR_CUDA;
+    return measure_alu_peaks(ms_per_test, out) == 0 ? LST_OK : LST_ERR_CUDA;
+}
+
+// ---- host-only test seams -------------------------------------------------------------------------
+int lst_host_window_for(const lst_params *p, const int32_t rect[4], double dis_x, double dis_y, int32_t out[4])
+{
+    if (!p || !rect || !out) return LST_ERR_INVALID;
+    Rect r{rect[0], rect[1], rect[2], rect[3]};
+    Rect w = window_for(*p, r, jint(dis_x), jint(dis_y), p->s_area, false, nullptr);
+    out[0] = w.x;
+    out[1] = w.y;
+    out[2] = w.w;
+    out[3] = w.h;
+    return LST_OK;
+}
+
+int lst_host_template_rect(const lst_params *p, float ref_x, float ref_y, int32_t out[4])
+{
+    if (!p || !out) return LST_ERR_INVALID;
+    Rect r = template_rect(*p, ref_x, ref_y);
+    out[0] = r.x;
+    out[1] = r.y;
+    out[2] = r.w;
+    out[3] = r.h;
+    return LST_OK;
+}
+
+namespace {
+struct CallbackExecutor : public Executor {
+    lst_compute_fn fn;
+    void *user;
+    ResolveInput *in;
+    int compute(const lst_task *tasks, int n, lst_task_result *results) override { return fn(user, tasks, n, results); }
+    int solve(const double *dis10, int n, double *out5) override
+    {
+        for (int i = 0; i < n; i++) {
+            double s0[2] = {in->spot0[0], in->spot0[1]};
+            calc_displacement(in->ref_xy, dis10 + 10 * i, in->p.mark_dist, 1, s0, out5 + 5 * i);
+        }
+        return LST_OK;
+    }
+};
+}  // namespace
+
+int lst_host_resolve(const lst_params *p, const int32_t rect[5][4], const float ref_xy[10], const double spot0[2],
+                     double dis_io[10], int64_t first_frame_index, int32_t n_frames, lst_compute_fn compute, void *user,
+                     lst_record *out, lst_stats *stats_io)
+{
+    if (!p || !rect || !ref_xy || !spot0 || !dis_io || !compute || !out) return LST_ERR_INVALID;
+    ResolveInput in;
+    in.p = *p;
+    for (int k = 0; k < 5; k++) in.rect[k] = Rect{rect[k][0], rect[k][1], rect[k][2], rect[k][3]};
+    memcpy(in.ref_xy, ref_xy, sizeof(in.ref_xy));
+    in.spot0[0] = spot0[0];
+    in.spot0[1] = spot0[1];
+    CallbackExecutor ex;
+    ex.fn = compute;
+    ex.user = user;
+    ex.in = &in;
+    int B = p->max_batch > 0 ? p->max_batch : 512;
+    for (int f0 = 0; f0 < n_frames; f0 += B) {
+        int nb = std::min(B, n_frames - f0);
+        // the callback sees batch-local frame indices; shift them to caller-global ones
+        struct Shift {
+            lst_compute_fn fn;
+            void *user;
+            int f0;
+        } sh{compute, user, f0};
+        struct ShiftExecutor : public Executor {
+            Shift *s;
+            CallbackExecutor *base;
+            int compute(const lst_task *tasks, int n, lst_task_result *results) override
+            {
+                std::vector<lst_task> t(tasks, tasks + n);
+                for (auto &x : t) x.frame += s->f0;
+                return s->fn(s->user, t.data(), n, results);
+            }
+            int solve(const double *d, int n, double *o) override { return base->solve(d, n, o); }
+        } sx;
+        sx.s = &sh;
+        sx.base = &ex;
+        int rc = resolve_batch(in, dis_io, first_frame_index + f0, nb, sx, out + f0, stats_io);
+        if (rc != LST_OK) return rc;
+    }
+    return LST_OK;
+}
+
+}  // extern "C"

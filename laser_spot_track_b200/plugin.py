@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference plugin's interface for the tracking path.
+
+The reference is an ImageJ ``PlugInFilter`` (one Java class); its toolchain (JVM, Maven) is not
+in this image, so the caller's side of the C ABI is written in Python, keeping the reference's
+method names, argument meaning and error behaviour:
+
+=====================================  =========================================================
+reference (Laser_Spot_Track4.java)     here
+=====================================  =========================================================
+getUserParameters()        LST4:2370   ``LaserSpotTrack4(width, height, bit_depth, **dialog)``
+template selection         LST4:486    ``set_reference(ref_slice, points)``
+for-loop + analyseSlice    LST4:793    ``track(stack)`` / ``analyseSlice(slice_pixels)``
+doMatch_coord_res (static) LST4:2502   ``doMatch_coord_res(src8, tpl8, method, subPix)``
+doMatch_test (static)      LST4:2724   ``doMatch_test(src8, method)``
+calcDisplacement()         LST4:2318   ``calcDisplacement(ref_xy, dis, markDist, spot0)``
+ResultsTable rows          LST4:864    ``results_table(records)``
+=====================================  =========================================================
+
+Everything computes on the GPU through ``liblst_b200.so``; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import native as N
+
+_PIX = {8: (N.PIX_U8, np.uint8), 16: (N.PIX_U16, np.uint16), 32: (N.PIX_F32, np.float32)}
+TEMPLATE_NAMES = ("spot", "mark1", "mark2", "mark3", "mark4")
+RESULT_COLUMNS = ("Time", "Frame", "File", "dX_pix", "dY_pix", "X_abs", "Y_abs", "dL")   # LST4:867-875
+
+
+class LstError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"lst_b200 error {code}: {msg}")
+        self.code = code
+
+
+class LaserSpotTrack4:
+    """One tracking session on one GPU (one ``lst_ctx``)."""
+
+    def __init__(self, width: int, height: int, bit_depth: int = 8, *, device: int = 0,
+                 method: int = 5, templSize: int = 120, sArea: int = 50, markDist: float = 100.0,
+                 subPixel: bool = True, matchIntensity: bool = True, alwaysAutoSkip: bool = True,
+                 doubling: bool = False, maxSArea: int = 500, range_mode: int = N.RANGE_DISPLAY,
+                 range_lo: float = 0.0, range_hi: float = 255.0, quant_mode: int = N.QUANT_ROUND255,
+                 max_batch: int = 0):
+        if bit_depth not in _PIX:
+            raise LstError(N.LST_ERR_UNSUPPORTED, "Unsupported image type")       # IJ.error, LST4:2537
+        self._lib = N.load()
+        self.width, self.height, self.bit_depth = width, height, bit_depth
+        self._np_dtype = _PIX[bit_depth][1]
+        self.params = N.default_params(
+            width, height, _PIX[bit_depth][0], method=method, templ_size=templSize, s_area=sArea,
+            mark_dist=markDist, sub_pixel=int(subPixel), match_intensity=int(matchIntensity),
+            auto_skip=int(alwaysAutoSkip), doubling=int(doubling), max_s_area=maxSArea,
+            range_mode=range_mode, range_lo=range_lo, range_hi=range_hi, quant_mode=quant_mode,
+            max_batch=max_batch)
+        self._ctx = C.c_void_p()
+        rc = self._lib.lst_create(C.byref(self.params), device, C.byref(self._ctx))
+        if rc != N.LST_OK:
+            msg = self._lib.lst_last_error(None).decode()
+            self._ctx = None
+            raise LstError(rc, msg)
+        self.reference: Optional[N.ReferenceInfo] = None
+        self.ref_xy: Optional[np.ndarray] = None
+
+    # -- lifecycle --------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.lst_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != N.LST_OK:
+            raise LstError(rc, self._lib.lst_last_error(self._ctx).decode())
+
+    def _frame(self, a: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=self._np_dtype)
+        if a.shape[-2:] != (self.height, self.width):
+            raise LstError(N.LST_ERR_INVALID, "slice size differs from the stack's (LST4:813-817)")
+        return a
+
+    # -- template selection: LST4:486-702 -----------------------------------------------------
+    def set_reference(self, ref_slice: np.ndarray, points: Sequence[Tuple[float, float]]) -> N.ReferenceInfo:
+        """points: click points of spot, mark1, mark2, mark3, mark4 (x, y)."""
+        fr = self._frame(ref_slice)
+        xy = np.asarray(points, dtype=np.float32).reshape(10)
+        info = N.ReferenceInfo()
+        self._check(self._lib.lst_set_reference(self._ctx, fr.ctypes.data, xy.ctypes.data_as(C.POINTER(C.c_float)),
+                                                C.byref(info)))
+        self.reference, self.ref_xy = info, xy
+        return info
+
+    # -- the loop body ---------------------------------------------------------------------------
+    def track(self, stack: np.ndarray, first_frame_index: int = 1) -> "C.Array[N.Record]":
+        """analyseSlice + calcDisplacement for every slice of ``stack`` ([n, H, W]) in order."""
+        st = self._frame(stack)
+        if st.ndim == 2:
+            st = st[None]
+        n = st.shape[0]
+        out = (N.Record * n)()
+        self._check(self._lib.lst_track(self._ctx, st.ctypes.data, 0, first_frame_index, n, out))
+        return out
+
+    def track_slices(self, slices: Iterable[np.ndarray], first_frame_index: int = 1):
+        """Same, from separately allocated slices (stack.getProcessor(i).getPixels())."""
+        fr = [self._frame(s) for s in slices]
+        n = len(fr)
+        ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in fr])
+        out = (N.Record * n)()
+        self._check(self._lib.lst_track_ptrs(self._ctx, ptrs, first_frame_index, n, out))
+        return out
+
+    def track_device(self, dev_ptr: int, n: int, frame_stride_bytes: int = 0, first_frame_index: int = 1):
+        out = (N.Record * n)()
+        self._check(self._lib.lst_track_device(self._ctx, C.c_void_p(dev_ptr), frame_stride_bytes,
+                                               first_frame_index, n, out))
+        return out
+
+    def analyseSlice(self, slice_pixels: np.ndarray, frame_index: int = 0) -> N.Record:
+        """One slice; returns the record whose ``status`` is analyseSlice's return value (LST4:1302)."""
+        return self.track(slice_pixels, frame_index)[0]
+
+    # -- state --------------------------------------------------------------------------------------
+    def get_state(self) -> np.ndarray:
+        d = (C.c_double * 10)()
+        self._check(self._lib.lst_get_state(self._ctx, d))
+        return np.array(d[:])
+
+    def set_state(self, dis: Sequence[float]):
+        d = (C.c_double * 10)(*[float(v) for v in dis])
+        self._check(self._lib.lst_set_state(self._ctx, d))
+
+    # -- the reference's public statics ----------------------------------------------------------------
+    def doMatch_coord_res(self, src8: np.ndarray, tpl8: np.ndarray, method: int = 5, subPix: bool = True,
+                          want_map: bool = False):
+        """doMatch_coord_res(src, tpl, method, subPix, null) on 8-bit images -> [x, y, score] (LST4:2502)."""
+        if method != 5:
+            raise LstError(N.LST_ERR_UNSUPPORTED, "only method 5 is on this path")
+        s = np.ascontiguousarray(src8, dtype=np.uint8)
+        t = np.ascontiguousarray(tpl8, dtype=np.uint8)
+        out = (C.c_double * 3)()
+        m = None
+        mp = None
+        if want_map:
+            m = np.zeros((s.shape[0] - t.shape[0] + 1, s.shape[1] - t.shape[1] + 1), dtype=np.float32)
+            mp = m.ctypes.data
+        self._check(self._lib.lst_match_single(self._ctx, s.ctypes.data, s.shape[1], s.shape[0], t.ctypes.data,
+                                               t.shape[1], t.shape[0], int(subPix), out, mp))
+        res = [out[0], out[1], out[2]]
+        return (res, m) if want_map else res
+
+    def doMatch_test(self, src8: np.ndarray, method: int = 5) -> float:
+        if method != 5:
+            raise LstError(N.LST_ERR_UNSUPPORTED, "only method 5 is on this path")
+        s = np.ascontiguousarray(src8, dtype=np.uint8)
+        out = C.c_double()
+        self._check(self._lib.lst_match_test(self._ctx, s.ctypes.data, s.shape[1], s.shape[0], C.byref(out)))
+        return out.value
+
+    def preprocess(self, frame: np.ndarray, x0: int, y0: int, w: int, h: int) -> np.ndarray:
+        """The 8-bit image handed to matchTemplate for one rectangle of ``frame``."""
+        fr = self._frame(frame)
+        out = np.zeros((h, w), dtype=np.uint8)
+        self._check(self._lib.lst_preprocess(self._ctx, fr.ctypes.data, x0, y0, w, h, out.ctypes.data))
+        return out
+
+    @staticmethod
+    def calcDisplacement(ref_xy, dis, markDist: float, spot0=None):
+        lib = N.load()
+        r = np.asarray(ref_xy, dtype=np.float32).reshape(10)
+        d = (C.c_double * 10)(*[float(v) for v in np.asarray(dis).reshape(10)])
+        s0 = (C.c_double * 2)(*spot0) if spot0 is not None else None
+        out = (C.c_double * 5)()
+        rc = lib.lst_calc_displacement(r.ctypes.data_as(C.POINTER(C.c_float)), d, float(markDist), s0, out)
+        if rc != N.LST_OK:
+            raise LstError(rc, "lst_calc_displacement")
+        return list(out)
+
+    # -- diagnostics ------------------------------------------------------------------------------------
+    def stats(self) -> N.Stats:
+        s = N.Stats()
+        self._check(self._lib.lst_get_stats(self._ctx, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        self._check(self._lib.lst_reset_stats(self._ctx))
+
+    def set_kernel_timing(self, on: bool):
+        self._check(self._lib.lst_set_kernel_timing(self._ctx, int(on)))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.lst_device_alloc(self._ctx, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        self._check(self._lib.lst_device_free(self._ctx, C.c_void_p(ptr)))
+
+    def device_upload(self, dst: int, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self._check(self._lib.lst_device_upload(self._ctx, C.c_void_p(dst), src.ctypes.data, src.nbytes))
+
+
+def results_table(records, ref_info: Optional[N.ReferenceInfo] = None, time_step: float = 1.0,
+                  file_label: str = "") -> List[dict]:
+    """The ResultsTable rows the plugin's loop appends (LST4:707-718 row 0, LST4:864-875):
+    skipped frames add no row; Time advances by the constant step (no EXIF) per analysed frame."""
+    rows = []
+    if ref_info is not None:
+        r = ref_info.ref_record
+        rows.append(dict(Time=0.0, Frame="1", File=file_label, dX_pix=r.dX_pix, dY_pix=r.dY_pix,
+                         X_abs=r.x_abs, Y_abs=r.y_abs, dL=r.dL))
+    seconds = 0.0
+    for r in records:
+        if r.status != N.STATUS_OK:
+            continue
+        seconds += time_step
+        rows.append(dict(Time=seconds, Frame=str(len(rows) + 1), File=file_label, dX_pix=r.dX_pix,
+                         dY_pix=r.dY_pix, X_abs=r.x_abs, Y_abs=r.y_abs, dL=r.dL))
+    return rows

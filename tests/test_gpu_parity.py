@@ -1,0 +1,201 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Integer/byte work must be bit-exact; float32 scores are compared
+bit-exactly against the exact oracle and within 1e-4 against OpenCV (cv2) whose DFT numerator
+carries ~5e-5 noise; sub-pixel positions within 1e-3 px against cv2."""
+import numpy as np
+import pytest
+
+from laser_spot_track_b200 import LaserSpotTrack4, native as N
+from laser_spot_track_b200.synth import CONFIGS, StackConfig, SyntheticStack
+from oracle import lst_oracle as O
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL_CV2 = 1e-4      # north_star: correlation scores within 1e-4
+SUBPIX_TOL_CV2 = 1e-3     # north_star: sub-pixel positions / displacements within 1e-3 px
+
+
+def _tracker(cfg, op, **kw):
+    bits = {"u8": 8, "u16": 16, "f32": 32}[cfg.dtype]
+    return LaserSpotTrack4(cfg.width, cfg.height, bits, templSize=op.templ_size, sArea=op.s_area,
+                           markDist=op.mark_dist, subPixel=op.sub_pixel, matchIntensity=op.match_intensity,
+                           doubling=op.doubling, maxSArea=op.max_s_area, range_mode=op.range_mode,
+                           range_lo=op.range_lo, range_hi=op.range_hi, quant_mode=op.quant_mode, **kw)
+
+
+@pytest.fixture(scope="module")
+def stack_a(built_lib, oracle_clib):
+    cfg = CONFIGS["A"]
+    st = SyntheticStack(cfg)
+    return cfg, st, [st.frame(i) for i in range(0, 61)]
+
+
+def test_device_present(built_lib):
+    assert N.load().lst_device_count() >= 1
+
+
+@pytest.mark.parametrize("dtype,mi,range_mode,quant", [
+    ("u8", False, O.RANGE_DISPLAY, O.QUANT_ROUND255),
+    ("u8", True, O.RANGE_DISPLAY, O.QUANT_ROUND255),
+    ("u8", True, O.RANGE_CROP, O.QUANT_ROUND255),
+    ("u8", True, O.RANGE_CROP, O.QUANT_TRUNC256),
+    ("u16", True, O.RANGE_DISPLAY, O.QUANT_ROUND255),
+    ("u16", True, O.RANGE_FIXED, O.QUANT_ROUND255),
+    ("f32", True, O.RANGE_DISPLAY, O.QUANT_ROUND255),
+])
+def test_preprocess_bit_exact(built_lib, dtype, mi, range_mode, quant):
+    """crop -> float -> blur -> 8-bit: every byte equal to the oracle's, incl. windows touching the borders."""
+    cfg = StackConfig(320, 240, dtype, 32, 24, 4)
+    st = SyntheticStack(cfg)
+    fr = st.frame(1)
+    op = util.oracle_params(cfg, match_intensity=mi, range_mode=range_mode, quant_mode=quant,
+                            range_lo=100.0, range_hi=60000.0 if dtype == "u16" else 200.0)
+    with _tracker(cfg, op) as t:
+        for (x0, y0, w, h) in [(0, 0, 80, 80), (240, 160, 80, 80), (37, 41, 96, 64), (100, 50, 160, 160),
+                               (0, 0, 320, 240), (300, 0, 20, 33), (5, 200, 150, 14)]:
+            got = t.preprocess(fr, x0, y0, w, h)
+            want = O.preprocess_crop(fr, x0, y0, w, h, op)
+            assert got.shape == want.shape
+            bad = np.argwhere(got != want)
+            assert bad.size == 0, f"{dtype} rect {(x0, y0, w, h)}: {len(bad)} bytes differ, first {bad[:3]}, got {got[tuple(bad[0])]} want {want[tuple(bad[0])]}"
+
+
+@pytest.mark.parametrize("S,T", [(96, 32), (160, 48), (64, 14), (75, 33), (200, 120), (150, 127)])
+def test_match_single_map(built_lib, oracle_clib, S, T):
+    """matchTemplate + minMaxLoc + sub-pixel on 8-bit inputs: full score map."""
+    rng = np.random.default_rng(S * 1000 + T)
+    base = rng.integers(0, 256, size=(S + 40, S + 40), dtype=np.uint8)
+    import cv2
+    base = cv2.GaussianBlur(base, (0, 0), 2.0)
+    win = np.ascontiguousarray(base[:S, :S])
+    tpl = np.ascontiguousarray(base[11:11 + T, 17:17 + T]) if S - T > 17 else np.ascontiguousarray(base[3:3 + T, 5:5 + T])
+    with LaserSpotTrack4(640, 480, 8) as t:
+        (res, m) = t.doMatch_coord_res(win, tpl, 5, True, want_map=True)
+        exact = O.ncc_map_exact(win, tpl)
+        assert m.shape == exact.shape
+        assert np.array_equal(m.view(np.uint32), exact.view(np.uint32)), f"score map differs from the exact oracle: max abs {np.abs(m - exact).max()}"
+        want, _ = O.do_match_coord_res(win, tpl, True, "exact")
+        assert res == want, (res, want)
+        cvm = O.ncc_map_cv2(win, tpl)
+        assert np.abs(m - cvm).max() <= SCORE_TOL_CV2
+        wcv, _ = O.do_match_coord_res(win, tpl, True, "cv2")
+        assert abs(res[2] - wcv[2]) <= SCORE_TOL_CV2
+        assert abs(res[0] - wcv[0]) <= SUBPIX_TOL_CV2 and abs(res[1] - wcv[1]) <= SUBPIX_TOL_CV2
+        # doMatch_test: 1x1 self match
+        assert t.doMatch_test(tpl) == O.do_match_test(tpl, "exact")
+
+
+def test_match_edge_cases(built_lib, oracle_clib):
+    with LaserSpotTrack4(640, 480, 8) as t:
+        rng = np.random.default_rng(5)
+        tpl = rng.integers(0, 256, size=(20, 20), dtype=np.uint8)
+        # flat window -> every score 0 -> first position wins
+        res, m = t.doMatch_coord_res(np.full((50, 60), 77, np.uint8), tpl, 5, True, want_map=True)
+        assert np.all(m == 0) and res == [0.0, 0.0, 0.0]
+        # flat template -> every score 1
+        res, m = t.doMatch_coord_res(rng.integers(0, 256, size=(50, 60), dtype=np.uint8), np.full((20, 20), 9, np.uint8), 5, True, want_map=True)
+        assert np.all(m == 1) and res == [0.0, 0.0, 1.0]
+        # two exact copies of the template -> first in row-major order
+        win = rng.integers(0, 40, size=(70, 90), dtype=np.uint8)
+        win[30:50, 50:70] = tpl
+        win[30:50, 10:30] = tpl
+        res = t.doMatch_coord_res(win, tpl, 5, False)
+        want, _ = O.do_match_coord_res(win, tpl, False, "exact")
+        assert res == want and (res[0], res[1]) == (10.0, 30.0)
+        # window == template size -> 1x1 map, peak on the border -> no sub-pixel shift
+        res = t.doMatch_coord_res(tpl, tpl, 5, True)
+        assert res[0] == 0.0 and res[1] == 0.0 and res[2] == O.do_match_test(tpl)
+
+
+@pytest.mark.parametrize("mi,max_batch", [(False, 0), (True, 7), (False, 1)])
+def test_track_config_a(stack_a, mi, max_batch):
+    """Config A (640x480 8-bit, T=32, s=32): the whole per-frame record, bit-exact vs the exact oracle."""
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=mi)
+    otr = O.OracleTracker(op)
+    oref = otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    with _tracker(cfg, op, max_batch=max_batch) as t:
+        info = t.set_reference(frames[0], st.ref_xy)
+        assert [tuple(r) for r in info.rect] == [tuple(r) for r in otr.rects]
+        assert list(info.mideal) == otr.mideal
+        assert (info.ref_record.x_abs, info.ref_record.y_abs, info.ref_record.dL) == (oref.x_abs, oref.y_abs, oref.dL)
+        got = t.track(np.stack(frames[1:]))
+        util.compare_records(got, want, label=f"A mi={mi}")
+        assert np.array_equal(t.get_state(), np.array([v for d in otr.dis for v in d]))
+        s = t.stats()
+        assert s.frames == len(want) and s.kernel_launches > 0
+
+
+def test_track_config_a_vs_cv2(stack_a):
+    """Same stack against the OpenCV-backed oracle (the reference's real third-party routine)."""
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=False)
+    otr = O.OracleTracker(op, backend="cv2")
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    with _tracker(cfg, op) as t:
+        t.set_reference(frames[0], st.ref_xy)
+        got = t.track(np.stack(frames[1:]))
+    near_ties = 0
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g.status == w.status
+        for k in range(5):
+            a, b = g.tm[k], w.tm[k]
+            if (a.ix, a.iy) != (b.ix, b.iy):     # only allowed for a documented near-tie
+                near_ties += 1
+                assert abs(a.score - b.score) <= SCORE_TOL_CV2, f"frame {i} tpl {k}: peaks differ and scores are not tied"
+                continue
+            assert abs(a.score - b.score) <= SCORE_TOL_CV2
+            assert abs(a.x - b.x) <= SUBPIX_TOL_CV2 and abs(a.y - b.y) <= SUBPIX_TOL_CV2
+        if w.status == 0:
+            assert abs(g.dX_pix - w.dX_pix) <= 2 * SUBPIX_TOL_CV2 and abs(g.dY_pix - w.dY_pix) <= 2 * SUBPIX_TOL_CV2
+    assert near_ties <= 2, f"{near_ties} near-tie peak disagreements with OpenCV"
+
+
+def test_track_u16_small(built_lib, oracle_clib):
+    """16-bit stack, T=48, s=56 (config B's template/search geometry on a small slice)."""
+    cfg = StackConfig(480, 400, "u16", 48, 56, 24)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 17)]
+    op = util.oracle_params(cfg)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    with _tracker(cfg, op) as t:
+        t.set_reference(frames[0], st.ref_xy)
+        got = t.track_slices(frames[1:])
+        util.compare_records(got, want, label="u16")
+
+
+def test_rejects_and_skips(stack_a):
+    """A frame whose spot is blanked is rejected and skipped; state is restored (LST4:832-846)."""
+    cfg, st, frames = stack_a
+    frames = [f.copy() for f in frames[:12]]
+    frames[5][:] = frames[5].mean().astype(np.uint8)      # nothing to match in slice 5
+    c = st.truth(8)[0].astype(int)
+    frames[8][c[1] - 40:c[1] + 40, c[0] - 40:c[0] + 40] = 30   # spot erased in slice 8
+    op = util.oracle_params(cfg, match_intensity=False)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    assert [w.status for w in want].count(1) >= 2
+    with _tracker(cfg, op) as t:
+        t.set_reference(frames[0], st.ref_xy)
+        got = t.track(np.stack(frames[1:]))
+        util.compare_records(got, want, label="skips")
+
+
+def test_unsupported_like_reference(built_lib):
+    from laser_spot_track_b200 import LstError
+    with pytest.raises(LstError):
+        LaserSpotTrack4(640, 480, 16, matchIntensity=False)     # null Mat in the reference, LST4:2510-2523
+    with pytest.raises(LstError):
+        LaserSpotTrack4(640, 480, 8, method=3)
+    with pytest.raises(LstError):
+        LaserSpotTrack4(640, 480, 24)
+    with LaserSpotTrack4(640, 480, 8) as t:
+        with pytest.raises(LstError):
+            t.track(np.zeros((1, 480, 640), np.uint8))            # no reference yet
