@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- tracked frames/s (5 templates/frame) of the Laser Spot Track hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config B]
+
+One process per GPU (the driver launches N>1 through torch.distributed.run).  A *step* is one
+pass of the hot path over one batch of ``--frames`` synthetic slices of the named configuration
+(default: BASELINE.json configs[1] -- 1920x1080 16-bit, 48x48 templates, 160x160 search ROIs).
+Frames are sharded over the ranks (each rank tracks its own contiguous chunk; nothing is reduced
+between GPUs, so there is no data-path collective); ``scaling`` is "weak".
+
+Two legs are timed, each with W warm-up steps and exactly K timed steps bracketed by a barrier +
+torch.cuda.synchronize() on both sides, CUDA events on the device, max over ranks:
+  value : slices already resident in HBM (a ring of distinct slices larger than L2)
+  e2e   : the public API with HOST buffers -- pinned slices, host->device copies and the
+          device->host read of the per-frame records inside the timed region.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from laser_spot_track_b200.synth import CONFIGS, StackConfig, SyntheticStack  # noqa: E402
+
+METRIC = "tracked frames/sec (5 templates/frame)"
+UNIT = "frames/s"
+WORKLOADS = {
+    "A": "synthetic 640x480 8-bit stack, 4 marks + spot, 32x32 templates, 96x96 search ROIs",
+    "B": "1920x1080 16-bit timelapse, 48x48 templates, 160x160 search ROIs",
+    "D": "large-template stress: 2048x2048 8-bit, 128x128 marks and spot over 512x512 ROIs",
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="B", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="slices per step per GPU (0 = per-config default)")
+    ap.add_argument("--ring", type=int, default=0, help="distinct slices in the ring (0 = per-config default)")
+    ap.add_argument("--max-batch", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="frames of the CPU baseline sample (0 = default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def bench_config(name: str, ring: int) -> StackConfig:
+    c = CONFIGS[name]
+    return StackConfig(c.width, c.height, c.dtype, c.templ_size, c.s_area, n_frames=ring, motion="periodic", period=ring)
+
+
+DEFAULTS = {  # frames per step, ring length, max_batch, cpu sample
+    "A": (8192, 256, 2048, 512),
+    "B": (2048, 64, 1024, 128),
+    "D": (64, 32, 64, 8),
+}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's OpenCV-backed loop on host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_chunk(args):
+    cfg_name, ring, lo, hi = args
+    from oracle import lst_oracle as O
+    import cv2
+    cv2.setNumThreads(1)
+    cfg = bench_config(cfg_name, ring)
+    st = SyntheticStack(cfg)
+    op = O.Params(cfg.width, cfg.height, cfg.templ_size, cfg.s_area)
+    tr = O.OracleTracker(op, backend="cv2")
+    tr.set_reference(st.frame(0), st.ref_xy)
+    frames = [st.frame(i) for i in range(lo, hi)]       # generation excluded from the timing
+    t0 = time.perf_counter()
+    recs = tr.run(frames)
+    dt = time.perf_counter() - t0
+    return hi - lo, dt, sum(r.status == 0 for r in recs)
+
+
+def cpu_reference_rate(cfg_name: str, ring: int, sample: int, procs: int):
+    """frames/s of the CPU path on `procs` host cores over `sample` frames.  Chunks start at
+    multiples of the ring period, where the periodic scene is back at its reference pose, so every
+    chunk legitimately starts from the reference displacement state."""
+    if procs <= 1:
+        n, dt, ok = _cpu_chunk((cfg_name, ring, 1, 1 + sample))
+        return n / dt, n, ok
+    import multiprocessing as mp
+    per = max(sample // procs, 16)
+    jobs = [(cfg_name, ring, 1 + (i * ring) % max(ring, 1), 1 + (i * ring) % max(ring, 1) + per) for i in range(procs)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_chunk, jobs)
+        wall = time.perf_counter() - t0
+    n = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)            # chunks run concurrently: the slowest one bounds the job
+    return n / busy, n, sum(r[2] for r in res)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    frames_d, ring_d, _, sample_d = DEFAULTS[args.config]
+    ring = args.ring or ring_d
+    procs = os.cpu_count() or 1
+    sample = args.cpu_sample or sample_d
+    per_step = max(sample, procs * 16)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        rate, n, ok = cpu_reference_rate(args.config, ring, per_step, procs)
+        if i >= args.warmup:
+            vals.append((rate, n))
+    rate = float(np.mean([v[0] for v in vals]))
+    nfr = vals[0][1]
+    cfg = bench_config(args.config, ring)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nfr / rate, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "frame": [cfg.width, cfg.height], "depth": cfg.dtype,
+                   "templ_size": cfg.templ_size, "s_area": cfg.s_area, "frames_per_step": nfr},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{nfr} frames per step on {procs} processes: oracle loop (numpy ImageJ blur + "
+                                   f"cv2.matchTemplate TM_CCOEFF_NORMED, IPP off, 1 thread each); the Java plugin "
+                                   f"itself cannot run here (no JVM)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from laser_spot_track_b200 import LaserSpotTrack4, native as N
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the tracking path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    frames_d, ring_d, mb_d, sample_d = DEFAULTS[args.config]
+    F = args.frames or frames_d
+    ring = args.ring or ring_d
+    cfg = bench_config(args.config, ring)
+    st = SyntheticStack(cfg)
+    bits = {"u8": 8, "u16": 16, "f32": 32}[cfg.dtype]
+    fb = cfg.width * cfg.height * (bits // 8)
+
+    lib = N.load()
+    trk = LaserSpotTrack4(cfg.width, cfg.height, bits, device=local_rank, templSize=cfg.templ_size, sArea=cfg.s_area,
+                          max_batch=args.max_batch or mb_d)
+    # ring of distinct slices: pinned host copy (e2e leg) and HBM copy (value leg)
+    host_ring = C.c_void_p()
+    assert lib.lst_alloc_pinned(ring * fb, C.byref(host_ring)) == 0
+    hr = np.ctypeslib.as_array(C.cast(host_ring, C.POINTER(C.c_uint8)), shape=(ring * fb,))
+    for i in range(ring):
+        hr[i * fb:(i + 1) * fb] = st.frame(i).view(np.uint8).reshape(-1)
+    dev_ring = trk.device_alloc(ring * fb)
+    trk._check(lib.lst_device_upload(trk._ctx, C.c_void_p(dev_ring), host_ring, ring * fb))
+    info = trk.set_reference(st.frame(0), st.ref_xy)
+
+    # this rank's chunk of each step: F consecutive slices of the (cyclic) stack, starting at slice 1
+    idx = [(1 + j) % ring for j in range(F)]
+    dev_ptrs = (C.c_void_p * F)(*[dev_ring + i * fb for i in idx])
+    host_ptrs = (C.c_void_p * F)(*[host_ring.value + i * fb for i in idx])
+    out = (N.Record * F)()
+
+    def step_device():
+        trk.track_device_ptrs(dev_ptrs, 1, out)
+
+    def step_e2e():
+        trk.track_host_ptrs(host_ptrs, 1, out)
+
+    def timed(step_fn, K, W):
+        for _ in range(W):
+            step_fn()
+        trk.reset_stats()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(K):
+            step_fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = trk.stats()
+        return float(t[0]), float(t[1]), s
+
+    K, W = args.steps, max(args.warmup, 0)
+    sampler = ClockSampler(local_rank)
+    peaks = (C.c_double * 2)()
+    have_peaks = lib.lst_measure_alu_peaks(local_rank, 20.0, peaks) == 0
+
+    trk.set_kernel_timing(True)
+    if rank == 0:
+        sampler.start()
+    ms_dev, wall_dev, s_dev = timed(step_device, K, W)
+    clocks = sampler.stop() if rank == 0 else None
+    ok_frames = sum(1 for r in out if r.status == 0)
+    trk.set_kernel_timing(False)
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e, wall_e2e, s_e2e = timed(step_e2e, K, W)
+        e2e = {"value": world * F * K / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(s_e2e.h2d_bytes // K), "d2h_bytes_per_step": int(s_e2e.d2h_bytes // K),
+               "ms_per_step": ms_e2e / K, "ingest": "whole slices, pinned host ring, double-buffered cudaMemcpyAsync"}
+
+    value = world * F * K / (ms_dev * 1e-3)
+    # roofline of the dominant kernel (lst_ncc_match): exact u8 x u8 -> s32 multiply-accumulates
+    macs_per_launch = s_dev.ncc_algorithmic_macs / max(s_dev.ncc_kernel_launches, 1)
+    kern_ms = s_dev.ncc_kernel_ms / max(s_dev.ncc_kernel_launches, 1)
+    achieved = 2.0 * macs_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None
+    peak = 2.0 * peaks[0] / 1e12 if have_peaks else None
+    roofline = {
+        "bound": "int8-dp4a-pipe", "kernel": "lst_ncc_match", "achieved": achieved, "peak": peak, "unit": "TOP/s",
+        "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+        "peak_source": "measured live: IDP.4A.U8.U8 microbenchmark (lst_measure_alu_peaks); MEASURED_PEAKS.json "
+                       "holds only HBM and bf16-tensor peaks and this kernel is bound by neither (SURVEY.md 8d)",
+        "ffma_peak_tflops": 2.0 * peaks[1] / 1e12 if have_peaks else None,
+        "algorithmic_ops_per_launch": 2.0 * macs_per_launch, "avg_launch_ms": kern_ms,
+        "kernel_share_of_step": s_dev.ncc_kernel_ms / ms_dev if ms_dev > 0 else None,
+        "launches_timed": int(s_dev.ncc_kernel_launches),
+        "window_bytes_per_frame": 5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 * (bits // 8),
+    }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample or sample_d
+        rate, n, ok = cpu_reference_rate(args.config, ring, sample, 1)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"first {n} frames of the same ring, oracle loop (numpy ImageJ blur + "
+                                  f"cv2.matchTemplate TM_CCOEFF_NORMED, IPP off), 1 thread"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "frame": [cfg.width, cfg.height], "depth": cfg.dtype,
+                       "templ_size": cfg.templ_size, "s_area": cfg.s_area, "frames_per_step_per_gpu": F,
+                       "ring_frames": ring, "ring_bytes": ring * fb,
+                       "l2": "inputs larger than L2 (ring of distinct slices cycled)" if ring * fb > 126e6 else
+                             "ring smaller than L2; windows are re-read from HBM/L2 each pass",
+                       "max_batch": args.max_batch or mb_d, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                       "accepted_frames_last_step": ok_frames},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(s_dev.kernel_launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated)},
+            "wall_ms_per_step": wall_dev / K,
+        }
+        print(json.dumps(line), flush=True)
+    trk.device_free(dev_ring)
+    lib.lst_free_pinned(host_ring)
+    trk.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,9 @@ int lst_track_ptrs(lst_ctx *ctx, const void *const *frame_ptrs, int64_t first_fr
 /* Same, slices already resident in device memory of ctx's device (benchmark "value" leg). */
 int lst_track_device(lst_ctx *ctx, const void *dev_frames, size_t frame_stride_bytes,
                      int64_t first_frame_index, int32_t n_frames, lst_record *out);
+/* Same, one device pointer per slice (e.g. a ring of decoded slices reused cyclically). */
+int lst_track_device_ptrs(lst_ctx *ctx, const void *const *dev_frame_ptrs, int64_t first_frame_index,
+                          int32_t n_frames, lst_record *out);
 
 /* Displacement state (disX/disY x5, LST4:100-108): read it, or overwrite it -- the caller's
  * "keep the result" override (LST4:1281-1300) and the chunk hand-off of a sharded run. */

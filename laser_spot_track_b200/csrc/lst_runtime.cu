@@ -666,6 +666,12 @@ int lst_track_device(lst_ctx *c, const void *dev_frames, size_t frame_stride_byt
     return track_impl(c, dev_frames, frame_stride_bytes, nullptr, true, first_frame_index, n_frames, out);
 }
 
+int lst_track_device_ptrs(lst_ctx *c, const void *const *dev_frame_ptrs, int64_t first_frame_index, int32_t n_frames,
+                          lst_record *out)
+{
+    return track_impl(c, nullptr, 0, dev_frame_ptrs, true, first_frame_index, n_frames, out);
+}
+
 int lst_get_state(const lst_ctx *c, double dis[10])
 {
     if (!c || !dis) return LST_ERR_INVALID;

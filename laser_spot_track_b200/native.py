@@ -20,7 +20,7 @@ STATUS_OK, STATUS_SKIP, STATUS_STOP = 0, 1, 2
 # every symbol include/lst_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "lst_abi_version", "lst_device_count", "lst_create", "lst_destroy", "lst_last_error",
-    "lst_set_reference", "lst_track", "lst_track_ptrs", "lst_track_device", "lst_get_state", "lst_set_state",
+    "lst_set_reference", "lst_track", "lst_track_ptrs", "lst_track_device", "lst_track_device_ptrs", "lst_get_state", "lst_set_state",
     "lst_match_single", "lst_match_test", "lst_preprocess", "lst_calc_displacement",
     "lst_alloc_pinned", "lst_free_pinned", "lst_host_register", "lst_host_unregister",
     "lst_device_alloc", "lst_device_free", "lst_device_upload",
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
         "lst_track": ([vp, vp, sz, i64, i32, P(Record)], C.c_int),
         "lst_track_ptrs": ([vp, P(vp), i64, i32, P(Record)], C.c_int),
         "lst_track_device": ([vp, vp, sz, i64, i32, P(Record)], C.c_int),
+        "lst_track_device_ptrs": ([vp, P(vp), i64, i32, P(Record)], C.c_int),
         "lst_get_state": ([vp, P(dbl)], C.c_int),
         "lst_set_state": ([vp, P(dbl)], C.c_int),
         "lst_match_single": ([vp, vp, i32, i32, vp, i32, i32, i32, P(dbl), vp], C.c_int),

@@ -132,6 +132,21 @@ class LaserSpotTrack4:
                                                first_frame_index, n, out))
         return out
 
+    def track_device_ptrs(self, dev_ptrs: Sequence[int], first_frame_index: int = 1, out=None):
+        n = len(dev_ptrs)
+        ptrs = dev_ptrs if isinstance(dev_ptrs, C.Array) else (C.c_void_p * n)(*dev_ptrs)
+        out = (N.Record * n)() if out is None else out
+        self._check(self._lib.lst_track_device_ptrs(self._ctx, ptrs, first_frame_index, n, out))
+        return out
+
+    def track_host_ptrs(self, host_ptrs, first_frame_index: int = 1, out=None):
+        """Slices given as raw host addresses (e.g. a pinned ring): no numpy conversion on the way."""
+        n = len(host_ptrs)
+        ptrs = host_ptrs if isinstance(host_ptrs, C.Array) else (C.c_void_p * n)(*host_ptrs)
+        out = (N.Record * n)() if out is None else out
+        self._check(self._lib.lst_track_ptrs(self._ctx, ptrs, first_frame_index, n, out))
+        return out
+
     def analyseSlice(self, slice_pixels: np.ndarray, frame_index: int = 0) -> N.Record:
         """One slice; returns the record whose ``status`` is analyseSlice's return value (LST4:1302)."""
         return self.track(slice_pixels, frame_index)[0]
