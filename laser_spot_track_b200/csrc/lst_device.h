@@ -19,7 +19,7 @@ struct DevTask {
     int32_t s_used;       // search area used by the accept test (searchWidth = 2*s_used)
     int32_t pad0, pad1;
     uint64_t win_off;     // byte offset of the 8-bit window in the win8 scratch
-    uint64_t sum_off;     // element offset of this task's rw*rh maps (wsum, wsq, scores)
+    uint64_t sum_off;     // element offset of this task's rw*rh score map (lst_match_single only)
 };
 
 struct DevResult {
@@ -50,9 +50,10 @@ struct PreprocParams {
 };
 
 struct MatchParams {
-    int band_rows;         // result rows per CTA
-    int tiles_per_cta;     // 32-wide result tiles per CTA
+    int chunk_words;       // result columns per CTA, in 4-column words (a CTA owns 32 rows x this)
     int smem_pitch;        // window tile pitch in shared memory (odd multiple of 16 bytes)
+    int v_pitch;           // pitch of the vertical-sum arrays (odd)
+    int max_th;            // tallest template of the pass (sizes the window tile)
     int sub_pixel;
     int templ_size;
     double thresh;
@@ -64,14 +65,11 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const void *cons
                   uint32_t *mm_keys, cudaStream_t stream);
 int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const void *const *frames,
                       const PreprocParams &pp, const uint32_t *mm_keys, uint8_t *win8, cudaStream_t stream);
-int launch_box_sums(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                    const DevTemplates *tpls, const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream);
 int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                     const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
-                     unsigned long long *best, float *score_map, const MatchParams &mp, cudaStream_t stream);
+                     const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *score_map,
+                     const MatchParams &mp, cudaStream_t stream);
 int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls, const uint8_t *win8,
-                    const uint32_t *wsum, const uint32_t *wsq, const unsigned long long *best, DevResult *results,
-                    const MatchParams &mp, cudaStream_t stream);
+                    const unsigned long long *best, DevResult *results, const MatchParams &mp, cudaStream_t stream);
 int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_dist, const double *spot0,
                  double *out5, cudaStream_t stream);
 int set_blur_kernel(const float kern[7], const float ksum[7]);

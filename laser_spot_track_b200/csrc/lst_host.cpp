@@ -175,6 +175,10 @@ TplConst template_consts(const uint8_t *tpl8, int tw, int th)
     norm = sqrt(norm);
     norm = norm / sqrt(c.inv_area);
     c.norm = norm;
+    {
+        double C = n * (double)q - (double)s * (double)s;   // exact: both terms < 2^53
+        c.inv_sqrt_c = C > 0.0 ? (float)(1.0 / sqrt(C)) : 0.0f;
+    }
     c.mideal = (double)ncc_score((double)q, (double)s, (double)q, c.inv_area, c.mean, c.norm, c.flat);
     return c;
 }

@@ -2,8 +2,8 @@
 //
 //   lst_minmax       per-window min/max of the raw crop (FloatProcessor.findMinAndMax of the crop)
 //   lst_preprocess   crop -> float -> ImageJ GaussianBlur(2,2,0.02) -> 8-bit   (LST4:1346-1347, 1456-1473, 2529)
-//   lst_box_sums     window sums of I and I^2 under the template footprint    (cv::integral in matchTemplate)
-//   lst_ncc_match    exact integer cross-correlation (IDP.4A) + TM_CCOEFF_NORMED normalisation + argmax
+//   lst_ncc_match    exact integer cross-correlation (IDP.4A) + window sums of I, I^2 (cv::integral in
+//                    matchTemplate) + TM_CCOEFF_NORMED normalisation + first-maximum argmax
 //                                                                              (LST4:2560 matchTemplate, 2670 minMaxLoc)
 //   lst_epilogue     3x3 sub-pixel fit + accept test per window                (LST4:2681-2717, 1225-1255)
 //   lst_solve        calcDisplacement per frame                                (LST4:2318-2365)
@@ -265,187 +265,88 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// window sums under the template footprint
-// ------------------------------------------------------------------------------------------------
-#define BOX_W 32
-#define BOX_H 32
-
-__global__ void __launch_bounds__(256)
-lst_box_sums(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
-             uint32_t *__restrict__ wsum, uint32_t *__restrict__ wsq, int max_tw, int max_th)
-{
-    extern __shared__ uint32_t smem_u[];
-    const DevTask t = tasks[blockIdx.y];
-    const int tw = tpls->c[t.tpl].tw, th = tpls->c[t.tpl].th;
-    const int tiles_x = (t.rw + BOX_W - 1) / BOX_W, tiles_y = (t.rh + BOX_H - 1) / BOX_H;
-    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
-    const int bx = (blockIdx.x % tiles_x) * BOX_W, by = (blockIdx.x / tiles_x) * BOX_H;
-    const int ow = min(BOX_W, t.rw - bx), oh = min(BOX_H, t.rh - by);   // outputs in this tile
-    const int cw = ow + tw - 1, ch = oh + th - 1;                       // window pixels needed
-    const int CP = BOX_W + max_tw - 1;                                  // pitch of V / V2 (words)
-    const int TP = (BOX_W + max_tw - 1 + 3) & ~3;                       // pitch of the byte tile
-    uint32_t *V = smem_u;                                               // [BOX_H][CP]
-    uint32_t *V2 = V + BOX_H * CP;
-    uint8_t *tile = (uint8_t *)(V2 + BOX_H * CP);                       // [(BOX_H+max_th-1)][TP]
-    const uint8_t *src = win8 + t.win_off + (size_t)by * t.pitch + bx;
-    for (int idx = threadIdx.x; idx < cw * ch; idx += blockDim.x) {
-        int r = idx / cw, c = idx - r * cw;
-        tile[r * TP + c] = src[(size_t)r * t.pitch + c];
-    }
-    __syncthreads();
-    // vertical sliding sums: V[y][c] = sum_{v<th} tile[y+v][c]
-    for (int c = threadIdx.x; c < cw; c += blockDim.x) {
-        uint32_t s = 0, q = 0;
-        for (int v = 0; v < th; v++) {
-            uint32_t p = tile[v * TP + c];
-            s += p;
-            q += p * p;
-        }
-        V[c] = s;
-        V2[c] = q;
-        for (int y = 1; y < oh; y++) {
-            uint32_t a = tile[(y + th - 1) * TP + c], b = tile[(y - 1) * TP + c];
-            s += a - b;
-            q += a * a - b * b;
-            V[y * CP + c] = s;
-            V2[y * CP + c] = q;
-        }
-    }
-    __syncthreads();
-    // horizontal: out[y][x] = sum_{u<tw} V[y][x+u]; each thread does a run of 8 outputs
-    const int segs = (ow + 7) / 8;
-    uint32_t *osum = wsum + t.sum_off, *osq = wsq + t.sum_off;
-    for (int idx = threadIdx.x; idx < oh * segs; idx += blockDim.x) {
-        int y = idx / segs, x0 = (idx - y * segs) * 8;
-        int x1 = min(x0 + 8, ow);
-        const uint32_t *vr = V + y * CP, *vr2 = V2 + y * CP;
-        uint32_t s = 0, q = 0;
-        for (int u = 0; u < tw; u++) {
-            s += vr[x0 + u];
-            q += vr2[x0 + u];
-        }
-        size_t o = (size_t)(by + y) * t.rw + bx;
-        osum[o + x0] = s;
-        osq[o + x0] = q;
-        for (int x = x0 + 1; x < x1; x++) {
-            s += vr[x + tw - 1] - vr[x - 1];
-            q += vr2[x + tw - 1] - vr2[x - 1];
-            osum[o + x] = s;
-            osq[o + x] = q;
-        }
-    }
-}
-
-static size_t box_smem(int tw, int th)
-{
-    size_t cp = BOX_W + tw - 1, tp = (BOX_W + tw - 1 + 3) & ~3;
-    return 2 * BOX_H * cp * sizeof(uint32_t) + (size_t)(BOX_H + th - 1) * tp;
-}
-
-int launch_box_sums(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                    const DevTemplates *tpls, const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream)
-{
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(lst_box_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
-    int tiles = ((max_rw + BOX_W - 1) / BOX_W) * ((max_rh + BOX_H - 1) / BOX_H);
-    size_t smem = box_smem(tw, th);
-    int launches = 0;
-    for (int base = 0; base < n_tasks; base += 65535) {
-        int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
-        dim3 grid(tiles, n);
-        lst_box_sums<<<grid, 256, smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, tw, th);
-        launches++;
-    }
-    return launches;
-}
-
-// ------------------------------------------------------------------------------------------------
-// exact NCC + argmax
+// exact NCC + window sums + argmax (one kernel)
 // ------------------------------------------------------------------------------------------------
 // Result position x = 4q + j.  With the template stored four times, shifted by j bytes and
 // zero padded (build_shifted_template), the correlation of one template row is
 //     sum_k IDP.4A(Wword[q + k], Tj[k])
 // over aligned 32-bit words of the window row: no unaligned loads and no byte shuffles.
-// A thread owns 8 consecutive q (32 result columns) of one result row; lanes of a warp own
-// consecutive rows, so template words are warp-uniform (shared-memory broadcast) and window
-// rows are conflict-free because the tile pitch is an odd multiple of 16 bytes.
+//
+// A CTA owns a band of 32 result rows x a chunk of result columns of one window.  It stages the
+// window rows it needs in shared memory (pitch = odd multiple of 16 B, so 128-bit row loads of 32
+// lanes that own 32 consecutive rows are conflict-free), builds the vertical sliding sums of I and
+// I^2 for its band (what cv::integral provides to matchTemplate), and then every thread takes
+// (tile, row) tasks: a tile is Q = 8, 4 or 1 window words = 32, 16 or 4 result columns, so that
+// the last columns of an odd-sized result map cost an eighth of a tile instead of a whole one.
+// Template words are warp-uniform read-only loads served by L1.
+//
+// Normalisation: an exact integer form of the score, A / sqrt(B*C) with
+//     A = N*corr - wsum*tsum,  B = N*wsq - wsum^2,  C = N*tsq - tsum^2,
+// is evaluated in float32 as a filter (relative error < 1e-6); only positions within 1e-5 of the
+// thread's running maximum -- the only ones that can win the argmax -- are evaluated with
+// OpenCV's double-precision formula (ncc_score), whose float32 result is what is compared and
+// reported.  Nearly flat windows (B <= ~N/2, where OpenCV's "avoid rounding errors" branch may
+// apply) always take the exact path.
 __device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx)
 {
     score = score + 0.0f;   // -0 -> +0: minMaxLoc compares values, not bit patterns
     return ((unsigned long long)f32_key(score) << 32) | (unsigned long long)(0xffffffffu - idx);
 }
 
-#define NCC_THREADS 256
+#define NCC_THREADS 128
+#define NCC_BAND 32
+#define NCC_EPS 1e-5f
 
-__global__ void __launch_bounds__(NCC_THREADS)
-lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls,
-              const uint8_t *__restrict__ win8, const uint32_t *__restrict__ wsum, const uint32_t *__restrict__ wsq,
-              unsigned long long *__restrict__ best, float *__restrict__ score_map, MatchParams mp)
+struct NccCtx {
+    const uint8_t *s_win;      // window tile in shared memory
+    const uint16_t *s_v;       // vertical sums of I   [NCC_BAND][vpitch]
+    const uint32_t *s_v2;      // vertical sums of I^2 [NCC_BAND][vpitch]
+    const uint4 *g_tpl;        // shifted template [th][k4] (global, L1)
+    int SP, VP, th, tw, k4, rw;
+    long long N, tsum, C_unused;
+    float inv_sqrt_c;
+    double inv_area, mean, norm;
+    size_t map_off;            // sum_off of the task (score map)
+    float *score_map;
+    int y;                     // absolute result row
+    int x_chunk0;              // first result column of the CTA's chunk
+};
+
+// One (tile, row) task: Q window words -> 4Q result columns starting at word `w0` of the chunk.
+template <int Q, bool MAP>
+__device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, int w0, unsigned long long &best)
 {
-    extern __shared__ __align__(16) uint8_t smem_b[];
-    __shared__ unsigned long long s_best[NCC_THREADS / 32];
-    const DevTask t = tasks[blockIdx.y];
-    const TplConst tc = tpls->c[t.tpl];
-    const int tw = tc.tw, th = tc.th, k4 = tc.k4;
-    const int tiles_x = (t.rw + 31) / 32;
-    const int chunks = (tiles_x + mp.tiles_per_cta - 1) / mp.tiles_per_cta;
-    const int bands = (t.rh + mp.band_rows - 1) / mp.band_rows;
-    if ((int)blockIdx.x >= chunks * bands) return;
-    const int chunk = blockIdx.x % chunks, band = blockIdx.x / chunks;
-    const int tile0 = chunk * mp.tiles_per_cta;
-    const int ntiles = min(mp.tiles_per_cta, tiles_x - tile0);
-    const int y0 = band * mp.band_rows;
-    const int nrows = min(mp.band_rows, t.rh - y0);
-    const int SP = mp.smem_pitch;
-
-    // shared memory: the window tile [(nrows+th-1)][SP].  The shifted template ([th][k4] uint4) is read
-    // with warp-uniform read-only loads and lives in L1: it costs no shared memory, so large
-    // templates (128x128 -> 67 KB) do not squeeze the window tile.
-    const uint4 *__restrict__ g_tpl = (const uint4 *)tpls->shifted[t.tpl];
-    uint8_t *s_win = smem_b;
-    {
-        const int wrows = nrows + th - 1;
-        const int vec = SP / 16;
-        const int xb0 = tile0 * 32;                      // first window byte column of this chunk
-        const uint8_t *src = win8 + t.win_off;
-        for (int i = threadIdx.x; i < wrows * vec; i += blockDim.x) {
-            int r = i / vec, c = (i - r * vec) * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            int gx = xb0 + c, gy = y0 + r;
-            if (gx < t.pitch && gy < t.h) v = *(const uint4 *)(src + (size_t)gy * t.pitch + gx);
-            *(uint4 *)(s_win + (size_t)r * SP + c) = v;
-        }
-    }
-    __syncthreads();
-
-    unsigned long long mybest = 0ull;
-    const int ntask = ntiles * nrows;
-    const int k4main = k4 & ~3;
-    for (int tt = threadIdx.x; tt < ntask; tt += blockDim.x) {
-        const int tile = tt / nrows, yy = tt - tile * nrows;
-        uint32_t acc[4][8];
+    uint32_t acc[4][Q];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+    for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int q = 0; q < 8; q++) acc[j][q] = 0u;
-        const uint8_t *wbase = s_win + (size_t)yy * SP + tile * 32;
-        for (int v = 0; v < th; v++) {
-            const uint8_t *wrow = wbase + (size_t)v * SP;
-            const uint4 *trow = g_tpl + v * k4;
-            int k = 0;
-            for (; k < k4main; k += 4) {
-                const uint4 wa = *(const uint4 *)(wrow + 4 * k);
-                const uint4 wb = *(const uint4 *)(wrow + 4 * k + 16);
-                const uint4 wc = *(const uint4 *)(wrow + 4 * k + 32);
-                const uint32_t ww[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+        for (int q = 0; q < Q; q++) acc[j][q] = 0u;
+    const uint8_t *wbase = c.s_win + (size_t)yy * c.SP + 4 * w0;
+    constexpr int NW = (Q + 3 + 3) / 4;   // uint4 loads covering words [k, k + Q + 3)
+    for (int v = 0; v < c.th; v++) {
+        const uint8_t *wrow = wbase + (size_t)v * c.SP;
+        const uint4 *trow = c.g_tpl + v * c.k4;
+        for (int k = 0; k < c.k4; k += 4) {
+            uint32_t ww[4 * NW];
+            if (Q == 1) {   // single-word tiles start at any word: 32-bit loads
 #pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
+                for (int i = 0; i < 4; i++) ww[i] = *(const uint32_t *)(wrow + 4 * (k + i));
+            } else {        // 4- and 8-word tiles start at multiples of 4 words: 128-bit loads
+#pragma unroll
+                for (int i = 0; i < NW; i++) {
+                    const uint4 t4 = *(const uint4 *)(wrow + 4 * k + 16 * i);
+                    ww[4 * i] = t4.x;
+                    ww[4 * i + 1] = t4.y;
+                    ww[4 * i + 2] = t4.z;
+                    ww[4 * i + 3] = t4.w;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                if (k + kk < c.k4) {   // warp-uniform: the last chunk of a row may be partial
                     const uint4 tj = __ldg(trow + k + kk);
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
+                    for (int q = 0; q < Q; q++) {
                         const uint32_t wv = ww[kk + q];
                         acc[0][q] = __dp4a(wv, tj.x, acc[0][q]);
                         acc[1][q] = __dp4a(wv, tj.y, acc[1][q]);
@@ -454,38 +355,179 @@ lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict_
                     }
                 }
             }
-            for (; k < k4; k++) {
-                const uint4 tj = __ldg(trow + k);
-                uint32_t ww[8];
+        }
+    }
+    // Normalisation.  The 4Q correlations move to a thread-local array so that the loops below are
+    // real loops (a few dozen instructions instead of 4Q inlined copies: the instruction cache matters).
+    // Pass 1: float32 filter score of every position, warp-wide maximum.
+    // Pass 2: positions within NCC_EPS of that maximum (and nearly flat windows) are evaluated with
+    // OpenCV's double-precision formula; only those can be the first maximum of the map.
+    uint32_t corr[4 * Q];
 #pragma unroll
-                for (int q = 0; q < 8; q++) ww[q] = *(const uint32_t *)(wrow + 4 * (k + q));
+    for (int p = 0; p < 4 * Q; p++) corr[p] = acc[p & 3][p >> 2];
+    const int xr = 4 * w0;                       // column relative to the chunk
+    const int x0 = c.x_chunk0 + xr;              // absolute result column
+    const int np = valid ? min(4 * Q, c.rw - x0) : 0;
+    const uint16_t *vr = c.s_v + (size_t)yy * c.VP + xr;
+    const uint32_t *vr2 = c.s_v2 + (size_t)yy * c.VP + xr;
+    uint32_t s0 = 0, sq0 = 0;
+    if (np > 0) {
+#pragma unroll 4
+        for (int u = 0; u < c.tw; u++) {
+            s0 += vr[u];
+            sq0 += vr2[u];
+        }
+    }
+    const uint32_t rowidx = (uint32_t)c.y * (uint32_t)c.rw;
+    float wmax = -3.0e38f;
+    if (!MAP) {
+        uint32_t s = s0, sq = sq0;
+        float tmax = -3.0e38f;
+#pragma unroll 1
+        for (int p = 0; p < np; p++) {
+            const long long A = c.N * (long long)corr[p] - (long long)s * c.tsum;
+            const long long B = c.N * (long long)sq - (long long)s * (long long)s;
+            if (2 * B > c.N + (c.N >> 5)) tmax = fmaxf(tmax, (float)A * rsqrtf((float)B) * c.inv_sqrt_c);
+            s += (uint32_t)vr[p + c.tw] - (uint32_t)vr[p];
+            sq += vr2[p + c.tw] - vr2[p];
+        }
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    acc[0][q] = __dp4a(ww[q], tj.x, acc[0][q]);
-                    acc[1][q] = __dp4a(ww[q], tj.y, acc[1][q]);
-                    acc[2][q] = __dp4a(ww[q], tj.z, acc[2][q]);
-                    acc[3][q] = __dp4a(ww[q], tj.w, acc[3][q]);
-                }
+        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        wmax = tmax;
+    }
+    {
+        uint32_t s = s0, sq = sq0;
+#pragma unroll 1
+        for (int p = 0; p < np; p++) {
+            bool exact = MAP;
+            if (!MAP) {
+                const long long A = c.N * (long long)corr[p] - (long long)s * c.tsum;
+                const long long B = c.N * (long long)sq - (long long)s * (long long)s;
+                if (2 * B <= c.N + (c.N >> 5)) exact = true;   // nearly flat: OpenCV's special branch may apply
+                else exact = (float)A * rsqrtf((float)B) * c.inv_sqrt_c >= wmax - NCC_EPS;
+            }
+            if (exact) {
+                const float sc = ncc_score((double)corr[p], (double)s, (double)sq, c.inv_area, c.mean, c.norm, 0);
+                if (MAP) c.score_map[c.map_off + rowidx + (uint32_t)(x0 + p)] = sc;
+                const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(x0 + p));
+                best = key > best ? key : best;
+            }
+            s += (uint32_t)vr[p + c.tw] - (uint32_t)vr[p];
+            sq += vr2[p + c.tw] - vr2[p];
+        }
+    }
+}
+
+template <bool MAP>
+__global__ void __launch_bounds__(NCC_THREADS, 4)
+lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls,
+              const uint8_t *__restrict__ win8, unsigned long long *__restrict__ best,
+              float *__restrict__ score_map, MatchParams mp)
+{
+    extern __shared__ __align__(16) uint8_t smem_b[];
+    __shared__ unsigned long long s_best[NCC_THREADS / 32];
+    const DevTask t = tasks[blockIdx.y];
+    const TplConst tc = tpls->c[t.tpl];
+    const int tw = tc.tw, th = tc.th;
+    const int words_total = (t.rw + 3) / 4;                       // result columns in 4-column words
+    const int chunks = (words_total + mp.chunk_words - 1) / mp.chunk_words;
+    const int bands = (t.rh + NCC_BAND - 1) / NCC_BAND;
+    if ((int)blockIdx.x >= chunks * bands) return;
+    const int chunk = blockIdx.x % chunks, band = blockIdx.x / chunks;
+    if (tc.flat) {   // templSdv^2 < DBL_EPSILON: OpenCV fills the result with 1 -> first position wins
+        if (blockIdx.x == 0) {
+            if (MAP)
+                for (int i = threadIdx.x; i < t.rw * t.rh; i += blockDim.x) score_map[t.sum_off + i] = 1.0f;
+            if (threadIdx.x == 0) atomicMax(&best[blockIdx.y], pack_key(1.0f, 0u));
+        }
+        return;
+    }
+    const int word0 = chunk * mp.chunk_words;
+    const int nwords = min(mp.chunk_words, words_total - word0);
+    const int y0 = band * NCC_BAND;
+    const int nrows = min(NCC_BAND, t.rh - y0);
+    const int SP = mp.smem_pitch, VP = mp.v_pitch;
+
+    uint8_t *s_win = smem_b;                                              // [(NCC_BAND+th-1)][SP]
+    uint32_t *s_v2 = (uint32_t *)(smem_b + (size_t)(NCC_BAND + mp.max_th - 1) * SP);   // [NCC_BAND][VP]
+    uint16_t *s_v = (uint16_t *)(s_v2 + (size_t)NCC_BAND * VP);           // [NCC_BAND][VP]
+    const int wrows = nrows + th - 1;
+    {
+        const int vec = SP / 16;
+        const int xb0 = word0 * 4;                       // first window byte column of this chunk
+        const uint8_t *src = win8 + t.win_off;
+        for (int i = threadIdx.x; i < wrows * vec; i += blockDim.x) {
+            int r = i / vec, cc = (i - r * vec) * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            int gx = xb0 + cc, gy = y0 + r;
+            if (gx < t.pitch && gy < t.h) v = *(const uint4 *)(src + (size_t)gy * t.pitch + gx);
+            *(uint4 *)(s_win + (size_t)r * SP + cc) = v;
+        }
+    }
+    __syncthreads();
+    {
+        // vertical sliding sums for the columns this chunk's positions touch: [0, 4*nwords + tw - 1)
+        const int ncols = min(4 * nwords + tw, VP);
+        for (int cc = threadIdx.x; cc < ncols; cc += blockDim.x) {
+            uint32_t s = 0, q = 0;
+            for (int v = 0; v < th; v++) {
+                uint32_t p = s_win[(size_t)v * SP + cc];
+                s += p;
+                q += p * p;
+            }
+            s_v[cc] = (uint16_t)s;
+            s_v2[cc] = q;
+            for (int y = 1; y < nrows; y++) {
+                uint32_t a = s_win[(size_t)(y + th - 1) * SP + cc], b = s_win[(size_t)(y - 1) * SP + cc];
+                s += a - b;
+                q += a * a - b * b;
+                s_v[(size_t)y * VP + cc] = (uint16_t)s;
+                s_v2[(size_t)y * VP + cc] = q;
             }
         }
-        // normalise (double, OpenCV order) and keep the first maximum
-        const int y = y0 + yy;
-        const int xbase = (tile0 + tile) * 32;
-        const size_t rowoff = t.sum_off + (size_t)y * t.rw;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = xbase + 4 * q + j;
-                if (x < t.rw) {
-                    const uint32_t s = wsum[rowoff + x], sq = wsq[rowoff + x];
-                    const float sc = ncc_score((double)acc[j][q], (double)s, (double)sq, tc.inv_area, tc.mean, tc.norm, tc.flat);
-                    if (score_map) score_map[rowoff + x] = sc;
-                    const unsigned long long key = pack_key(sc, (uint32_t)(y * t.rw + x));
-                    mybest = key > mybest ? key : mybest;
-                }
-            }
-        }
+    }
+    __syncthreads();
+
+    NccCtx c;
+    c.s_win = s_win;
+    c.s_v = s_v;
+    c.s_v2 = s_v2;
+    c.g_tpl = (const uint4 *)tpls->shifted[t.tpl];
+    c.SP = SP;
+    c.VP = VP;
+    c.th = th;
+    c.tw = tw;
+    c.k4 = tc.k4;
+    c.rw = t.rw;
+    c.N = (long long)tw * th;
+    c.tsum = (long long)tc.tsum;
+    c.inv_sqrt_c = tc.inv_sqrt_c;
+    c.inv_area = tc.inv_area;
+    c.mean = tc.mean;
+    c.norm = tc.norm;
+    c.map_off = t.sum_off;
+    c.score_map = score_map;
+    c.x_chunk0 = word0 * 4;
+
+    // tiles of the chunk: n8 x (8 words), n4 x (4 words), n1 x (1 word)
+    const int n8 = nwords >> 3, n4 = (nwords & 7) >> 2, n1 = nwords & 3;
+    // a warp owns one tile x 32 rows (rows beyond the band are masked, not skipped: the filter's
+    // warp-wide maximum needs all 32 lanes)
+    unsigned long long mybest = 0ull;
+    const int ntile = n8 + n4 + n1;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int tile = 0; tile < ntile; tile++) {
+        // tiles are ordered by decreasing cost; the first four go to warps 0..3, later (cheaper)
+        // ones to the warps that got the cheapest tiles: longest-processing-time-first balance
+        const int owner = tile < 4 ? tile : 3 - ((tile - 4) & 3);
+        if (owner != warp) continue;
+        const bool valid = lane < nrows;
+        const int yy = valid ? lane : 0;
+        c.y = y0 + yy;
+        if (tile < n8) ncc_tile<8, MAP>(c, valid, yy, tile * 8, mybest);
+        else if (tile < n8 + n4) ncc_tile<4, MAP>(c, valid, yy, n8 * 8 + (tile - n8) * 4, mybest);
+        else ncc_tile<1, MAP>(c, valid, yy, n8 * 8 + n4 * 4 + (tile - n8 - n4), mybest);
     }
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);
@@ -499,71 +541,81 @@ lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict_
     }
 }
 
+static int ncc_pitch(int chunk_words, int k4)
+{
+    // widest read: a 4-word tile at word (chunk_words - 4) loading words [k, k + 8) for k <= k4 - 1 rounded
+    // down to a multiple of 4, i.e. up to word chunk_words + k4 + 3 -> +4 for the vertical-sum columns
+    int p = 4 * chunk_words + 4 * (k4 + 4);
+    p = (p + 15) & ~15;
+    if (((p / 16) & 1) == 0) p += 16;   // odd multiple of 16 B: conflict-free 128-bit row loads
+    return p;
+}
+static int ncc_vpitch(int chunk_words, int tw)
+{
+    int v = 4 * chunk_words + tw;
+    return v | 1;                        // odd: conflict-free when 32 lanes own 32 rows
+}
+static size_t ncc_smem(int chunk_words, int tw, int th)
+{
+    int k4 = (tw + 2) / 4 + 1;
+    return (size_t)(NCC_BAND + th - 1) * ncc_pitch(chunk_words, k4) + (size_t)NCC_BAND * ncc_vpitch(chunk_words, tw) * 6 + 16;
+}
+
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes)
 {
-    const int k4 = (tw + 2) / 4 + 1;
-    const int tiles_x = (max_rw + 31) / 32;
-    const size_t budget = 100 * 1024;   // <= ~100 KB per CTA keeps two CTAs resident per SM
-    auto pitch_of = [&](int tiles) {
-        int p = 32 * tiles + 4 * k4;
-        p = (p + 15) & ~15;
-        if (((p / 16) & 1) == 0) p += 16;   // odd multiple of 16 B: conflict-free 128-bit row loads
-        return p;
-    };
-    auto smem_of = [&](int tiles, int rows) { return (size_t)(rows + th - 1) * pitch_of(tiles); };
-    auto ctas_of = [&](int tiles, int rows) {
-        return (long)n_tasks * ((tiles_x + tiles - 1) / tiles) * ((max_rh + rows - 1) / rows);
-    };
-    // Start from one CTA per window; split rows (in multiples of 32: lanes own rows) and then
-    // column tiles until the tile fits and there are enough CTAs to fill 148 SMs a few times.
-    int tiles = tiles_x, rows = max_rh;
-    const long want_ctas = 148L * 4;
-    for (;;) {
-        bool too_big = smem_of(tiles, rows) > budget;
-        bool too_few = ctas_of(tiles, rows) < want_ctas && (long)tiles * rows > 2 * NCC_THREADS;
-        if (!too_big && !too_few) break;
-        if (rows > 32) rows = (((rows + 1) / 2) + 31) & ~31;
-        else if (tiles > 1) tiles = (tiles + 1) / 2;
-        else break;
-    }
-    mp->band_rows = rows;
-    mp->tiles_per_cta = tiles;
-    mp->smem_pitch = pitch_of(tiles);
-    *smem_bytes = smem_of(tiles, rows);
+    // One CTA = 32 result rows x chunk_words*4 result columns.  Start from the whole row and halve
+    // (in multiples of 8 words) until the tile fits ~56 KB, which keeps 4 CTAs resident per SM.
+    const int words_total = (max_rw + 3) / 4;
+    int cw = (words_total + 7) & ~7;
+    const size_t budget = 56 * 1024;
+    while (cw > 8 && ncc_smem(cw, tw, th) > budget) cw = (((cw + 1) / 2) + 7) & ~7;
+    // too few CTAs to fill the machine (single windows): split further
+    auto ctas = [&](int w) { return (long)n_tasks * ((words_total + w - 1) / w) * ((max_rh + NCC_BAND - 1) / NCC_BAND); };
+    while (cw > 8 && ctas(cw) < 148L * 4) cw = (((cw + 1) / 2) + 7) & ~7;
+    mp->chunk_words = cw;
+    mp->smem_pitch = ncc_pitch(cw, (tw + 2) / 4 + 1);
+    mp->v_pitch = ncc_vpitch(cw, tw);
+    mp->max_th = th;
+    *smem_bytes = ncc_smem(cw, tw, th);
 }
 
 int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                     const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
-                     unsigned long long *best, float *score_map, const MatchParams &mp, cudaStream_t stream)
+                     const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *score_map,
+                     const MatchParams &mp, cudaStream_t stream)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(lst_ncc_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_set = true;
     }
-    const int tiles_x = (max_rw + 31) / 32;
-    const int chunks = (tiles_x + mp.tiles_per_cta - 1) / mp.tiles_per_cta;
-    const int bands = (max_rh + mp.band_rows - 1) / mp.band_rows;
-    size_t smem = (size_t)(mp.band_rows + th - 1) * mp.smem_pitch;
-    (void)tw;
+    const int words_total = (max_rw + 3) / 4;
+    const int chunks = (words_total + mp.chunk_words - 1) / mp.chunk_words;
+    const int bands = (max_rh + NCC_BAND - 1) / NCC_BAND;
+    size_t smem = ncc_smem(mp.chunk_words, tw, th);
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
         dim3 grid(chunks * bands, n);
-        lst_ncc_match<<<grid, NCC_THREADS, smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, best + base, score_map, mp);
+        if (score_map)
+            lst_ncc_match<true><<<grid, NCC_THREADS, smem, stream>>>(tasks + base, tpls, win8, best + base, score_map, mp);
+        else
+            lst_ncc_match<false><<<grid, NCC_THREADS, smem, stream>>>(tasks + base, tpls, win8, best + base, score_map, mp);
         launches++;
     }
     return launches;
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // per-window epilogue: 3x3 neighbourhood, sub-pixel fit, accept test
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(288)
 lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
-             const uint32_t *__restrict__ wsum, const uint32_t *__restrict__ wsq,
              const unsigned long long *__restrict__ best, DevResult *__restrict__ results, MatchParams mp)
 {
+    // nine warps: warp w recomputes the score of neighbour (w%3-1, w/3-1) of the peak exactly
+    // (correlation and window sums in integers, normalisation by ncc_score as in the match kernel)
     __shared__ float nb[9];
     const DevTask t = tasks[blockIdx.x];
     const TplConst tc = tpls->c[t.tpl];
@@ -577,14 +629,20 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
     if (nx >= 0 && nx < t.rw && ny >= 0 && ny < t.rh) {
         const uint8_t *w = win8 + t.win_off + (size_t)ny * t.pitch + nx;
         const uint8_t *tp = tpls->raw[t.tpl];
-        uint32_t acc = 0;
+        uint32_t acc = 0, s = 0, q = 0;
         for (int e = lane; e < tc.tw * tc.th; e += 32) {
             int v = e / tc.tw, u = e - v * tc.tw;
-            acc += (uint32_t)w[(size_t)v * t.pitch + u] * (uint32_t)tp[e];
+            uint32_t px = w[(size_t)v * t.pitch + u];
+            acc += px * (uint32_t)tp[e];
+            s += px;
+            q += px * px;
         }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        size_t o = t.sum_off + (size_t)ny * t.rw + nx;
-        sc = ncc_score((double)acc, (double)wsum[o], (double)wsq[o], tc.inv_area, tc.mean, tc.norm, tc.flat);
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        sc = ncc_score((double)acc, (double)s, (double)q, tc.inv_area, tc.mean, tc.norm, tc.flat);
     }
     if (lane == 0) nb[warp] = sc;
     __syncthreads();
@@ -607,10 +665,9 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
 }
 
 int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls, const uint8_t *win8,
-                    const uint32_t *wsum, const uint32_t *wsq, const unsigned long long *best, DevResult *results,
-                    const MatchParams &mp, cudaStream_t stream)
+                    const unsigned long long *best, DevResult *results, const MatchParams &mp, cudaStream_t stream)
 {
-    lst_epilogue<<<n_tasks, 288, 0, stream>>>(tasks, tpls, win8, wsum, wsq, best, results, mp);
+    lst_epilogue<<<n_tasks, 288, 0, stream>>>(tasks, tpls, win8, best, results, mp);
     return 1;
 }
 

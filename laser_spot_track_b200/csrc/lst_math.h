@@ -26,6 +26,8 @@ struct TplConst {
     int32_t k4;         // 32-bit words per shifted template row (see build_shifted_template)
     uint32_t tsum, tsq_lo;
     double mideal;      // doMatch_test of the template (LST4:2724-2767)
+    float inv_sqrt_c;   // 1/sqrt(N*tsq - tsum^2): float32 filter of the match kernel
+    float pad;
 };
 
 // One position of common_matchTemplate for TM_CCOEFF_NORMED with an exact integer numerator:

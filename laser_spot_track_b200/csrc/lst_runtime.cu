@@ -47,8 +47,6 @@ struct lst_ctx : public Executor {
     DevResult *d_results = nullptr, *h_results = nullptr;
     uint8_t *d_win8 = nullptr;
     size_t win8_cap = 0;
-    uint32_t *d_wsum = nullptr, *d_wsq = nullptr;
-    size_t sum_cap = 0;
     float *d_map = nullptr;
     size_t map_cap = 0;
     // frame table + ring
@@ -64,6 +62,7 @@ struct lst_ctx : public Executor {
     bool timing = false;
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
+    std::vector<int> order;   // device slot -> caller's task index (tasks are grouped by template)
     size_t scratch_limit = (size_t)6 << 30;
 
     size_t bpp() const { return p.pixel_type == LST_PIX_U8 ? 1 : (p.pixel_type == LST_PIX_U16 ? 2 : 4); }
@@ -87,7 +86,7 @@ struct lst_ctx : public Executor {
                   int tpl_override, float *map_out_host);
     int ensure_tasks(int n);
     int ensure_frames(int n);
-    int ensure_scratch(size_t win_bytes, size_t sum_elems, size_t map_elems);
+    int ensure_scratch(size_t win_bytes, size_t map_elems);
     int upload_template(int slot, const uint8_t *tpl8, int tw, int th);
     void preproc_params(PreprocParams *pp, int max_w) const;
     void drain_timers();
@@ -145,20 +144,13 @@ int lst_ctx::ensure_frames(int n)
     return LST_OK;
 }
 
-int lst_ctx::ensure_scratch(size_t win_bytes, size_t sum_elems, size_t map_elems)
+int lst_ctx::ensure_scratch(size_t win_bytes, size_t map_elems)
 {
     if (win_bytes > win8_cap) {
         CU(cudaStreamSynchronize(s_compute));
         size_t cap = std::max(win_bytes, win8_cap + win8_cap / 2);
         CU(regrow(&d_win8, cap));
         win8_cap = cap;
-    }
-    if (sum_elems > sum_cap) {
-        CU(cudaStreamSynchronize(s_compute));
-        size_t cap = std::max(sum_elems, sum_cap + sum_cap / 2);
-        CU(regrow(&d_wsum, cap));
-        CU(regrow(&d_wsq, cap));
-        sum_cap = cap;
     }
     if (map_elems > map_cap) {
         CU(cudaStreamSynchronize(s_compute));
@@ -247,8 +239,13 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     size_t win_off = 0, sum_off = 0;
     int max_w = 0, max_h = 0, max_rw = 0, max_rh = 0, max_tw = 0, max_th = 0;
     double macs = 0;
+    // device order: grouped by template, so that CTAs resident on one SM read the same shifted
+    // template through L1 (order[i] = index of the caller's task in device slot i)
+    order.resize(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].tpl < tasks[b].tpl; });
     for (int i = 0; i < n; i++) {
-        const lst_task &t = tasks[i];
+        const lst_task &t = tasks[order[i]];
         DevTask &d = h_tasks[i];
         memset(&d, 0, sizeof(d));
         Rect c = have_win8 ? Rect{0, 0, t.ww, t.wh} : clip_rect(t.wx, t.wy, t.ww, t.wh, p.width, p.height);
@@ -280,7 +277,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         max_w = std::max(max_w, d.w);
         max_h = std::max(max_h, d.h);
     }
-    rc = ensure_scratch(win_off + 64, sum_off + 32, map_out_host ? sum_off + 32 : 0);
+    rc = ensure_scratch(win_off + 64, map_out_host ? sum_off + 32 : 0);
     if (rc != LST_OK) return rc;
     CU(cudaMemcpyAsync(d_tasks, h_tasks, sizeof(DevTask) * n, cudaMemcpyHostToDevice, s_compute));
     stats.h2d_bytes += (int64_t)sizeof(DevTask) * n;
@@ -300,7 +297,6 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         mp.templ_size = p.templ_size;
         mp.thresh = p.match_threshold;
         if (smem > 200 * 1024) return fail(LST_ERR_UNSUPPORTED, "match tile needs %zu bytes of shared memory", smem);
-        launches += launch_box_sums(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, s_compute);
         TimedLaunch tl;
         if (timing) {
             for (cudaEvent_t *e : {&tl.e0, &tl.e1}) {
@@ -314,13 +310,13 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             tl.macs = macs;
             CU(cudaEventRecord(tl.e0, s_compute));
         }
-        launches += launch_ncc_match(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, d_best,
+        launches += launch_ncc_match(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_best,
                                      map_out_host ? d_map : nullptr, mp, s_compute);
         if (timing) {
             CU(cudaEventRecord(tl.e1, s_compute));
             timed.push_back(tl);
         }
-        launches += launch_epilogue(d_tasks, n, d_tpls, d_win8, d_wsum, d_wsq, d_best, d_results, mp, s_compute);
+        launches += launch_epilogue(d_tasks, n, d_tpls, d_win8, d_best, d_results, mp, s_compute);
         CU(cudaMemcpyAsync(h_results, d_results, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s_compute));
         stats.d2h_bytes += (int64_t)sizeof(DevResult) * n;
     }
@@ -333,13 +329,14 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             const DevResult &r = h_results[i];
             if (!r.peak_check)
                 return fail(LST_ERR_CUDA, "internal: epilogue peak score differs from the argmax score (task %d)", i);
-            results[i].x = r.x;
-            results[i].y = r.y;
-            results[i].score = r.score;
-            results[i].ix = r.ix;
-            results[i].iy = r.iy;
-            results[i].accepted = r.accepted;
-            results[i].reserved = 0;
+            lst_task_result &o = results[order[i]];
+            o.x = r.x;
+            o.y = r.y;
+            o.score = r.score;
+            o.ix = r.ix;
+            o.iy = r.iy;
+            o.accepted = r.accepted;
+            o.reserved = 0;
         }
     }
     if (map_out_host && !preprocess_only) {
@@ -359,7 +356,7 @@ int lst_ctx::compute(const lst_task *tasks, int n, lst_task_result *results)
         while (j < n) {
             const lst_task &t = tasks[j];
             size_t pitch = (t.ww + 15) & ~15;
-            size_t need = pitch * t.wh + 256 + 2 * sizeof(uint32_t) * ((size_t)t.ww * t.wh + 32);
+            size_t need = pitch * t.wh + 256;
             if (j > i && bytes + need > scratch_limit) break;
             bytes += need;
             j++;
@@ -480,8 +477,6 @@ void lst_destroy(lst_ctx *c)
     cudaFree(c->d_best);
     cudaFree(c->d_results);
     cudaFree(c->d_win8);
-    cudaFree(c->d_wsum);
-    cudaFree(c->d_wsq);
     cudaFree(c->d_map);
     cudaFree(c->d_frames);
     cudaFree(c->d_ring[0]);
@@ -548,7 +543,9 @@ int lst_set_reference(lst_ctx *c, const void *ref_frame, const float ref_xy[10],
     if (rc != LST_OK) return rc;
     for (int k = 0; k < 5; k++) {
         std::vector<uint8_t> t8((size_t)crop[k].w * crop[k].h);
-        const DevTask &d = c->h_tasks[k];
+        int slot = 0;
+        while (c->order[slot] != k) slot++;
+        const DevTask &d = c->h_tasks[slot];
         CUC(c, cudaMemcpy2D(t8.data(), crop[k].w, c->d_win8 + d.win_off, d.pitch, crop[k].w, crop[k].h, cudaMemcpyDeviceToHost));
         c->stats.d2h_bytes += (int64_t)t8.size();
         rc = c->upload_template(k, t8.data(), crop[k].w, crop[k].h);
@@ -694,7 +691,7 @@ int lst_match_single(lst_ctx *c, const uint8_t *src8, int32_t sw, int32_t sh, co
     int rc = c->upload_template(kMaxTpl - 1, tpl8, tw, th);
     if (rc != LST_OK) return rc;
     size_t pitch = (sw + 15) & ~15;
-    rc = c->ensure_scratch(pitch * sh + 512, (size_t)sw * sh + 64, score_map ? (size_t)sw * sh + 64 : 0);
+    rc = c->ensure_scratch(pitch * sh + 512, score_map ? (size_t)sw * sh + 64 : 0);
     if (rc != LST_OK) return rc;
     CUC(c, cudaMemsetAsync(c->d_win8, 0, pitch * sh, c->s_compute));
     CUC(c, cudaMemcpy2DAsync(c->d_win8, pitch, src8, sw, sw, sh, cudaMemcpyHostToDevice, c->s_compute));
