@@ -323,18 +323,24 @@ __device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, in
         for (int q = 0; q < Q; q++) acc[j][q] = 0u;
     const uint8_t *wbase = c.s_win + (size_t)yy * c.SP + 4 * w0;
     constexpr int NW = (Q + 3 + 3) / 4;   // uint4 loads covering words [k, k + Q + 3)
-    for (int v = 0; v < c.th; v++) {
-        const uint8_t *wrow = wbase + (size_t)v * c.SP;
-        const uint4 *trow = c.g_tpl + v * c.k4;
-        for (int k = 0; k < c.k4; k += 4) {
+    // Per template row: nfull chunks of 4 template words (16*Q IDP.4A each, no guards) and one tail
+    // chunk of k4 % 4 words.  All loads of a chunk are issued before its IDP.4A block; IDP.4A is
+    // half-rate, so the other warps of the SM sub-partition cover the remaining latency.
+    const int nfull = c.k4 >> 2, rem = c.k4 & 3;
+    const uint4 *trow = c.g_tpl;
+    const uint8_t *wrow = wbase;
+    for (int v = 0; v < c.th; v++, wrow += c.SP) {
+        const uint8_t *wp = wrow;
+        for (int kc = 0; kc < nfull; kc++, wp += 16, trow += 4) {
             uint32_t ww[4 * NW];
+            uint4 tj[4];
             if (Q == 1) {   // single-word tiles start at any word: 32-bit loads
 #pragma unroll
-                for (int i = 0; i < 4; i++) ww[i] = *(const uint32_t *)(wrow + 4 * (k + i));
+                for (int i = 0; i < 4; i++) ww[i] = *(const uint32_t *)(wp + 4 * i);
             } else {        // 4- and 8-word tiles start at multiples of 4 words: 128-bit loads
 #pragma unroll
                 for (int i = 0; i < NW; i++) {
-                    const uint4 t4 = *(const uint4 *)(wrow + 4 * k + 16 * i);
+                    const uint4 t4 = *(const uint4 *)(wp + 16 * i);
                     ww[4 * i] = t4.x;
                     ww[4 * i + 1] = t4.y;
                     ww[4 * i + 2] = t4.z;
@@ -342,9 +348,42 @@ __device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, in
                 }
             }
 #pragma unroll
+            for (int kk = 0; kk < 4; kk++) tj[kk] = __ldg(trow + kk);
+#pragma unroll
             for (int kk = 0; kk < 4; kk++) {
-                if (k + kk < c.k4) {   // warp-uniform: the last chunk of a row may be partial
-                    const uint4 tj = __ldg(trow + k + kk);
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const uint32_t wv = ww[kk + q];
+                    acc[0][q] = __dp4a(wv, tj[kk].x, acc[0][q]);
+                    acc[1][q] = __dp4a(wv, tj[kk].y, acc[1][q]);
+                    acc[2][q] = __dp4a(wv, tj[kk].z, acc[2][q]);
+                    acc[3][q] = __dp4a(wv, tj[kk].w, acc[3][q]);
+                }
+            }
+        }
+        if (rem) {   // warp-uniform
+            uint32_t ww[Q + 2];
+            if (Q == 1) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) ww[i] = *(const uint32_t *)(wp + 4 * i);
+            } else {
+                constexpr int NT = (Q + 2 + 3) / 4;
+                uint32_t wt[4 * NT];
+#pragma unroll
+                for (int i = 0; i < NT; i++) {
+                    const uint4 t4 = *(const uint4 *)(wp + 16 * i);
+                    wt[4 * i] = t4.x;
+                    wt[4 * i + 1] = t4.y;
+                    wt[4 * i + 2] = t4.z;
+                    wt[4 * i + 3] = t4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < Q + 2; i++) ww[i] = wt[i];
+            }
+#pragma unroll
+            for (int kk = 0; kk < 3; kk++) {
+                if (kk < rem) {
+                    const uint4 tj = __ldg(trow + kk);
 #pragma unroll
                     for (int q = 0; q < Q; q++) {
                         const uint32_t wv = ww[kk + q];
@@ -355,6 +394,7 @@ __device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, in
                     }
                 }
             }
+            trow += rem;
         }
     }
     // Normalisation.  The 4Q correlations move to a thread-local array so that the loops below are
