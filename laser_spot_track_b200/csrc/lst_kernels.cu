@@ -186,39 +186,84 @@ lst_preprocess(const DevTask *__restrict__ tasks, const void *const *__restrict_
     }
     __syncthreads();
 
-    // X pass: rows [ry0,ry1), columns [cx0,cx1)
+    // X pass: rows [ry0,ry1), columns [cx0,cx1).  A thread produces 4 consecutive columns from 16
+    // loads when the run is interior (no edge replication); edge runs take the general form.
     const int ncw = cx1 - cx0;
-    for (int idx = threadIdx.x; idx < ncw * nrh; idx += blockDim.x) {
-        int r = idx / ncw, c = idx - r * ncw;
+    const int nsegx = (ncw + 3) >> 2;
+    for (int idx = threadIdx.x; idx < nsegx * nrh; idx += blockDim.x) {
+        int r = idx / nsegx, sg = idx - r * nsegx;
         const float *line = raw + r * RWP - rx0;   // line[i] = crop row pixel i
-        int i = cx0 + c;
-        float res;
+        const int i0 = cx0 + 4 * sg;
+        float *dstx = xp + r * XWP + 4 * sg;
+        if (i0 >= KR && i0 + 3 + KR < t.w && i0 + 3 < cx1) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = line[i0 - (KR - 1) + j];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float res = v[KR - 1 + j] * c_kern[0];
+#pragma unroll
+                for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
+                dstx[j] = res;
+            }
+        } else {
+            for (int j = 0; j < 4 && i0 + j < cx1; j++) {
+                const int i = i0 + j;
+                float res;
 #define IN_X(ii) line[(ii)]
-        LST_BLUR_AT(res, i, t.w, IN_X)
+                LST_BLUR_AT(res, i, t.w, IN_X)
 #undef IN_X
-        xp[r * XWP + c] = res;
+                dstx[j] = res;
+            }
+        }
     }
     __syncthreads();
 
-    // Y pass + quantise: rows [cy0,cy1), columns [cx0,cx1)
+    // Y pass + quantise: rows [cy0,cy1), columns [cx0,cx1).  A thread produces 4 consecutive rows of
+    // one column (consecutive threads own consecutive columns: conflict-free, coalesced stores).
     float scale = (pp.quant_mode == LST_QUANT_ROUND255 ? 255.0f : 256.0f) / (hi - lo);
     const int nch = cy1 - cy0;
+    const int nsegy = (nch + 3) >> 2;
     uint8_t *dst = win8 + t.win_off;
-    for (int idx = threadIdx.x; idx < ncw * nch; idx += blockDim.x) {
-        int r = idx / ncw, c = idx - r * ncw;
-        const float *col = xp + c - ry0 * XWP;     // col[i*XWP] = x-pass value at crop row i
-        int i = cy0 + r;
-        float res;
+    for (int idx = threadIdx.x; idx < ncw * nsegy; idx += blockDim.x) {
+        int sg = idx / ncw, cc = idx - sg * ncw;
+        const float *col = xp + cc - ry0 * XWP;     // col[i*XWP] = x-pass value at crop row i
+        const int i0 = cy0 + 4 * sg;
+        float out[4];
+        int nout = min(4, cy1 - i0);
+        if (i0 >= KR && i0 + 3 + KR < t.h && nout == 4) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = col[(i0 - (KR - 1) + j) * XWP];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float res = v[KR - 1 + j] * c_kern[0];
+#pragma unroll
+                for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
+                out[j] = res;
+            }
+        } else {
+            for (int j = 0; j < nout; j++) {
+                const int i = i0 + j;
+                float res;
 #define IN_Y(ii) col[(ii)*XWP]
-        LST_BLUR_AT(res, i, t.h, IN_Y)
+                LST_BLUR_AT(res, i, t.h, IN_Y)
 #undef IN_Y
-        float value = res - lo;
-        if (value < 0.0f) value = 0.0f;
-        float q = value * scale;
-        if (pp.quant_mode == LST_QUANT_ROUND255) q = q + 0.5f;
-        int iv = __float2int_rz(q);            // Java (int): NaN -> 0, saturating
-        iv = iv > 255 ? 255 : (iv < 0 ? 0 : iv);
-        dst[(size_t)i * t.pitch + (cx0 + c)] = (uint8_t)iv;
+                out[j] = res;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (j < nout) {
+                float value = out[j] - lo;
+                if (value < 0.0f) value = 0.0f;
+                float q = value * scale;
+                if (pp.quant_mode == LST_QUANT_ROUND255) q = q + 0.5f;
+                int iv = __float2int_rz(q);            // Java (int): NaN -> 0, saturating
+                iv = iv > 255 ? 255 : (iv < 0 ? 0 : iv);
+                dst[(size_t)(i0 + j) * t.pitch + (cx0 + cc)] = (uint8_t)iv;
+            }
+        }
     }
     // zero the pitch padding so the match kernel can load whole 16-byte words
     if (cx1 == t.w && t.pitch > t.w) {

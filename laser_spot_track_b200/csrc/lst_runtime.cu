@@ -185,7 +185,7 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w) const
         pp->range_per_task = 1;
     }
     int tw = (max_w + 7) & ~7;
-    pp->tile_w = tw < 128 ? tw : 128;
+    pp->tile_w = tw < 192 ? tw : 192;   // whole window rows for the named configurations (S <= 192)
     pp->tile_h = 32;
 }
 

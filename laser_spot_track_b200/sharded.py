@@ -1,0 +1,138 @@
+"""Frame sharding of one stack over several GPUs (north_star item 4).
+
+One process per GPU.  The stack is cut into ``world`` contiguous chunks; rank r tracks chunk r.
+Nothing is reduced between GPUs -- there is no data-path collective.  The only coupling between
+chunks is the reference's frame-to-frame recurrence: the search windows of the first frame of
+chunk r are placed from the *integer-truncated* displacements left by the last accepted frame of
+chunk r-1 (LST4:1327-1328, 832-846).  That is 10 numbers per boundary, handled by
+speculate-and-verify:
+
+1. every rank tracks its chunk from a *speculated* start state (optionally refined by tracking a
+   short lead-in of the previous chunk's last frames first);
+2. the ranks exchange their end states (10 doubles each, host side);
+3. walking the boundaries in order, a rank whose speculated start state places the windows
+   differently from the true state re-tracks its chunk (rare: the state only matters through
+   ``(int)dis``), and passes its corrected end state on.
+
+``comm`` is any object with ``all_gather(list_of_10_floats) -> list over ranks`` and
+``broadcast(list_or_None, src) -> list`` (see TorchComm); ``tracker`` is anything with
+``set_state(dis)``, ``get_state()`` and ``track(frames, first_frame_index) -> records``
+(LaserSpotTrack4, or the CPU stand-in of the tests).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+
+def _jint(v: float) -> int:
+    if v != v:
+        return 0
+    return int(math.trunc(v))
+
+
+def same_windows(a: Sequence[float], b: Sequence[float]) -> bool:
+    """Two displacement states place all five search windows identically (LST4:1327-1328)."""
+    return all(_jint(x) == _jint(y) for x, y in zip(a, b))
+
+
+def chunk_bounds(n_frames: int, world: int):
+    """Contiguous chunks, sizes differing by at most one frame."""
+    base, extra = divmod(n_frames, world)
+    out, lo = [], 0
+    for r in range(world):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class TorchComm:
+    """Host-side exchange over a torch.distributed process group (gloo on CPU tensors; with an NCCL
+    group the 10 doubles travel as a tiny device tensor).  Not on the data path."""
+
+    def __init__(self, group=None, device="cpu"):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.device = torch, dist, group, device
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_gather(self, vals: Sequence[float]) -> List[List[float]]:
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return [o.cpu().tolist() for o in out]
+
+    def broadcast(self, vals: Optional[Sequence[float]], src: int, n: int = 11) -> List[float]:
+        t = self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
+        if self.rank == src:
+            t[:] = self.torch.tensor(list(vals), dtype=self.torch.float64)
+        self.dist.broadcast(t, src=src, group=self.group)
+        return t.cpu().tolist()
+
+
+class LocalComm:
+    """world == 1."""
+    rank, world = 0, 1
+
+    def all_gather(self, vals):
+        return [list(vals)]
+
+    def broadcast(self, vals, src, n=11):
+        return list(vals)
+
+
+class ShardedTracker:
+    def __init__(self, tracker, comm=None):
+        self.tracker = tracker
+        self.comm = comm or LocalComm()
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.retracked = 0
+
+    def track_chunk(self, frames, first_frame_index: int, start_state: Sequence[float],
+                    lead_in: Optional[Sequence] = None):
+        """Track this rank's chunk.  ``start_state``: speculated displacement state before the chunk
+        (rank 0: the true one).  ``lead_in``: optionally the last few frames of the previous chunk,
+        tracked first from ``start_state`` to refine the speculation.  Returns (records, end_state);
+        both are final after the boundary verification."""
+        tr = self.tracker
+        guess = list(start_state)
+        if self.rank > 0 and lead_in is not None and len(lead_in) > 0:
+            tr.set_state(guess)
+            tr.track(lead_in, first_frame_index - len(lead_in))
+            guess = list(tr.get_state())
+        tr.set_state(guess)
+        recs = tr.track(frames, first_frame_index)
+        end = list(tr.get_state())
+        # boundary verification, in rank order; payload = 10 doubles (+1 flag)
+        prev_end = None
+        for r in range(1, self.world):
+            # rank r-1 owns the verified end state of chunk r-1
+            msg = self.comm.broadcast(end + [0.0] if self.rank == r - 1 else None, src=r - 1)
+            if self.rank == r:
+                prev_end = msg[:10]
+                if not same_windows(prev_end, guess):
+                    tr.set_state(prev_end)
+                    recs = tr.track(frames, first_frame_index)
+                    end = list(tr.get_state())
+                    self.retracked += 1
+                else:
+                    # same windows => same matches; only the carried doubles differ while no frame
+                    # of the chunk has been accepted yet (skipped frames restore the state, LST4:832-846)
+                    recs, end = self._patch_carried_state(recs, end, guess, prev_end)
+                tr.set_state(end)
+        return recs, end
+
+    @staticmethod
+    def _patch_carried_state(recs, end, guess, true_start):
+        all_skipped = True
+        for r in recs:
+            if r.status == 0:
+                all_skipped = False
+                break
+            for k in range(10):
+                r.dis[k] = true_start[k]
+        if all_skipped:
+            end = list(true_start)
+        return recs, end

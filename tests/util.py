@@ -109,3 +109,29 @@ def compare_records(got, want, *, score_tol=0.0, pos_tol=0.0, out_tol=0.0, label
         if w.status == 0:
             for name in ("dX_pix", "dY_pix", "x_abs", "y_abs", "dL"):
                 assert same_float(getattr(g, name), getattr(w, name), out_tol), f"{where}: {name} {getattr(g, name)!r} != {getattr(w, name)!r}"
+
+
+class CpuResolverTracker:
+    """Tracker-shaped CPU stand-in for the sharding tests: the library's resolver (C++) with the
+    oracle as the device.  Same set_state/get_state/track surface as LaserSpotTrack4."""
+
+    def __init__(self, op: O.Params, ref_frame, ref_xy, pixel_type, max_batch=8):
+        self.op, self.pixel_type, self.max_batch = op, pixel_type, max_batch
+        self.otr = O.OracleTracker(op)
+        self.otr.set_reference(ref_frame, ref_xy)
+        self.state = [0.0] * 10
+        self.tasks = 0
+
+    def set_state(self, dis):
+        self.state = [float(v) for v in dis]
+
+    def get_state(self):
+        return list(self.state)
+
+    def track(self, frames, first_frame_index=1):
+        frames = list(frames)
+        out, dis, st, dev = host_resolve(self.op, self.otr, frames, self.pixel_type, self.max_batch,
+                                         dis0=self.state, first_index=first_frame_index)
+        self.state = dis
+        self.tasks += st.tasks
+        return out
