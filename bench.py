@@ -208,9 +208,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the tracking path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")     # chunk-boundary hand-off: 21 doubles, host side
 
     def barrier():
         if world > 1:
@@ -244,11 +246,33 @@ def main():
     host_ptrs = (C.c_void_p * F)(*[host_ring.value + i * fb for i in idx])
     out = (N.Record * F)()
 
+    # Sharding: the step's stack is world*F slices; rank r owns the contiguous chunk r.  The state
+    # at the chunk boundary is speculated (the ring is periodic, so "my own previous end state" is
+    # the natural guess), exchanged host-side and verified (laser_spot_track_b200/sharded.py).
+    from laser_spot_track_b200.sharded import ShardedTracker, TorchComm
+
+    class _Adapter:
+        def __init__(self, fn):
+            self.fn = fn
+
+        def set_state(self, d):
+            trk.set_state(d)
+
+        def get_state(self):
+            return trk.get_state()
+
+        def track(self, frames, first):
+            return self.fn(frames, first, out)
+
+    comm = TorchComm(host_group, "cpu") if world > 1 else None
+    sh_dev = ShardedTracker(_Adapter(trk.track_device_ptrs), comm)
+    sh_e2e = ShardedTracker(_Adapter(trk.track_host_ptrs), comm)
+
     def step_device():
-        trk.track_device_ptrs(dev_ptrs, 1, out)
+        sh_dev.track_chunk(dev_ptrs, 1 + rank * F, trk.get_state())
 
     def step_e2e():
-        trk.track_host_ptrs(host_ptrs, 1, out)
+        sh_e2e.track_chunk(host_ptrs, 1 + rank * F, trk.get_state())
 
     def timed(step_fn, K, W):
         for _ in range(W):
@@ -331,7 +355,8 @@ def main():
                        "accepted_frames_last_step": ok_frames},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated)},
+            "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
+                         "chunks_retracked": sh_dev.retracked},
             "wall_ms_per_step": wall_dev / K,
         }
         print(json.dumps(line), flush=True)

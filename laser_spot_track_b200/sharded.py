@@ -9,7 +9,7 @@ speculate-and-verify:
 
 1. every rank tracks its chunk from a *speculated* start state (optionally refined by tracking a
    short lead-in of the previous chunk's last frames first);
-2. the ranks exchange their end states (10 doubles each, host side);
+2. the ranks exchange their end states and speculations (21 doubles each, host side, one all_gather);
 3. walking the boundaries in order, a rank whose speculated start state places the windows
    differently from the true state re-tracks its chunk (rare: the state only matters through
    ``(int)dis``), and passes its corrected end state on.
@@ -64,7 +64,7 @@ class TorchComm:
         self.dist.all_gather(out, t, group=self.group)
         return [o.cpu().tolist() for o in out]
 
-    def broadcast(self, vals: Optional[Sequence[float]], src: int, n: int = 11) -> List[float]:
+    def broadcast(self, vals: Optional[Sequence[float]], src: int, n: int = 10) -> List[float]:
         t = self.torch.zeros(n, dtype=self.torch.float64, device=self.device)
         if self.rank == src:
             t[:] = self.torch.tensor(list(vals), dtype=self.torch.float64)
@@ -79,7 +79,7 @@ class LocalComm:
     def all_gather(self, vals):
         return [list(vals)]
 
-    def broadcast(self, vals, src, n=11):
+    def broadcast(self, vals, src, n=10):
         return list(vals)
 
 
@@ -105,23 +105,39 @@ class ShardedTracker:
         tr.set_state(guess)
         recs = tr.track(frames, first_frame_index)
         end = list(tr.get_state())
-        # boundary verification, in rank order; payload = 10 doubles (+1 flag)
-        prev_end = None
+        # Boundary verification.  One all_gather of (end state, speculated start, any-accepted flag)
+        # lets every rank walk the chain of boundaries identically; in the common case (every
+        # speculation placed the windows right) that is all.  From the first wrong speculation on,
+        # the ranks fall back to handing the verified state down one boundary at a time.
+        accepted_any = any(r.status == 0 for r in recs)
+        gathered = self.comm.all_gather(end + guess + [1.0 if accepted_any else 0.0])
+        verified = list(gathered[0][:10])          # rank 0 started from the true state
+        first_bad = None
         for r in range(1, self.world):
-            # rank r-1 owns the verified end state of chunk r-1
-            msg = self.comm.broadcast(end + [0.0] if self.rank == r - 1 else None, src=r - 1)
-            if self.rank == r:
-                prev_end = msg[:10]
-                if not same_windows(prev_end, guess):
-                    tr.set_state(prev_end)
-                    recs = tr.track(frames, first_frame_index)
-                    end = list(tr.get_state())
-                    self.retracked += 1
-                else:
-                    # same windows => same matches; only the carried doubles differ while no frame
-                    # of the chunk has been accepted yet (skipped frames restore the state, LST4:832-846)
-                    recs, end = self._patch_carried_state(recs, end, guess, prev_end)
-                tr.set_state(end)
+            g_end, g_guess, g_any = gathered[r][:10], gathered[r][10:20], gathered[r][20] != 0.0
+            if not same_windows(verified, g_guess):
+                first_bad = r
+                break
+            if r == self.rank:
+                recs, end = self._patch_carried_state(recs, end, guess, verified)
+            verified = g_end if g_any else verified
+        if first_bad is not None:
+            for r in range(first_bad, self.world):
+                # `verified` is the true state before chunk r on every rank that needs it (r's owner
+                # got it from the walk above or from the previous iteration's broadcast)
+                if self.rank == r:
+                    if not same_windows(verified, guess):
+                        tr.set_state(verified)
+                        recs = tr.track(frames, first_frame_index)
+                        end = list(tr.get_state())
+                        self.retracked += 1
+                    else:
+                        recs, end = self._patch_carried_state(recs, end, guess, verified)
+                    accepted_any = any(x.status == 0 for x in recs)
+                    if not accepted_any:
+                        end = list(verified)
+                verified = self.comm.broadcast(end if self.rank == r else None, src=r, n=10)
+        tr.set_state(end)
         return recs, end
 
     @staticmethod
