@@ -313,7 +313,8 @@ def main():
         ms_e2e, wall_e2e, s_e2e = timed(step_e2e, K, W)
         e2e = {"value": world * F * K / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(s_e2e.h2d_bytes // K), "d2h_bytes_per_step": int(s_e2e.d2h_bytes // K),
-               "ms_per_step": ms_e2e / K, "ingest": "whole slices, pinned host ring, double-buffered cudaMemcpyAsync"}
+               "ms_per_step": ms_e2e / K, "ingest": "pinned host ring of whole slices; only the five search regions (+16 px margin) of each slice cross "
+                         "PCIe, gathered by a kernel on the copy stream while the previous batch computes"}
 
     value = world * F * K / (ms_dev * 1e-3)
     # roofline of the dominant kernel (lst_ncc_match): exact u8 x u8 -> s32 multiply-accumulates

@@ -81,7 +81,8 @@ typedef struct lst_params {
     int32_t auto_skip;         /* alwaysAutoSkip; headless policy: rejected frame => LST_STATUS_SKIP */
     int32_t max_s_area;        /* maxSArea LST4:131 (0 = no limit) */
     int32_t max_batch;         /* frames resolved per device pass (0 = default) */
-    int32_t reserved0;
+    int32_t ingest_mode;       /* host slices: 0 = auto (pinned memory: gather only the search regions;
+                                  pageable: whole-slice copies), 1 = always whole-slice copies */
     double  mark_dist;         /* markDist LST4:85 */
     double  range_lo, range_hi;/* LST_RANGE_FIXED */
     double  match_threshold;   /* matchThreshold[5] = 0.2, LST4:147 */
@@ -127,6 +128,7 @@ typedef struct lst_stats {
     double  ncc_kernel_ms;     /* CUDA-event time accumulated over lst_ncc_match launches (if timing on) */
     int64_t ncc_kernel_launches;
     double  ncc_algorithmic_macs; /* sum over timed launches of Rw*Rh*Tw*Th */
+    int64_t roi_fallback_tasks;/* ROI ingest: windows read straight from pinned host memory (margin exceeded) */
 } lst_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
@@ -150,7 +152,10 @@ int lst_set_reference(lst_ctx *ctx, const void *ref_frame, const float ref_xy[10
 /* frames: host memory, n_frames slices, consecutive slices frame_stride_bytes apart (0 = tightly
  * packed).  Slices are analysed in order with the reference's frame-to-frame recurrence
  * (LST4:1327-1328, 832-846); out receives n_frames records.  Synchronous.  Pageable or pinned
- * memory both work; pinned (lst_alloc_pinned / lst_host_register) lets copies overlap compute. */
+ * memory both work.  Pinned slices (lst_alloc_pinned / lst_host_register) stay where they are: only
+ * the five search regions of each slice cross PCIe (gathered by a kernel on a copy stream while the
+ * previous batch computes).  Pageable slices are copied whole with cudaMemcpyAsync into a
+ * double-buffered device ring. */
 int lst_track(lst_ctx *ctx, const void *frames, size_t frame_stride_bytes, int64_t first_frame_index,
               int32_t n_frames, lst_record *out);
 /* Same, scattered slices (one pointer per slice -- stack.getProcessor(i).getPixels()). */

@@ -10,7 +10,7 @@ namespace lst {
 
 // One (frame, template) search window resident in the per-pass device scratch.
 struct DevTask {
-    int32_t frame;        // index into the pass's frame-pointer table
+    int32_t frame;        // index into the pass's surface table
     int32_t tpl;          // template slot (0..4; match_single uses slot 5)
     int32_t x0, y0;       // window origin in the frame (already clipped to the frame)
     int32_t w, h;         // window size
@@ -20,6 +20,21 @@ struct DevTask {
     int32_t pad0, pad1;
     uint64_t win_off;     // byte offset of the 8-bit window in the win8 scratch
     uint64_t sum_off;     // element offset of this task's rw*rh score map (lst_match_single only)
+};
+
+// Where a task's pixels live: a whole slice in HBM, a gathered ROI in HBM, or a pinned host slice
+// mapped into the device address space (zero-copy fallback of the ROI ingest).
+struct Surface {
+    const void *ptr;
+    int32_t pitch_px;     // row pitch in pixels
+    int32_t org_x, org_y; // slice coordinates of the surface's first pixel
+    int32_t pad;
+};
+
+// One region of interest gathered from every slice of a batch (same rectangle for all slices).
+struct RoiDesc {
+    int32_t x, y, w, h;   // slice coordinates
+    uint64_t off;         // byte offset inside a slice's block of the ROI ring
 };
 
 struct DevResult {
@@ -61,10 +76,14 @@ struct MatchParams {
 
 // launchers (all asynchronous on `stream`); each returns the number of kernels it launched or <0
 int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, cudaStream_t stream);
-int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const void *const *frames, const PreprocParams &pp,
+int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *surfaces, const PreprocParams &pp,
                   uint32_t *mm_keys, cudaStream_t stream);
-int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const void *const *frames,
+int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces,
                       const PreprocParams &pp, const uint32_t *mm_keys, uint8_t *win8, cudaStream_t stream);
+// ROI ingest: copy 5 rectangles of each of n_frames pinned host slices (device-mapped pointers) into
+// the ROI ring; slice i's block starts at dst + i*block_bytes.
+int launch_gather_rois(const void *const *mapped_frames, int n_frames, const RoiDesc rois[5], int frame_w, int bpp,
+                       uint8_t *dst, size_t block_bytes, cudaStream_t stream);
 int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
                      const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *score_map,
                      const MatchParams &mp, cudaStream_t stream);

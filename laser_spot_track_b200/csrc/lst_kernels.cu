@@ -89,14 +89,15 @@ int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, c
 // min / max of the raw crop
 // ------------------------------------------------------------------------------------------------
 template <int PIX>
-__global__ void lst_minmax(const DevTask *__restrict__ tasks, const void *const *__restrict__ frames, int frame_w,
+__global__ void lst_minmax(const DevTask *__restrict__ tasks, const Surface *__restrict__ surfaces,
                            uint32_t *__restrict__ mm_keys)
 {
     const DevTask t = tasks[blockIdx.y];
-    const void *fr = frames[t.frame];
+    const Surface sf = surfaces[t.frame];
+    const void *fr = sf.ptr;
     uint32_t lo = 0xffffffffu, hi = 0u;
     for (int r = blockIdx.x; r < t.h; r += gridDim.x) {
-        size_t row = (size_t)(t.y0 + r) * frame_w + t.x0;
+        size_t row = (size_t)(t.y0 - sf.org_y + r) * sf.pitch_px + (t.x0 - sf.org_x);
         for (int c = threadIdx.x; c < t.w; c += blockDim.x) {
             uint32_t k = px_key<PIX>(fr, row + c);
             lo = min(lo, k);
@@ -113,7 +114,7 @@ __global__ void lst_minmax(const DevTask *__restrict__ tasks, const void *const 
     }
 }
 
-int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const void *const *frames, const PreprocParams &pp,
+int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *surfaces, const PreprocParams &pp,
                   uint32_t *mm_keys, cudaStream_t stream)
 {
     int launches = 0;
@@ -123,11 +124,76 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const void *cons
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
         dim3 grid(gx, n);
         if (pp.pixel_type == LST_PIX_U8)
-            lst_minmax<LST_PIX_U8><<<grid, 128, 0, stream>>>(tasks + base, frames, pp.frame_w, mm_keys + 2 * base);
+            lst_minmax<LST_PIX_U8><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base);
         else if (pp.pixel_type == LST_PIX_U16)
-            lst_minmax<LST_PIX_U16><<<grid, 128, 0, stream>>>(tasks + base, frames, pp.frame_w, mm_keys + 2 * base);
+            lst_minmax<LST_PIX_U16><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base);
         else
-            lst_minmax<LST_PIX_F32><<<grid, 128, 0, stream>>>(tasks + base, frames, pp.frame_w, mm_keys + 2 * base);
+            lst_minmax<LST_PIX_F32><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base);
+        launches++;
+    }
+    return launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROI ingest: gather the five search regions of every slice of a batch from pinned host memory
+// ------------------------------------------------------------------------------------------------
+// The slices stay in the caller's pinned memory; only the rectangles the windows can fall in
+// cross PCIe (256 KB instead of 4.1 MB per 1080p slice).  blockIdx.y = slice*5 + roi,
+// blockIdx.x = group of rows; a row is copied with 16-byte loads when the addresses allow.
+struct GatherArgs {
+    RoiDesc roi[5];
+    int frame_w, bpp;
+    size_t block_bytes;
+};
+
+#define GATHER_ROWS 8
+
+__global__ void __launch_bounds__(256)
+lst_gather_rois(const void *const *__restrict__ frames, GatherArgs a, uint8_t *__restrict__ dst)
+{
+    const int f = blockIdx.y / 5, k = blockIdx.y - f * 5;
+    const RoiDesc r = a.roi[k];
+    const int row0 = blockIdx.x * GATHER_ROWS;
+    if (row0 >= r.h) return;
+    const int nrows = min(GATHER_ROWS, r.h - row0);
+    const uint8_t *src = (const uint8_t *)frames[f];
+    uint8_t *out = dst + (size_t)f * a.block_bytes + r.off;
+    const size_t src_pitch = (size_t)a.frame_w * a.bpp, row_bytes = (size_t)r.w * a.bpp;
+    const size_t src0 = ((size_t)r.y * a.frame_w + r.x) * a.bpp;
+    const bool vec = (((uintptr_t)src + src0) % 16 == 0) && (src_pitch % 16 == 0) && (row_bytes % 16 == 0) &&
+                     (((uintptr_t)out) % 16 == 0);
+    if (vec) {
+        const int per_row = (int)(row_bytes / 16);
+        for (int i = threadIdx.x; i < per_row * nrows; i += blockDim.x) {
+            int rr = i / per_row, cc = i - rr * per_row;
+            const uint4 v = *(const uint4 *)(src + src0 + (size_t)(row0 + rr) * src_pitch + (size_t)cc * 16);
+            *(uint4 *)(out + (size_t)(row0 + rr) * row_bytes + (size_t)cc * 16) = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < (int)row_bytes * nrows; i += blockDim.x) {
+            int rr = i / (int)row_bytes, cc = i - rr * (int)row_bytes;
+            out[(size_t)(row0 + rr) * row_bytes + cc] = src[src0 + (size_t)(row0 + rr) * src_pitch + cc];
+        }
+    }
+}
+
+int launch_gather_rois(const void *const *mapped_frames, int n_frames, const RoiDesc rois[5], int frame_w, int bpp,
+                       uint8_t *dst, size_t block_bytes, cudaStream_t stream)
+{
+    GatherArgs a;
+    int max_h = 0;
+    for (int k = 0; k < 5; k++) {
+        a.roi[k] = rois[k];
+        max_h = rois[k].h > max_h ? rois[k].h : max_h;
+    }
+    a.frame_w = frame_w;
+    a.bpp = bpp;
+    a.block_bytes = block_bytes;
+    int launches = 0;
+    for (int base = 0; base < n_frames; base += 13000) {
+        int n = n_frames - base < 13000 ? n_frames - base : 13000;
+        dim3 grid((max_h + GATHER_ROWS - 1) / GATHER_ROWS, n * 5);
+        lst_gather_rois<<<grid, 256, 0, stream>>>(mapped_frames + base, a, dst + (size_t)base * block_bytes);
         launches++;
     }
     return launches;
@@ -154,7 +220,7 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const void *cons
 
 template <int PIX>
 __global__ void __launch_bounds__(256)
-lst_preprocess(const DevTask *__restrict__ tasks, const void *const *__restrict__ frames, PreprocParams pp,
+lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ surfaces, PreprocParams pp,
                const uint32_t *__restrict__ mm_keys, uint8_t *__restrict__ win8)
 {
     extern __shared__ float smem_f[];
@@ -171,12 +237,13 @@ lst_preprocess(const DevTask *__restrict__ tasks, const void *const *__restrict_
     const int XWP = TW + 1;                    // x-pass tile pitch
     float *raw = smem_f;                                   // [(TH+12)][RWP]
     float *xp = smem_f + (size_t)(TH + 2 * (KR - 1)) * RWP;   // [(TH+12)][XWP]
-    const void *fr = frames[t.frame];
+    const Surface sf = surfaces[t.frame];
+    const void *fr = sf.ptr;
     const int nrw = rx1 - rx0, nrh = ry1 - ry0;
 
     for (int idx = threadIdx.x; idx < nrw * nrh; idx += blockDim.x) {
         int r = idx / nrw, c = idx - r * nrw;
-        size_t src = (size_t)(t.y0 + ry0 + r) * pp.frame_w + (t.x0 + rx0 + c);
+        size_t src = (size_t)(t.y0 - sf.org_y + ry0 + r) * sf.pitch_px + (t.x0 - sf.org_x + rx0 + c);
         raw[r * RWP + c] = load_px<PIX>(fr, src);
     }
     float lo = pp.lo, hi = pp.hi;
@@ -281,7 +348,7 @@ static size_t preprocess_smem(const PreprocParams &pp)
     return rows * (size_t)(pp.tile_w + 2 * (KR - 1) + 1 + pp.tile_w + 1) * sizeof(float);
 }
 
-int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const void *const *frames,
+int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces,
                       const PreprocParams &pp, const uint32_t *mm_keys, uint8_t *win8, cudaStream_t stream)
 {
     int tiles = ((max_w + pp.tile_w - 1) / pp.tile_w) * ((max_h + pp.tile_h - 1) / pp.tile_h);
@@ -299,11 +366,11 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
         dim3 grid(tiles, n);
         const uint32_t *mm = mm_keys + 2 * base;
         if (pp.pixel_type == LST_PIX_U8)
-            lst_preprocess<LST_PIX_U8><<<grid, 256, smem, stream>>>(tasks + base, frames, pp, mm, win8);
+            lst_preprocess<LST_PIX_U8><<<grid, 256, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         else if (pp.pixel_type == LST_PIX_U16)
-            lst_preprocess<LST_PIX_U16><<<grid, 256, smem, stream>>>(tasks + base, frames, pp, mm, win8);
+            lst_preprocess<LST_PIX_U16><<<grid, 256, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         else
-            lst_preprocess<LST_PIX_F32><<<grid, 256, smem, stream>>>(tasks + base, frames, pp, mm, win8);
+            lst_preprocess<LST_PIX_F32><<<grid, 256, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         launches++;
     }
     return launches;

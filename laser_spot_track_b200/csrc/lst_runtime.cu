@@ -49,11 +49,21 @@ struct lst_ctx : public Executor {
     size_t win8_cap = 0;
     float *d_map = nullptr;
     size_t map_cap = 0;
-    // frame table + ring
+    // surface table (where each task's pixels live) + slice ring (whole-slice ingest)
     int frame_cap = 0;
-    const void **d_frames = nullptr, **h_frames = nullptr;
+    Surface *d_surf = nullptr, *h_surf = nullptr;
     uint8_t *d_ring[2] = {nullptr, nullptr};
     size_t ring_cap = 0;   // bytes per half
+    // ROI ingest: pinned host slices stay on the host, only the search regions are gathered
+    uint8_t *d_roi[2] = {nullptr, nullptr};
+    size_t roi_cap = 0;    // bytes per half
+    const void **d_gptr[2] = {nullptr, nullptr}, **h_gptr[2] = {nullptr, nullptr};
+    int gptr_cap = 0;
+    RoiDesc roi[2][5];     // per half: the rectangles gathered for that batch
+    size_t roi_block[2] = {0, 0};
+    bool roi_active = false;   // the batch being resolved uses ROI surfaces
+    int roi_half = 0, roi_nb = 0;
+    int roi_margin = 16;
     // solve buffers
     int solve_cap = 0;
     double *d_dis10 = nullptr, *d_out5 = nullptr, *h_dis10 = nullptr, *h_out5 = nullptr;
@@ -138,10 +148,21 @@ int lst_ctx::ensure_frames(int n)
     if (n <= frame_cap) return LST_OK;
     CU(cudaStreamSynchronize(s_compute));
     int cap = std::max(n, frame_cap * 2);
-    CU(regrow(&d_frames, cap));
-    CU(regrow_host(&h_frames, cap));
+    CU(regrow(&d_surf, cap));
+    CU(regrow_host(&h_surf, cap));
     frame_cap = cap;
     return LST_OK;
+}
+
+static Surface whole_slice(const void *ptr, int width)
+{
+    Surface s;
+    s.ptr = ptr;
+    s.pitch_px = width;
+    s.org_x = 0;
+    s.org_y = 0;
+    s.pad = 0;
+    return s;
 }
 
 int lst_ctx::ensure_scratch(size_t win_bytes, size_t map_elems)
@@ -250,6 +271,18 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         memset(&d, 0, sizeof(d));
         Rect c = have_win8 ? Rect{0, 0, t.ww, t.wh} : clip_rect(t.wx, t.wy, t.ww, t.wh, p.width, p.height);
         d.frame = t.frame;
+        if (roi_active && !have_win8) {
+            // pixels come from the gathered ROI of (slice, template) when the window lies inside it,
+            // else straight from the pinned host slice (zero-copy; rare: speculation margin exceeded)
+            const RoiDesc &rr = roi[roi_half][t.tpl];
+            if (c.x >= rr.x && c.y >= rr.y && c.x + c.w <= rr.x + rr.w && c.y + c.h <= rr.y + rr.h) {
+                d.frame = t.frame * 5 + t.tpl;
+            } else {
+                d.frame = 5 * roi_nb + t.frame;
+                stats.roi_fallback_tasks++;
+                stats.h2d_bytes += (int64_t)c.w * c.h * (int64_t)bpp() * 2;
+            }
+        }
         d.tpl = tpl_override >= 0 ? tpl_override : t.tpl;
         d.x0 = c.x;
         d.y0 = c.y;
@@ -286,8 +319,8 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     if (!have_win8) {
         PreprocParams pp;
         preproc_params(&pp, max_w);
-        if (pp.range_per_task) launches += launch_minmax(d_tasks, n, max_h, d_frames, pp, d_mm, s_compute);
-        launches += launch_preprocess(d_tasks, n, max_w, max_h, d_frames, pp, d_mm, d_win8, s_compute);
+        if (pp.range_per_task) launches += launch_minmax(d_tasks, n, max_h, d_surf, pp, d_mm, s_compute);
+        launches += launch_preprocess(d_tasks, n, max_w, max_h, d_surf, pp, d_mm, d_win8, s_compute);
     }
     if (!preprocess_only) {
         MatchParams mp;
@@ -478,14 +511,19 @@ void lst_destroy(lst_ctx *c)
     cudaFree(c->d_results);
     cudaFree(c->d_win8);
     cudaFree(c->d_map);
-    cudaFree(c->d_frames);
+    cudaFree(c->d_surf);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_roi[i]);
+        cudaFree(c->d_gptr[i]);
+        cudaFreeHost(c->h_gptr[i]);
+    }
     cudaFree(c->d_ring[0]);
     cudaFree(c->d_ring[1]);
     cudaFree(c->d_dis10);
     cudaFree(c->d_out5);
     cudaFreeHost(c->h_tasks);
     cudaFreeHost(c->h_results);
-    cudaFreeHost(c->h_frames);
+    cudaFreeHost(c->h_surf);
     cudaFreeHost(c->h_dis10);
     cudaFreeHost(c->h_out5);
     for (TimedLaunch &t : c->timed) {
@@ -520,8 +558,8 @@ int lst_set_reference(lst_ctx *c, const void *ref_frame, const float ref_xy[10],
     if (rc != LST_OK) return rc;
     CUC(c, cudaMemcpyAsync(c->d_ring[0], ref_frame, c->frame_bytes(), cudaMemcpyHostToDevice, c->s_compute));
     c->stats.h2d_bytes += (int64_t)c->frame_bytes();
-    c->h_frames[0] = c->d_ring[0];
-    CUC(c, cudaMemcpyAsync(c->d_frames, c->h_frames, sizeof(void *), cudaMemcpyHostToDevice, c->s_compute));
+    c->h_surf[0] = whole_slice(c->d_ring[0], c->p.width);
+    CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface), cudaMemcpyHostToDevice, c->s_compute));
     lst_task tasks[5];
     Rect crop[5];
     for (int k = 0; k < 5; k++) {
@@ -585,7 +623,68 @@ static void fill_resolve_input(const lst_ctx *c, ResolveInput *in)
     in->spot0[1] = c->spot0[1];
 }
 
-// frames_of(i) -> host pointer of frame i, or device pointer when on_device
+static int ensure_roi(lst_ctx *c, size_t bytes_per_half, int n_ptrs)
+{
+    if (bytes_per_half > c->roi_cap) {
+        CUC(c, cudaStreamSynchronize(c->s_compute));
+        CUC(c, cudaStreamSynchronize(c->s_copy));
+        for (int i = 0; i < 2; i++) CUC(c, regrow(&c->d_roi[i], bytes_per_half));
+        c->roi_cap = bytes_per_half;
+    }
+    if (n_ptrs > c->gptr_cap) {
+        CUC(c, cudaStreamSynchronize(c->s_copy));
+        for (int i = 0; i < 2; i++) {
+            CUC(c, regrow(&c->d_gptr[i], n_ptrs));
+            CUC(c, regrow_host(&c->h_gptr[i], n_ptrs));
+        }
+        c->gptr_cap = n_ptrs;
+    }
+    return LST_OK;
+}
+
+// Device-visible address of a pinned host pointer, or nullptr when the memory is pageable.
+static const void *mapped_host_ptr(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
+// The five regions a batch can need, from the displacement state known when the copy is enqueued:
+// each search window grown by `margin` pixels (the state may drift while earlier batches resolve),
+// x aligned to 64 bytes so rows move as whole PCIe-friendly segments, clipped to the slice.
+static size_t plan_rois(const lst_ctx *c, const double dis[10], RoiDesc out[5])
+{
+    const int bpp = (int)c->bpp();
+    const int ax = 64 / bpp;   // pixels per 64 bytes
+    size_t off = 0;
+    for (int k = 0; k < 5; k++) {
+        Rect w = window_for(c->p, c->rect[k], jint(dis[2 * k]), jint(dis[2 * k + 1]), c->p.s_area, false, nullptr);
+        int x0 = w.x - c->roi_margin, y0 = w.y - c->roi_margin;
+        int x1 = w.x + w.w + c->roi_margin, y1 = w.y + w.h + c->roi_margin;
+        x0 = x0 < 0 ? 0 : (x0 / ax) * ax;
+        x1 = ((x1 + ax - 1) / ax) * ax;
+        if (x1 > c->p.width) x1 = c->p.width;
+        if (y0 < 0) y0 = 0;
+        if (y1 > c->p.height) y1 = c->p.height;
+        out[k].x = x0;
+        out[k].y = y0;
+        out[k].w = x1 - x0 > 0 ? x1 - x0 : 0;
+        out[k].h = y1 - y0 > 0 ? y1 - y0 : 0;
+        out[k].off = off;
+        off += (((size_t)out[k].w * out[k].h * bpp) + 255) & ~(size_t)255;
+    }
+    return off;
+}
+
+// The tracking loop body over n_frames slices given as one strided block (base) or as pointers
+// (ptrs); host memory unless on_device.  Host slices in pinned memory use the ROI ingest (only the
+// search regions cross PCIe, gathered by a kernel on the copy stream while the previous batch
+// computes); pageable slices and ingest_mode == 1 use whole-slice cudaMemcpyAsync into a ring.
 static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *const *ptrs, bool on_device,
                       int64_t first_index, int32_t n_frames, lst_record *out)
 {
@@ -598,28 +697,68 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     const int B = c->p.max_batch;
     ResolveInput in;
     fill_resolve_input(c, &in);
-    int rc = c->ensure_frames(B);
+    auto src_of = [&](int64_t i) -> const void * { return ptrs ? ptrs[i] : (const uint8_t *)base + (size_t)i * stride; };
+    const int nbatches = (int)((n_frames + B - 1) / B);
+
+    bool use_roi = !on_device && c->p.s_area > 0 && c->p.ingest_mode == 0;
+    std::vector<const void *> mapped;
+    if (use_roi) {
+        mapped.resize(n_frames);
+        for (int64_t i = 0; i < n_frames && use_roi; i++) {
+            mapped[i] = mapped_host_ptr(src_of(i));
+            if (!mapped[i]) use_roi = false;     // pageable memory: whole-slice copies
+        }
+    }
+    int rc = c->ensure_frames(use_roi ? 6 * B : B);
     if (rc != LST_OK) return rc;
-    if (!on_device) {
+    // the ROI ring is sized once from an upper bound of plan_rois (both halves are live at once)
+    size_t roi_block_max = 0;
+    if (use_roi) {
+        const int ax = 64 / (int)c->bpp();
+        for (int k = 0; k < 5; k++) {
+            size_t w = (size_t)c->rect[k].w + 2 * c->p.s_area + 2 * c->roi_margin + 2 * ax;
+            size_t h = (size_t)c->rect[k].h + 2 * c->p.s_area + 2 * c->roi_margin;
+            w = std::min<size_t>(w, (size_t)c->p.width + ax);
+            h = std::min<size_t>(h, (size_t)c->p.height);
+            roi_block_max += ((w * h * c->bpp()) + 255) & ~(size_t)255;
+        }
+        rc = ensure_roi(c, roi_block_max * (size_t)std::min<int64_t>(B, n_frames), B);
+        if (rc != LST_OK) return rc;
+    }
+    if (!on_device && !use_roi) {
         rc = ensure_ring(c, (size_t)std::min<int64_t>(B, n_frames) * fb);
         if (rc != LST_OK) return rc;
     }
-    auto src_of = [&](int64_t i) -> const void * { return ptrs ? ptrs[i] : (const uint8_t *)base + (size_t)i * stride; };
+
     auto enqueue_copy = [&](int b) -> int {
         int64_t f0 = (int64_t)b * B;
         int nb = (int)std::min<int64_t>(B, n_frames - f0);
-        uint8_t *dst = c->d_ring[b & 1];
-        if (!ptrs && stride == fb) {
-            CUC(c, cudaMemcpyAsync(dst, src_of(f0), (size_t)nb * fb, cudaMemcpyHostToDevice, c->s_copy));
+        const int half = b & 1;
+        if (use_roi) {
+            c->roi_block[half] = plan_rois(c, c->dis, c->roi[half]);
+            if (c->roi_block[half] > roi_block_max) return c->fail(LST_ERR_STATE, "internal: ROI block larger than planned");
+            for (int i = 0; i < nb; i++) c->h_gptr[half][i] = mapped[f0 + i];
+            CUC(c, cudaMemcpyAsync(c->d_gptr[half], c->h_gptr[half], sizeof(void *) * nb, cudaMemcpyHostToDevice, c->s_copy));
+            c->stats.kernel_launches += launch_gather_rois(c->d_gptr[half], nb, c->roi[half], c->p.width, (int)c->bpp(),
+                                                           c->d_roi[half], c->roi_block[half], c->s_copy);
+            CUC(c, cudaGetLastError());
+            size_t bytes = 0;
+            for (int k = 0; k < 5; k++) bytes += (size_t)c->roi[half][k].w * c->roi[half][k].h * c->bpp();
+            c->stats.h2d_bytes += (int64_t)(bytes * nb + sizeof(void *) * nb);
         } else {
-            for (int i = 0; i < nb; i++)
-                CUC(c, cudaMemcpyAsync(dst + (size_t)i * fb, src_of(f0 + i), fb, cudaMemcpyHostToDevice, c->s_copy));
+            uint8_t *dst = c->d_ring[half];
+            if (!ptrs && stride == fb) {
+                CUC(c, cudaMemcpyAsync(dst, src_of(f0), (size_t)nb * fb, cudaMemcpyHostToDevice, c->s_copy));
+            } else {
+                for (int i = 0; i < nb; i++)
+                    CUC(c, cudaMemcpyAsync(dst + (size_t)i * fb, src_of(f0 + i), fb, cudaMemcpyHostToDevice, c->s_copy));
+            }
+            c->stats.h2d_bytes += (int64_t)nb * (int64_t)fb;
         }
-        CUC(c, cudaEventRecord(c->ev_copy[b & 1], c->s_copy));
-        c->stats.h2d_bytes += (int64_t)nb * (int64_t)fb;
+        CUC(c, cudaEventRecord(c->ev_copy[half], c->s_copy));
         return LST_OK;
     };
-    const int nbatches = (int)((n_frames + B - 1) / B);
+
     if (!on_device) {
         rc = enqueue_copy(0);
         if (rc != LST_OK) return rc;
@@ -627,19 +766,41 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     for (int b = 0; b < nbatches; b++) {
         int64_t f0 = (int64_t)b * B;
         int nb = (int)std::min<int64_t>(B, n_frames - f0);
+        const int half = b & 1;
+        int nsurf = nb;
         if (!on_device) {
-            if (b + 1 < nbatches) {   // double buffering: next batch's copy overlaps this batch's kernels
+            if (b + 1 < nbatches) {   // double buffering: next batch's ingest overlaps this batch's kernels
                 rc = enqueue_copy(b + 1);
                 if (rc != LST_OK) return rc;
             }
-            CUC(c, cudaStreamWaitEvent(c->s_compute, c->ev_copy[b & 1], 0));
-            for (int i = 0; i < nb; i++) c->h_frames[i] = c->d_ring[b & 1] + (size_t)i * fb;
-        } else {
-            for (int i = 0; i < nb; i++) c->h_frames[i] = src_of(f0 + i);
+            CUC(c, cudaStreamWaitEvent(c->s_compute, c->ev_copy[half], 0));
         }
-        CUC(c, cudaMemcpyAsync(c->d_frames, c->h_frames, sizeof(void *) * nb, cudaMemcpyHostToDevice, c->s_compute));
-        c->stats.h2d_bytes += (int64_t)sizeof(void *) * nb;
+        if (use_roi) {
+            for (int i = 0; i < nb; i++) {
+                for (int k = 0; k < 5; k++) {
+                    const RoiDesc &r = c->roi[half][k];
+                    Surface &sf = c->h_surf[i * 5 + k];
+                    sf.ptr = c->d_roi[half] + (size_t)i * c->roi_block[half] + r.off;
+                    sf.pitch_px = r.w;
+                    sf.org_x = r.x;
+                    sf.org_y = r.y;
+                    sf.pad = 0;
+                }
+                c->h_surf[5 * nb + i] = whole_slice(mapped[f0 + i], c->p.width);   // zero-copy fallback
+            }
+            nsurf = 6 * nb;
+        } else if (!on_device) {
+            for (int i = 0; i < nb; i++) c->h_surf[i] = whole_slice(c->d_ring[half] + (size_t)i * fb, c->p.width);
+        } else {
+            for (int i = 0; i < nb; i++) c->h_surf[i] = whole_slice(src_of(f0 + i), c->p.width);
+        }
+        CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface) * nsurf, cudaMemcpyHostToDevice, c->s_compute));
+        c->stats.h2d_bytes += (int64_t)sizeof(Surface) * nsurf;
+        c->roi_active = use_roi;
+        c->roi_half = half;
+        c->roi_nb = nb;
         rc = resolve_batch(in, c->dis, first_index + f0, nb, *c, out + f0, &c->stats);
+        c->roi_active = false;
         if (rc != LST_OK) {
             if (c->err.empty()) c->fail(rc, "resolver failed (%d)", rc);
             return rc;
@@ -731,8 +892,8 @@ int lst_preprocess(lst_ctx *c, const void *frame, int32_t x0, int32_t y0, int32_
     rc = c->ensure_frames(1);
     if (rc != LST_OK) return rc;
     CUC(c, cudaMemcpyAsync(c->d_ring[1], frame, c->frame_bytes(), cudaMemcpyHostToDevice, c->s_compute));
-    c->h_frames[0] = c->d_ring[1];
-    CUC(c, cudaMemcpyAsync(c->d_frames, c->h_frames, sizeof(void *), cudaMemcpyHostToDevice, c->s_compute));
+    c->h_surf[0] = whole_slice(c->d_ring[1], c->p.width);
+    CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface), cudaMemcpyHostToDevice, c->s_compute));
     lst_task t;
     memset(&t, 0, sizeof(t));
     t.wx = x0;

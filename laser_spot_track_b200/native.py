@@ -35,7 +35,7 @@ class Params(C.Structure):
         ("method", C.c_int32), ("templ_size", C.c_int32), ("s_area", C.c_int32), ("sub_pixel", C.c_int32),
         ("match_intensity", C.c_int32), ("range_mode", C.c_int32), ("quant_mode", C.c_int32),
         ("doubling", C.c_int32), ("auto_skip", C.c_int32), ("max_s_area", C.c_int32), ("max_batch", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("ingest_mode", C.c_int32),
         ("mark_dist", C.c_double), ("range_lo", C.c_double), ("range_hi", C.c_double),
         ("match_threshold", C.c_double),
     ]
@@ -69,6 +69,7 @@ class Stats(C.Structure):
         ("frames", C.c_int64), ("tasks", C.c_int64), ("respeculated", C.c_int64), ("passes", C.c_int64),
         ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ncc_kernel_ms", C.c_double), ("ncc_kernel_launches", C.c_int64), ("ncc_algorithmic_macs", C.c_double),
+        ("roi_fallback_tasks", C.c_int64),
     ]
 
 

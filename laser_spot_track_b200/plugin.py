@@ -46,7 +46,7 @@ class LaserSpotTrack4:
                  subPixel: bool = True, matchIntensity: bool = True, alwaysAutoSkip: bool = True,
                  doubling: bool = False, maxSArea: int = 500, range_mode: int = N.RANGE_DISPLAY,
                  range_lo: float = 0.0, range_hi: float = 255.0, quant_mode: int = N.QUANT_ROUND255,
-                 max_batch: int = 0):
+                 max_batch: int = 0, ingest_mode: int = 0):
         if bit_depth not in _PIX:
             raise LstError(N.LST_ERR_UNSUPPORTED, "Unsupported image type")       # IJ.error, LST4:2537
         self._lib = N.load()
@@ -57,7 +57,7 @@ class LaserSpotTrack4:
             mark_dist=markDist, sub_pixel=int(subPixel), match_intensity=int(matchIntensity),
             auto_skip=int(alwaysAutoSkip), doubling=int(doubling), max_s_area=maxSArea,
             range_mode=range_mode, range_lo=range_lo, range_hi=range_hi, quant_mode=quant_mode,
-            max_batch=max_batch)
+            max_batch=max_batch, ingest_mode=ingest_mode)
         self._ctx = C.c_void_p()
         rc = self._lib.lst_create(C.byref(self.params), device, C.byref(self._ctx))
         if rc != N.LST_OK:

@@ -199,3 +199,85 @@ def test_unsupported_like_reference(built_lib):
     with LaserSpotTrack4(640, 480, 8) as t:
         with pytest.raises(LstError):
             t.track(np.zeros((1, 480, 640), np.uint8))            # no reference yet
+
+
+def _pinned_stack(frames):
+    """Copy slices into one lst_alloc_pinned block; returns (numpy view, raw pointer)."""
+    import ctypes as C
+    lib = N.load()
+    a = np.stack(frames)
+    ptr = C.c_void_p()
+    assert lib.lst_alloc_pinned(a.nbytes, C.byref(ptr)) == 0
+    view = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(a.nbytes,)).view(a.dtype).reshape(a.shape)
+    view[...] = a
+    return view, ptr
+
+
+@pytest.mark.parametrize("max_batch", [4, 16])
+def test_roi_ingest_pinned_equals_whole_slice(stack_a, max_batch):
+    """Pinned host slices take the ROI ingest (only the search regions cross PCIe); results must be
+    identical to the oracle and to the whole-slice ingest, including when the windows outrun the
+    speculation margin and are read straight from host memory."""
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=True, range_mode=O.RANGE_CROP)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:41])
+    view, ptr = _pinned_stack(frames[1:41])
+    try:
+        with _tracker(cfg, op, max_batch=max_batch) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            got = t.track(view)
+            util.compare_records(got, want, label="roi")
+            s = t.stats()
+            assert s.h2d_bytes < 0.5 * view.nbytes, "ROI ingest should move a fraction of the stack"
+        with _tracker(cfg, op, max_batch=max_batch, ingest_mode=1) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            util.compare_records(t.track(view), want, label="whole")
+            assert t.stats().h2d_bytes >= view.nbytes
+    finally:
+        N.load().lst_free_pinned(ptr)
+
+
+def test_roi_ingest_margin_exceeded(built_lib, oracle_clib):
+    """Fast target: the search windows leave the gathered regions -> zero-copy fallback, same results."""
+    cfg = StackConfig(640, 480, "u16", 32, 40, 30, spot_travel=2.0)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 25)]
+    op = util.oracle_params(cfg)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    assert abs(want[-1].dis[0][0]) > 40
+    view, ptr = _pinned_stack(frames[1:])
+    try:
+        with _tracker(cfg, op, max_batch=6) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            got = t.track(view)
+            util.compare_records(got, want, label="fallback")
+            assert t.stats().roi_fallback_tasks > 0
+    finally:
+        N.load().lst_free_pinned(ptr)
+
+
+@pytest.mark.parametrize("name", ["track_a_u8.npz", "track_small_u16.npz"])
+def test_golden_fixtures_on_gpu(built_lib, name):
+    """The CUDA path against the committed fixtures (no oracle at run time)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    w, h, T, s, n = [int(v) for v in g["cfg"]]
+    cfg = StackConfig(w, h, str(g["dtype"]), T, s, 200 if name.startswith("track_a") else 24)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(n + 1)]
+    bits = {"u8": 8, "u16": 16}[cfg.dtype]
+    with LaserSpotTrack4(w, h, bits, templSize=T, sArea=s, matchIntensity=bool(g["match_intensity"])) as t:
+        info = t.set_reference(frames[0], st.ref_xy)
+        assert np.array_equal(np.array([list(r) for r in info.rect]), g["rects"])
+        assert list(info.mideal) == g["mideal"].tolist()
+        got = t.track(np.stack(frames[1:]))
+        for i, r in enumerate(got):
+            assert r.status == g["status"][i]
+            assert [(m.ix, m.iy) for m in r.tm] == [tuple(p) for p in g["peaks"][i]]
+            assert [m.score for m in r.tm] == g["scores"][i].tolist()
+            assert [(m.x, m.y) for m in r.tm] == [tuple(p) for p in g["pos"][i]]
+            assert [r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL] == g["out"][i].tolist()
