@@ -67,7 +67,7 @@ def bench_config(name: str, ring: int) -> StackConfig:
 
 DEFAULTS = {  # frames per step, ring length, max_batch, cpu sample
     "A": (8192, 256, 2048, 512),
-    "B": (2048, 64, 1024, 128),
+    "B": (10240, 64, 1024, 128),
     "D": (64, 32, 64, 8),
 }
 

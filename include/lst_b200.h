@@ -81,8 +81,9 @@ typedef struct lst_params {
     int32_t auto_skip;         /* alwaysAutoSkip; headless policy: rejected frame => LST_STATUS_SKIP */
     int32_t max_s_area;        /* maxSArea LST4:131 (0 = no limit) */
     int32_t max_batch;         /* frames resolved per device pass (0 = default) */
-    int32_t ingest_mode;       /* host slices: 0 = auto (pinned memory: gather only the search regions;
-                                  pageable: whole-slice copies), 1 = always whole-slice copies */
+    int32_t ingest_mode;       /* host slices: 0 = auto (pinned memory: only the search regions cross PCIe, as
+                                  strided 3-D DMA copies; pageable: whole-slice copies), 1 = always whole-slice
+                                  copies, 2 = search regions gathered by a kernel from mapped host memory */
     double  mark_dist;         /* markDist LST4:85 */
     double  range_lo, range_hi;/* LST_RANGE_FIXED */
     double  match_threshold;   /* matchThreshold[5] = 0.2, LST4:147 */

@@ -32,9 +32,11 @@ struct Surface {
 };
 
 // One region of interest gathered from every slice of a batch (same rectangle for all slices).
+// Ring layout: for each of the five regions a dense array [slice][h][w].
 struct RoiDesc {
     int32_t x, y, w, h;   // slice coordinates
-    uint64_t off;         // byte offset inside a slice's block of the ROI ring
+    uint64_t off;         // byte offset of this region's array in the ring half
+    uint64_t slice_bytes; // w*h*bytes_per_pixel: distance between consecutive slices
 };
 
 struct DevResult {
@@ -80,10 +82,10 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *s
                   uint32_t *mm_keys, cudaStream_t stream);
 int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces,
                       const PreprocParams &pp, const uint32_t *mm_keys, uint8_t *win8, cudaStream_t stream);
-// ROI ingest: copy 5 rectangles of each of n_frames pinned host slices (device-mapped pointers) into
-// the ROI ring; slice i's block starts at dst + i*block_bytes.
+// ROI ingest by kernel (irregularly placed slices): copy 5 rectangles of each of n_frames pinned host
+// slices (device-mapped pointers) into the ROI ring.
 int launch_gather_rois(const void *const *mapped_frames, int n_frames, const RoiDesc rois[5], int frame_w, int bpp,
-                       uint8_t *dst, size_t block_bytes, cudaStream_t stream);
+                       uint8_t *dst, cudaStream_t stream);
 int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
                      const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *score_map,
                      const MatchParams &mp, cudaStream_t stream);
@@ -91,6 +93,10 @@ int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls,
                     const unsigned long long *best, DevResult *results, const MatchParams &mp, cudaStream_t stream);
 int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_dist, const double *spot0,
                  double *out5, cudaStream_t stream);
+// Small host->device uploads on the compute stream go through a kernel reading pinned (mapped) host
+// memory instead of the H2D copy engine: the engine's queue is busy for milliseconds with the bulk
+// ingest of the *next* batch, and a 300 KB task list must not wait behind it.
+int launch_upload(void *dst_dev, const void *src_pinned_host, size_t bytes, cudaStream_t stream);
 int set_blur_kernel(const float kern[7], const float ksum[7]);
 // picks band/tile split and the shared-memory pitch for lst_ncc_match
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes);

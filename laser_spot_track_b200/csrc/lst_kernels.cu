@@ -24,8 +24,11 @@ namespace lst {
 __constant__ float c_kern[KR];
 __constant__ float c_ksum[KR];
 
+static void prefer_max_shared_everywhere();
+
 int set_blur_kernel(const float kern[7], const float ksum[7])
 {
+    prefer_max_shared_everywhere();
     if (cudaMemcpyToSymbol(c_kern, kern, sizeof(float) * KR) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_ksum, ksum, sizeof(float) * KR) != cudaSuccess) return -1;
     return 0;
@@ -64,6 +67,30 @@ __device__ __forceinline__ float key_to_float(uint32_t k)
 {
     if (PIX == LST_PIX_F32) return key_f32(k);
     return (float)k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small uploads by kernel (see lst_device.h)
+// ------------------------------------------------------------------------------------------------
+__global__ void lst_upload(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t nwords)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+int launch_upload(void *dst_dev, const void *src_pinned_host, size_t bytes, cudaStream_t stream)
+{
+    size_t nwords = (bytes + 3) / 4;   // buffers are allocated in multiples of 4 bytes
+    if (nwords == 0) return 0;
+    const void *mapped = nullptr;
+    if (cudaHostGetDevicePointer((void **)&mapped, (void *)src_pinned_host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    int blocks = (int)((nwords + 255) / 256);
+    if (blocks > 296) blocks = 296;
+    lst_upload<<<blocks, 256, 0, stream>>>((uint32_t *)dst_dev, (const uint32_t *)mapped, nwords);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -143,42 +170,49 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *s
 struct GatherArgs {
     RoiDesc roi[5];
     int frame_w, bpp;
-    size_t block_bytes;
 };
 
 #define GATHER_ROWS 8
 
+// Persistent: a small fixed grid (2 CTAs per SM) walks all (slice, roi, row group) items, so the
+// gather keeps enough PCIe reads in flight without taking the SMs away from the match kernels of
+// the previous batch that run concurrently on the compute stream.
 __global__ void __launch_bounds__(256)
-lst_gather_rois(const void *const *__restrict__ frames, GatherArgs a, uint8_t *__restrict__ dst)
+lst_gather_rois(const void *const *__restrict__ frames, int n_frames, GatherArgs a, int groups, uint8_t *__restrict__ dst)
 {
-    const int f = blockIdx.y / 5, k = blockIdx.y - f * 5;
-    const RoiDesc r = a.roi[k];
-    const int row0 = blockIdx.x * GATHER_ROWS;
-    if (row0 >= r.h) return;
-    const int nrows = min(GATHER_ROWS, r.h - row0);
-    const uint8_t *src = (const uint8_t *)frames[f];
-    uint8_t *out = dst + (size_t)f * a.block_bytes + r.off;
-    const size_t src_pitch = (size_t)a.frame_w * a.bpp, row_bytes = (size_t)r.w * a.bpp;
-    const size_t src0 = ((size_t)r.y * a.frame_w + r.x) * a.bpp;
-    const bool vec = (((uintptr_t)src + src0) % 16 == 0) && (src_pitch % 16 == 0) && (row_bytes % 16 == 0) &&
-                     (((uintptr_t)out) % 16 == 0);
-    if (vec) {
-        const int per_row = (int)(row_bytes / 16);
-        for (int i = threadIdx.x; i < per_row * nrows; i += blockDim.x) {
-            int rr = i / per_row, cc = i - rr * per_row;
-            const uint4 v = *(const uint4 *)(src + src0 + (size_t)(row0 + rr) * src_pitch + (size_t)cc * 16);
-            *(uint4 *)(out + (size_t)(row0 + rr) * row_bytes + (size_t)cc * 16) = v;
-        }
-    } else {
-        for (int i = threadIdx.x; i < (int)row_bytes * nrows; i += blockDim.x) {
-            int rr = i / (int)row_bytes, cc = i - rr * (int)row_bytes;
-            out[(size_t)(row0 + rr) * row_bytes + cc] = src[src0 + (size_t)(row0 + rr) * src_pitch + cc];
+    const long total = (long)n_frames * 5 * groups;
+    for (long item = blockIdx.x; item < total; item += gridDim.x) {
+        const int g = (int)(item % groups);
+        const int fk = (int)(item / groups);
+        const int f = fk / 5, k = fk - f * 5;
+        const RoiDesc r = a.roi[k];
+        const int row0 = g * GATHER_ROWS;
+        if (row0 >= r.h) continue;
+        const int nrows = min(GATHER_ROWS, r.h - row0);
+        const uint8_t *src = (const uint8_t *)frames[f];
+        uint8_t *out = dst + r.off + (size_t)f * r.slice_bytes;
+        const size_t src_pitch = (size_t)a.frame_w * a.bpp, row_bytes = (size_t)r.w * a.bpp;
+        const size_t src0 = ((size_t)r.y * a.frame_w + r.x) * a.bpp;
+        const bool vec = (((uintptr_t)src + src0) % 16 == 0) && (src_pitch % 16 == 0) && (row_bytes % 16 == 0) &&
+                         (((uintptr_t)out) % 16 == 0);
+        if (vec) {
+            const int per_row = (int)(row_bytes / 16);
+            for (int i = threadIdx.x; i < per_row * nrows; i += blockDim.x) {
+                int rr = i / per_row, cc = i - rr * per_row;
+                const uint4 v = *(const uint4 *)(src + src0 + (size_t)(row0 + rr) * src_pitch + (size_t)cc * 16);
+                *(uint4 *)(out + (size_t)(row0 + rr) * row_bytes + (size_t)cc * 16) = v;
+            }
+        } else {
+            for (int i = threadIdx.x; i < (int)row_bytes * nrows; i += blockDim.x) {
+                int rr = i / (int)row_bytes, cc = i - rr * (int)row_bytes;
+                out[(size_t)(row0 + rr) * row_bytes + cc] = src[src0 + (size_t)(row0 + rr) * src_pitch + cc];
+            }
         }
     }
 }
 
 int launch_gather_rois(const void *const *mapped_frames, int n_frames, const RoiDesc rois[5], int frame_w, int bpp,
-                       uint8_t *dst, size_t block_bytes, cudaStream_t stream)
+                       uint8_t *dst, cudaStream_t stream)
 {
     GatherArgs a;
     int max_h = 0;
@@ -188,15 +222,18 @@ int launch_gather_rois(const void *const *mapped_frames, int n_frames, const Roi
     }
     a.frame_w = frame_w;
     a.bpp = bpp;
-    a.block_bytes = block_bytes;
-    int launches = 0;
-    for (int base = 0; base < n_frames; base += 13000) {
-        int n = n_frames - base < 13000 ? n_frames - base : 13000;
-        dim3 grid((max_h + GATHER_ROWS - 1) / GATHER_ROWS, n * 5);
-        lst_gather_rois<<<grid, 256, 0, stream>>>(mapped_frames + base, a, dst + (size_t)base * block_bytes);
-        launches++;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
     }
-    return launches;
+    const int groups = (max_h + GATHER_ROWS - 1) / GATHER_ROWS;
+    long total = (long)n_frames * 5 * groups;
+    int grid = (int)(total < 2L * sms ? total : 2L * sms);
+    lst_gather_rois<<<grid, 256, 0, stream>>>(mapped_frames, n_frames, a, groups, dst);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -854,6 +891,30 @@ int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_di
     a.spot0[1] = spot0[1];
     lst_solve<<<(n + 127) / 128, 128, 0, stream>>>(dis10, n, a, out5);
     return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One shared-memory carve-out for every kernel of the library.  An SM cannot host CTAs of kernels
+// that were given different L1/shared splits at the same time; the ROI gather (no shared memory)
+// runs on the copy stream *while* the match kernels (200+ KB of shared memory per SM) run on the
+// compute stream, so all kernels ask for the maximum-shared split and can co-reside.
+static void prefer_max_shared_everywhere()
+{
+    const int mx = (int)cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(lst_init_pass, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_upload, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_minmax<LST_PIX_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_minmax<LST_PIX_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_minmax<LST_PIX_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_epilogue, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_solve, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_gather_rois, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

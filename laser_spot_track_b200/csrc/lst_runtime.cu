@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/lst_b200.h"
@@ -60,10 +61,10 @@ struct lst_ctx : public Executor {
     const void **d_gptr[2] = {nullptr, nullptr}, **h_gptr[2] = {nullptr, nullptr};
     int gptr_cap = 0;
     RoiDesc roi[2][5];     // per half: the rectangles gathered for that batch
-    size_t roi_block[2] = {0, 0};
     bool roi_active = false;   // the batch being resolved uses ROI surfaces
     int roi_half = 0, roi_nb = 0;
     int roi_margin = 16;
+    std::unordered_map<const void *, const void *> mapped_cache;   // pinned host ptr -> device-visible ptr
     // solve buffers
     int solve_cap = 0;
     double *d_dis10 = nullptr, *d_out5 = nullptr, *h_dis10 = nullptr, *h_out5 = nullptr;
@@ -312,9 +313,13 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     }
     rc = ensure_scratch(win_off + 64, map_out_host ? sum_off + 32 : 0);
     if (rc != LST_OK) return rc;
-    CU(cudaMemcpyAsync(d_tasks, h_tasks, sizeof(DevTask) * n, cudaMemcpyHostToDevice, s_compute));
-    stats.h2d_bytes += (int64_t)sizeof(DevTask) * n;
     int launches = 0;
+    {
+        int up = launch_upload(d_tasks, h_tasks, sizeof(DevTask) * n, s_compute);
+        if (up < 0) return fail(LST_ERR_CUDA, "task upload failed");
+        launches += up;
+    }
+    stats.h2d_bytes += (int64_t)sizeof(DevTask) * n;
     launches += launch_init_pass(n, d_mm, d_best, s_compute);
     if (!have_win8) {
         PreprocParams pp;
@@ -413,7 +418,8 @@ int lst_ctx::solve(const double *dis10, int n, double *out5)
         solve_cap = cap;
     }
     memcpy(h_dis10, dis10, sizeof(double) * 10 * n);
-    CU(cudaMemcpyAsync(d_dis10, h_dis10, sizeof(double) * 10 * n, cudaMemcpyHostToDevice, s_compute));
+    if (launch_upload(d_dis10, h_dis10, sizeof(double) * 10 * n, s_compute) < 0) return fail(LST_ERR_CUDA, "upload failed");
+    stats.kernel_launches += 1;
     stats.kernel_launches += launch_solve(d_dis10, n, ref_xy, p.mark_dist, spot0, d_out5, s_compute);
     CU(cudaMemcpyAsync(h_out5, d_out5, sizeof(double) * 5 * n, cudaMemcpyDeviceToHost, s_compute));
     CU(cudaGetLastError());
@@ -483,7 +489,11 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
         return LST_ERR_CUDA;
     };
     if ((ce = cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "stream");
-    if ((ce = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "stream");
+    {   // the ingest stream outranks the compute stream: its few CTAs must not queue behind a full grid
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((ce = cudaStreamCreateWithPriority(&c->s_copy, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(ce, "stream");
+    }
     for (int i = 0; i < 2; i++)
         if ((ce = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
     if ((ce = cudaMalloc((void **)&c->d_tpls, sizeof(DevTemplates))) != cudaSuccess) return bail(ce, "cudaMalloc");
@@ -643,7 +653,9 @@ static int ensure_roi(lst_ctx *c, size_t bytes_per_half, int n_ptrs)
 }
 
 // Device-visible address of a pinned host pointer, or nullptr when the memory is pageable.
-static const void *mapped_host_ptr(const void *p)
+// cudaPointerGetAttributes costs microseconds; slices of a stack are usually re-submitted from
+// the same pinned buffers (rings), so successful lookups are cached per context.
+static const void *mapped_host_ptr_uncached(const void *p)
 {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -654,10 +666,23 @@ static const void *mapped_host_ptr(const void *p)
     return at.devicePointer;
 }
 
+static const void *mapped_host_ptr(lst_ctx *c, const void *p)
+{
+    auto it = c->mapped_cache.find(p);
+    if (it != c->mapped_cache.end()) return it->second;
+    const void *d = mapped_host_ptr_uncached(p);
+    if (d) {
+        if (c->mapped_cache.size() > (1u << 16)) c->mapped_cache.clear();
+        c->mapped_cache[p] = d;
+    }
+    return d;
+}
+
 // The five regions a batch can need, from the displacement state known when the copy is enqueued:
 // each search window grown by `margin` pixels (the state may drift while earlier batches resolve),
 // x aligned to 64 bytes so rows move as whole PCIe-friendly segments, clipped to the slice.
-static size_t plan_rois(const lst_ctx *c, const double dis[10], RoiDesc out[5])
+// Returns the bytes of one ring half for nb slices.
+static size_t plan_rois(const lst_ctx *c, const double dis[10], int nb, RoiDesc out[5])
 {
     const int bpp = (int)c->bpp();
     const int ax = 64 / bpp;   // pixels per 64 bytes
@@ -676,7 +701,8 @@ static size_t plan_rois(const lst_ctx *c, const double dis[10], RoiDesc out[5])
         out[k].w = x1 - x0 > 0 ? x1 - x0 : 0;
         out[k].h = y1 - y0 > 0 ? y1 - y0 : 0;
         out[k].off = off;
-        off += (((size_t)out[k].w * out[k].h * bpp) + 255) & ~(size_t)255;
+        out[k].slice_bytes = (size_t)out[k].w * out[k].h * bpp;
+        off += ((out[k].slice_bytes * (size_t)nb) + 255) & ~(size_t)255;
     }
     return off;
 }
@@ -698,14 +724,27 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     ResolveInput in;
     fill_resolve_input(c, &in);
     auto src_of = [&](int64_t i) -> const void * { return ptrs ? ptrs[i] : (const uint8_t *)base + (size_t)i * stride; };
-    const int nbatches = (int)((n_frames + B - 1) / B);
+    // Batch schedule.  Host slices: the ingest of batch b+1 overlaps the kernels of batch b, so only the
+    // first batch's ingest is exposed -- start small (128 slices) and double up to max_batch.
+    std::vector<int64_t> bstart;
+    {
+        int64_t f = 0;
+        int sz = on_device ? B : std::min(B, 128);
+        while (f < n_frames) {
+            bstart.push_back(f);
+            f += sz;
+            sz = std::min(B, sz * 2);
+        }
+        bstart.push_back(n_frames);
+    }
+    const int nbatches = (int)bstart.size() - 1;
 
     bool use_roi = !on_device && c->p.s_area > 0 && c->p.ingest_mode == 0;
     std::vector<const void *> mapped;
     if (use_roi) {
         mapped.resize(n_frames);
         for (int64_t i = 0; i < n_frames && use_roi; i++) {
-            mapped[i] = mapped_host_ptr(src_of(i));
+            mapped[i] = mapped_host_ptr(c, src_of(i));
             if (!mapped[i]) use_roi = false;     // pageable memory: whole-slice copies
         }
     }
@@ -722,7 +761,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
             h = std::min<size_t>(h, (size_t)c->p.height);
             roi_block_max += ((w * h * c->bpp()) + 255) & ~(size_t)255;
         }
-        rc = ensure_roi(c, roi_block_max * (size_t)std::min<int64_t>(B, n_frames), B);
+        rc = ensure_roi(c, (roi_block_max + 256) * (size_t)std::min<int64_t>(B, n_frames), B);
         if (rc != LST_OK) return rc;
     }
     if (!on_device && !use_roi) {
@@ -731,20 +770,62 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     }
 
     auto enqueue_copy = [&](int b) -> int {
-        int64_t f0 = (int64_t)b * B;
-        int nb = (int)std::min<int64_t>(B, n_frames - f0);
+        int64_t f0 = bstart[b];
+        int nb = (int)(bstart[b + 1] - f0);
         const int half = b & 1;
         if (use_roi) {
-            c->roi_block[half] = plan_rois(c, c->dis, c->roi[half]);
-            if (c->roi_block[half] > roi_block_max) return c->fail(LST_ERR_STATE, "internal: ROI block larger than planned");
-            for (int i = 0; i < nb; i++) c->h_gptr[half][i] = mapped[f0 + i];
-            CUC(c, cudaMemcpyAsync(c->d_gptr[half], c->h_gptr[half], sizeof(void *) * nb, cudaMemcpyHostToDevice, c->s_copy));
-            c->stats.kernel_launches += launch_gather_rois(c->d_gptr[half], nb, c->roi[half], c->p.width, (int)c->bpp(),
-                                                           c->d_roi[half], c->roi_block[half], c->s_copy);
-            CUC(c, cudaGetLastError());
-            size_t bytes = 0;
-            for (int k = 0; k < 5; k++) bytes += (size_t)c->roi[half][k].w * c->roi[half][k].h * c->bpp();
-            c->stats.h2d_bytes += (int64_t)(bytes * nb + sizeof(void *) * nb);
+            size_t need = plan_rois(c, c->dis, nb, c->roi[half]);
+            if (need > c->roi_cap) return c->fail(LST_ERR_STATE, "internal: ROI ring smaller than planned");
+            // Runs of equally spaced slices move with one strided 3-D DMA per region (copy engine: no SM
+            // is taken from the kernels of the previous batch); irregularly placed slices (or
+            // ingest_mode == 2) are gathered by a kernel reading the mapped host memory.
+            const size_t rowb = (size_t)c->p.width * c->bpp();
+            std::vector<std::pair<int, int>> runs;   // [first, last) of constant positive stride
+            bool dma = c->p.ingest_mode != 2;
+            auto at = [&](int i) { return (const uint8_t *)src_of(f0 + i); };
+            for (int i = 0; i < nb && dma;) {
+                int j = i + 1;
+                if (j < nb) {
+                    const ptrdiff_t st = at(j) - at(i);
+                    if (st > 0 && (size_t)st % rowb == 0 && (size_t)st / rowb >= (size_t)c->p.height) {
+                        j++;
+                        while (j < nb && at(j) - at(j - 1) == st) j++;
+                    }
+                }
+                runs.push_back({i, j});
+                i = j;
+                if ((int)runs.size() > 64 + nb / 8) dma = false;   // too fragmented: one kernel is cheaper
+            }
+            if (dma) {
+                for (auto &rn : runs) {
+                    const int i0 = rn.first, len = rn.second - rn.first;
+                    const uint8_t *p0 = (const uint8_t *)src_of(f0 + i0);
+                    size_t ysize = (size_t)c->p.height;
+                    if (len > 1) ysize = (size_t)((const uint8_t *)src_of(f0 + i0 + 1) - p0) / rowb;
+                    for (int k = 0; k < 5; k++) {
+                        const RoiDesc &r = c->roi[half][k];
+                        if (r.w <= 0 || r.h <= 0) continue;
+                        cudaMemcpy3DParms pr;
+                        memset(&pr, 0, sizeof(pr));
+                        pr.srcPtr = make_cudaPitchedPtr((void *)p0, rowb, rowb, ysize);
+                        pr.srcPos = make_cudaPos((size_t)r.x * c->bpp(), (size_t)r.y, 0);
+                        pr.dstPtr = make_cudaPitchedPtr(c->d_roi[half] + r.off + (size_t)i0 * r.slice_bytes,
+                                                        (size_t)r.w * c->bpp(), (size_t)r.w * c->bpp(), (size_t)r.h);
+                        pr.dstPos = make_cudaPos(0, 0, 0);
+                        pr.extent = make_cudaExtent((size_t)r.w * c->bpp(), (size_t)r.h, (size_t)len);
+                        pr.kind = cudaMemcpyHostToDevice;
+                        CUC(c, cudaMemcpy3DAsync(&pr, c->s_copy));
+                    }
+                }
+            } else {
+                for (int i = 0; i < nb; i++) c->h_gptr[half][i] = mapped[f0 + i];
+                CUC(c, cudaMemcpyAsync(c->d_gptr[half], c->h_gptr[half], sizeof(void *) * nb, cudaMemcpyHostToDevice, c->s_copy));
+                c->stats.kernel_launches += launch_gather_rois(c->d_gptr[half], nb, c->roi[half], c->p.width, (int)c->bpp(),
+                                                               c->d_roi[half], c->s_copy);
+                CUC(c, cudaGetLastError());
+                c->stats.h2d_bytes += (int64_t)(sizeof(void *) * nb);
+            }
+            for (int k = 0; k < 5; k++) c->stats.h2d_bytes += (int64_t)(c->roi[half][k].slice_bytes * nb);
         } else {
             uint8_t *dst = c->d_ring[half];
             if (!ptrs && stride == fb) {
@@ -764,8 +845,8 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
         if (rc != LST_OK) return rc;
     }
     for (int b = 0; b < nbatches; b++) {
-        int64_t f0 = (int64_t)b * B;
-        int nb = (int)std::min<int64_t>(B, n_frames - f0);
+        int64_t f0 = bstart[b];
+        int nb = (int)(bstart[b + 1] - f0);
         const int half = b & 1;
         int nsurf = nb;
         if (!on_device) {
@@ -780,7 +861,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
                 for (int k = 0; k < 5; k++) {
                     const RoiDesc &r = c->roi[half][k];
                     Surface &sf = c->h_surf[i * 5 + k];
-                    sf.ptr = c->d_roi[half] + (size_t)i * c->roi_block[half] + r.off;
+                    sf.ptr = c->d_roi[half] + r.off + (size_t)i * r.slice_bytes;
                     sf.pitch_px = r.w;
                     sf.org_x = r.x;
                     sf.org_y = r.y;
@@ -794,7 +875,9 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
         } else {
             for (int i = 0; i < nb; i++) c->h_surf[i] = whole_slice(src_of(f0 + i), c->p.width);
         }
-        CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface) * nsurf, cudaMemcpyHostToDevice, c->s_compute));
+        if (launch_upload(c->d_surf, c->h_surf, sizeof(Surface) * nsurf, c->s_compute) < 0)
+            return c->fail(LST_ERR_CUDA, "surface upload failed");
+        c->stats.kernel_launches += 1;
         c->stats.h2d_bytes += (int64_t)sizeof(Surface) * nsurf;
         c->roi_active = use_roi;
         c->roi_half = half;
