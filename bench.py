@@ -357,7 +357,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
-                         "chunks_retracked": sh_dev.retracked},
+                         "chunks_retracked": sh_dev.retracked, "host_ms_per_step": s_dev.host_ms / K,
+                         "device_wait_ms_per_step": s_dev.device_wait_ms / K},
             "wall_ms_per_step": wall_dev / K,
         }
         print(json.dumps(line), flush=True)

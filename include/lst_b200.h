@@ -130,6 +130,8 @@ typedef struct lst_stats {
     int64_t ncc_kernel_launches;
     double  ncc_algorithmic_macs; /* sum over timed launches of Rw*Rh*Tw*Th */
     int64_t roi_fallback_tasks;/* ROI ingest: windows read straight from pinned host memory (margin exceeded) */
+    double  device_wait_ms;    /* host time blocked in stream synchronisation (device busy) */
+    double  host_ms;           /* host time inside the tracking entry points, total */
 } lst_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------- */

@@ -53,7 +53,7 @@ static const int kMaxTpl = 6;   // five tracked templates + one scratch slot for
 // Per-context template table as the kernels see it.
 struct DevTemplates {
     TplConst c[kMaxTpl];
-    const uint32_t *shifted[kMaxTpl];   // [th][k4][4] words, see build_shifted_template
+    const uint32_t *packed[kMaxTpl];    // [th][kw] words, see build_packed_template
     const uint8_t *raw[kMaxTpl];        // [th][tw] bytes
 };
 

@@ -163,7 +163,7 @@ TplConst template_consts(const uint8_t *tpl8, int tw, int th)
     double n = (double)(tw * th);
     c.tw = tw;
     c.th = th;
-    c.k4 = shifted_k4(tw);
+    c.kw = packed_words(tw);
     c.tsum = (uint32_t)s;
     c.tsq_lo = (uint32_t)q;
     c.inv_area = 1.0 / n;
@@ -184,23 +184,14 @@ TplConst template_consts(const uint8_t *tpl8, int tw, int th)
     return c;
 }
 
-int shifted_k4(int tw) { return (tw + 2) / 4 + 1; }
+int packed_words(int tw) { return ((tw + 3) / 4 + 3) & ~3; }
 
-void build_shifted_template(const uint8_t *tpl8, int tw, int th, std::vector<uint32_t> *out)
+void build_packed_template(const uint8_t *tpl8, int tw, int th, std::vector<uint32_t> *out)
 {
-    int k4 = shifted_k4(tw);
-    out->assign((size_t)th * k4 * 4, 0u);
+    int kw = packed_words(tw);
+    out->assign((size_t)th * kw, 0u);
     for (int v = 0; v < th; v++)
-        for (int k = 0; k < k4; k++)
-            for (int j = 0; j < 4; j++) {
-                uint32_t word = 0;
-                for (int b = 0; b < 4; b++) {
-                    int u = 4 * k - j + b;
-                    uint32_t val = (u >= 0 && u < tw) ? tpl8[v * tw + u] : 0u;
-                    word |= val << (8 * b);
-                }
-                (*out)[((size_t)v * k4 + k) * 4 + j] = word;
-            }
+        for (int u = 0; u < tw; u++) (*out)[(size_t)v * kw + u / 4] |= (uint32_t)tpl8[v * tw + u] << (8 * (u & 3));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -211,44 +202,55 @@ namespace {
 struct Entry {
     Rect win;
     int s_used;
+    int prev;   // previous entry of the same (frame, template) slot, -1 = none
     lst_task_result r;
 };
 
+// Results are kept per (frame, template) slot as a chain in one flat vector (newest first): no
+// per-slot allocations on the hot path -- a batch is a few thousand slots with 1-2 entries each.
 struct Resolver {
     const ResolveInput &in;
     Executor &ex;
     int n;
-    std::vector<std::vector<Entry>> store;   // [frame*5 + tpl]
+    std::vector<Entry> entries;
+    std::vector<int> head;        // [frame*5 + tpl] -> newest entry, -1 = none
     std::vector<lst_task> pending;
-    std::vector<std::vector<int>> pend_of;   // [frame*5 + tpl] -> indices into pending
+    std::vector<int> pend_prev;   // chain of pending tasks of the same slot
+    std::vector<int> pend_head;   // [frame*5 + tpl] -> newest pending task, -1 = none
+    std::vector<lst_task_result> res;
     lst_stats *st;
 
     Resolver(const ResolveInput &i, Executor &e, int nn, lst_stats *s)
-        : in(i), ex(e), n(nn), store((size_t)nn * 5), pend_of((size_t)nn * 5), st(s) {}
+        : in(i), ex(e), n(nn), head((size_t)nn * 5, -1), pend_head((size_t)nn * 5, -1), st(s)
+    {
+        entries.reserve((size_t)nn * 8);
+        pending.reserve((size_t)nn * 5);
+        pend_prev.reserve((size_t)nn * 5);
+    }
 
     const Entry *find(int j, int k, const Rect &w, int s_used) const
     {
-        const std::vector<Entry> &v = store[(size_t)j * 5 + k];
-        for (size_t i = v.size(); i-- > 0;)
-            if (v[i].win == w && v[i].s_used == s_used) return &v[i];
+        for (int i = head[(size_t)j * 5 + k]; i >= 0; i = entries[i].prev)
+            if (entries[i].win == w && entries[i].s_used == s_used) return &entries[i];
         return nullptr;
     }
     const Entry *latest(int j, int k) const
     {
-        const std::vector<Entry> &v = store[(size_t)j * 5 + k];
-        return v.empty() ? nullptr : &v.back();
+        int i = head[(size_t)j * 5 + k];
+        return i < 0 ? nullptr : &entries[i];
     }
     const Entry *need(int j, int k, const Rect &w, int s_used)
     {
         const Entry *e = find(j, k, w, s_used);
         if (e) return e;
-        for (int pi : pend_of[(size_t)j * 5 + k]) {
+        const size_t slot = (size_t)j * 5 + k;
+        for (int pi = pend_head[slot]; pi >= 0; pi = pend_prev[pi]) {
             const lst_task &t = pending[pi];
             if (t.wx == w.x && t.wy == w.y && t.ww == w.w && t.wh == w.h && t.s_used == s_used) return nullptr;
         }
-        pend_of[(size_t)j * 5 + k].push_back((int)pending.size());
+        pend_prev.push_back(pend_head[slot]);
+        pend_head[slot] = (int)pending.size();
         lst_task t;
-        memset(&t, 0, sizeof(t));
         t.frame = j;
         t.tpl = k;
         t.wx = w.x;
@@ -256,6 +258,7 @@ struct Resolver {
         t.ww = w.w;
         t.wh = w.h;
         t.s_used = s_used;
+        t.reserved = 0;
         pending.push_back(t);
         return nullptr;
     }
@@ -263,23 +266,27 @@ struct Resolver {
     int run_pending(bool first_pass)
     {
         if (pending.empty()) return LST_OK;
-        std::vector<lst_task_result> res(pending.size());
+        res.resize(pending.size());
         int rc = ex.compute(pending.data(), (int)pending.size(), res.data());
         if (rc != LST_OK) return rc;
         for (size_t i = 0; i < pending.size(); i++) {
+            const size_t slot = (size_t)pending[i].frame * 5 + pending[i].tpl;
             Entry e;
             e.win = Rect{pending[i].wx, pending[i].wy, pending[i].ww, pending[i].wh};
             e.s_used = pending[i].s_used;
+            e.prev = head[slot];
             e.r = res[i];
-            store[(size_t)pending[i].frame * 5 + pending[i].tpl].push_back(e);
+            head[slot] = (int)entries.size();
+            entries.push_back(e);
+            pend_head[slot] = -1;
         }
         if (st) {
             st->tasks += (int64_t)pending.size();
             if (!first_pass) st->respeculated += (int64_t)pending.size();
             st->passes += 1;
         }
-        for (const lst_task &t : pending) pend_of[(size_t)t.frame * 5 + t.tpl].clear();
         pending.clear();
+        pend_prev.clear();
         return LST_OK;
     }
 
@@ -315,9 +322,11 @@ struct Resolver {
         }
         memcpy(dis, dis_in, sizeof(dis));
         memcpy(dis_out, dis_in, sizeof(dis));
-        memset(rec, 0, sizeof(*rec));
-        rec->status = LST_STATUS_OK;
-        rec->reject = -1;
+        if (rec) {   // prediction walks only need the state
+            memset(rec, 0, sizeof(*rec));
+            rec->status = LST_STATUS_OK;
+            rec->reject = -1;
+        }
         bool incomplete = false;
         for (int kk = 0; kk < 5; kk++) {
             int k = kMatchOrder[kk];
@@ -368,10 +377,12 @@ struct Resolver {
                     }
                 }
             }
-            fill_tm(&rec->tm[k], cur);
+            if (rec) fill_tm(&rec->tm[k], cur);
             if (!cur.r.accepted) {
-                rec->status = LST_STATUS_SKIP;
-                rec->reject = k;
+                if (rec) {
+                    rec->status = LST_STATUS_SKIP;
+                    rec->reject = k;
+                }
                 return incomplete ? 2 : 1;
             }
             dis[2 * k] = cur.r.x + cur.win.x - in.rect[k].x;       // LST4:1891-1892, 2182-2183
@@ -393,9 +404,8 @@ int resolve_batch(const ResolveInput &in, double dis_io[10], int64_t first_frame
     memcpy(state, dis_io, sizeof(state));
     // pass 1: every frame speculated with the window origins of the state at batch start
     {
-        lst_record tmp;
         double nd[10];
-        for (int j = 0; j < n; j++) R.eval_frame(j, state, false, &tmp, nd);
+        for (int j = 0; j < n; j++) R.eval_frame(j, state, false, nullptr, nd);
         int rc = R.run_pending(true);
         if (rc != LST_OK) return rc;
     }
@@ -420,7 +430,7 @@ int resolve_batch(const ResolveInput &in, double dis_io[10], int64_t first_frame
                 }
                 exact = false;
             }
-            R.eval_frame(j, walk, false, &rec, nd);   // prediction: queue what the chain will probably need
+            R.eval_frame(j, walk, false, nullptr, nd);   // prediction: queue what the chain will probably need
             memcpy(walk, nd, sizeof(nd));
         }
         if (first >= n) break;

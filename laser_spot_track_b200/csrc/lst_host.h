@@ -34,10 +34,10 @@ void make_gaussian_kernel(float kern[kBlurRadius], float ksum[kBlurRadius]);
 
 // cv::meanStdDev + the template constants of common_matchTemplate; tpl8 has row pitch tw.
 TplConst template_consts(const uint8_t *tpl8, int tw, int th);
-// Four byte-shifted, zero-padded copies of the template packed for IDP.4A:
-// word[(v*k4 + k)*4 + j] holds template bytes T[v][4k-j .. 4k-j+3] (0 outside [0,tw)).
-int shifted_k4(int tw);
-void build_shifted_template(const uint8_t *tpl8, int tw, int th, std::vector<uint32_t> *out);
+// The template packed for IDP.4A: word[v*kw + k] holds template bytes T[v][4k .. 4k+3] (0 beyond tw);
+// kw = words per row, rounded up to a multiple of 4 so that rows load as 128-bit words.
+int packed_words(int tw);
+void build_packed_template(const uint8_t *tpl8, int tw, int th, std::vector<uint32_t> *out);
 
 // The device (or, in CPU tests, a stand-in) as seen by the resolver.
 struct Executor {

@@ -416,10 +416,11 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
 // ------------------------------------------------------------------------------------------------
 // exact NCC + window sums + argmax (one kernel)
 // ------------------------------------------------------------------------------------------------
-// Result position x = 4q + j.  With the template stored four times, shifted by j bytes and
-// zero padded (build_shifted_template), the correlation of one template row is
-//     sum_k IDP.4A(Wword[q + k], Tj[k])
-// over aligned 32-bit words of the window row: no unaligned loads and no byte shuffles.
+// Result position x = 4q + j.  The correlation of one template row is
+//     sum_k IDP.4A(Wj[q + k], T[k]),   Wj[m] = window bytes 4m+j .. 4m+j+3,
+// where T[k] are the packed template words (build_packed_template) and Wj is made from two
+// adjacent aligned window words with one funnel shift (SHF, ALU pipe -- it runs beside the
+// IDP.4A pipe).  Every load is an aligned word; one shifted word serves 4 template words.
 //
 // A CTA owns a band of 32 result rows x a chunk of result columns of one window.  It stages the
 // window rows it needs in shared memory (pitch = odd multiple of 16 B, so 128-bit row loads of 32
@@ -450,8 +451,8 @@ struct NccCtx {
     const uint8_t *s_win;      // window tile in shared memory
     const uint16_t *s_v;       // vertical sums of I   [NCC_BAND][vpitch]
     const uint32_t *s_v2;      // vertical sums of I^2 [NCC_BAND][vpitch]
-    const uint4 *g_tpl;        // shifted template [th][k4] (global, L1)
-    int SP, VP, th, tw, k4, rw;
+    const uint4 *g_tpl;        // packed template [th][kw/4] uint4 (global, L1)
+    int SP, VP, th, tw, kw, rw;
     long long N, tsum, C_unused;
     float inv_sqrt_c;
     double inv_area, mean, norm;
@@ -471,21 +472,20 @@ __device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, in
 #pragma unroll
         for (int q = 0; q < Q; q++) acc[j][q] = 0u;
     const uint8_t *wbase = c.s_win + (size_t)yy * c.SP + 4 * w0;
-    constexpr int NW = (Q + 3 + 3) / 4;   // uint4 loads covering words [k, k + Q + 3)
-    // Per template row: nfull chunks of 4 template words (16*Q IDP.4A each, no guards) and one tail
-    // chunk of k4 % 4 words.  All loads of a chunk are issued before its IDP.4A block; IDP.4A is
-    // half-rate, so the other warps of the SM sub-partition cover the remaining latency.
-    const int nfull = c.k4 >> 2, rem = c.k4 & 3;
+    constexpr int NL = Q + 4;              // window words [k, k + Q + 4) feed one chunk of 4 template words
+    constexpr int NW = (NL + 3) / 4;       // as 128-bit loads
+    // Per template row: kw/4 chunks of 4 packed template words (one LDG.128, warp-uniform, L1) against
+    // NL window words (LDS.128).  Shift j uses Wj[i] = funnelshift(ww[i], ww[i+1], 8j); 16*Q IDP.4A per chunk.
+    const int nchunk = c.kw >> 2;
     const uint4 *trow = c.g_tpl;
     const uint8_t *wrow = wbase;
     for (int v = 0; v < c.th; v++, wrow += c.SP) {
         const uint8_t *wp = wrow;
-        for (int kc = 0; kc < nfull; kc++, wp += 16, trow += 4) {
+        for (int kc = 0; kc < nchunk; kc++, wp += 16, trow++) {
             uint32_t ww[4 * NW];
-            uint4 tj[4];
             if (Q == 1) {   // single-word tiles start at any word: 32-bit loads
 #pragma unroll
-                for (int i = 0; i < 4; i++) ww[i] = *(const uint32_t *)(wp + 4 * i);
+                for (int i = 0; i < NL; i++) ww[i] = *(const uint32_t *)(wp + 4 * i);
             } else {        // 4- and 8-word tiles start at multiples of 4 words: 128-bit loads
 #pragma unroll
                 for (int i = 0; i < NW; i++) {
@@ -496,54 +496,18 @@ __device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, in
                     ww[4 * i + 3] = t4.w;
                 }
             }
+            const uint4 tq = __ldg(trow);
+            const uint32_t tk[4] = {tq.x, tq.y, tq.z, tq.w};
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) tj[kk] = __ldg(trow + kk);
+            for (int j = 0; j < 4; j++) {
+                uint32_t wj[Q + 3];
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
+                for (int i = 0; i < Q + 3; i++) wj[i] = j == 0 ? ww[i] : __funnelshift_r(ww[i], ww[i + 1], 8 * j);
 #pragma unroll
-                for (int q = 0; q < Q; q++) {
-                    const uint32_t wv = ww[kk + q];
-                    acc[0][q] = __dp4a(wv, tj[kk].x, acc[0][q]);
-                    acc[1][q] = __dp4a(wv, tj[kk].y, acc[1][q]);
-                    acc[2][q] = __dp4a(wv, tj[kk].z, acc[2][q]);
-                    acc[3][q] = __dp4a(wv, tj[kk].w, acc[3][q]);
-                }
+                for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                    for (int q = 0; q < Q; q++) acc[j][q] = __dp4a(wj[kk + q], tk[kk], acc[j][q]);
             }
-        }
-        if (rem) {   // warp-uniform
-            uint32_t ww[Q + 2];
-            if (Q == 1) {
-#pragma unroll
-                for (int i = 0; i < 3; i++) ww[i] = *(const uint32_t *)(wp + 4 * i);
-            } else {
-                constexpr int NT = (Q + 2 + 3) / 4;
-                uint32_t wt[4 * NT];
-#pragma unroll
-                for (int i = 0; i < NT; i++) {
-                    const uint4 t4 = *(const uint4 *)(wp + 16 * i);
-                    wt[4 * i] = t4.x;
-                    wt[4 * i + 1] = t4.y;
-                    wt[4 * i + 2] = t4.z;
-                    wt[4 * i + 3] = t4.w;
-                }
-#pragma unroll
-                for (int i = 0; i < Q + 2; i++) ww[i] = wt[i];
-            }
-#pragma unroll
-            for (int kk = 0; kk < 3; kk++) {
-                if (kk < rem) {
-                    const uint4 tj = __ldg(trow + kk);
-#pragma unroll
-                    for (int q = 0; q < Q; q++) {
-                        const uint32_t wv = ww[kk + q];
-                        acc[0][q] = __dp4a(wv, tj.x, acc[0][q]);
-                        acc[1][q] = __dp4a(wv, tj.y, acc[1][q]);
-                        acc[2][q] = __dp4a(wv, tj.z, acc[2][q]);
-                        acc[3][q] = __dp4a(wv, tj.w, acc[3][q]);
-                    }
-                }
-            }
-            trow += rem;
         }
     }
     // Normalisation.  The 4Q correlations move to a thread-local array so that the loops below are
@@ -681,12 +645,12 @@ lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict_
     c.s_win = s_win;
     c.s_v = s_v;
     c.s_v2 = s_v2;
-    c.g_tpl = (const uint4 *)tpls->shifted[t.tpl];
+    c.g_tpl = (const uint4 *)tpls->packed[t.tpl];
     c.SP = SP;
     c.VP = VP;
     c.th = th;
     c.tw = tw;
-    c.k4 = tc.k4;
+    c.kw = tc.kw;
     c.rw = t.rw;
     c.N = (long long)tw * th;
     c.tsum = (long long)tc.tsum;
@@ -730,11 +694,11 @@ lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict_
     }
 }
 
-static int ncc_pitch(int chunk_words, int k4)
+static int ncc_pitch(int chunk_words, int kw)
 {
-    // widest read: a 4-word tile at word (chunk_words - 4) loading words [k, k + 8) for k <= k4 - 1 rounded
-    // down to a multiple of 4, i.e. up to word chunk_words + k4 + 3 -> +4 for the vertical-sum columns
-    int p = 4 * chunk_words + 4 * (k4 + 4);
+    // widest read: an 8-word tile at word (chunk_words - 8) loading words [k, k + 12) for k <= kw - 4,
+    // i.e. up to word chunk_words + kw; a 4-word tile reads up to chunk_words - 4 + kw - 4 + 8: the same
+    int p = 4 * chunk_words + 4 * (kw + 1);
     p = (p + 15) & ~15;
     if (((p / 16) & 1) == 0) p += 16;   // odd multiple of 16 B: conflict-free 128-bit row loads
     return p;
@@ -746,8 +710,8 @@ static int ncc_vpitch(int chunk_words, int tw)
 }
 static size_t ncc_smem(int chunk_words, int tw, int th)
 {
-    int k4 = (tw + 2) / 4 + 1;
-    return (size_t)(NCC_BAND + th - 1) * ncc_pitch(chunk_words, k4) + (size_t)NCC_BAND * ncc_vpitch(chunk_words, tw) * 6 + 16;
+    int kw = ((tw + 3) / 4 + 3) & ~3;
+    return (size_t)(NCC_BAND + th - 1) * ncc_pitch(chunk_words, kw) + (size_t)NCC_BAND * ncc_vpitch(chunk_words, tw) * 6 + 16;
 }
 
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes)
@@ -762,7 +726,7 @@ void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams
     auto ctas = [&](int w) { return (long)n_tasks * ((words_total + w - 1) / w) * ((max_rh + NCC_BAND - 1) / NCC_BAND); };
     while (cw > 8 && ctas(cw) < 148L * 4) cw = (((cw + 1) / 2) + 7) & ~7;
     mp->chunk_words = cw;
-    mp->smem_pitch = ncc_pitch(cw, (tw + 2) / 4 + 1);
+    mp->smem_pitch = ncc_pitch(cw, ((tw + 3) / 4 + 3) & ~3);
     mp->v_pitch = ncc_vpitch(cw, tw);
     mp->max_th = th;
     *smem_bytes = ncc_smem(cw, tw, th);

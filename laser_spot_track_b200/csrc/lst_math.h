@@ -23,7 +23,7 @@ struct TplConst {
     double norm;        // sqrt(templSdv^2)/sqrt(invArea)
     int32_t flat;       // templSdv^2 < DBL_EPSILON  => whole result is 1
     int32_t tw, th;
-    int32_t k4;         // 32-bit words per shifted template row (see build_shifted_template)
+    int32_t kw;         // 32-bit words per packed template row, multiple of 4 (see build_packed_template)
     uint32_t tsum, tsq_lo;
     double mideal;      // doMatch_test of the template (LST4:2724-2767)
     float inv_sqrt_c;   // 1/sqrt(N*tsq - tsum^2): float32 filter of the match kernel

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -17,6 +18,11 @@
 using namespace lst;
 
 static thread_local std::string g_create_error;
+
+static double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct TimedLaunch {
     cudaEvent_t e0, e1;
@@ -37,9 +43,9 @@ struct lst_ctx : public Executor {
     double dis[10] = {0};
     DevTemplates h_tpls;
     DevTemplates *d_tpls = nullptr;
-    uint32_t *d_shifted[kMaxTpl] = {nullptr};
+    uint32_t *d_packed[kMaxTpl] = {nullptr};
     uint8_t *d_raw[kMaxTpl] = {nullptr};
-    size_t shifted_cap[kMaxTpl] = {0}, raw_cap[kMaxTpl] = {0};
+    size_t packed_cap[kMaxTpl] = {0}, raw_cap[kMaxTpl] = {0};
     // per-pass scratch
     int task_cap = 0;
     DevTask *d_tasks = nullptr, *h_tasks = nullptr;
@@ -215,19 +221,19 @@ int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th)
 {
     TplConst c = template_consts(tpl8, tw, th);
     std::vector<uint32_t> sh;
-    build_shifted_template(tpl8, tw, th, &sh);
-    if (sh.size() > shifted_cap[slot]) {
-        CU(regrow(&d_shifted[slot], sh.size()));
-        shifted_cap[slot] = sh.size();
+    build_packed_template(tpl8, tw, th, &sh);
+    if (sh.size() > packed_cap[slot]) {
+        CU(regrow(&d_packed[slot], sh.size()));
+        packed_cap[slot] = sh.size();
     }
     if ((size_t)tw * th > raw_cap[slot]) {
         CU(regrow(&d_raw[slot], (size_t)tw * th));
         raw_cap[slot] = (size_t)tw * th;
     }
-    CU(cudaMemcpyAsync(d_shifted[slot], sh.data(), sh.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s_compute));
+    CU(cudaMemcpyAsync(d_packed[slot], sh.data(), sh.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s_compute));
     CU(cudaMemcpyAsync(d_raw[slot], tpl8, (size_t)tw * th, cudaMemcpyHostToDevice, s_compute));
     h_tpls.c[slot] = c;
-    h_tpls.shifted[slot] = d_shifted[slot];
+    h_tpls.packed[slot] = d_packed[slot];
     h_tpls.raw[slot] = d_raw[slot];
     CU(cudaMemcpyAsync(d_tpls, &h_tpls, sizeof(DevTemplates), cudaMemcpyHostToDevice, s_compute));
     CU(cudaStreamSynchronize(s_compute));   // sh / h_tpls are pageable: finish before they go away
@@ -261,11 +267,15 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     size_t win_off = 0, sum_off = 0;
     int max_w = 0, max_h = 0, max_rw = 0, max_rh = 0, max_tw = 0, max_th = 0;
     double macs = 0;
-    // device order: grouped by template, so that CTAs resident on one SM read the same shifted
+    // device order: grouped by template, so that CTAs resident on one SM read the same packed
     // template through L1 (order[i] = index of the caller's task in device slot i)
     order.resize(n);
-    for (int i = 0; i < n; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].tpl < tasks[b].tpl; });
+    {
+        int cnt[kMaxTpl + 1] = {0};
+        for (int i = 0; i < n; i++) cnt[std::min(std::max(tasks[i].tpl, 0), kMaxTpl - 1) + 1]++;
+        for (int k = 0; k < kMaxTpl; k++) cnt[k + 1] += cnt[k];
+        for (int i = 0; i < n; i++) order[cnt[std::min(std::max(tasks[i].tpl, 0), kMaxTpl - 1)]++] = i;
+    }
     for (int i = 0; i < n; i++) {
         const lst_task &t = tasks[order[i]];
         DevTask &d = h_tasks[i];
@@ -359,7 +369,11 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         stats.d2h_bytes += (int64_t)sizeof(DevResult) * n;
     }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s_compute));
+    {
+        double t0 = now_ms();
+        CU(cudaStreamSynchronize(s_compute));
+        stats.device_wait_ms += now_ms() - t0;
+    }
     stats.kernel_launches += launches;
     if (timing) drain_timers();
     if (!preprocess_only && results) {
@@ -423,7 +437,11 @@ int lst_ctx::solve(const double *dis10, int n, double *out5)
     stats.kernel_launches += launch_solve(d_dis10, n, ref_xy, p.mark_dist, spot0, d_out5, s_compute);
     CU(cudaMemcpyAsync(h_out5, d_out5, sizeof(double) * 5 * n, cudaMemcpyDeviceToHost, s_compute));
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(s_compute));
+    {
+        double t0 = now_ms();
+        CU(cudaStreamSynchronize(s_compute));
+        stats.device_wait_ms += now_ms() - t0;
+    }
     memcpy(out5, h_out5, sizeof(double) * 5 * n);
     stats.h2d_bytes += (int64_t)sizeof(double) * 10 * n;
     stats.d2h_bytes += (int64_t)sizeof(double) * 5 * n;
@@ -511,7 +529,7 @@ void lst_destroy(lst_ctx *c)
     if (c->s_compute) cudaStreamSynchronize(c->s_compute);
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
     for (int i = 0; i < kMaxTpl; i++) {
-        cudaFree(c->d_shifted[i]);
+        cudaFree(c->d_packed[i]);
         cudaFree(c->d_raw[i]);
     }
     cudaFree(c->d_tpls);
@@ -718,6 +736,11 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     if (!c->have_ref) return c->fail(LST_ERR_STATE, "lst_set_reference must be called before tracking");
     CUC(c, cudaSetDevice(c->device));
     if (n_frames == 0) return LST_OK;
+    struct HostTimer {
+        lst_ctx *c;
+        double t0;
+        ~HostTimer() { c->stats.host_ms += now_ms() - t0; }
+    } host_timer{c, now_ms()};
     const size_t fb = c->frame_bytes();
     if (stride == 0) stride = fb;
     const int B = c->p.max_batch;

@@ -69,7 +69,7 @@ class Stats(C.Structure):
         ("frames", C.c_int64), ("tasks", C.c_int64), ("respeculated", C.c_int64), ("passes", C.c_int64),
         ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ncc_kernel_ms", C.c_double), ("ncc_kernel_launches", C.c_int64), ("ncc_algorithmic_macs", C.c_double),
-        ("roi_fallback_tasks", C.c_int64),
+        ("roi_fallback_tasks", C.c_int64), ("device_wait_ms", C.c_double), ("host_ms", C.c_double),
     ]
 
 
