@@ -63,7 +63,8 @@ struct PreprocParams {
     int range_per_task;    // 1: lo/hi from the per-task min/max keys, 0: fixed lo/hi below
     float lo, hi;
     int quant_mode;        // LST_QUANT_*
-    int tile_w, tile_h;    // blur tile (output) size
+    int tile_w;            // columns per CTA of the blur kernel (whole window when it fits)
+    int minmax_in_kernel;  // the blur kernel finds the crop min/max itself (single column block)
 };
 
 struct MatchParams {

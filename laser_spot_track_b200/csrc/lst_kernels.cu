@@ -255,140 +255,199 @@ int launch_gather_rois(const void *const *mapped_frames, int n_frames, const Roi
         }                                                                     \
     }
 
+// A CTA owns a column block (up to tile_w columns, the whole window for the named configurations) of
+// one window over its full height and walks it in strips of PRE_STRIP rows.  X-pass rows live in a
+// ring of PRE_RING rows indexed by (row mod PRE_RING), so the 12 rows two consecutive strips share
+// are computed once.  When the range convention needs the crop's min/max and the window is a
+// single column block, the CTA finds them itself first (no separate kernel).
+#define PRE_STRIP 32
+#define PRE_RING (PRE_STRIP + 2 * (KR - 1))   // 44
+
 template <int PIX>
 __global__ void __launch_bounds__(256)
 lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ surfaces, PreprocParams pp,
                const uint32_t *__restrict__ mm_keys, uint8_t *__restrict__ win8)
 {
     extern __shared__ float smem_f[];
+    __shared__ uint32_t s_mm[2];
     const DevTask t = tasks[blockIdx.y];
-    const int TW = pp.tile_w, TH = pp.tile_h;
-    const int tiles_x = (t.w + TW - 1) / TW, tiles_y = (t.h + TH - 1) / TH;
-    if ((int)blockIdx.x >= tiles_x * tiles_y) return;
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-    const int cx0 = tx * TW, cy0 = ty * TH;
-    const int cx1 = min(cx0 + TW, t.w), cy1 = min(cy0 + TH, t.h);
+    const int TW = pp.tile_w;
+    const int tiles_x = (t.w + TW - 1) / TW;
+    if ((int)blockIdx.x >= tiles_x) return;
+    const int cx0 = blockIdx.x * TW;
+    const int cx1 = min(cx0 + TW, t.w);
     const int rx0 = max(cx0 - (KR - 1), 0), rx1 = min(cx1 + (KR - 1), t.w);
-    const int ry0 = max(cy0 - (KR - 1), 0), ry1 = min(cy1 + (KR - 1), t.h);
-    const int RWP = TW + 2 * (KR - 1) + 1;     // raw tile pitch (floats)
-    const int XWP = TW + 1;                    // x-pass tile pitch
-    float *raw = smem_f;                                   // [(TH+12)][RWP]
-    float *xp = smem_f + (size_t)(TH + 2 * (KR - 1)) * RWP;   // [(TH+12)][XWP]
+    const int RWP = TW + 2 * (KR - 1) + 1;     // raw strip pitch (floats)
+    const int XWP = TW + 1;                    // x-pass ring pitch
+    float *raw = smem_f;                                            // [PRE_STRIP + KR - 1][RWP]
+    float *xp = smem_f + (size_t)(PRE_STRIP + KR - 1) * RWP;        // [PRE_RING][XWP]
     const Surface sf = surfaces[t.frame];
     const void *fr = sf.ptr;
-    const int nrw = rx1 - rx0, nrh = ry1 - ry0;
+    const int nrw = rx1 - rx0, ncw = cx1 - cx0;
+    const size_t src00 = (size_t)(t.y0 - sf.org_y) * sf.pitch_px + (t.x0 - sf.org_x);
 
-    for (int idx = threadIdx.x; idx < nrw * nrh; idx += blockDim.x) {
-        int r = idx / nrw, c = idx - r * nrw;
-        size_t src = (size_t)(t.y0 - sf.org_y + ry0 + r) * sf.pitch_px + (t.x0 - sf.org_x + rx0 + c);
-        raw[r * RWP + c] = load_px<PIX>(fr, src);
-    }
     float lo = pp.lo, hi = pp.hi;
     if (pp.range_per_task) {
-        lo = key_to_float<PIX>(mm_keys[2 * blockIdx.y]);
-        hi = key_to_float<PIX>(mm_keys[2 * blockIdx.y + 1]);
-    }
-    __syncthreads();
-
-    // X pass: rows [ry0,ry1), columns [cx0,cx1).  A thread produces 4 consecutive columns from 16
-    // loads when the run is interior (no edge replication); edge runs take the general form.
-    const int ncw = cx1 - cx0;
-    const int nsegx = (ncw + 3) >> 2;
-    for (int idx = threadIdx.x; idx < nsegx * nrh; idx += blockDim.x) {
-        int r = idx / nsegx, sg = idx - r * nsegx;
-        const float *line = raw + r * RWP - rx0;   // line[i] = crop row pixel i
-        const int i0 = cx0 + 4 * sg;
-        float *dstx = xp + r * XWP + 4 * sg;
-        if (i0 >= KR && i0 + 3 + KR < t.w && i0 + 3 < cx1) {
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = line[i0 - (KR - 1) + j];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float res = v[KR - 1 + j] * c_kern[0];
-#pragma unroll
-                for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
-                dstx[j] = res;
+        if (pp.minmax_in_kernel) {
+            if (threadIdx.x == 0) {
+                s_mm[0] = 0xffffffffu;
+                s_mm[1] = 0u;
             }
+            __syncthreads();
+            uint32_t klo = 0xffffffffu, khi = 0u;
+            for (int r = threadIdx.x >> 5; r < t.h; r += 8) {
+                const size_t rowoff = src00 + (size_t)r * sf.pitch_px;
+#pragma unroll 8
+                for (int c = threadIdx.x & 31; c < t.w; c += 32) {
+                    uint32_t k = px_key<PIX>(fr, rowoff + c);
+                    klo = min(klo, k);
+                    khi = max(khi, k);
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
+                khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(&s_mm[0], klo);
+                atomicMax(&s_mm[1], khi);
+            }
+            __syncthreads();
+            lo = key_to_float<PIX>(s_mm[0]);
+            hi = key_to_float<PIX>(s_mm[1]);
         } else {
-            for (int j = 0; j < 4 && i0 + j < cx1; j++) {
-                const int i = i0 + j;
-                float res;
-#define IN_X(ii) line[(ii)]
-                LST_BLUR_AT(res, i, t.w, IN_X)
-#undef IN_X
-                dstx[j] = res;
-            }
+            lo = key_to_float<PIX>(mm_keys[2 * blockIdx.y]);
+            hi = key_to_float<PIX>(mm_keys[2 * blockIdx.y + 1]);
         }
     }
-    __syncthreads();
-
-    // Y pass + quantise: rows [cy0,cy1), columns [cx0,cx1).  A thread produces 4 consecutive rows of
-    // one column (consecutive threads own consecutive columns: conflict-free, coalesced stores).
-    float scale = (pp.quant_mode == LST_QUANT_ROUND255 ? 255.0f : 256.0f) / (hi - lo);
-    const int nch = cy1 - cy0;
-    const int nsegy = (nch + 3) >> 2;
+    const float scale = (pp.quant_mode == LST_QUANT_ROUND255 ? 255.0f : 256.0f) / (hi - lo);
     uint8_t *dst = win8 + t.win_off;
-    for (int idx = threadIdx.x; idx < ncw * nsegy; idx += blockDim.x) {
-        int sg = idx / ncw, cc = idx - sg * ncw;
-        const float *col = xp + cc - ry0 * XWP;     // col[i*XWP] = x-pass value at crop row i
-        const int i0 = cy0 + 4 * sg;
-        float out[4];
-        int nout = min(4, cy1 - i0);
-        if (i0 >= KR && i0 + 3 + KR < t.h && nout == 4) {
-            float v[16];
+    const int nsegx = (ncw + 3) >> 2;
+
+    int xdone = 0;   // x-pass rows [0, xdone) are in the ring (the newest PRE_RING of them)
+    for (int cy0 = 0; cy0 < t.h; cy0 += PRE_STRIP) {
+        const int cy1 = min(cy0 + PRE_STRIP, t.h);
+        const int need = min(cy1 + (KR - 1), t.h);          // x-pass rows needed up to here
+        const int newr = need - xdone;                      // <= PRE_STRIP + KR - 1
+        // raw rows [xdone, need), columns [rx0, rx1)
+        for (int r = threadIdx.x >> 5; r < newr; r += 8) {
+            const size_t rowoff = src00 + (size_t)(xdone + r) * sf.pitch_px + rx0;
+#pragma unroll 8
+            for (int c = threadIdx.x & 31; c < nrw; c += 32) raw[r * RWP + c] = load_px<PIX>(fr, rowoff + c);
+        }
+        __syncthreads();
+        // X pass of the new rows.  Interior runs of 4 columns (no edge replication) take 16 loads per
+        // 4 results; the few runs next to the crop's left/right border take the general form.  The two
+        // kinds are walked by separate loops so that no warp executes both paths.
+        {
+            int sg_lo = cx0 >= KR ? 0 : (KR - cx0 + 3) >> 2;
+            int lim = min(t.w - (KR + 4), cx1 - 4) - cx0;              // i0 - cx0 <= lim
+            int sg_hi = lim < 0 ? -1 : lim >> 2;                        // last interior run
+            if (sg_hi >= nsegx) sg_hi = nsegx - 1;
+            const int nint = sg_hi >= sg_lo ? sg_hi - sg_lo + 1 : 0;
+            for (int idx = threadIdx.x; idx < nint * newr; idx += blockDim.x) {
+                const int r = idx / nint, sg = sg_lo + (idx - r * nint);
+                const float *line = raw + r * RWP - rx0;   // line[i] = crop row pixel i
+                const int i0 = cx0 + 4 * sg;
+                float *dstx = xp + ((xdone + r) % PRE_RING) * XWP + 4 * sg;
+                float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = col[(i0 - (KR - 1) + j) * XWP];
+                for (int j = 0; j < 16; j++) v[j] = line[i0 - (KR - 1) + j];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float res = v[KR - 1 + j] * c_kern[0];
+#pragma unroll
+                    for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
+                    dstx[j] = res;
+                }
+            }
+            const int nedge = nsegx - nint;                              // runs [0, sg_lo) and (sg_hi, nsegx)
+            for (int idx = threadIdx.x; idx < nedge * 4 * newr; idx += blockDim.x) {
+                const int r = idx / (nedge * 4), e = idx - r * (nedge * 4);
+                const int es = e >> 2, j = e & 3;
+                const int sg = nint == 0 ? es : (es < sg_lo ? es : sg_hi + 1 + (es - sg_lo));
+                const int i = cx0 + 4 * sg + j;
+                if (i < cx1) {
+                    const float *line = raw + r * RWP - rx0;
+                    float res;
+#define IN_X(ii) line[(ii)]
+                    LST_BLUR_AT(res, i, t.w, IN_X)
+#undef IN_X
+                    xp[((xdone + r) % PRE_RING) * XWP + 4 * sg + j] = res;
+                }
+            }
+        }
+        xdone = need;
+        __syncthreads();
+        // Y pass + quantise of rows [cy0, cy1): a thread produces 4 consecutive rows of one column
+        // (consecutive threads own consecutive columns: conflict-free, coalesced stores).
+        const int nch = cy1 - cy0;
+        const int nsegy = (nch + 3) >> 2;
+        for (int idx = threadIdx.x; idx < ncw * nsegy; idx += blockDim.x) {
+            const int sg = idx / ncw, cc = idx - sg * ncw;
+            const float *col = xp + cc;                // x-pass value at crop row i: col[(i % PRE_RING) * XWP]
+            const int i0 = cy0 + 4 * sg;
+            float out[4];
+            const int nout = min(4, cy1 - i0);
+            if (i0 >= KR && i0 + 3 + KR < t.h && nout == 4) {
+                float v[16];
+                int slot = (i0 - (KR - 1)) % PRE_RING;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    v[j] = col[slot * XWP];
+                    slot = slot + 1 == PRE_RING ? 0 : slot + 1;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float res = v[KR - 1 + j] * c_kern[0];
+#pragma unroll
+                    for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
+                    out[j] = res;
+                }
+            } else {
+                for (int j = 0; j < nout; j++) {
+                    const int i = i0 + j;
+                    float res;
+#define IN_Y(ii) col[((ii) % PRE_RING) * XWP]
+                    LST_BLUR_AT(res, i, t.h, IN_Y)
+#undef IN_Y
+                    out[j] = res;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                float res = v[KR - 1 + j] * c_kern[0];
-#pragma unroll
-                for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
-                out[j] = res;
-            }
-        } else {
-            for (int j = 0; j < nout; j++) {
-                const int i = i0 + j;
-                float res;
-#define IN_Y(ii) col[(ii)*XWP]
-                LST_BLUR_AT(res, i, t.h, IN_Y)
-#undef IN_Y
-                out[j] = res;
+                if (j < nout) {
+                    float value = out[j] - lo;
+                    if (value < 0.0f) value = 0.0f;
+                    float q = value * scale;
+                    if (pp.quant_mode == LST_QUANT_ROUND255) q = q + 0.5f;
+                    int iv = __float2int_rz(q);            // Java (int): NaN -> 0, saturating
+                    iv = iv > 255 ? 255 : (iv < 0 ? 0 : iv);
+                    dst[(size_t)(i0 + j) * t.pitch + (cx0 + cc)] = (uint8_t)iv;
+                }
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (j < nout) {
-                float value = out[j] - lo;
-                if (value < 0.0f) value = 0.0f;
-                float q = value * scale;
-                if (pp.quant_mode == LST_QUANT_ROUND255) q = q + 0.5f;
-                int iv = __float2int_rz(q);            // Java (int): NaN -> 0, saturating
-                iv = iv > 255 ? 255 : (iv < 0 ? 0 : iv);
-                dst[(size_t)(i0 + j) * t.pitch + (cx0 + cc)] = (uint8_t)iv;
+        // zero the pitch padding so the match kernel can load whole 16-byte words
+        if (cx1 == t.w && t.pitch > t.w) {
+            int padw = t.pitch - t.w;
+            for (int idx = threadIdx.x; idx < padw * nch; idx += blockDim.x) {
+                int r = idx / padw, c = idx - r * padw;
+                dst[(size_t)(cy0 + r) * t.pitch + t.w + c] = 0;
             }
         }
-    }
-    // zero the pitch padding so the match kernel can load whole 16-byte words
-    if (cx1 == t.w && t.pitch > t.w) {
-        int padw = t.pitch - t.w;
-        for (int idx = threadIdx.x; idx < padw * nch; idx += blockDim.x) {
-            int r = idx / padw, c = idx - r * padw;
-            dst[(size_t)(cy0 + r) * t.pitch + t.w + c] = 0;
-        }
+        __syncthreads();   // the next strip overwrites raw and the oldest ring rows
     }
 }
 
 static size_t preprocess_smem(const PreprocParams &pp)
 {
-    size_t rows = pp.tile_h + 2 * (KR - 1);
-    return rows * (size_t)(pp.tile_w + 2 * (KR - 1) + 1 + pp.tile_w + 1) * sizeof(float);
+    return ((size_t)(PRE_STRIP + KR - 1) * (pp.tile_w + 2 * (KR - 1) + 1) + (size_t)PRE_RING * (pp.tile_w + 1)) * sizeof(float);
 }
 
 int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces,
                       const PreprocParams &pp, const uint32_t *mm_keys, uint8_t *win8, cudaStream_t stream)
 {
-    int tiles = ((max_w + pp.tile_w - 1) / pp.tile_w) * ((max_h + pp.tile_h - 1) / pp.tile_h);
+    int tiles = (max_w + pp.tile_w - 1) / pp.tile_w;
     size_t smem = preprocess_smem(pp);
     static bool attr_set = false;
     if (!attr_set) {
@@ -397,6 +456,7 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
         cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
+    (void)max_h;
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;

@@ -105,7 +105,7 @@ struct lst_ctx : public Executor {
     int ensure_frames(int n);
     int ensure_scratch(size_t win_bytes, size_t map_elems);
     int upload_template(int slot, const uint8_t *tpl8, int tw, int th);
-    void preproc_params(PreprocParams *pp, int max_w) const;
+    void preproc_params(PreprocParams *pp, int max_w, int max_h) const;
     void drain_timers();
 };
 
@@ -188,7 +188,7 @@ int lst_ctx::ensure_scratch(size_t win_bytes, size_t map_elems)
     return LST_OK;
 }
 
-void lst_ctx::preproc_params(PreprocParams *pp, int max_w) const
+void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
 {
     memset(pp, 0, sizeof(*pp));
     pp->pixel_type = p.pixel_type;
@@ -214,7 +214,7 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w) const
     }
     int tw = (max_w + 7) & ~7;
     pp->tile_w = tw < 192 ? tw : 192;   // whole window rows for the named configurations (S <= 192)
-    pp->tile_h = 32;
+    pp->minmax_in_kernel = (pp->range_per_task && max_w <= pp->tile_w && (long)max_w * max_h <= 256L * 256) ? 1 : 0;
 }
 
 int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th)
@@ -333,8 +333,8 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     launches += launch_init_pass(n, d_mm, d_best, s_compute);
     if (!have_win8) {
         PreprocParams pp;
-        preproc_params(&pp, max_w);
-        if (pp.range_per_task) launches += launch_minmax(d_tasks, n, max_h, d_surf, pp, d_mm, s_compute);
+        preproc_params(&pp, max_w, max_h);
+        if (pp.range_per_task && !pp.minmax_in_kernel) launches += launch_minmax(d_tasks, n, max_h, d_surf, pp, d_mm, s_compute);
         launches += launch_preprocess(d_tasks, n, max_w, max_h, d_surf, pp, d_mm, d_win8, s_compute);
     }
     if (!preprocess_only) {
