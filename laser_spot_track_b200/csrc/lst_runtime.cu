@@ -69,7 +69,8 @@ struct lst_ctx : public Executor {
     RoiDesc roi[2][5];     // per half: the rectangles gathered for that batch
     bool roi_active = false;   // the batch being resolved uses ROI surfaces
     int roi_half = 0, roi_nb = 0;
-    int roi_margin = 16;
+    int roi_margin = 8;
+    int roi_align_bytes = 32;
     std::unordered_map<const void *, const void *> mapped_cache;   // pinned host ptr -> device-visible ptr
     // solve buffers
     int solve_cap = 0;
@@ -703,7 +704,7 @@ static const void *mapped_host_ptr(lst_ctx *c, const void *p)
 static size_t plan_rois(const lst_ctx *c, const double dis[10], int nb, RoiDesc out[5])
 {
     const int bpp = (int)c->bpp();
-    const int ax = 64 / bpp;   // pixels per 64 bytes
+    const int ax = c->roi_align_bytes / bpp;   // x origin/extent granularity in pixels
     size_t off = 0;
     for (int k = 0; k < 5; k++) {
         Rect w = window_for(c->p, c->rect[k], jint(dis[2 * k]), jint(dis[2 * k + 1]), c->p.s_area, false, nullptr);
@@ -776,7 +777,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     // the ROI ring is sized once from an upper bound of plan_rois (both halves are live at once)
     size_t roi_block_max = 0;
     if (use_roi) {
-        const int ax = 64 / (int)c->bpp();
+        const int ax = c->roi_align_bytes / (int)c->bpp();
         for (int k = 0; k < 5; k++) {
             size_t w = (size_t)c->rect[k].w + 2 * c->p.s_area + 2 * c->roi_margin + 2 * ax;
             size_t h = (size_t)c->rect[k].h + 2 * c->p.s_area + 2 * c->roi_margin;

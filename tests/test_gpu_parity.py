@@ -285,3 +285,65 @@ def test_golden_fixtures_on_gpu(built_lib, name):
             assert [m.score for m in r.tm] == g["scores"][i].tolist()
             assert [(m.x, m.y) for m in r.tm] == [tuple(p) for p in g["pos"][i]]
             assert [r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL] == g["out"][i].tolist()
+
+
+def test_track_whole_slice_search(built_lib, oracle_clib):
+    """sArea == 0: every template is searched over the whole slice (LST4:1316-1320); no edge test."""
+    cfg = StackConfig(232, 184, "u16", 24, 0, 8)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 5)]
+    op = util.oracle_params(cfg)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    assert all(w.tm[0].ww == cfg.width and w.tm[0].wh == cfg.height for w in want)
+    with _tracker(cfg, op) as t:
+        t.set_reference(frames[0], st.ref_xy)
+        got = t.track(np.stack(frames[1:]))
+        util.compare_records(got, want, label="sArea=0")
+
+
+def test_large_template_regime(built_lib, oracle_clib):
+    """Config D geometry (128x128 templates, 512x512 ROIs) on a 1024x1024 slice: one frame against the
+    exact oracle, peaks/scores/sub-pixel against OpenCV within the north_star tolerances."""
+    cfg = StackConfig(1024, 1024, "u8", 128, 192, 4)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 3)]
+    op = util.oracle_params(cfg, match_intensity=False)
+    ocv = O.OracleTracker(op, backend="cv2")
+    ocv.set_reference(frames[0], st.ref_xy)
+    want_cv = ocv.run(frames[1:])
+    with _tracker(cfg, op) as t:
+        t.set_reference(frames[0], st.ref_xy)
+        got = t.track(np.stack(frames[1:]))
+        for g, w in zip(got, want_cv):
+            assert g.status == w.status == 0
+            for k in range(5):
+                assert (g.tm[k].ix, g.tm[k].iy) == (w.tm[k].ix, w.tm[k].iy)
+                assert abs(g.tm[k].score - w.tm[k].score) <= SCORE_TOL_CV2
+                assert abs(g.tm[k].x - w.tm[k].x) <= SUBPIX_TOL_CV2 and abs(g.tm[k].y - w.tm[k].y) <= SUBPIX_TOL_CV2
+        # one window bit-exact against the exact oracle (the C correlation takes a few seconds)
+        m = got[0].tm[0]
+        win8 = O.preprocess_crop(frames[1], m.wx, m.wy, m.ww, m.wh, op)
+        ex, _ = O.do_match_coord_res(win8, ocv.tpl8[0], True, "exact")
+        assert [m.x, m.y, m.score] == ex
+
+
+def test_batch_size_invariance_full_size(built_lib):
+    """BASELINE config B at full slice size (1920x1080 16-bit, T=48, s=56): results do not depend on
+    how frames are batched (property test; the oracle would need minutes at this size)."""
+    cfg = StackConfig(1920, 1080, "u16", 48, 56, 48, motion="periodic", period=48)
+    st = SyntheticStack(cfg)
+    frames = np.stack([st.frame(i) for i in range(0, 25)])
+    outs = []
+    for mb in (1, 5, 24):
+        with LaserSpotTrack4(1920, 1080, 16, templSize=48, sArea=56, max_batch=mb) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            recs = t.track(frames[1:])
+            outs.append([(r.status, [(m.ix, m.iy, m.wx, m.wy, m.score, m.x, m.y) for m in r.tm],
+                          r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL) for r in recs])
+            assert all(r.status == 0 for r in recs)
+    assert outs[0] == outs[1] == outs[2]
+    # accuracy sanity against the synthetic ground truth
+    t24 = st.truth(24) - st.truth(0)
+    assert abs(outs[0][-1][2] - (t24[0, 0] - t24[1, 0])) < 0.2
