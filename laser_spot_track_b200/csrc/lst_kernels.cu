@@ -14,6 +14,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "../../include/lst_b200.h"
 #include "lst_device.h"
 
@@ -776,15 +778,35 @@ static size_t ncc_smem(int chunk_words, int tw, int th)
 
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes)
 {
-    // One CTA = 32 result rows x chunk_words*4 result columns.  Start from the whole row and halve
-    // (in multiples of 8 words) until the tile fits ~56 KB, which keeps 4 CTAs resident per SM.
+    // One CTA = 32 result rows x chunk_words*4 result columns, 4 warps, one 8-word tile per warp at a
+    // time.  Pick the chunk width that keeps the most warps busy per SM: wide chunks give every warp of
+    // the CTA a tile but cost shared memory (window rows + vertical sums), i.e. resident CTAs.  Small
+    // templates fit a whole result row in ~50 KB (4 CTAs/SM, 16 warps); 128x128 templates need ~90 KB
+    // for 4 tiles (2 CTAs/SM, 8 warps), which still beats narrow chunks that idle 3 of 4 warps.
     const int words_total = (max_rw + 3) / 4;
-    int cw = (words_total + 7) & ~7;
-    const size_t budget = 56 * 1024;
-    while (cw > 8 && ncc_smem(cw, tw, th) > budget) cw = (((cw + 1) / 2) + 7) & ~7;
+    const int cw_max = (words_total + 7) & ~7;
+    const size_t smem_sm = 220 * 1024;
+    int best_cw = 8;
+    double best_score = -1.0;
+    for (int cw = 8; cw <= cw_max && cw <= 64; cw += 8) {
+        size_t sm = ncc_smem(cw, tw, th);
+        if (sm > 200 * 1024) break;
+        int ctas = (int)(smem_sm / (sm + 1024));
+        if (ctas > 4) ctas = 4;                       // registers: 4 CTAs of 128 threads
+        if (ctas < 1) break;
+        int tiles = (std::min(cw, words_total) + 7) / 8;
+        int busy = ctas * (tiles < 4 ? tiles : 4);
+        // prefer more busy warps; among equals the wider chunk (less redundant window staging)
+        double score = busy + 0.01 * cw;
+        if (score > best_score) {
+            best_score = score;
+            best_cw = cw;
+        }
+    }
+    int cw = best_cw;
     // too few CTAs to fill the machine (single windows): split further
-    auto ctas = [&](int w) { return (long)n_tasks * ((words_total + w - 1) / w) * ((max_rh + NCC_BAND - 1) / NCC_BAND); };
-    while (cw > 8 && ctas(cw) < 148L * 4) cw = (((cw + 1) / 2) + 7) & ~7;
+    auto ctas_total = [&](int w) { return (long)n_tasks * ((words_total + w - 1) / w) * ((max_rh + NCC_BAND - 1) / NCC_BAND); };
+    while (cw > 8 && ctas_total(cw) < 148L * 4) cw = (((cw + 1) / 2) + 7) & ~7;
     mp->chunk_words = cw;
     mp->smem_pitch = ncc_pitch(cw, ((tw + 3) / 4 + 3) & ~3);
     mp->v_pitch = ncc_vpitch(cw, tw);
