@@ -508,6 +508,7 @@ __device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx
 #define NCC_THREADS 128
 #define NCC_BAND 32
 #define NCC_EPS 1e-5f
+#define NCC_ROWTASK_MAX 16
 
 struct NccCtx {
     const uint8_t *s_win;      // window tile in shared memory
@@ -726,23 +727,36 @@ lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict_
 
     // tiles of the chunk: n8 x (8 words), n4 x (4 words), n1 x (1 word)
     const int n8 = nwords >> 3, n4 = (nwords & 7) >> 2, n1 = nwords & 3;
-    // a warp owns one tile x 32 rows (rows beyond the band are masked, not skipped: the filter's
-    // warp-wide maximum needs all 32 lanes)
     unsigned long long mybest = 0ull;
-    const int ntile = n8 + n4 + n1;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    for (int tile = 0; tile < ntile; tile++) {
-        // tiles are ordered by decreasing cost; the first four go to warps 0..3, later (cheaper)
-        // ones to the warps that got the cheapest tiles: longest-processing-time-first balance
-        const int owner = tile < 4 ? tile : 3 - ((tile - 4) & 3);
-        if (owner != warp) continue;
-        const bool valid = lane < nrows;
-        const int yy = valid ? lane : 0;
-        c.y = y0 + yy;
-        if (tile < n8) ncc_tile<8, MAP>(c, valid, yy, tile * 8, mybest);
-        else if (tile < n8 + n4) ncc_tile<4, MAP>(c, valid, yy, n8 * 8 + (tile - n8) * 4, mybest);
-        else ncc_tile<1, MAP>(c, valid, yy, n8 * 8 + n4 * 4 + (tile - n8 - n4), mybest);
+    if (nrows <= NCC_ROWTASK_MAX) {
+        // Short band (the last rows of a map whose height is not a multiple of 32): lanes own 32
+        // consecutive single-word tiles of ONE row instead of 32 rows of one tile, so a leftover row
+        // costs one cheap warp task rather than a whole band of mostly masked lanes.
+        const int groups = (nwords + 31) >> 5;
+        for (int task = warp; task < nrows * groups; task += NCC_THREADS / 32) {
+            const int row = task / groups, word = (task - row * groups) * 32 + lane;
+            const bool valid = word < nwords;
+            c.y = y0 + row;
+            ncc_tile<1, MAP>(c, valid, row, valid ? word : 0, mybest);
+        }
+    } else {
+        // a warp owns one tile x 32 rows (rows beyond the band are masked, not skipped: the filter's
+        // warp-wide maximum needs all 32 lanes)
+        const int ntile = n8 + n4 + n1;
+        for (int tile = 0; tile < ntile; tile++) {
+            // tiles are ordered by decreasing cost; the first four go to warps 0..3, later (cheaper)
+            // ones to the warps that got the cheapest tiles: longest-processing-time-first balance
+            const int owner = tile < 4 ? tile : 3 - ((tile - 4) & 3);
+            if (owner != warp) continue;
+            const bool valid = lane < nrows;
+            const int yy = valid ? lane : 0;
+            c.y = y0 + yy;
+            if (tile < n8) ncc_tile<8, MAP>(c, valid, yy, tile * 8, mybest);
+            else if (tile < n8 + n4) ncc_tile<4, MAP>(c, valid, yy, n8 * 8 + (tile - n8) * 4, mybest);
+            else ncc_tile<1, MAP>(c, valid, yy, n8 * 8 + n4 * 4 + (tile - n8 - n4), mybest);
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);

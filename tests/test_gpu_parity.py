@@ -347,3 +347,28 @@ def test_batch_size_invariance_full_size(built_lib):
     # accuracy sanity against the synthetic ground truth
     t24 = st.truth(24) - st.truth(0)
     assert abs(outs[0][-1][2] - (t24[0, 0] - t24[1, 0])) < 0.2
+
+
+def test_search_area_doubling_on_gpu(built_lib, oracle_clib):
+    """SURVEY 8f-N1 on the device: a scene jump larger than sArea is recovered by doubling the search
+    area (mark1: LST4:1666-1882 with the shift of the other four windows; spot: LST4:2058-2128).
+    Windows of different sizes share one device pass."""
+    cfg = StackConfig(400, 320, "u8", 24, 10, 12)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 9)]
+    for i in range(4, 9):
+        frames[i] = np.roll(frames[i], (-14, 17), axis=(0, 1))
+    c = st.truth(7)[0].astype(int) + np.array([17, -14])
+    patch = frames[7][c[1] - 12:c[1] + 12, c[0] - 12:c[0] + 12].copy()
+    frames[7][c[1] - 12:c[1] + 12, c[0] - 12:c[0] + 12] = frames[7][c[1] - 12:c[1] + 12, c[0] + 40:c[0] + 64]
+    frames[7][c[1] - 12:c[1] + 12, c[0] + 13:c[0] + 37] = patch
+    op = util.oracle_params(cfg, match_intensity=False, doubling=True, max_s_area=0)
+    seq = O.OracleTracker(op)
+    seq.set_reference(frames[0], st.ref_xy)
+    want = seq.run(frames[1:])
+    assert any(w.tm[1].s_used > cfg.s_area and w.status == 0 for w in want)
+    for mb in (1, 8):
+        with _tracker(cfg, op, max_batch=mb) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            got = t.track(np.stack(frames[1:]))
+            util.compare_records(got, want, label=f"doubling mb={mb}")
