@@ -176,6 +176,25 @@ int lst_track_device_ptrs(lst_ctx *ctx, const void *const *dev_frame_ptrs, int64
 int lst_get_state(const lst_ctx *ctx, double dis[10]);
 int lst_set_state(lst_ctx *ctx, const double dis[10]);
 
+/* ---- several GPUs in one process (north_star item 4) ----------------------------------- */
+/* One lst_ctx, one host worker thread and one stream set per device.  lst_multi_track cuts the slices it
+ * is given into contiguous chunks, one per device, and tracks them concurrently; nothing is reduced
+ * between GPUs and there is no NCCL.  The only coupling is the recurrence (LST4:1327-1328): chunk r starts
+ * from a speculated displacement state (refined by first tracking the last slices of chunk r-1), and
+ * after all chunks finish the boundaries are verified in order on the host -- a chunk whose speculated
+ * (int)dis was wrong is tracked again from the true state.  Records are identical to lst_track's. */
+typedef struct lst_multi lst_multi;
+int lst_multi_create(const lst_params *params, const int32_t *devices, int32_t n_devices, lst_multi **out);
+void lst_multi_destroy(lst_multi *m);
+const char *lst_multi_last_error(const lst_multi *m);
+int lst_multi_set_reference(lst_multi *m, const void *ref_frame, const float ref_xy[10], lst_reference_info *out);
+int lst_multi_track(lst_multi *m, const void *const *frame_ptrs, int64_t first_frame_index, int32_t n_frames,
+                    lst_record *out);
+int lst_multi_get_state(const lst_multi *m, double dis[10]);
+int lst_multi_set_state(lst_multi *m, const double dis[10]);
+/* chunks tracked a second time because their speculated start state placed a window differently */
+int64_t lst_multi_retracked(const lst_multi *m);
+
 /* ---- the primitives, exposed like the reference's public statics ---------------------- */
 /* doMatch_coord_res(src, tpl, 5, subPix, null) on the 8-bit images that reach OpenCV
  * (LST4:2525-2535).  out[3] = {x, y, score}; score_map (nullable) receives the

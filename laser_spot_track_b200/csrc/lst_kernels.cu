@@ -451,13 +451,6 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
 {
     int tiles = (max_w + pp.tile_w - 1) / pp.tile_w;
     size_t smem = preprocess_smem(pp);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(lst_preprocess<LST_PIX_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(lst_preprocess<LST_PIX_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
     (void)max_h;
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
@@ -832,12 +825,6 @@ int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, 
                      const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *score_map,
                      const MatchParams &mp, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        attr_set = true;
-    }
     const int words_total = (max_rw + 3) / 4;
     const int chunks = (words_total + mp.chunk_words - 1) / mp.chunk_words;
     const int bands = (max_rh + NCC_BAND - 1) / NCC_BAND;
@@ -960,6 +947,12 @@ int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_di
 // compute stream, so all kernels ask for the maximum-shared split and can co-reside.
 static void prefer_max_shared_everywhere()
 {
+    // function attributes belong to the current device: this runs once per lst_create
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     const int mx = (int)cudaSharedmemCarveoutMaxShared;
     cudaFuncSetAttribute(lst_init_pass, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_upload, cudaFuncAttributePreferredSharedMemoryCarveout, mx);

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -935,6 +936,151 @@ int lst_track_device_ptrs(lst_ctx *c, const void *const *dev_frame_ptrs, int64_t
                           lst_record *out)
 {
     return track_impl(c, nullptr, 0, dev_frame_ptrs, true, first_frame_index, n_frames, out);
+}
+
+// ---- several GPUs in one process ------------------------------------------------------------------
+struct lst_multi {
+    std::vector<lst_ctx *> ctx;
+    std::string err;
+    double dis[10] = {0};
+    int64_t retracked = 0;
+    int lead_in = 2;
+};
+
+static bool same_windows(const double a[10], const double b[10])
+{
+    for (int i = 0; i < 10; i++)
+        if (jint(a[i]) != jint(b[i])) return false;
+    return true;
+}
+
+int lst_multi_create(const lst_params *params, const int32_t *devices, int32_t n_devices, lst_multi **out)
+{
+    if (!params || !devices || n_devices < 1 || !out) return LST_ERR_INVALID;
+    *out = nullptr;
+    lst_multi *m = new lst_multi();
+    for (int i = 0; i < n_devices; i++) {
+        lst_ctx *c = nullptr;
+        int rc = lst_create(params, devices[i], &c);
+        if (rc != LST_OK) {
+            lst_multi_destroy(m);
+            return rc;   // lst_last_error(NULL) holds the message
+        }
+        m->ctx.push_back(c);
+    }
+    *out = m;
+    return LST_OK;
+}
+
+void lst_multi_destroy(lst_multi *m)
+{
+    if (!m) return;
+    for (lst_ctx *c : m->ctx) lst_destroy(c);
+    delete m;
+}
+
+const char *lst_multi_last_error(const lst_multi *m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+int lst_multi_set_reference(lst_multi *m, const void *ref_frame, const float ref_xy[10], lst_reference_info *out)
+{
+    if (!m) return LST_ERR_INVALID;
+    for (size_t i = 0; i < m->ctx.size(); i++) {
+        int rc = lst_set_reference(m->ctx[i], ref_frame, ref_xy, i == 0 ? out : nullptr);
+        if (rc != LST_OK) {
+            m->err = m->ctx[i]->err;
+            return rc;
+        }
+    }
+    for (int i = 0; i < 10; i++) m->dis[i] = 0.0;
+    return LST_OK;
+}
+
+int lst_multi_get_state(const lst_multi *m, double dis[10])
+{
+    if (!m || !dis) return LST_ERR_INVALID;
+    memcpy(dis, m->dis, sizeof(m->dis));
+    return LST_OK;
+}
+int lst_multi_set_state(lst_multi *m, const double dis[10])
+{
+    if (!m || !dis) return LST_ERR_INVALID;
+    memcpy(m->dis, dis, sizeof(m->dis));
+    return LST_OK;
+}
+int64_t lst_multi_retracked(const lst_multi *m) { return m ? m->retracked : 0; }
+
+int lst_multi_track(lst_multi *m, const void *const *frame_ptrs, int64_t first_frame_index, int32_t n_frames,
+                    lst_record *out)
+{
+    if (!m || !frame_ptrs || !out || n_frames < 0) return LST_ERR_INVALID;
+    const int G = (int)m->ctx.size();
+    if (n_frames == 0) return LST_OK;
+    // contiguous chunks, sizes differing by at most one slice
+    std::vector<int> lo(G + 1, 0);
+    for (int r = 0; r < G; r++) lo[r + 1] = lo[r] + n_frames / G + (r < n_frames % G ? 1 : 0);
+    std::vector<int> rcs(G, LST_OK);
+    std::vector<std::vector<double>> guess(G, std::vector<double>(10)), end(G, std::vector<double>(10));
+    auto work = [&](int r) {
+        lst_ctx *c = m->ctx[r];
+        const int n = lo[r + 1] - lo[r];
+        lst_set_state(c, m->dis);
+        if (r > 0 && n > 0) {   // refine the speculated start state on the last slices of the previous chunk
+            int li = std::min(m->lead_in, lo[r]);
+            if (li > 0) {
+                std::vector<lst_record> tmp(li);
+                rcs[r] = lst_track_ptrs(c, frame_ptrs + lo[r] - li, first_frame_index + lo[r] - li, li, tmp.data());
+                if (rcs[r] != LST_OK) return;
+            }
+        }
+        lst_get_state(c, guess[r].data());
+        if (n > 0) rcs[r] = lst_track_ptrs(c, frame_ptrs + lo[r], first_frame_index + lo[r], n, out + lo[r]);
+        lst_get_state(c, end[r].data());
+    };
+    {
+        std::vector<std::thread> th;
+        for (int r = 1; r < G; r++) th.emplace_back(work, r);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    for (int r = 0; r < G; r++)
+        if (rcs[r] != LST_OK) {
+            m->err = m->ctx[r]->err;
+            return rcs[r];
+        }
+    // boundary verification in order (host side, 10 doubles per boundary)
+    double verified[10];
+    memcpy(verified, end[0].data(), sizeof(verified));
+    if (lo[1] - lo[0] == 0) memcpy(verified, m->dis, sizeof(verified));
+    for (int r = 1; r < G; r++) {
+        const int n = lo[r + 1] - lo[r];
+        if (n == 0) continue;
+        lst_ctx *c = m->ctx[r];
+        bool any_ok = false;
+        if (!same_windows(verified, guess[r].data())) {
+            lst_set_state(c, verified);
+            int rc = lst_track_ptrs(c, frame_ptrs + lo[r], first_frame_index + lo[r], n, out + lo[r]);
+            if (rc != LST_OK) {
+                m->err = c->err;
+                return rc;
+            }
+            lst_get_state(c, end[r].data());
+            m->retracked++;
+            for (int j = lo[r]; j < lo[r + 1]; j++) any_ok |= out[j].status == LST_STATUS_OK;
+        } else {
+            // same windows => same matches; only the carried state of leading skipped slices differs
+            for (int j = lo[r]; j < lo[r + 1]; j++) {
+                if (out[j].status == LST_STATUS_OK) {
+                    any_ok = true;
+                    break;
+                }
+                memcpy(out[j].dis, verified, sizeof(verified));
+            }
+        }
+        if (any_ok) memcpy(verified, end[r].data(), sizeof(verified));
+    }
+    memcpy(m->dis, verified, sizeof(verified));
+    for (lst_ctx *c : m->ctx) lst_set_state(c, verified);
+    return LST_OK;
 }
 
 int lst_get_state(const lst_ctx *c, double dis[10])

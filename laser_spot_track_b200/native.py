@@ -26,6 +26,8 @@ EXPORTS = [
     "lst_device_alloc", "lst_device_free", "lst_device_upload",
     "lst_get_stats", "lst_reset_stats", "lst_set_kernel_timing", "lst_measure_alu_peaks",
     "lst_host_window_for", "lst_host_template_rect", "lst_host_resolve",
+    "lst_multi_create", "lst_multi_destroy", "lst_multi_last_error", "lst_multi_set_reference", "lst_multi_track",
+    "lst_multi_get_state", "lst_multi_set_state", "lst_multi_retracked",
 ]
 
 
@@ -129,6 +131,14 @@ def load() -> C.CDLL:
         "lst_measure_alu_peaks": ([C.c_int, dbl, P(dbl)], C.c_int),
         "lst_host_window_for": ([P(Params), P(i32), dbl, dbl, P(i32)], C.c_int),
         "lst_host_template_rect": ([P(Params), C.c_float, C.c_float, P(i32)], C.c_int),
+        "lst_multi_create": ([P(Params), P(i32), i32, P(vp)], C.c_int),
+        "lst_multi_destroy": ([vp], None),
+        "lst_multi_last_error": ([vp], C.c_char_p),
+        "lst_multi_set_reference": ([vp, vp, P(C.c_float), P(ReferenceInfo)], C.c_int),
+        "lst_multi_track": ([vp, P(vp), i64, i32, P(Record)], C.c_int),
+        "lst_multi_get_state": ([vp, P(dbl)], C.c_int),
+        "lst_multi_set_state": ([vp, P(dbl)], C.c_int),
+        "lst_multi_retracked": ([vp], C.c_int64),
         "lst_host_resolve": ([P(Params), P((i32 * 4) * 5), P(C.c_float), P(dbl), P(dbl), i64, i32, COMPUTE_FN, vp,
                               P(Record), P(Stats)], C.c_int),
     }

@@ -232,6 +232,78 @@ class LaserSpotTrack4:
         self._check(self._lib.lst_device_upload(self._ctx, C.c_void_p(dst), src.ctypes.data, src.nbytes))
 
 
+class LaserSpotTrack4Multi:
+    """The same session spread over several GPUs of one process (lst_multi_*): slices are cut into
+    contiguous chunks, one per device; records are identical to the single-GPU ones."""
+
+    def __init__(self, width: int, height: int, bit_depth: int, devices: Sequence[int], **dialog):
+        proto = LaserSpotTrack4.__new__(LaserSpotTrack4)
+        self._lib = N.load()
+        self.width, self.height, self._np_dtype = width, height, _PIX[bit_depth][1]
+        kw = dict(method=5, templSize=120, sArea=50, markDist=100.0, subPixel=True, matchIntensity=True,
+                  alwaysAutoSkip=True, doubling=False, maxSArea=500, range_mode=N.RANGE_DISPLAY, range_lo=0.0,
+                  range_hi=255.0, quant_mode=N.QUANT_ROUND255, max_batch=0, ingest_mode=0)
+        kw.update(dialog)
+        self.params = N.default_params(
+            width, height, _PIX[bit_depth][0], method=kw["method"], templ_size=kw["templSize"], s_area=kw["sArea"],
+            mark_dist=kw["markDist"], sub_pixel=int(kw["subPixel"]), match_intensity=int(kw["matchIntensity"]),
+            auto_skip=int(kw["alwaysAutoSkip"]), doubling=int(kw["doubling"]), max_s_area=kw["maxSArea"],
+            range_mode=kw["range_mode"], range_lo=kw["range_lo"], range_hi=kw["range_hi"],
+            quant_mode=kw["quant_mode"], max_batch=kw["max_batch"], ingest_mode=kw["ingest_mode"])
+        dev = (C.c_int32 * len(devices))(*devices)
+        self._m = C.c_void_p()
+        rc = self._lib.lst_multi_create(C.byref(self.params), dev, len(devices), C.byref(self._m))
+        if rc != N.LST_OK:
+            self._m = None
+            raise LstError(rc, self._lib.lst_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.lst_multi_destroy(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != N.LST_OK:
+            raise LstError(rc, self._lib.lst_multi_last_error(self._m).decode())
+
+    def set_reference(self, ref_slice, points):
+        fr = np.ascontiguousarray(ref_slice, dtype=self._np_dtype)
+        xy = np.asarray(points, dtype=np.float32).reshape(10)
+        info = N.ReferenceInfo()
+        self._check(self._lib.lst_multi_set_reference(self._m, fr.ctypes.data, xy.ctypes.data_as(C.POINTER(C.c_float)),
+                                                      C.byref(info)))
+        return info
+
+    def track(self, stack, first_frame_index: int = 1):
+        st = np.ascontiguousarray(stack, dtype=self._np_dtype)
+        n = st.shape[0]
+        ptrs = (C.c_void_p * n)(*[st[i].ctypes.data for i in range(n)])
+        out = (N.Record * n)()
+        self._check(self._lib.lst_multi_track(self._m, ptrs, first_frame_index, n, out))
+        return out
+
+    def get_state(self):
+        d = (C.c_double * 10)()
+        self._check(self._lib.lst_multi_get_state(self._m, d))
+        return np.array(d[:])
+
+    @property
+    def retracked(self) -> int:
+        return int(self._lib.lst_multi_retracked(self._m))
+
+
 def results_table(records, ref_info: Optional[N.ReferenceInfo] = None, time_step: float = 1.0,
                   file_label: str = "") -> List[dict]:
     """The ResultsTable rows the plugin's loop appends (LST4:707-718 row 0, LST4:864-875):

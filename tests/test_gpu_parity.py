@@ -372,3 +372,26 @@ def test_search_area_doubling_on_gpu(built_lib, oracle_clib):
             t.set_reference(frames[0], st.ref_xy)
             got = t.track(np.stack(frames[1:]))
             util.compare_records(got, want, label=f"doubling mb={mb}")
+
+
+@pytest.mark.parametrize("n_ctx", [2, 3])
+def test_multi_context_sharding(stack_a, n_ctx):
+    """lst_multi_*: one context + host thread per device, contiguous chunks, chunk-boundary state
+    speculated and verified.  Uses every visible GPU (cycling), so it also runs on one."""
+    from laser_spot_track_b200 import LaserSpotTrack4Multi
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=False)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    ndev = N.load().lst_device_count()
+    devices = [i % ndev for i in range(n_ctx)]
+    with LaserSpotTrack4Multi(cfg.width, cfg.height, 8, devices, templSize=op.templ_size, sArea=op.s_area,
+                              matchIntensity=False, max_batch=16) as t:
+        info = t.set_reference(frames[0], st.ref_xy)
+        assert list(info.mideal) == otr.mideal
+        got = t.track(np.stack(frames[1:31]))
+        util.compare_records(got, want[:30], label=f"multi{n_ctx} a")
+        got2 = t.track(np.stack(frames[31:]), first_frame_index=31)     # the state carries over between calls
+        util.compare_records(got2, want[30:], label=f"multi{n_ctx} b")
+        assert np.array_equal(t.get_state(), np.array([v for d in otr.dis for v in d]))
