@@ -65,6 +65,10 @@ def bench_config(name: str, ring: int) -> StackConfig:
     return StackConfig(c.width, c.height, c.dtype, c.templ_size, c.s_area, n_frames=ring, motion="periodic", period=ring)
 
 
+# DRAM bytes per window of lst_ncc_match from the committed ncu --set full captures (profiles/):
+# config B: 66.9 MB for 2560 windows of 160x160 8-bit pixels (the window is read once; 25.6 KB algorithmic)
+NCU_DRAM_BYTES_PER_WINDOW = {"B": 66.9e6 / 2560}
+
 DEFAULTS = {  # frames per step, ring length, max_batch, cpu sample
     "A": (8192, 256, 2048, 512),
     "B": (10240, 64, 1024, 128),
@@ -308,23 +312,53 @@ def main():
     ok_frames = sum(1 for r in out if r.status == 0)
     trk.set_kernel_timing(False)
 
+    def pcie_peak_gbs():
+        """Measured host->device copy bandwidth of this rank (256 MB pinned cudaMemcpyAsync, all ranks
+        at the same time): the denominator of the end-to-end leg, which is ingest bound."""
+        nbytes = 256 << 20
+        src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            dst.copy_(src, non_blocking=True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return 4 * nbytes / (float(t[0]) * 1e-3) / 1e9
+
     e2e = None
     if not args.no_e2e:
         ms_e2e, wall_e2e, s_e2e = timed(step_e2e, K, W)
+        pcie = pcie_peak_gbs()
         e2e = {"value": world * F * K / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(s_e2e.h2d_bytes // K), "d2h_bytes_per_step": int(s_e2e.d2h_bytes // K),
-               "ms_per_step": ms_e2e / K, "ingest": "pinned host ring of whole slices; only the five search regions (+16 px margin) of each slice cross "
+               "ms_per_step": ms_e2e / K,
+               "pcie": {"achieved_gbs_per_gpu": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9,
+                        "peak_gbs_per_gpu": pcie, "frac": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9 / pcie,
+                        "how": "peak = 256 MB pinned cudaMemcpyAsync H2D, every rank at the same time, slowest rank"},
+               "ingest": "pinned host ring of whole slices; only the five search regions (+16 px margin) of each slice cross "
                          "PCIe, gathered by a kernel on the copy stream while the previous batch computes"}
 
     value = world * F * K / (ms_dev * 1e-3)
     # roofline of the dominant kernel (lst_ncc_match): exact u8 x u8 -> s32 multiply-accumulates
+    win_macs = float((2 * cfg.s_area + 1) ** 2 * cfg.templ_size ** 2)
     macs_per_launch = s_dev.ncc_algorithmic_macs / max(s_dev.ncc_kernel_launches, 1)
     kern_ms = s_dev.ncc_kernel_ms / max(s_dev.ncc_kernel_launches, 1)
     achieved = 2.0 * macs_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None
     peak = 2.0 * peaks[0] / 1e12 if have_peaks else None
     roofline = {
         "bound": "int8-dp4a-pipe", "kernel": "lst_ncc_match", "achieved": achieved, "peak": peak, "unit": "TOP/s",
-        "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+        "frac": (achieved / peak) if (achieved and peak) else None,
+        "traffic": (NCU_DRAM_BYTES_PER_WINDOW.get(args.config) or 0) * (macs_per_launch / max(win_macs, 1)) or None,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel "
+                          "(profiles/), per window, times the windows of an average launch",
         "peak_source": "measured live: IDP.4A.U8.U8 microbenchmark (lst_measure_alu_peaks); MEASURED_PEAKS.json "
                        "holds only HBM and bf16-tensor peaks and this kernel is bound by neither (SURVEY.md 8d)",
         "ffma_peak_tflops": 2.0 * peaks[1] / 1e12 if have_peaks else None,
