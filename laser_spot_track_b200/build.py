@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblst_b200.so")
-SOURCES = ["lst_kernels.cu", "lst_runtime.cu", "lst_host.cpp"]
+SOURCES = ["lst_kernels.cu", "lst_ncc_tc.cu", "lst_runtime.cu", "lst_host.cpp"]
 HEADERS = ["lst_math.h", "lst_host.h", "lst_device.h", os.path.join("..", "..", "include", "lst_b200.h")]
 
 NVCC_FLAGS = [

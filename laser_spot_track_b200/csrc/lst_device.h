@@ -55,6 +55,7 @@ struct DevTemplates {
     TplConst c[kMaxTpl];
     const uint32_t *packed[kMaxTpl];    // [th][kw] words, see build_packed_template
     const uint8_t *raw[kMaxTpl];        // [th][tw] bytes
+    const uint8_t *toeplitz[kMaxTpl];   // tensor-core engine: [th][2*KS][32][16] bytes, see tc_build_table
 };
 
 struct PreprocParams {
@@ -102,5 +103,34 @@ int set_blur_kernel(const float kern[7], const float ksum[7]);
 // picks band/tile split and the shared-memory pitch for lst_ncc_match
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes);
 int measure_alu_peaks(double ms_per_test, double out[2]);
+
+// Tensor-core engine of the match (lst_ncc_tc.cu): Toeplitz table of a template and the launcher.
+// table[v][kc][n][j] = T[v][16*kc + j - n] (0 outside the template), kc < 2*KS, n < 32, j < 16.
+int tc_ksteps(int tw);                                  // KS = ceil((31 + tw) / 32)
+size_t tc_table_bytes(int tw, int th);
+void tc_build_table(const uint8_t *tpl8, int tw, int th, uint8_t *out);
+bool tc_supported(int tw, int th);
+int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
+                  const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, cudaStream_t stream);
+void tc_init_device();
+
+#if defined(__CUDACC__)
+// order-preserving float <-> uint32 keys (argmax by atomicMax on 64-bit keys)
+__device__ __forceinline__ uint32_t f32_key(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t k)
+{
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx)
+{
+    score = score + 0.0f;   // -0 -> +0: minMaxLoc compares values, not bit patterns
+    return ((unsigned long long)f32_key(score) << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+#endif
 
 }  // namespace lst

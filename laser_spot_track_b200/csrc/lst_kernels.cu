@@ -39,16 +39,6 @@ int set_blur_kernel(const float kern[7], const float ksum[7])
 // ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t f32_key(float f)
-{
-    uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_f32(uint32_t k)
-{
-    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return __uint_as_float(u);
-}
 
 template <int PIX>
 __device__ __forceinline__ float load_px(const void *base, size_t idx)
@@ -492,11 +482,6 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
 // OpenCV's double-precision formula (ncc_score), whose float32 result is what is compared and
 // reported.  Nearly flat windows (B <= ~N/2, where OpenCV's "avoid rounding errors" branch may
 // apply) always take the exact path.
-__device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx)
-{
-    score = score + 0.0f;   // -0 -> +0: minMaxLoc compares values, not bit patterns
-    return ((unsigned long long)f32_key(score) << 32) | (unsigned long long)(0xffffffffu - idx);
-}
 
 #define NCC_THREADS 128
 #define NCC_BAND 32

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -46,6 +47,9 @@ struct lst_ctx : public Executor {
     DevTemplates *d_tpls = nullptr;
     uint32_t *d_packed[kMaxTpl] = {nullptr};
     uint8_t *d_raw[kMaxTpl] = {nullptr};
+    uint8_t *d_toep[kMaxTpl] = {nullptr};   // tensor-core engine: Toeplitz tables
+    size_t toep_cap[kMaxTpl] = {0};
+    int ncc_engine = 0;                     // 0 = IDP.4A (lst_ncc_match), 1 = tensor cores (lst_ncc_tc)
     size_t packed_cap[kMaxTpl] = {0}, raw_cap[kMaxTpl] = {0};
     // per-pass scratch
     int task_cap = 0;
@@ -237,6 +241,18 @@ int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th)
     h_tpls.c[slot] = c;
     h_tpls.packed[slot] = d_packed[slot];
     h_tpls.raw[slot] = d_raw[slot];
+    std::vector<uint8_t> toep;
+    if (ncc_engine == 1 && tc_supported(tw, th)) {
+        toep.resize(tc_table_bytes(tw, th));
+        tc_build_table(tpl8, tw, th, toep.data());
+        if (toep.size() > toep_cap[slot]) {
+            CU(regrow(&d_toep[slot], toep.size()));
+            toep_cap[slot] = toep.size();
+        }
+        CU(cudaMemcpyAsync(d_toep[slot], toep.data(), toep.size(), cudaMemcpyHostToDevice, s_compute));
+        h_tpls.toeplitz[slot] = d_toep[slot];
+        stats.h2d_bytes += (int64_t)toep.size();
+    }
     CU(cudaMemcpyAsync(d_tpls, &h_tpls, sizeof(DevTemplates), cudaMemcpyHostToDevice, s_compute));
     CU(cudaStreamSynchronize(s_compute));   // sh / h_tpls are pageable: finish before they go away
     stats.h2d_bytes += (int64_t)(sh.size() * 4 + (size_t)tw * th + sizeof(DevTemplates));
@@ -360,8 +376,15 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             tl.macs = macs;
             CU(cudaEventRecord(tl.e0, s_compute));
         }
-        launches += launch_ncc_match(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_best,
-                                     map_out_host ? d_map : nullptr, mp, s_compute);
+        bool use_tc = ncc_engine == 1 && !map_out_host && tc_supported(max_tw, max_th);
+        if (use_tc)
+            for (int i = 0; i < n && use_tc; i++) use_tc = h_tpls.toeplitz[h_tasks[i].tpl] != nullptr;
+        int tcl = use_tc ? launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_best, s_compute) : -1;
+        if (tcl >= 0)
+            launches += tcl;
+        else
+            launches += launch_ncc_match(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_best,
+                                         map_out_host ? d_map : nullptr, mp, s_compute);
         if (timing) {
             CU(cudaEventRecord(tl.e1, s_compute));
             timed.push_back(tl);
@@ -517,6 +540,11 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
     for (int i = 0; i < 2; i++)
         if ((ce = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
     if ((ce = cudaMalloc((void **)&c->d_tpls, sizeof(DevTemplates))) != cudaSuccess) return bail(ce, "cudaMalloc");
+    {
+        const char *e = getenv("LST_NCC_ENGINE");
+        c->ncc_engine = (e && (!strcmp(e, "tc") || !strcmp(e, "1"))) ? 1 : 0;
+        tc_init_device();
+    }
     float kern[7], ksum[7];
     make_gaussian_kernel(kern, ksum);
     if (set_blur_kernel(kern, ksum) != 0) return bail(cudaGetLastError(), "blur kernel upload");
@@ -532,6 +560,7 @@ void lst_destroy(lst_ctx *c)
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
     for (int i = 0; i < kMaxTpl; i++) {
         cudaFree(c->d_packed[i]);
+        cudaFree(c->d_toep[i]);
         cudaFree(c->d_raw[i]);
     }
     cudaFree(c->d_tpls);
