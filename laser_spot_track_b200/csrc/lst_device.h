@@ -110,8 +110,9 @@ int tc_ksteps(int tw);                                  // KS = ceil((31 + tw) /
 size_t tc_table_bytes(int tw, int th);
 void tc_build_table(const uint8_t *tpl8, int tw, int th, uint8_t *out);
 bool tc_supported(int tw, int th);
-int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                  const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, cudaStream_t stream);
+int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_w, int max_rw, int max_rh, int tw, int th,
+                  const DevTemplates *tpls, const uint8_t *win8, uint32_t *wsum, uint32_t *wsq,
+                  unsigned long long *best, cudaStream_t stream);
 void tc_init_device();
 
 #if defined(__CUDACC__)

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/lst_b200.h"
@@ -29,8 +30,8 @@ namespace lst {
 #define TC_M 128          // result rows per CTA (TMEM lanes)
 #define TC_NB 32          // result columns per MMA (N)
 #define TC_MAXNB 4        // column blocks per CTA (128 TMEM columns)
-#define TC_STAGES 4
-#define TC_THREADS 192    // warps 0-3 epilogue, warp 4 MMA issue + TMEM alloc, warp 5 TMA producer
+#define TC_STAGES 3
+#define TC_THREADS 160    // warps 0-3 epilogue, warp 4: one thread feeds the ring (TMA) and issues the MMAs; TMEM alloc
 #define TC_EPS 1e-5f
 
 int tc_ksteps(int tw) { return (TC_NB - 1 + tw + 31) / 32; }
@@ -124,23 +125,130 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- window sums for the tensor-core engine ------------------------------------------------------
+// The IDP.4A engine derives the sums of I and I^2 under the template footprint inside its CTAs; the
+// tensor-core engine wants its shared memory for operands and its warps for the epilogue, so the
+// sums are produced once per window by this kernel and read back (L2) by the epilogue.
+// CTA = 32 result rows of one window: vertical sliding sums per column, then one prefix scan per row
+// (warp shuffles) turns them into box sums: out[x] = P[x + tw - 1] - P[x - 1].
+#define BS_ROWS 32
+
+__global__ void __launch_bounds__(256)
+lst_box_sums(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
+             uint32_t *__restrict__ wsum, uint32_t *__restrict__ wsq, int wp)
+{
+    extern __shared__ __align__(16) uint8_t smem_bs[];
+    const DevTask t = tasks[blockIdx.y];
+    const int tw = tpls->c[t.tpl].tw, th = tpls->c[t.tpl].th;
+    const int y0 = blockIdx.x * BS_ROWS;
+    if (y0 >= t.rh) return;
+    const int nrows = min(BS_ROWS, t.rh - y0);
+    const int trows = nrows + th - 1;
+    uint32_t *P2 = (uint32_t *)smem_bs;                 // [BS_ROWS][wp]  sums of squares, then prefix
+    uint32_t *P1 = P2 + (size_t)BS_ROWS * wp;           // [BS_ROWS][wp]  sums, then prefix
+    uint8_t *tile = (uint8_t *)(P1 + (size_t)BS_ROWS * wp);   // [trows][pitch]
+    const int pitch = t.pitch;
+    {
+        const uint8_t *src = win8 + t.win_off + (size_t)y0 * pitch;
+        const int vec = pitch / 16;
+        for (int i = threadIdx.x; i < trows * vec; i += blockDim.x) {
+            int r = i / vec, c = (i - r * vec) * 16;
+            *(uint4 *)(tile + (size_t)r * pitch + c) = *(const uint4 *)(src + (size_t)r * pitch + c);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < t.w; c += blockDim.x) {
+        uint32_t s = 0, q = 0;
+        for (int v = 0; v < th; v++) {
+            uint32_t p = tile[(size_t)v * pitch + c];
+            s += p;
+            q += p * p;
+        }
+        P1[c] = s;
+        P2[c] = q;
+        for (int r = 1; r < nrows; r++) {
+            uint32_t a = tile[(size_t)(r + th - 1) * pitch + c], b = tile[(size_t)(r - 1) * pitch + c];
+            s += a - b;
+            q += a * a - b * b;
+            P1[(size_t)r * wp + c] = s;
+            P2[(size_t)r * wp + c] = q;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < nrows; r += 8) {
+        uint32_t *p1 = P1 + (size_t)r * wp, *p2 = P2 + (size_t)r * wp;
+        uint32_t c1 = 0, c2 = 0;
+        for (int b = 0; b < t.w; b += 32) {
+            const int c = b + lane;
+            uint32_t a1 = c < t.w ? p1[c] : 0u, a2 = c < t.w ? p2[c] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t n1 = __shfl_up_sync(0xffffffffu, a1, o), n2 = __shfl_up_sync(0xffffffffu, a2, o);
+                if (lane >= o) {
+                    a1 += n1;
+                    a2 += n2;
+                }
+            }
+            a1 += c1;
+            a2 += c2;
+            if (c < t.w) {
+                p1[c] = a1;
+                p2[c] = a2;
+            }
+            c1 = __shfl_sync(0xffffffffu, a1, 31);
+            c2 = __shfl_sync(0xffffffffu, a2, 31);
+        }
+    }
+    __syncthreads();
+    // Output layout [band of 32 rows][x][row in band]: the epilogue of lst_ncc_tc owns one row per lane
+    // and walks x, so one warp load is 32 consecutive words.  Lanes = rows here too: the prefix arrays
+    // are read with stride wp (odd: conflict-free) and written 128 bytes at a time.
+    {
+        uint32_t *o1 = wsum + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS;
+        uint32_t *o2 = wsq + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS;
+        const uint32_t *p1 = P1 + (size_t)lane * wp, *p2 = P2 + (size_t)lane * wp;
+        for (int x = warp; x < t.rw; x += 8) {
+            if (lane < nrows) {
+                uint32_t lo1 = x > 0 ? p1[x - 1] : 0u, lo2 = x > 0 ? p2[x - 1] : 0u;
+                o1[(size_t)x * BS_ROWS + lane] = p1[x + tw - 1] - lo1;
+                o2[(size_t)x * BS_ROWS + lane] = p2[x + tw - 1] - lo2;
+            }
+        }
+    }
+}
+
+// The exact (double-precision, OpenCV order) score of one candidate position, out of line: the
+// epilogue visits 32 positions with unrolled code and only a few of them get here, so the long
+// division / square-root sequences must not be replicated 32 times (instruction cache).
+__device__ __noinline__ unsigned long long tc_exact_key(uint32_t corr, const uint32_t *ws, const uint32_t *wq, double inv_area,
+                                                        double mean, double norm, uint32_t idx)
+{
+    const uint32_t s = __ldg(ws), sq = __ldg(wq);
+    const float sc = ncc_score((double)corr, (double)s, (double)sq, inv_area, mean, norm, 0);
+    return pack_key(sc, idx);
+}
+
 struct TcParams {
     int rows_a;       // window rows staged per CTA: TC_M + max_th - 1
     int kc_a;         // 16-byte column chunks staged per CTA
     int ks;           // K steps (32 bytes) per column block
-    int vp;           // pitch of the per-warp vertical-sum scratch (odd)
     int nb_per_cta;   // column blocks per CTA
+    int vb;           // template rows (Toeplitz blocks) per ring stage
+    unsigned long long *dbg;   // optional: per-CTA phase clocks (LST_TC_DEBUG)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 4)
 lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
-           unsigned long long *__restrict__ best, TcParams tp)
+           const uint32_t *__restrict__ wsum, const uint32_t *__restrict__ wsq, unsigned long long *__restrict__ best,
+           TcParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem_tc[];
     __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done;
     __shared__ uint32_t s_tmem;
     __shared__ unsigned long long s_best[4];
 
+    const long long clk0 = clock64();
     const DevTask t = tasks[blockIdx.y];
     const TplConst tc = tpls->c[t.tpl];
     const int tw = tc.tw, th = tc.th;
@@ -158,11 +266,13 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
     const int nbc = min(tp.nb_per_cta, nb_total - nb0);     // column blocks of this CTA
     const int x0 = nb0 * TC_NB, y0 = yt * TC_M;
     const int ROWS = tp.rows_a, KCA = tp.kc_a, KS = tp.ks;
-    const uint32_t bv_bytes = (uint32_t)(2 * KS * TC_NB * 16);
+    const uint32_t bv_bytes = (uint32_t)(2 * KS * TC_NB * 16);   // one Toeplitz block B_v
+    const int VB = tp.vb;                                        // blocks per ring stage
+    const uint32_t st_bytes = bv_bytes * (uint32_t)VB;
+    const int nsteps = (th + VB - 1) / VB;
 
     uint8_t *sA = smem_tc;                                          // [KCA][ROWS][16]
-    uint8_t *sB = sA + (size_t)KCA * ROWS * 16;                     // [TC_STAGES][2*KS][32][16]
-    uint8_t *sV = sB + (size_t)TC_STAGES * bv_bytes;                // 4 warps x ([32][vp] u32 + [32][vp] u16)
+    uint8_t *sB = sA + (size_t)KCA * ROWS * 16;                     // [TC_STAGES][VB][2*KS][32][16]
 
     // ---- stage the window: rows [y0, y0 + ROWS), byte columns [x0, x0 + 16*KCA), zero filled ----
     {
@@ -193,130 +303,119 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    const long long clk1 = clock64();
+    long long clk2 = clk1, clk3 = clk1;
 
-    if (warp == 5) {
-        // ---- TMA producer: stream the Toeplitz blocks B_v through the ring ----
-        if (lane == 0) {
-            const uint8_t *table = tpls->toeplitz[t.tpl];
-            for (int v = 0; v < th; v++) {
-                const int s = v % TC_STAGES;
-                if (v >= TC_STAGES) mbar_wait(&bar_empty[s], ((v / TC_STAGES) - 1) & 1);
-                mbar_expect_tx(&bar_full[s], bv_bytes);
-                bulk_g2s(sB + (size_t)s * bv_bytes, table + (size_t)v * bv_bytes, bv_bytes, &bar_full[s]);
-            }
-        }
-    } else if (warp == 4) {
+    if (warp == 4) {
         // ---- MMA issuer ----
+        // One thread issues everything, so the loop body must be a handful of instructions: the
+        // descriptors are 64-bit integers whose low field is (address >> 4), advanced by plain adds.
         if (lane == 0) {
             const uint32_t idesc = instr_desc_u8(TC_M, TC_NB);
-            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-            for (int v = 0; v < th; v++) {
-                const int s = v % TC_STAGES;
-                mbar_wait(&bar_full[s], (v / TC_STAGES) & 1);
+            const uint64_t a_desc0 = smem_desc(smem_u32(sA), (uint32_t)ROWS * 16, 128);
+            const uint64_t b_desc0 = smem_desc(smem_u32(sB), TC_NB * 16, 128);
+            const uint64_t a_kstep = (uint64_t)(2 * ROWS);            // two 16-byte column chunks, in 16-byte units
+            const uint64_t b_kstep = (uint64_t)(2 * TC_NB);
+            const uint64_t b_vstep = (uint64_t)(bv_bytes >> 4), b_sstep = (uint64_t)(st_bytes >> 4);
+            // ring producer and MMA issue in one thread: the copy for step st+1 goes out before the MMAs
+            // of step st; its slot was last read by the MMAs of step st-2 (3 stages), long finished
+            const uint8_t *table = tpls->toeplitz[t.tpl];
+            auto feed = [&](int st) {
+                const int s = st % TC_STAGES;
+                const int nv = min(VB, th - st * VB);
+                if (st >= TC_STAGES) mbar_wait(&bar_empty[s], ((st / TC_STAGES) - 1) & 1);
+                mbar_expect_tx(&bar_full[s], bv_bytes * (uint32_t)nv);
+                bulk_g2s(sB + (size_t)s * st_bytes, table + (size_t)st * st_bytes, bv_bytes * (uint32_t)nv, &bar_full[s]);
+            };
+            feed(0);
+            uint32_t acc = 0;
+            int v = 0;
+            for (int st = 0; st < nsteps; st++) {
+                const int s = st % TC_STAGES;
+                const int nv = min(VB, th - st * VB);
+                if (st + 1 < nsteps) feed(st + 1);
+                mbar_wait(&bar_full[s], (st / TC_STAGES) & 1);
                 tc_fence_after();
-                for (int nb = 0; nb < nbc; nb++) {
-                    for (int ks = 0; ks < KS; ks++) {
-                        // window columns 32*nb + 32*ks .. +31 of rows v .. v+127  x  B_v k-step ks
-                        const uint32_t a_addr = a_base + (uint32_t)(((2 * nb + 2 * ks) * ROWS + v) * 16);
-                        const uint32_t b_addr = b_base + (uint32_t)(s * bv_bytes + (2 * ks) * TC_NB * 16);
-                        mma_i8(tmem + (uint32_t)(nb * TC_NB), smem_desc(a_addr, (uint32_t)ROWS * 16, 128),
-                               smem_desc(b_addr, TC_NB * 16, 128), idesc, (v > 0 || ks > 0) ? 1u : 0u);
+                uint64_t b_v = b_desc0 + (uint64_t)s * b_sstep;
+                for (int vv = 0; vv < nv; vv++, v++, b_v += b_vstep) {
+                    uint64_t a_nb = a_desc0 + (uint64_t)v;            // rows v .. v+127
+                    for (int nb = 0; nb < nbc; nb++, a_nb += a_kstep) {
+                        uint64_t a_d = a_nb, b_d = b_v;
+                        const uint32_t d = tmem + (uint32_t)(nb * TC_NB);
+                        mma_i8(d, a_d, b_d, idesc, acc);              // first k-step: overwrites D only for v == 0
+#pragma unroll 1
+                        for (int ks = 1; ks < KS; ks++) {
+                            a_d += a_kstep;
+                            b_d += b_kstep;
+                            mma_i8(d, a_d, b_d, idesc, 1u);
+                        }
                     }
+                    acc = 1u;
                 }
                 tc_commit(&bar_empty[s]);     // the ring slot is free once these MMAs have read it
             }
             tc_commit(&bar_done);
         }
     } else {
-        // ---- epilogue warps: rows 32*warp .. +31 of the tile ----
-        const int vp = tp.vp;
-        uint32_t *v2 = (uint32_t *)(sV + (size_t)warp * ((size_t)32 * vp * 6));
-        uint16_t *v1 = (uint16_t *)(v2 + (size_t)32 * vp);
+        // ---- epilogue warps: rows 32*warp .. +31 of the tile (TMEM lanes of this warp) ----
         const int yy = 32 * warp + lane;                  // row of the tile owned by this lane
         const int y = y0 + yy;
         const bool row_ok = y < t.rh;
-        const long long N = (long long)tw * th, tsum = (long long)tc.tsum;
+        const uint32_t N = (uint32_t)(tw * th), tsum = tc.tsum;
+        const long long Nflat = (long long)N + (long long)(N >> 5);
+        // sums of this lane's row: [band][x][row in band] (see lst_box_sums), band = y / 32
+        const size_t rowoff = t.sum_off + (size_t)(y0 / 32 + warp) * t.rw * 32 + lane;
         unsigned long long mybest = 0ull;
-        bool waited = false;
+        mbar_wait(&bar_done, 0);
+        tc_fence_after();
+        clk2 = clock64();
         for (int nb = 0; nb < nbc; nb++) {
-            // vertical sliding sums of I and I^2 for rows 32*warp..+31, window columns 32*nb .. 32*nb + 31 + tw - 1
-            const int ncols = TC_NB + tw - 1;
-            __syncwarp();
-            for (int cc = lane; cc < ncols; cc += 32) {
-                const int col = TC_NB * nb + cc;          // byte column inside the staged tile
-                const uint8_t *colp = sA + ((size_t)(col >> 4) * ROWS) * 16 + (col & 15);
-                uint32_t s = 0, q = 0;
-                const int r0 = 32 * warp;
-                for (int v = 0; v < th; v++) {
-                    uint32_t p = colp[(size_t)(r0 + v) * 16];
-                    s += p;
-                    q += p * p;
-                }
-                v1[cc] = (uint16_t)s;
-                v2[cc] = q;
-                for (int r = 1; r < 32; r++) {
-                    uint32_t a = colp[(size_t)(r0 + r + th - 1) * 16], b = colp[(size_t)(r0 + r - 1) * 16];
-                    s += a - b;
-                    q += a * a - b * b;
-                    v1[r * vp + cc] = (uint16_t)s;
-                    v2[r * vp + cc] = q;
-                }
-            }
-            __syncwarp();
-            if (!waited) {
-                mbar_wait(&bar_done, 0);
-                tc_fence_after();
-                waited = true;
-            }
             uint32_t corr[32];
             tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(nb * TC_NB), corr);
             const int xb = x0 + TC_NB * nb;
             const int np = row_ok ? min(32, t.rw - xb) : 0;
-            const uint16_t *vr = v1 + lane * vp;
-            const uint32_t *vr2 = v2 + lane * vp;
-            uint32_t s0 = 0, sq0 = 0;
-            if (np > 0)
-                for (int u = 0; u < tw; u++) {
-                    s0 += vr[u];
-                    sq0 += vr2[u];
-                }
-            // pass 1: float32 filter, warp-wide maximum (see lst_ncc_match)
+            const uint32_t *ws = wsum + rowoff + (size_t)xb * 32, *wq = wsq + rowoff + (size_t)xb * 32;
+            // pass 1: float32 filter score of the 32 positions of this lane's row (all loads of a half
+            // are issued before they are used), warp-wide maximum.  3e38 marks "nearly flat: always exact".
+            float sf[32];
             float tmax = -3.0e38f;
-            {
-                uint32_t s = s0, sq = sq0;
 #pragma unroll
-                for (int p = 0; p < 32; p++) {
-                    if (p < np) {
-                        const long long A = N * (long long)corr[p] - (long long)s * tsum;
-                        const long long B = N * (long long)sq - (long long)s * (long long)s;
-                        if (2 * B > N + (N >> 5)) tmax = fmaxf(tmax, (float)A * rsqrtf((float)B) * tc.inv_sqrt_c);
-                        s += (uint32_t)vr[p + tw] - (uint32_t)vr[p];
-                        sq += vr2[p + tw] - vr2[p];
+            for (int h = 0; h < 2; h++) {
+                uint32_t sv[16], qv[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int p = 16 * h + i;
+                    const int pc = p < np ? p : 0;            // clamped: the load is always legal
+                    sv[i] = __ldg(ws + pc * 32);
+                    qv[i] = __ldg(wq + pc * 32);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int p = 16 * h + i;
+                    // 32 x 32 -> 64-bit products (IMAD.WIDE.U32): every factor fits 32 bits
+                    const long long A = (long long)((unsigned long long)N * corr[p]) - (long long)((unsigned long long)sv[i] * tsum);
+                    const long long B = (long long)((unsigned long long)N * qv[i]) - (long long)((unsigned long long)sv[i] * sv[i]);
+                    float f;
+                    if (p >= np) f = -3.0e38f;
+                    else if (2 * B <= Nflat) f = 3.0e38f;
+                    else {
+                        f = (float)A * rsqrtf((float)B) * tc.inv_sqrt_c;
+                        tmax = fmaxf(tmax, f);
                     }
+                    sf[p] = f;
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-            // pass 2: exact double-precision score of the candidates
-            {
-                uint32_t s = s0, sq = sq0;
-                const uint32_t rowidx = (uint32_t)y * (uint32_t)t.rw;
+            // pass 2: OpenCV's double-precision score for the candidates only
+            const uint32_t rowidx = (uint32_t)y * (uint32_t)t.rw;
+            const float thr = tmax - TC_EPS;
 #pragma unroll
-                for (int p = 0; p < 32; p++) {
-                    if (p < np) {
-                        const long long A = N * (long long)corr[p] - (long long)s * tsum;
-                        const long long B = N * (long long)sq - (long long)s * (long long)s;
-                        bool exact;
-                        if (2 * B <= N + (N >> 5)) exact = true;
-                        else exact = (float)A * rsqrtf((float)B) * tc.inv_sqrt_c >= tmax - TC_EPS;
-                        if (exact) {
-                            const float sc = ncc_score((double)corr[p], (double)s, (double)sq, tc.inv_area, tc.mean, tc.norm, 0);
-                            const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(xb + p));
-                            mybest = key > mybest ? key : mybest;
-                        }
-                        s += (uint32_t)vr[p + tw] - (uint32_t)vr[p];
-                        sq += vr2[p + tw] - vr2[p];
-                    }
+            for (int p = 0; p < 32; p++) {
+                if (sf[p] >= thr && p < np) {
+                    const unsigned long long key =
+                        tc_exact_key(corr[p], ws + p * 32, wq + p * 32, tc.inv_area, tc.mean, tc.norm, rowidx + (uint32_t)(xb + p));
+                    mybest = key > mybest ? key : mybest;
                 }
             }
         }
@@ -325,6 +424,14 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
             mybest = other > mybest ? other : mybest;
         }
         if (lane == 0) s_best[warp] = mybest;
+        clk3 = clock64();
+        if (tp.dbg && threadIdx.x == 0 && blockIdx.y < 4096) {
+            unsigned long long *d = tp.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 4;
+            d[0] = (unsigned long long)(clk1 - clk0);
+            d[1] = (unsigned long long)(clk2 - clk1);
+            d[2] = (unsigned long long)(clk3 - clk2);
+            d[3] = (unsigned long long)clk0;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -346,8 +453,11 @@ static size_t tc_smem(int tw, int th, TcParams *tp, int max_rw)
     tp->ks = tc_ksteps(tw);
     tp->rows_a = TC_M + th - 1;
     tp->kc_a = 2 * (tp->nb_per_cta - 1) + 2 * tp->ks;
-    tp->vp = (TC_NB + tw) | 1;
-    return (size_t)tp->kc_a * tp->rows_a * 16 + (size_t)TC_STAGES * 2 * tp->ks * TC_NB * 16 + (size_t)4 * 32 * tp->vp * 6 + 64;
+    const size_t bv = (size_t)2 * tp->ks * TC_NB * 16;
+    tp->vb = (int)(6144 / bv);                        // ~6 KB per ring stage: 3 stages + the window stay under 56 KB
+    if (tp->vb < 1) tp->vb = 1;
+    if (tp->vb > th) tp->vb = th;
+    return (size_t)tp->kc_a * tp->rows_a * 16 + (size_t)TC_STAGES * tp->vb * bv + 64;
 }
 
 void tc_init_device()
@@ -355,27 +465,58 @@ void tc_init_device()
     cudaError_t e = cudaFuncSetAttribute(lst_ncc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
     if (e != cudaSuccess) fprintf(stderr, "lst_ncc_tc: MaxDynamicSharedMemorySize: %s\n", cudaGetErrorString(e));
     cudaFuncSetAttribute(lst_ncc_tc, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lst_box_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
+    cudaFuncSetAttribute(lst_box_sums, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     cudaGetLastError();
 }
 
-int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                  const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, cudaStream_t stream)
+int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_w, int max_rw, int max_rh, int tw, int th,
+                  const DevTemplates *tpls, const uint8_t *win8, uint32_t *wsum, uint32_t *wsq,
+                  unsigned long long *best, cudaStream_t stream)
 {
     TcParams tp;
     size_t smem = tc_smem(tw, th, &tp, max_rw);
-    if (smem > 227 * 1024) return -1;
+    if (smem > 226 * 1024) return -1;
+    static unsigned long long *dbg = nullptr;
+    static int dbg_on = -1;
+    if (dbg_on < 0) {
+        dbg_on = getenv("LST_TC_DEBUG") ? 1 : 0;
+        if (dbg_on) cudaMalloc((void **)&dbg, 4096 * 16 * 4 * sizeof(unsigned long long));
+    }
+    tp.dbg = dbg_on ? dbg : nullptr;
+    const int wp = ((max_w + 15) & ~15) | 1;
+    const size_t bs_smem = (size_t)2 * BS_ROWS * wp * 4 + (size_t)(BS_ROWS + th - 1) * ((max_w + 15) & ~15) + 16;
+    if (bs_smem > 226 * 1024) return -1;
     const int nb_total = (max_rw + TC_NB - 1) / TC_NB;
     const int xchunks = (nb_total + tp.nb_per_cta - 1) / tp.nb_per_cta;
     const int ytiles = (max_rh + TC_M - 1) / TC_M;
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
+        dim3 bgrid((max_rh + BS_ROWS - 1) / BS_ROWS, n);
+        lst_box_sums<<<bgrid, 256, bs_smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, wp);
+        launches++;
         dim3 grid(xchunks * ytiles, n);
-        lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(tasks + base, tpls, win8, best + base, tp);
+        lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, best + base, tp);
         cudaError_t e = cudaPeekAtLastError();
         if (e != cudaSuccess)
             fprintf(stderr, "lst_ncc_tc launch failed: %s (grid %d x %d, smem %zu)\n", cudaGetErrorString(e), grid.x, grid.y, smem);
         launches++;
+    }
+    if (dbg_on && n_tasks >= 1024) {
+        cudaStreamSynchronize(stream);
+        const int ncta = xchunks * ytiles * (n_tasks < 4096 ? n_tasks : 4096);
+        unsigned long long *h = (unsigned long long *)malloc((size_t)ncta * 32);
+        cudaMemcpy(h, dbg, (size_t)ncta * 32, cudaMemcpyDeviceToHost);
+        double a = 0, b = 0, c = 0;
+        for (int i = 0; i < ncta; i++) {
+            a += (double)h[4 * i];
+            b += (double)h[4 * i + 1];
+            c += (double)h[4 * i + 2];
+        }
+        fprintf(stderr, "lst_ncc_tc phases (cycles, mean over %d CTAs): stage %.0f  mma-wait %.0f  epilogue %.0f  smem %zu\n", ncta,
+                a / ncta, b / ncta, c / ncta, smem);
+        free(h);
     }
     return launches;
 }

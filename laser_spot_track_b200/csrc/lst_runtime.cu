@@ -61,6 +61,8 @@ struct lst_ctx : public Executor {
     size_t win8_cap = 0;
     float *d_map = nullptr;
     size_t map_cap = 0;
+    uint32_t *d_wsum = nullptr, *d_wsq = nullptr;   // tensor-core engine: window sums per result position
+    size_t sum_cap = 0;
     // surface table (where each task's pixels live) + slice ring (whole-slice ingest)
     int frame_cap = 0;
     Surface *d_surf = nullptr, *h_surf = nullptr;
@@ -335,7 +337,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         d.win_off = win_off;
         d.sum_off = sum_off;
         win_off += ((size_t)d.pitch * d.h + 255) & ~(size_t)255;
-        sum_off += ((size_t)d.rw * d.rh + 31) & ~(size_t)31;
+        sum_off += (size_t)d.rw * (((size_t)d.rh + 31) & ~(size_t)31);   // banded layout of the window sums pads rows to 32
         max_w = std::max(max_w, d.w);
         max_h = std::max(max_h, d.h);
     }
@@ -379,7 +381,21 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         bool use_tc = ncc_engine == 1 && !map_out_host && tc_supported(max_tw, max_th);
         if (use_tc)
             for (int i = 0; i < n && use_tc; i++) use_tc = h_tpls.toeplitz[h_tasks[i].tpl] != nullptr;
-        int tcl = use_tc ? launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_best, s_compute) : -1;
+        if (use_tc && sum_off + 32 > sum_cap) {
+            CU(cudaStreamSynchronize(s_compute));
+            size_t cap = std::max(sum_off + 32, sum_cap + sum_cap / 2);
+            CU(regrow(&d_wsum, cap));
+            CU(regrow(&d_wsq, cap));
+            sum_cap = cap;
+        }
+        int tcl = use_tc ? launch_ncc_tc(d_tasks, n, max_w, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq,
+                                         d_best, s_compute)
+                         : -1;
+        if (use_tc && tcl < 0) {
+            static bool warned = false;
+            if (!warned) fprintf(stderr, "lst_b200: tensor-core match engine not applicable to this window/template size; using IDP.4A\n");
+            warned = true;
+        }
         if (tcl >= 0)
             launches += tcl;
         else
@@ -433,7 +449,7 @@ int lst_ctx::compute(const lst_task *tasks, int n, lst_task_result *results)
         while (j < n) {
             const lst_task &t = tasks[j];
             size_t pitch = (t.ww + 15) & ~15;
-            size_t need = pitch * t.wh + 256;
+            size_t need = pitch * t.wh + 256 + (ncc_engine == 1 ? 2 * sizeof(uint32_t) * ((size_t)t.ww * t.wh + 32) : 0);
             if (j > i && bytes + need > scratch_limit) break;
             bytes += need;
             j++;
@@ -570,6 +586,8 @@ void lst_destroy(lst_ctx *c)
     cudaFree(c->d_results);
     cudaFree(c->d_win8);
     cudaFree(c->d_map);
+    cudaFree(c->d_wsum);
+    cudaFree(c->d_wsq);
     cudaFree(c->d_surf);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_roi[i]);
