@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames of the CPU baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--engine", default="auto", choices=["auto", "dp4a", "tc"], help="match kernel: tensor cores (default when the template fits) or IDP.4A")
     return ap.parse_args()
 
 
@@ -67,7 +68,7 @@ def bench_config(name: str, ring: int) -> StackConfig:
 
 # DRAM bytes per window of lst_ncc_match from the committed ncu --set full captures (profiles/):
 # config B: 66.9 MB for 2560 windows of 160x160 8-bit pixels (the window is read once; 25.6 KB algorithmic)
-NCU_DRAM_BYTES_PER_WINDOW = {"B": 66.9e6 / 2560}
+NCU_DRAM_BYTES_PER_WINDOW = {("B", False): 66.9e6 / 2560, ("B", True): 67.5e6 / 2560}
 
 DEFAULTS = {  # frames per step, ring length, max_batch, cpu sample
     "A": (8192, 256, 2048, 512),
@@ -233,7 +234,9 @@ def main():
 
     lib = N.load()
     trk = LaserSpotTrack4(cfg.width, cfg.height, bits, device=local_rank, templSize=cfg.templ_size, sArea=cfg.s_area,
-                          max_batch=args.max_batch or mb_d)
+                          max_batch=args.max_batch or mb_d, ncc_engine={"auto": 0, "dp4a": 1, "tc": 2}[args.engine])
+    env_engine = os.environ.get("LST_NCC_ENGINE")
+    use_tc = (args.engine != "dp4a" and env_engine != "dp4a" and cfg.templ_size <= 181) or env_engine == "tc"
     # ring of distinct slices: pinned host copy (e2e leg) and HBM copy (value leg)
     host_ring = C.c_void_p()
     assert lib.lst_alloc_pinned(ring * fb, C.byref(host_ring)) == 0
@@ -301,7 +304,7 @@ def main():
 
     K, W = args.steps, max(args.warmup, 0)
     sampler = ClockSampler(local_rank)
-    peaks = (C.c_double * 2)()
+    peaks = (C.c_double * 3)()
     have_peaks = lib.lst_measure_alu_peaks(local_rank, 20.0, peaks) == 0
 
     trk.set_kernel_timing(True)
@@ -343,30 +346,80 @@ def main():
                "pcie": {"achieved_gbs_per_gpu": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9,
                         "peak_gbs_per_gpu": pcie, "frac": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9 / pcie,
                         "how": "peak = 256 MB pinned cudaMemcpyAsync H2D, every rank at the same time, slowest rank"},
-               "ingest": "pinned host ring of whole slices; only the five search regions (+16 px margin) of each slice cross "
-                         "PCIe, gathered by a kernel on the copy stream while the previous batch computes"}
+               "ingest": "pinned host ring of whole slices; only the five search regions (+8 px margin, 32-byte aligned) of "
+                         "each slice cross PCIe, as strided 3-D DMA copies on a copy stream while the previous batch computes"}
 
     value = world * F * K / (ms_dev * 1e-3)
-    # roofline of the dominant kernel (lst_ncc_match): exact u8 x u8 -> s32 multiply-accumulates
+    # roofline of the dominant kernel (the template match): exact u8 x u8 -> s32 multiply-accumulates
     win_macs = float((2 * cfg.s_area + 1) ** 2 * cfg.templ_size ** 2)
     macs_per_launch = s_dev.ncc_algorithmic_macs / max(s_dev.ncc_kernel_launches, 1)
     kern_ms = s_dev.ncc_kernel_ms / max(s_dev.ncc_kernel_launches, 1)
     achieved = 2.0 * macs_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None
-    peak = 2.0 * peaks[0] / 1e12 if have_peaks else None
-    roofline = {
-        "bound": "int8-dp4a-pipe", "kernel": "lst_ncc_match", "achieved": achieved, "peak": peak, "unit": "TOP/s",
-        "frac": (achieved / peak) if (achieved and peak) else None,
-        "traffic": (NCU_DRAM_BYTES_PER_WINDOW.get(args.config) or 0) * (macs_per_launch / max(win_macs, 1)) or None,
+    dp4a_peak = 2.0 * peaks[0] / 1e12 if have_peaks else None
+    imma_peak = 2.0 * peaks[2] / 1e12 if (have_peaks and peaks[2] > 0) else None
+    try:
+        measured = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        measured = {}
+    if use_tc:
+        # tensor-core engine: exact u8 x u8 -> s32 Toeplitz GEMM on tcgen05.mma kind::i8.  Denominator: the
+        # int8 tensor peak measured live (MEASURED_PEAKS.json only has the bf16 figure; int8 is nominally 2x)
+        peak = imma_peak
+        roofline = {
+            "bound": "tensor", "kernel": "lst_ncc_tc", "achieved": achieved, "peak": peak, "unit": "TOP/s",
+            "frac": (achieved / peak) if (achieved and peak) else None,
+            "peak_source": "measured live: tcgen05.mma.kind::i8 M128 N256 K32 microbenchmark (lst_measure_alu_peaks); "
+                           "MEASURED_PEAKS.json bf16_tflops=%s for comparison" % measured.get("bf16_tflops"),
+            "note": "achieved counts ALGORITHMIC ops (2*R^2*T^2 per window); the Toeplitz embedding executes ~2.6x more "
+                    "MACs and small-N MMAs are bound by the shared-memory read of the A operand, so the fraction of the "
+                    "tensor peak is low while the kernel is several times faster than the IDP.4A engine, whose own "
+                    "roofline is given as dp4a_engine_peak",
+            "dp4a_engine_peak": dp4a_peak, "achieved_over_dp4a_peak": (achieved / dp4a_peak) if (achieved and dp4a_peak) else None,
+        }
+    else:
+        peak = dp4a_peak
+        roofline = {
+            "bound": "int8-dp4a-pipe", "kernel": "lst_ncc_match", "achieved": achieved, "peak": peak, "unit": "TOP/s",
+            "frac": (achieved / peak) if (achieved and peak) else None,
+            "peak_source": "measured live: IDP.4A.U8.U8 microbenchmark (lst_measure_alu_peaks); MEASURED_PEAKS.json "
+                           "holds only HBM and bf16-tensor peaks and this kernel is bound by neither (SURVEY.md 8d)",
+            "int8_tensor_peak": imma_peak,
+        }
+    roofline.update({
+        "traffic": (NCU_DRAM_BYTES_PER_WINDOW.get((args.config, use_tc)) or 0) * (macs_per_launch / max(win_macs, 1)) or None,
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel "
                           "(profiles/), per window, times the windows of an average launch",
-        "peak_source": "measured live: IDP.4A.U8.U8 microbenchmark (lst_measure_alu_peaks); MEASURED_PEAKS.json "
-                       "holds only HBM and bf16-tensor peaks and this kernel is bound by neither (SURVEY.md 8d)",
         "ffma_peak_tflops": 2.0 * peaks[1] / 1e12 if have_peaks else None,
         "algorithmic_ops_per_launch": 2.0 * macs_per_launch, "avg_launch_ms": kern_ms,
         "kernel_share_of_step": s_dev.ncc_kernel_ms / ms_dev if ms_dev > 0 else None,
         "launches_timed": int(s_dev.ncc_kernel_launches),
         "window_bytes_per_frame": 5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 * (bits // 8),
-    }
+        "hbm_view": {"peak_gbs": measured.get("hbm_gbs"),
+                     "window_bytes_per_s": value * 5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 * (bits // 8) / 1e9},
+    })
+
+    # the other match engine on the same device-resident workload, for its roofline (not the headline)
+    roofline_alt = None
+    if world == 1 and args.engine == "auto" and env_engine is None and cfg.templ_size <= 181:
+        alt = LaserSpotTrack4(cfg.width, cfg.height, bits, device=local_rank, templSize=cfg.templ_size, sArea=cfg.s_area,
+                              max_batch=args.max_batch or mb_d, ncc_engine=1)
+        alt.set_reference(st.frame(0), st.ref_xy)
+        alt.set_kernel_timing(True)
+        out2 = (N.Record * F)()
+        for _ in range(2):
+            alt.track_device_ptrs(dev_ptrs, 1, out2)
+        alt.reset_stats()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        alt.track_device_ptrs(dev_ptrs, 1, out2)
+        dt = time.perf_counter() - t0
+        sa = alt.stats()
+        a_ach = 2.0 * sa.ncc_algorithmic_macs / (sa.ncc_kernel_ms * 1e-3) / 1e12 if sa.ncc_kernel_ms > 0 else None
+        roofline_alt = {"bound": "int8-dp4a-pipe", "kernel": "lst_ncc_match", "achieved": a_ach, "peak": dp4a_peak, "unit": "TOP/s",
+                        "frac": (a_ach / dp4a_peak) if (a_ach and dp4a_peak) else None,
+                        "value_with_this_engine": F / dt, "identical_results": all(
+                            (a.status, a.x_abs, a.y_abs, a.dL) == (b.status, b.x_abs, b.y_abs, b.dL) for a, b in zip(out, out2))}
+        alt.close()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -389,7 +442,7 @@ def main():
                        "max_batch": args.max_batch or mb_d, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                        "accepted_frames_last_step": ok_frames},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(s_dev.kernel_launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
                          "chunks_retracked": sh_dev.retracked, "host_ms_per_step": s_dev.host_ms / K,
                          "device_wait_ms_per_step": s_dev.device_wait_ms / K},

@@ -87,6 +87,9 @@ typedef struct lst_params {
     double  mark_dist;         /* markDist LST4:85 */
     double  range_lo, range_hi;/* LST_RANGE_FIXED */
     double  match_threshold;   /* matchThreshold[5] = 0.2, LST4:147 */
+    int32_t ncc_engine;        /* match kernel: 0 = auto (tensor cores when the template fits, else IDP.4A),
+                                  1 = IDP.4A (lst_ncc_match), 2 = tensor cores (lst_ncc_tc); identical results */
+    int32_t reserved1;
 } lst_params;
 
 /* One template's match in one frame: the double[3] of doMatch_coord_res plus context. */
@@ -226,9 +229,10 @@ int lst_get_stats(const lst_ctx *ctx, lst_stats *out);
 int lst_reset_stats(lst_ctx *ctx);
 /* Time every lst_ncc_match launch with CUDA events on its stream (for bench.py's roofline). */
 int lst_set_kernel_timing(lst_ctx *ctx, int32_t on);
-/* Measured ALU peaks of the device, for the roofline denominator: out[0] = int8 dp4a
- * MAC/s (IDP.4A.U8.U8), out[1] = fp32 FFMA/s.  Runs ~ms_per_test per test. */
-int lst_measure_alu_peaks(int device, double ms_per_test, double out[2]);
+/* Measured peaks of the device, for the roofline denominators: out[0] = int8 dp4a MAC/s
+ * (IDP.4A.U8.U8), out[1] = fp32 FFMA/s, out[2] = int8 tensor-core MAC/s (tcgen05.mma kind::i8,
+ * M128 N256 K32 from shared memory).  Runs ~ms_per_test per test. */
+int lst_measure_alu_peaks(int device, double ms_per_test, double out[3]);
 
 /* ---- test seams: host logic only, no device, no arithmetic of the path ----------------- */
 /* Window placement of analyseSlice for template k (LST4:1325-1345): rect + (int)dis - sArea,

@@ -102,7 +102,7 @@ int launch_upload(void *dst_dev, const void *src_pinned_host, size_t bytes, cuda
 int set_blur_kernel(const float kern[7], const float ksum[7]);
 // picks band/tile split and the shared-memory pitch for lst_ncc_match
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes);
-int measure_alu_peaks(double ms_per_test, double out[2]);
+int measure_alu_peaks(double ms_per_test, double out[3]);
 
 // Tensor-core engine of the match (lst_ncc_tc.cu): Toeplitz table of a template and the launcher.
 // table[v][kc][n][j] = T[v][16*kc + j - n] (0 outside the template), kc < 2*KS, n < 32, j < 16.
@@ -110,9 +110,12 @@ int tc_ksteps(int tw);                                  // KS = ceil((31 + tw) /
 size_t tc_table_bytes(int tw, int th);
 void tc_build_table(const uint8_t *tpl8, int tw, int th, uint8_t *out);
 bool tc_supported(int tw, int th);
-int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_w, int max_rw, int max_rh, int tw, int th,
-                  const DevTemplates *tpls, const uint8_t *win8, uint32_t *wsum, uint32_t *wsq,
+int launch_box_sums(const DevTask *tasks, int n_tasks, int max_w, int max_rh, int th, const DevTemplates *tpls,
+                    const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream);
+int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
+                  const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
                   unsigned long long *best, cudaStream_t stream);
+double measure_imma_peak(double ms_per_test);   // int8 tensor-core MAC/s (tcgen05.mma kind::i8)
 void tc_init_device();
 
 #if defined(__CUDACC__)

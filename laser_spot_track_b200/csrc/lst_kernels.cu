@@ -999,7 +999,7 @@ __global__ void __launch_bounds__(256) lst_peak_ffma(float *out, int iters, floa
     if (s == 123.456f) out[0] = s;
 }
 
-int measure_alu_peaks(double ms_per_test, double out[2])
+int measure_alu_peaks(double ms_per_test, double out[3])
 {
     uint32_t *d = nullptr;
     if (cudaMalloc(&d, 256) != cudaSuccess) return -1;
@@ -1040,6 +1040,7 @@ int measure_alu_peaks(double ms_per_test, double out[2])
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(d);
+    out[2] = measure_imma_peak(ms_per_test);
     return 0;
 }
 

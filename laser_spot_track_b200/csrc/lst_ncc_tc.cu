@@ -470,8 +470,24 @@ void tc_init_device()
     cudaGetLastError();
 }
 
-int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_w, int max_rw, int max_rh, int tw, int th,
-                  const DevTemplates *tpls, const uint8_t *win8, uint32_t *wsum, uint32_t *wsq,
+int launch_box_sums(const DevTask *tasks, int n_tasks, int max_w, int max_rh, int th, const DevTemplates *tpls,
+                    const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream)
+{
+    const int wp = ((max_w + 15) & ~15) | 1;
+    const size_t bs_smem = (size_t)2 * BS_ROWS * wp * 4 + (size_t)(BS_ROWS + th - 1) * ((max_w + 15) & ~15) + 16;
+    if (bs_smem > 226 * 1024) return -1;
+    int launches = 0;
+    for (int base = 0; base < n_tasks; base += 65535) {
+        int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
+        dim3 bgrid((max_rh + BS_ROWS - 1) / BS_ROWS, n);
+        lst_box_sums<<<bgrid, 256, bs_smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, wp);
+        launches++;
+    }
+    return launches;
+}
+
+int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
+                  const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
                   unsigned long long *best, cudaStream_t stream)
 {
     TcParams tp;
@@ -484,18 +500,12 @@ int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_w, int max_rw, int 
         if (dbg_on) cudaMalloc((void **)&dbg, 4096 * 16 * 4 * sizeof(unsigned long long));
     }
     tp.dbg = dbg_on ? dbg : nullptr;
-    const int wp = ((max_w + 15) & ~15) | 1;
-    const size_t bs_smem = (size_t)2 * BS_ROWS * wp * 4 + (size_t)(BS_ROWS + th - 1) * ((max_w + 15) & ~15) + 16;
-    if (bs_smem > 226 * 1024) return -1;
     const int nb_total = (max_rw + TC_NB - 1) / TC_NB;
     const int xchunks = (nb_total + tp.nb_per_cta - 1) / tp.nb_per_cta;
     const int ytiles = (max_rh + TC_M - 1) / TC_M;
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
-        dim3 bgrid((max_rh + BS_ROWS - 1) / BS_ROWS, n);
-        lst_box_sums<<<bgrid, 256, bs_smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, wp);
-        launches++;
         dim3 grid(xchunks * ytiles, n);
         lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, best + base, tp);
         cudaError_t e = cudaPeekAtLastError();
@@ -519,6 +529,83 @@ int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_w, int max_rw, int 
         free(h);
     }
     return launches;
+}
+
+
+// ---- int8 tensor-core peak (roofline denominator of lst_ncc_tc) ------------------------------------
+// One CTA per SM issues `iters` x 2 tcgen05.mma kind::i8 of M128 N256 K32 from (uninitialised) shared
+// memory into two TMEM accumulators: the operand values do not matter for the rate.
+__global__ void __launch_bounds__(128, 1) lst_peak_imma(int iters)
+{
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_t;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (4096 + 8192) / 16; i += blockDim.x) ((uint4 *)sm)[i] = make_uint4(0x01010101u, 0x02020202u, 0, 0x03030303u);
+    fence_async_smem();
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_t)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_t;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = instr_desc_u8(128, 256);
+        const uint64_t a = smem_desc(smem_u32(sm), 128 * 16, 128), b = smem_desc(smem_u32(sm + 4096), 256 * 16, 128);
+        for (int i = 0; i < iters; i++) {
+            mma_i8(tmem, a, b, idesc, 1u);
+            mma_i8(tmem + 256, a, b, idesc, 1u);
+        }
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+}
+
+double measure_imma_peak(double ms_per_test)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int iters = 4000;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        lst_peak_imma<<<sms, 128, 4096 + 8192>>>(iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+            cudaGetLastError();
+            best = 0.0;
+            break;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double macs = (double)sms * iters * 2.0 * 128.0 * 256.0 * 32.0;
+        if (rep > 0 && macs / (ms * 1e-3) > best) best = macs / (ms * 1e-3);
+        if (rep == 0 && ms > 0) {
+            double f = ms_per_test / ms;
+            f = f > 32 ? 32 : (f < 0.25 ? 0.25 : f);
+            iters = (int)(iters * f);
+            if (iters < 200) iters = 200;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
 }
 
 }  // namespace lst

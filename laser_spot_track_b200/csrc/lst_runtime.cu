@@ -388,9 +388,15 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             CU(regrow(&d_wsq, cap));
             sum_cap = cap;
         }
-        int tcl = use_tc ? launch_ncc_tc(d_tasks, n, max_w, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq,
-                                         d_best, s_compute)
-                         : -1;
+        int tcl = -1;
+        if (use_tc) {
+            int bl = launch_box_sums(d_tasks, n, max_w, max_rh, max_th, d_tpls, d_win8, d_wsum, d_wsq, s_compute);
+            if (bl >= 0) {
+                launches += bl;
+                if (timing) CU(cudaEventRecord(tl.e0, s_compute));   // time the match kernel alone
+                tcl = launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, d_best, s_compute);
+            }
+        }
         if (use_tc && tcl < 0) {
             static bool warned = false;
             if (!warned) fprintf(stderr, "lst_b200: tensor-core match engine not applicable to this window/template size; using IDP.4A\n");
@@ -557,8 +563,12 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
         if ((ce = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming)) != cudaSuccess) return bail(ce, "event");
     if ((ce = cudaMalloc((void **)&c->d_tpls, sizeof(DevTemplates))) != cudaSuccess) return bail(ce, "cudaMalloc");
     {
+        // engine of the match kernel: params.ncc_engine, overridable by LST_NCC_ENGINE=dp4a|tc for A/B runs
+        int eng = params->ncc_engine;
         const char *e = getenv("LST_NCC_ENGINE");
-        c->ncc_engine = (e && (!strcmp(e, "tc") || !strcmp(e, "1"))) ? 1 : 0;
+        if (e && !strcmp(e, "dp4a")) eng = 1;
+        if (e && !strcmp(e, "tc")) eng = 2;
+        c->ncc_engine = eng == 1 ? 0 : 1;      // internal: 1 = tensor cores wherever lst_ncc_tc applies
         tc_init_device();
     }
     float kern[7], ksum[7];

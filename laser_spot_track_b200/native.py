@@ -39,7 +39,7 @@ class Params(C.Structure):
         ("doubling", C.c_int32), ("auto_skip", C.c_int32), ("max_s_area", C.c_int32), ("max_batch", C.c_int32),
         ("ingest_mode", C.c_int32),
         ("mark_dist", C.c_double), ("range_lo", C.c_double), ("range_hi", C.c_double),
-        ("match_threshold", C.c_double),
+        ("match_threshold", C.c_double), ("ncc_engine", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -160,6 +160,7 @@ def default_params(width: int, height: int, pixel_type: int, **kw) -> Params:
     p.range_mode, p.quant_mode = RANGE_DISPLAY, QUANT_ROUND255
     p.doubling, p.auto_skip, p.max_s_area, p.max_batch = 0, 1, 500, 0
     p.mark_dist, p.range_lo, p.range_hi, p.match_threshold = 100.0, 0.0, 255.0, 0.2
+    p.ncc_engine = 0
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)

@@ -46,7 +46,7 @@ class LaserSpotTrack4:
                  subPixel: bool = True, matchIntensity: bool = True, alwaysAutoSkip: bool = True,
                  doubling: bool = False, maxSArea: int = 500, range_mode: int = N.RANGE_DISPLAY,
                  range_lo: float = 0.0, range_hi: float = 255.0, quant_mode: int = N.QUANT_ROUND255,
-                 max_batch: int = 0, ingest_mode: int = 0):
+                 max_batch: int = 0, ingest_mode: int = 0, ncc_engine: int = 0):
         if bit_depth not in _PIX:
             raise LstError(N.LST_ERR_UNSUPPORTED, "Unsupported image type")       # IJ.error, LST4:2537
         self._lib = N.load()
@@ -57,7 +57,7 @@ class LaserSpotTrack4:
             mark_dist=markDist, sub_pixel=int(subPixel), match_intensity=int(matchIntensity),
             auto_skip=int(alwaysAutoSkip), doubling=int(doubling), max_s_area=maxSArea,
             range_mode=range_mode, range_lo=range_lo, range_hi=range_hi, quant_mode=quant_mode,
-            max_batch=max_batch, ingest_mode=ingest_mode)
+            max_batch=max_batch, ingest_mode=ingest_mode, ncc_engine=ncc_engine)
         self._ctx = C.c_void_p()
         rc = self._lib.lst_create(C.byref(self.params), device, C.byref(self._ctx))
         if rc != N.LST_OK:
@@ -242,14 +242,15 @@ class LaserSpotTrack4Multi:
         self.width, self.height, self._np_dtype = width, height, _PIX[bit_depth][1]
         kw = dict(method=5, templSize=120, sArea=50, markDist=100.0, subPixel=True, matchIntensity=True,
                   alwaysAutoSkip=True, doubling=False, maxSArea=500, range_mode=N.RANGE_DISPLAY, range_lo=0.0,
-                  range_hi=255.0, quant_mode=N.QUANT_ROUND255, max_batch=0, ingest_mode=0)
+                  range_hi=255.0, quant_mode=N.QUANT_ROUND255, max_batch=0, ingest_mode=0, ncc_engine=0)
         kw.update(dialog)
         self.params = N.default_params(
             width, height, _PIX[bit_depth][0], method=kw["method"], templ_size=kw["templSize"], s_area=kw["sArea"],
             mark_dist=kw["markDist"], sub_pixel=int(kw["subPixel"]), match_intensity=int(kw["matchIntensity"]),
             auto_skip=int(kw["alwaysAutoSkip"]), doubling=int(kw["doubling"]), max_s_area=kw["maxSArea"],
             range_mode=kw["range_mode"], range_lo=kw["range_lo"], range_hi=kw["range_hi"],
-            quant_mode=kw["quant_mode"], max_batch=kw["max_batch"], ingest_mode=kw["ingest_mode"])
+            quant_mode=kw["quant_mode"], max_batch=kw["max_batch"], ingest_mode=kw["ingest_mode"],
+            ncc_engine=kw["ncc_engine"])
         dev = (C.c_int32 * len(devices))(*devices)
         self._m = C.c_void_p()
         rc = self._lib.lst_multi_create(C.byref(self.params), dev, len(devices), C.byref(self._m))
