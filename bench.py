@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames of the CPU baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ingest", type=int, default=0, choices=[0, 1, 2], help="0 ROI DMA (default), 1 whole slices, 2 ROI gather kernel")
     ap.add_argument("--engine", default="auto", choices=["auto", "dp4a", "tc"], help="match kernel: tensor cores (default when the template fits) or IDP.4A")
     return ap.parse_args()
 
@@ -234,7 +235,8 @@ def main():
 
     lib = N.load()
     trk = LaserSpotTrack4(cfg.width, cfg.height, bits, device=local_rank, templSize=cfg.templ_size, sArea=cfg.s_area,
-                          max_batch=args.max_batch or mb_d, ncc_engine={"auto": 0, "dp4a": 1, "tc": 2}[args.engine])
+                          max_batch=args.max_batch or mb_d, ncc_engine={"auto": 0, "dp4a": 1, "tc": 2}[args.engine],
+                          ingest_mode=args.ingest)
     env_engine = os.environ.get("LST_NCC_ENGINE")
     use_tc = (args.engine != "dp4a" and env_engine != "dp4a" and cfg.templ_size <= 181) or env_engine == "tc"
     # ring of distinct slices: pinned host copy (e2e leg) and HBM copy (value leg)
@@ -342,7 +344,7 @@ def main():
         pcie = pcie_peak_gbs()
         e2e = {"value": world * F * K / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(s_e2e.h2d_bytes // K), "d2h_bytes_per_step": int(s_e2e.d2h_bytes // K),
-               "ms_per_step": ms_e2e / K,
+               "ms_per_step": ms_e2e / K, "roi_fallback_windows_per_step": int(s_e2e.roi_fallback_tasks // K),
                "pcie": {"achieved_gbs_per_gpu": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9,
                         "peak_gbs_per_gpu": pcie, "frac": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9 / pcie,
                         "how": "peak = 256 MB pinned cudaMemcpyAsync H2D, every rank at the same time, slowest rank"},

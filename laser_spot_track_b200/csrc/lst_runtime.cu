@@ -20,6 +20,7 @@
 using namespace lst;
 
 static thread_local std::string g_create_error;
+static const int kRoiMarginMax = 32;   // ROI ingest: the region ring is sized for this margin
 
 static double now_ms()
 {
@@ -76,8 +77,9 @@ struct lst_ctx : public Executor {
     RoiDesc roi[2][5];     // per half: the rectangles gathered for that batch
     bool roi_active = false;   // the batch being resolved uses ROI surfaces
     int roi_half = 0, roi_nb = 0;
-    int roi_margin = 8;
-    int roi_align_bytes = 32;
+    int roi_margin = 8;          // current margin; adapts to the excursion of the windows seen in the last batch
+    int roi_margin_fixed = -1;   // LST_ROI_MARGIN pins it
+    int roi_align_bytes = 16;
     std::unordered_map<const void *, const void *> mapped_cache;   // pinned host ptr -> device-visible ptr
     // solve buffers
     int solve_cap = 0;
@@ -570,6 +572,8 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
         if (e && !strcmp(e, "tc")) eng = 2;
         c->ncc_engine = eng == 1 ? 0 : 1;      // internal: 1 = tensor cores wherever lst_ncc_tc applies
         tc_init_device();
+        if (const char *m = getenv("LST_ROI_MARGIN")) c->roi_margin = c->roi_margin_fixed = std::max(0, atoi(m));
+        if (const char *a = getenv("LST_ROI_ALIGN")) c->roi_align_bytes = std::max(4, atoi(a));
     }
     float kern[7], ksum[7];
     make_gaussian_kernel(kern, ksum);
@@ -821,7 +825,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     }
     const int nbatches = (int)bstart.size() - 1;
 
-    bool use_roi = !on_device && c->p.s_area > 0 && c->p.ingest_mode == 0;
+    bool use_roi = !on_device && c->p.s_area > 0 && c->p.ingest_mode != 1;
     std::vector<const void *> mapped;
     if (use_roi) {
         mapped.resize(n_frames);
@@ -837,8 +841,9 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     if (use_roi) {
         const int ax = c->roi_align_bytes / (int)c->bpp();
         for (int k = 0; k < 5; k++) {
-            size_t w = (size_t)c->rect[k].w + 2 * c->p.s_area + 2 * c->roi_margin + 2 * ax;
-            size_t h = (size_t)c->rect[k].h + 2 * c->p.s_area + 2 * c->roi_margin;
+            const int mg = std::max(c->roi_margin, kRoiMarginMax);   // the margin adapts up to this
+            size_t w = (size_t)c->rect[k].w + 2 * c->p.s_area + 2 * mg + 2 * ax;
+            size_t h = (size_t)c->rect[k].h + 2 * c->p.s_area + 2 * mg;
             w = std::min<size_t>(w, (size_t)c->p.width + ax);
             h = std::min<size_t>(h, (size_t)c->p.height);
             roi_block_max += ((w * h * c->bpp()) + 255) & ~(size_t)255;
@@ -969,6 +974,23 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
         if (rc != LST_OK) {
             if (c->err.empty()) c->fail(rc, "resolver failed (%d)", rc);
             return rc;
+        }
+        if (use_roi && c->roi_margin_fixed < 0) {
+            // adapt the margin: how far did the windows of this batch stray from where its regions were
+            // planned?  The next region plan gets that excursion + 3 px (4..kRoiMarginMax).
+            int exc = 0;
+            for (int i = 0; i < nb; i++) {
+                const lst_record &r = out[f0 + i];
+                for (int k = 0; k < 5; k++) {
+                    if (r.tm[k].ww == 0) continue;
+                    const RoiDesc &rd = c->roi[half][k];
+                    int inner_x = r.tm[k].wx - rd.x, inner_y = r.tm[k].wy - rd.y;
+                    int outer_x = rd.x + rd.w - (r.tm[k].wx + r.tm[k].ww), outer_y = rd.y + rd.h - (r.tm[k].wy + r.tm[k].wh);
+                    int slack = std::min(std::min(inner_x, inner_y), std::min(outer_x, outer_y));   // < 0: fell outside
+                    exc = std::max(exc, c->roi_margin - slack);
+                }
+            }
+            c->roi_margin = std::min(kRoiMarginMax, std::max(4, exc + 3));
         }
     }
     return LST_OK;
