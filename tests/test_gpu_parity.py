@@ -395,3 +395,29 @@ def test_multi_context_sharding(stack_a, n_ctx):
         got2 = t.track(np.stack(frames[31:]), first_frame_index=31)     # the state carries over between calls
         util.compare_records(got2, want[30:], label=f"multi{n_ctx} b")
         assert np.array_equal(t.get_state(), np.array([v for d in otr.dis for v in d]))
+
+
+def test_both_match_engines_identical(stack_a):
+    """lst_ncc_tc (tcgen05.mma kind::i8, default) and lst_ncc_match (IDP.4A) return identical records."""
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=False)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:25])
+    for engine in (1, 2):
+        with _tracker(cfg, op, ncc_engine=engine, max_batch=9) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            got = t.track(np.stack(frames[1:25]))
+            util.compare_records(got, want, label=f"engine {engine}")
+    # odd template / window sizes through both engines (match_single uses IDP.4A for the map; tracking uses auto)
+    cfg2 = StackConfig(300, 260, "u8", 33, 21, 10)
+    st2 = SyntheticStack(cfg2)
+    fr2 = [st2.frame(i) for i in range(0, 6)]
+    op2 = util.oracle_params(cfg2, match_intensity=False)
+    o2 = O.OracleTracker(op2)
+    o2.set_reference(fr2[0], st2.ref_xy)
+    w2 = o2.run(fr2[1:])
+    for engine in (1, 2):
+        with _tracker(cfg2, op2, ncc_engine=engine) as t:
+            t.set_reference(fr2[0], st2.ref_xy)
+            util.compare_records(t.track(np.stack(fr2[1:])), w2, label=f"odd sizes engine {engine}")
