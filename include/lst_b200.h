@@ -199,14 +199,15 @@ int lst_multi_set_state(lst_multi *m, const double dis[10]);
 int64_t lst_multi_retracked(const lst_multi *m);
 
 /* ---- the primitives, exposed like the reference's public statics ---------------------- */
-/* doMatch_coord_res(src, tpl, 5, subPix, null) on the 8-bit images that reach OpenCV
- * (LST4:2525-2535).  out[3] = {x, y, score}; score_map (nullable) receives the
- * (sh-th+1) x (sw-tw+1) float32 result of matchTemplate. */
+/* doMatch_coord_res(src, tpl, method, subPix, null) on the 8-bit images that reach OpenCV
+ * (LST4:2502-2563, 2665-2722); method 0..5 as in the dialog (LST4:2381).  out[3] = {x, y, score}
+ * (the minimum of the map for methods 0 and 1, else the maximum); score_map (nullable) receives
+ * the (sh-th+1) x (sw-tw+1) float32 result of matchTemplate. */
 int lst_match_single(lst_ctx *ctx, const uint8_t *src8, int32_t sw, int32_t sh,
-                     const uint8_t *tpl8, int32_t tw, int32_t th, int32_t sub_pix,
+                     const uint8_t *tpl8, int32_t tw, int32_t th, int32_t method, int32_t sub_pix,
                      double out[3], float *score_map);
-/* doMatch_test(src, 5): matchTemplate(src, src) 1x1 (LST4:2724-2767). */
-int lst_match_test(lst_ctx *ctx, const uint8_t *src8, int32_t sw, int32_t sh, double *out);
+/* doMatch_test(src, method): matchTemplate(src, src) 1x1 (LST4:2724-2767). */
+int lst_match_test(lst_ctx *ctx, const uint8_t *src8, int32_t sw, int32_t sh, int32_t method, double *out);
 /* crop -> [convertToGray32] -> blurGaussian(2,2,0.02) -> 8-bit of one rectangle of a host frame:
  * the image handed to matchTemplate (LST4:1346-1347, 1456-1473, 2529).  out8: w*h bytes. */
 int lst_preprocess(lst_ctx *ctx, const void *frame, int32_t x0, int32_t y0, int32_t w, int32_t h, uint8_t *out8);

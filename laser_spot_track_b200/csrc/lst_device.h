@@ -130,10 +130,19 @@ __device__ __forceinline__ float key_f32(uint32_t k)
     uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
     return __uint_as_float(u);
 }
-__device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx)
+// 64-bit argmax key: larger key = better score, ties -> smaller index (minMaxLoc: first in row-major
+// order).  want_min flips the score order for the methods that look for the minimum.
+__device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx, bool want_min = false)
 {
     score = score + 0.0f;   // -0 -> +0: minMaxLoc compares values, not bit patterns
-    return ((unsigned long long)f32_key(score) << 32) | (unsigned long long)(0xffffffffu - idx);
+    uint32_t k = f32_key(score);
+    if (want_min) k = ~k;
+    return ((unsigned long long)k << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+__device__ __forceinline__ float key_score(unsigned long long key, bool want_min = false)
+{
+    uint32_t k = (uint32_t)(key >> 32);
+    return key_f32(want_min ? ~k : k);
 }
 #endif
 

@@ -39,8 +39,7 @@ int validate_params(const lst_params &p, std::string *err)
         return fail(LST_ERR_INVALID, "bad slice size");
     if (p.pixel_type != LST_PIX_U8 && p.pixel_type != LST_PIX_U16 && p.pixel_type != LST_PIX_F32)
         return fail(LST_ERR_UNSUPPORTED, "Unsupported image type");   // IJ.error text of LST4:2537
-    if (p.method != 5)
-        return fail(LST_ERR_UNSUPPORTED, "only matching method 5 (normalized correlation coefficient) is on this path");
+    if (p.method < 0 || p.method > 5) return fail(LST_ERR_INVALID, "matching method must be 0..5 (LST4:2381)");
     if (p.pixel_type == LST_PIX_U16 && !p.match_intensity)
         return fail(LST_ERR_UNSUPPORTED,
                     "16-bit stacks need matchIntensity=true (the reference dereferences a null Mat, LST4:2510-2523)");
@@ -152,7 +151,7 @@ void make_gaussian_kernel(float kern[kBlurRadius], float ksum[kBlurRadius])
     }
 }
 
-TplConst template_consts(const uint8_t *tpl8, int tw, int th)
+TplConst template_consts(const uint8_t *tpl8, int tw, int th, int method)
 {
     TplConst c;
     memset(&c, 0, sizeof(c));
@@ -181,7 +180,15 @@ TplConst template_consts(const uint8_t *tpl8, int tw, int th)
         double C = n * (double)q - (double)s * (double)s;   // exact: both terms < 2^53
         c.inv_sqrt_c = C > 0.0 ? (float)(1.0 / sqrt(C)) : 0.0f;
     }
-    c.mideal = (double)ncc_score((double)q, (double)s, (double)q, c.inv_area, c.mean, c.norm, c.flat);
+    {   // templSum2 and the templNorm of the non-CCOEFF methods, in common_matchTemplate's order
+        double sum2 = sdv * sdv + c.mean * c.mean;
+        c.norm_raw = sqrt(sum2) / sqrt(c.inv_area);
+        c.sum2 = sum2 / c.inv_area;
+    }
+    // *_mideal = doMatch_test(tpl, method == 0 ? 2 : method): the template matched against itself (LST4:566)
+    c.method = method == 0 ? 2 : method;
+    c.mideal = (double)match_score(c, (double)q, (double)s, (double)q);
+    c.method = method;
     return c;
 }
 

@@ -494,6 +494,7 @@ struct NccCtx {
     const uint32_t *s_v2;      // vertical sums of I^2 [NCC_BAND][vpitch]
     const uint4 *g_tpl;        // packed template [th][kw/4] uint4 (global, L1)
     int SP, VP, th, tw, kw, rw;
+    const TplConst *tc;        // all constants of the template (methods other than 5 use them)
     long long N, tsum, C_unused;
     float inv_sqrt_c;
     double inv_area, mean, norm;
@@ -574,7 +575,7 @@ __device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, in
     }
     const uint32_t rowidx = (uint32_t)c.y * (uint32_t)c.rw;
     float wmax = -3.0e38f;
-    if (!MAP) {
+    if (!MAP && c.tc->method == 5) {
         uint32_t s = s0, sq = sq0;
         float tmax = -3.0e38f;
 #pragma unroll 1
@@ -593,17 +594,17 @@ __device__ __forceinline__ void ncc_tile(const NccCtx &c, bool valid, int yy, in
         uint32_t s = s0, sq = sq0;
 #pragma unroll 1
         for (int p = 0; p < np; p++) {
-            bool exact = MAP;
-            if (!MAP) {
+            bool exact = MAP || c.tc->method != 5;   // the float32 filter is derived for TM_CCOEFF_NORMED only
+            if (!exact) {
                 const long long A = c.N * (long long)corr[p] - (long long)s * c.tsum;
                 const long long B = c.N * (long long)sq - (long long)s * (long long)s;
                 if (2 * B <= c.N + (c.N >> 5)) exact = true;   // nearly flat: OpenCV's special branch may apply
                 else exact = (float)A * rsqrtf((float)B) * c.inv_sqrt_c >= wmax - NCC_EPS;
             }
             if (exact) {
-                const float sc = ncc_score((double)corr[p], (double)s, (double)sq, c.inv_area, c.mean, c.norm, 0);
+                const float sc = match_score(*c.tc, (double)corr[p], (double)s, (double)sq);
                 if (MAP) c.score_map[c.map_off + rowidx + (uint32_t)(x0 + p)] = sc;
-                const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(x0 + p));
+                const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(x0 + p), method_wants_min(c.tc->method));
                 best = key > best ? key : best;
             }
             s += (uint32_t)vr[p + c.tw] - (uint32_t)vr[p];
@@ -628,7 +629,7 @@ lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict_
     const int bands = (t.rh + NCC_BAND - 1) / NCC_BAND;
     if ((int)blockIdx.x >= chunks * bands) return;
     const int chunk = blockIdx.x % chunks, band = blockIdx.x / chunks;
-    if (tc.flat) {   // templSdv^2 < DBL_EPSILON: OpenCV fills the result with 1 -> first position wins
+    if (tc.flat && tc.method == 5) {   // templSdv^2 < DBL_EPSILON: OpenCV fills the result with 1 -> first position wins
         if (blockIdx.x == 0) {
             if (MAP)
                 for (int i = threadIdx.x; i < t.rw * t.rh; i += blockDim.x) score_map[t.sum_off + i] = 1.0f;
@@ -687,6 +688,7 @@ lst_ncc_match(const DevTask *__restrict__ tasks, const DevTemplates *__restrict_
     c.s_v = s_v;
     c.s_v2 = s_v2;
     c.g_tpl = (const uint4 *)tpls->packed[t.tpl];
+    c.tc = &tpls->c[t.tpl];
     c.SP = SP;
     c.VP = VP;
     c.th = th;
@@ -843,7 +845,7 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
     const unsigned long long key = best[blockIdx.x];
     const uint32_t idx = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
     const int ix = (int)(idx % (uint32_t)t.rw), iy = (int)(idx / (uint32_t)t.rw);
-    const float peak = key_f32((uint32_t)(key >> 32));
+    const float peak = key_score(key, method_wants_min(tc.method));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nx = ix + (warp % 3) - 1, ny = iy + (warp / 3) - 1;
     float sc = 0.0f;
@@ -863,7 +865,7 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
             s += __shfl_xor_sync(0xffffffffu, s, o);
             q += __shfl_xor_sync(0xffffffffu, q, o);
         }
-        sc = ncc_score((double)acc, (double)s, (double)q, tc.inv_area, tc.mean, tc.norm, tc.flat);
+        sc = match_score(tc, (double)acc, (double)s, (double)q);
     }
     if (lane == 0) nb[warp] = sc;
     __syncthreads();
@@ -878,7 +880,7 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
         if (mp.sub_pixel) subpixel_fit(nb, border, &dx, &dy);
         r.x = (double)ix + dx;
         r.y = (double)iy + dy;
-        r.accepted = test_match_result(r.score, tc.mideal, mp.thresh, r.x, r.y, 2 * t.s_used, mp.templ_size);
+        r.accepted = test_match_result(tc.method, r.score, tc.mideal, mp.thresh, r.x, r.y, 2 * t.s_used, mp.templ_size);
         for (int i = 0; i < 9; i++) r.nb[i] = nb[i];
         r.pad = 0.0f;
         results[blockIdx.x] = r;

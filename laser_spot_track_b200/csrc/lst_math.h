@@ -27,7 +27,9 @@ struct TplConst {
     uint32_t tsum, tsq_lo;
     double mideal;      // doMatch_test of the template (LST4:2724-2767)
     float inv_sqrt_c;   // 1/sqrt(N*tsq - tsum^2): float32 filter of the match kernel
-    float pad;
+    int32_t method;     // OpenCV match method 0..5 (LST4:2547-2552); 5 = TM_CCOEFF_NORMED
+    double sum2;        // templSum2 = sum of t^2 as common_matchTemplate derives it
+    double norm_raw;    // sqrt(E[t^2])/sqrt(invArea): templNorm of the non-CCOEFF methods
 };
 
 // One position of common_matchTemplate for TM_CCOEFF_NORMED with an exact integer numerator:
@@ -52,6 +54,45 @@ LST_HD float ncc_score(double corr, double wsum, double wsq, double inv_area, do
     return (float)r;
 }
 
+// One position of common_matchTemplate (templmatch.cpp) for any of the six methods of the plugin's dialog
+// (LST4:2381): 0 SQDIFF, 1 SQDIFF_NORMED, 2 CCORR, 3 CCORR_NORMED, 4 CCOEFF, 5 CCOEFF_NORMED, from the
+// exact integer correlation and window sums.  Double arithmetic in OpenCV's order, stored as float32.
+LST_HD float match_score(const TplConst &c, double corr, double wsum, double wsq)
+{
+    const int method = c.method;
+    if (method == 5) return ncc_score(corr, wsum, wsq, c.inv_area, c.mean, c.norm, c.flat);
+    const int num_type = (method == 2 || method == 3) ? 0 : (method == 4 ? 1 : 2);
+    const bool normed = method == 1 || method == 3;
+    double num = corr, wnd_mean2 = 0.0, wnd_sum2 = 0.0;
+    if (num_type == 1) {
+        double t = wsum;
+        wnd_mean2 = (t * t) * c.inv_area;
+        num = num - t * c.mean;
+    }
+    if (normed || num_type == 2) {
+        wnd_sum2 = wsq;
+        if (num_type == 2) {
+            num = wnd_sum2 - 2.0 * num + c.sum2;
+            if (num < 0.0) num = 0.0;
+        }
+    }
+    if (normed) {
+        double diff2 = wnd_sum2 - wnd_mean2;
+        if (diff2 < 0.0) diff2 = 0.0;
+        double thr = 10.0 * 1.1920928955078125e-07 * wnd_sum2;
+        if (thr > 0.5) thr = 0.5;
+        double tt = (diff2 <= thr) ? 0.0 : sqrt(diff2) * c.norm_raw;
+        double a = fabs(num);
+        if (a < tt) num = num / tt;
+        else if (a < tt * 1.125) num = num > 0.0 ? 1.0 : -1.0;
+        else num = method != 1 ? 0.0 : 1.0;
+    }
+    return (float)num;
+}
+
+// methods 0 and 1 look for the minimum of the map, the others for the maximum (LST4:2671-2679)
+LST_HD bool method_wants_min(int method) { return method == 0 || method == 1; }
+
 // 3x3 quadratic sub-pixel fit, LST4:2681-2717.  nb = 3x3 neighbourhood (row-major, centre nb[4])
 // read as float32 and computed in double.  border != 0 => peak on the map border => (0,0).
 LST_HD void subpixel_fit(const float *nb, int border, double *dx, double *dy)
@@ -74,13 +115,21 @@ LST_HD void subpixel_fit(const float *nb, int border, double *dx, double *dy)
     *dy = ddy;
 }
 
-// testMatchResult for method 5, LST4:1225-1255.
-LST_HD int test_match_result(double result, double ref, double thresh, double x, double y, int search_width, int tpl_size)
+// testMatchResult, LST4:1225-1255 (all six methods).
+LST_HD int test_match_result(int method, double result, double ref, double thresh, double x, double y, int search_width,
+                             int tpl_size)
 {
     int ok = 1;
     double d1 = 0.05 * tpl_size, d2 = 0.05 * search_width;
     double dist = d1 < d2 ? d1 : d2;
-    if (fabs(result - ref) > thresh) ok = 0;
+    switch (method) {
+        case 0: if (result / ref > thresh) ok = 0; break;
+        case 1: if (result > thresh) ok = 0; break;
+        case 2: if (fabs((result - ref) / ref) > thresh) ok = 0; break;
+        case 3: if (fabs(result - ref) > thresh) ok = 0; break;
+        case 4: if (fabs(result - ref) / ref > thresh) ok = 0; break;
+        default: if (fabs(result - ref) > thresh) ok = 0; break;
+    }
     if (search_width != 0 && ((x < dist) || (y < dist) || (x > search_width - dist) || (y > search_width - dist))) ok = 0;
     return ok;
 }

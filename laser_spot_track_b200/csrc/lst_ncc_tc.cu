@@ -221,12 +221,12 @@ lst_box_sums(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
 // The exact (double-precision, OpenCV order) score of one candidate position, out of line: the
 // epilogue visits 32 positions with unrolled code and only a few of them get here, so the long
 // division / square-root sequences must not be replicated 32 times (instruction cache).
-__device__ __noinline__ unsigned long long tc_exact_key(uint32_t corr, const uint32_t *ws, const uint32_t *wq, double inv_area,
-                                                        double mean, double norm, uint32_t idx)
+__device__ __noinline__ unsigned long long tc_exact_key(uint32_t corr, const uint32_t *ws, const uint32_t *wq,
+                                                        const TplConst *tc, uint32_t idx)
 {
     const uint32_t s = __ldg(ws), sq = __ldg(wq);
-    const float sc = ncc_score((double)corr, (double)s, (double)sq, inv_area, mean, norm, 0);
-    return pack_key(sc, idx);
+    const float sc = match_score(*tc, (double)corr, (double)s, (double)sq);
+    return pack_key(sc, idx, method_wants_min(tc->method));
 }
 
 struct TcParams {
@@ -257,7 +257,7 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
     const int ytiles = (t.rh + TC_M - 1) / TC_M;
     if ((int)blockIdx.x >= xchunks * ytiles) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (tc.flat) {   // templSdv^2 < DBL_EPSILON: OpenCV fills the result with 1 -> first position wins
+    if (tc.flat && tc.method == 5) {   // templSdv^2 < DBL_EPSILON: OpenCV fills the result with 1 -> first position wins
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&best[blockIdx.y], pack_key(1.0f, 0u));
         return;
     }
@@ -397,7 +397,7 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
                     const long long B = (long long)((unsigned long long)N * qv[i]) - (long long)((unsigned long long)sv[i] * sv[i]);
                     float f;
                     if (p >= np) f = -3.0e38f;
-                    else if (2 * B <= Nflat) f = 3.0e38f;
+                    else if (2 * B <= Nflat || tc.method != 5) f = 3.0e38f;   // other methods: every position exact
                     else {
                         f = (float)A * rsqrtf((float)B) * tc.inv_sqrt_c;
                         tmax = fmaxf(tmax, f);
@@ -414,7 +414,7 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
             for (int p = 0; p < 32; p++) {
                 if (sf[p] >= thr && p < np) {
                     const unsigned long long key =
-                        tc_exact_key(corr[p], ws + p * 32, wq + p * 32, tc.inv_area, tc.mean, tc.norm, rowidx + (uint32_t)(xb + p));
+                        tc_exact_key(corr[p], ws + p * 32, wq + p * 32, &tpls->c[t.tpl], rowidx + (uint32_t)(xb + p));
                     mybest = key > mybest ? key : mybest;
                 }
             }

@@ -114,7 +114,7 @@ struct lst_ctx : public Executor {
     int ensure_tasks(int n);
     int ensure_frames(int n);
     int ensure_scratch(size_t win_bytes, size_t map_elems);
-    int upload_template(int slot, const uint8_t *tpl8, int tw, int th);
+    int upload_template(int slot, const uint8_t *tpl8, int tw, int th, int method_override = -1);
     void preproc_params(PreprocParams *pp, int max_w, int max_h) const;
     void drain_timers();
 };
@@ -227,9 +227,9 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
     pp->minmax_in_kernel = (pp->range_per_task && max_w <= pp->tile_w && (long)max_w * max_h <= 256L * 256) ? 1 : 0;
 }
 
-int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th)
+int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th, int method_override)
 {
-    TplConst c = template_consts(tpl8, tw, th);
+    TplConst c = template_consts(tpl8, tw, th, method_override >= 0 ? method_override : p.method);
     std::vector<uint32_t> sh;
     build_packed_template(tpl8, tw, th, &sh);
     if (sh.size() > packed_cap[slot]) {
@@ -546,7 +546,10 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
     lst_ctx *c = new lst_ctx();
     c->p = *params;
     if (c->p.max_batch == 0) c->p.max_batch = 512;
-    if (c->p.match_threshold == 0.0) c->p.match_threshold = 0.2;
+    if (c->p.match_threshold == 0.0) {   // matchThreshold[] of LST4:147
+        static const double kThr[6] = {0.1, 0.1, 0.05, 0.05, 0.2, 0.2};
+        c->p.match_threshold = kThr[c->p.method];
+    }
     c->device = device;
     memset(&c->stats, 0, sizeof(c->stats));
     memset(&c->h_tpls, 0, sizeof(c->h_tpls));
@@ -1176,12 +1179,13 @@ int lst_set_state(lst_ctx *c, const double dis[10])
 }
 
 int lst_match_single(lst_ctx *c, const uint8_t *src8, int32_t sw, int32_t sh, const uint8_t *tpl8, int32_t tw,
-                     int32_t th, int32_t sub_pix, double out[3], float *score_map)
+                     int32_t th, int32_t method, int32_t sub_pix, double out[3], float *score_map)
 {
     if (!c || !src8 || !tpl8 || !out) return LST_ERR_INVALID;
+    if (method < 0 || method > 5) return c->fail(LST_ERR_INVALID, "matching method must be 0..5");
     if (tw < 1 || th < 1 || tw > 256 || th > 256 || sw < tw || sh < th) return c->fail(LST_ERR_INVALID, "bad sizes");
     CUC(c, cudaSetDevice(c->device));
-    int rc = c->upload_template(kMaxTpl - 1, tpl8, tw, th);
+    int rc = c->upload_template(kMaxTpl - 1, tpl8, tw, th, method);
     if (rc != LST_OK) return rc;
     size_t pitch = (sw + 15) & ~15;
     rc = c->ensure_scratch(pitch * sh + 512, score_map ? (size_t)sw * sh + 64 : 0);
@@ -1205,10 +1209,10 @@ int lst_match_single(lst_ctx *c, const uint8_t *src8, int32_t sw, int32_t sh, co
     return LST_OK;
 }
 
-int lst_match_test(lst_ctx *c, const uint8_t *src8, int32_t sw, int32_t sh, double *out)
+int lst_match_test(lst_ctx *c, const uint8_t *src8, int32_t sw, int32_t sh, int32_t method, double *out)
 {
     double o[3];
-    int rc = lst_match_single(c, src8, sw, sh, src8, sw, sh, 0, o, nullptr);
+    int rc = lst_match_single(c, src8, sw, sh, src8, sw, sh, method, 0, o, nullptr);
     if (rc == LST_OK && out) *out = o[2];
     return rc;
 }

@@ -114,8 +114,8 @@ def load() -> C.CDLL:
         "lst_track_device_ptrs": ([vp, P(vp), i64, i32, P(Record)], C.c_int),
         "lst_get_state": ([vp, P(dbl)], C.c_int),
         "lst_set_state": ([vp, P(dbl)], C.c_int),
-        "lst_match_single": ([vp, vp, i32, i32, vp, i32, i32, i32, P(dbl), vp], C.c_int),
-        "lst_match_test": ([vp, vp, i32, i32, P(dbl)], C.c_int),
+        "lst_match_single": ([vp, vp, i32, i32, vp, i32, i32, i32, i32, P(dbl), vp], C.c_int),
+        "lst_match_test": ([vp, vp, i32, i32, i32, P(dbl)], C.c_int),
         "lst_preprocess": ([vp, vp, i32, i32, i32, i32, vp], C.c_int),
         "lst_calc_displacement": ([P(C.c_float), P(dbl), dbl, P(dbl), P(dbl)], C.c_int),
         "lst_alloc_pinned": ([sz, P(vp)], C.c_int),

@@ -165,8 +165,6 @@ class LaserSpotTrack4:
     def doMatch_coord_res(self, src8: np.ndarray, tpl8: np.ndarray, method: int = 5, subPix: bool = True,
                           want_map: bool = False):
         """doMatch_coord_res(src, tpl, method, subPix, null) on 8-bit images -> [x, y, score] (LST4:2502)."""
-        if method != 5:
-            raise LstError(N.LST_ERR_UNSUPPORTED, "only method 5 is on this path")
         s = np.ascontiguousarray(src8, dtype=np.uint8)
         t = np.ascontiguousarray(tpl8, dtype=np.uint8)
         out = (C.c_double * 3)()
@@ -176,16 +174,14 @@ class LaserSpotTrack4:
             m = np.zeros((s.shape[0] - t.shape[0] + 1, s.shape[1] - t.shape[1] + 1), dtype=np.float32)
             mp = m.ctypes.data
         self._check(self._lib.lst_match_single(self._ctx, s.ctypes.data, s.shape[1], s.shape[0], t.ctypes.data,
-                                               t.shape[1], t.shape[0], int(subPix), out, mp))
+                                               t.shape[1], t.shape[0], int(method), int(subPix), out, mp))
         res = [out[0], out[1], out[2]]
         return (res, m) if want_map else res
 
     def doMatch_test(self, src8: np.ndarray, method: int = 5) -> float:
-        if method != 5:
-            raise LstError(N.LST_ERR_UNSUPPORTED, "only method 5 is on this path")
         s = np.ascontiguousarray(src8, dtype=np.uint8)
         out = C.c_double()
-        self._check(self._lib.lst_match_test(self._ctx, s.ctypes.data, s.shape[1], s.shape[0], C.byref(out)))
+        self._check(self._lib.lst_match_test(self._ctx, s.ctypes.data, s.shape[1], s.shape[0], int(method), C.byref(out)))
         return out.value
 
     def preprocess(self, frame: np.ndarray, x0: int, y0: int, w: int, h: int) -> np.ndarray:

@@ -63,7 +63,7 @@ class Params:
     templ_size: int = 120          # templSize  LST4:84
     s_area: int = 50               # sArea      LST4:83
     mark_dist: float = 100.0       # markDist   LST4:85
-    method: int = TM_CCOEFF_NORMED # only method 5 is on the path (north_star)
+    method: int = TM_CCOEFF_NORMED # 0..5 (LST4:2381); 5 is the plugin's default and the north_star path
     sub_pixel: bool = True         # LST4:89
     match_intensity: bool = True   # LST4:88
     range_mode: int = RANGE_DISPLAY
@@ -366,16 +366,56 @@ def ncc_from_sums(corr, wsum, wsq, inv_area: float, templ_mean: float, templ_nor
     return out.astype(f32)
 
 
-def ncc_map_exact(win8: np.ndarray, tpl8: np.ndarray) -> np.ndarray:
-    """matchTemplate(win, tpl, TM_CCOEFF_NORMED) with an exact numerator (LST4:2560)."""
+def match_from_sums(method: int, corr, wsum, wsq, tpl8: np.ndarray):
+    """common_matchTemplate (templmatch.cpp), cn=1, for any of the six methods of LST4:2381
+    (0 SQDIFF, 1 SQDIFF_NORMED, 2 CCORR, 3 CCORR_NORMED, 4 CCOEFF, 5 CCOEFF_NORMED) with the
+    *exact* integer correlation.  Double arithmetic in OpenCV's order, stored as float32."""
+    tsum, tsq, inv_area, mean, norm, flat = template_stats(tpl8)
+    if method == 5:
+        return ncc_from_sums(corr, wsum, wsq, inv_area, mean, norm, flat)
+    corr = np.asarray(corr, dtype=np.float64)
+    if method == 2:
+        return corr.astype(f32)
+    num_type = 0 if method in (2, 3) else (1 if method == 4 else 2)
+    normed = method in (1, 3)
+    # templSum2 / templNorm as derived from meanStdDev (not from the integer sums)
+    var = float(tsq) / float(tpl8.size) - mean * mean
+    sdv = math.sqrt(max(var, 0.0))
+    sum2 = sdv * sdv + mean * mean
+    norm_raw = math.sqrt(sum2) / math.sqrt(inv_area)
+    sum2 = sum2 / inv_area
+    num = corr
+    wnd_mean2 = 0.0
+    wnd_sum2 = 0.0
+    if num_type == 1:
+        t = np.asarray(wsum, dtype=np.float64)
+        wnd_mean2 = (t * t) * inv_area
+        num = num - t * mean
+    if normed or num_type == 2:
+        wnd_sum2 = np.asarray(wsq, dtype=np.float64)
+        if num_type == 2:
+            num = np.maximum(wnd_sum2 - 2.0 * num + sum2, 0.0)
+    if normed:
+        diff2 = np.maximum(wnd_sum2 - wnd_mean2, 0.0)
+        thr = np.minimum(0.5, 10.0 * FLT_EPSILON * wnd_sum2)
+        tt = np.where(diff2 <= thr, 0.0, np.sqrt(diff2) * norm_raw)
+        anum = np.abs(num)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            q = num / tt
+        other = 1.0 if method == 1 else 0.0
+        num = np.where(anum < tt, q, np.where(anum < tt * 1.125, np.where(num > 0, 1.0, -1.0), other))
+    return np.asarray(num).astype(f32)
+
+
+def ncc_map_exact(win8: np.ndarray, tpl8: np.ndarray, method: int = TM_CCOEFF_NORMED) -> np.ndarray:
+    """matchTemplate(win, tpl, method) with an exact numerator (LST4:2560)."""
     th, tw = tpl8.shape
     corr = xcorr_exact(win8, tpl8)
     wsum, wsq = box_sums(win8, th, tw)
-    _, _, inv_area, mean, norm, flat = template_stats(tpl8)
-    return ncc_from_sums(corr, wsum, wsq, inv_area, mean, norm, flat)
+    return match_from_sums(method, corr, wsum, wsq, tpl8)
 
 
-def ncc_map_cv2(win8: np.ndarray, tpl8: np.ndarray) -> np.ndarray:
+def ncc_map_cv2(win8: np.ndarray, tpl8: np.ndarray, method: int = TM_CCOEFF_NORMED) -> np.ndarray:
     """The real third-party routine (OpenCV in this image, IPP off, 1 thread)."""
     import cv2
     cv2.setNumThreads(1)
@@ -383,7 +423,16 @@ def ncc_map_cv2(win8: np.ndarray, tpl8: np.ndarray) -> np.ndarray:
         cv2.ipp.setUseIPP(False)
     except Exception:
         pass
-    return cv2.matchTemplate(np.ascontiguousarray(win8), np.ascontiguousarray(tpl8), cv2.TM_CCOEFF_NORMED)
+    return cv2.matchTemplate(np.ascontiguousarray(win8), np.ascontiguousarray(tpl8), method)   # cv2.TM_* == 0..5
+
+
+def best_loc_first(res: np.ndarray, method: int = TM_CCOEFF_NORMED):
+    """minMaxLoc + the min/max choice of LST4:2671-2679: minimum for methods 0 and 1."""
+    if method in (0, 1):
+        idx = int(np.argmin(res))
+        y, x = divmod(idx, res.shape[1])
+        return x, y, float(res[y, x])
+    return max_loc_first(res)
 
 
 def max_loc_first(res: np.ndarray):
@@ -417,11 +466,12 @@ def subpixel_fit(res: np.ndarray, x: int, y: int) -> Tuple[float, float]:
     return dx, dy
 
 
-def do_match_coord_res(win8: np.ndarray, tpl8: np.ndarray, sub_pix: bool, backend: str = "exact"):
+def do_match_coord_res(win8: np.ndarray, tpl8: np.ndarray, sub_pix: bool, backend: str = "exact",
+                       method: int = TM_CCOEFF_NORMED):
     """doMatch_coord_res(src, tpl, 5, subPix, null) on the 8-bit images that reach OpenCV
     (LST4:2502-2563, 2665-2722).  Returns ([x, y, score], result_map)."""
-    res = ncc_map_exact(win8, tpl8) if backend == "exact" else ncc_map_cv2(win8, tpl8)
-    x, y, v = max_loc_first(res)
+    res = ncc_map_exact(win8, tpl8, method) if backend == "exact" else ncc_map_cv2(win8, tpl8, method)
+    x, y, v = best_loc_first(res, method)
     cx, cy = float(x), float(y)
     if sub_pix:
         dx, dy = subpixel_fit(res, x, y)
@@ -430,18 +480,32 @@ def do_match_coord_res(win8: np.ndarray, tpl8: np.ndarray, sub_pix: bool, backen
     return [cx, cy, v], res
 
 
-def do_match_test(tpl8: np.ndarray, backend: str = "exact") -> float:
+def do_match_test(tpl8: np.ndarray, backend: str = "exact", method: int = TM_CCOEFF_NORMED) -> float:
     """doMatch_test: matchTemplate(tpl, tpl) -> 1x1 result (LST4:2724-2767)."""
-    res = ncc_map_exact(tpl8, tpl8) if backend == "exact" else ncc_map_cv2(tpl8, tpl8)
+    res = ncc_map_exact(tpl8, tpl8, method) if backend == "exact" else ncc_map_cv2(tpl8, tpl8, method)
     return float(res[0, 0])
 
 
 def test_match_result(result: float, ref: float, x: float, y: float, search_width: int, tpl_size: int,
-                      thresh: float = MATCH_THRESHOLD[5]) -> bool:
-    """testMatchResult, method 5 (LST4:1225-1255)."""
+                      thresh: Optional[float] = None, method: int = TM_CCOEFF_NORMED) -> bool:
+    """testMatchResult (LST4:1225-1255)."""
     ok = True
     dist = min(0.05 * tpl_size, 0.05 * search_width)
-    if abs(result - ref) > thresh:
+    if thresh is None:
+        thresh = MATCH_THRESHOLD[method]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        result, ref = np.float64(result), np.float64(ref)    # Java double division: x/0 = inf, 0/0 = NaN
+        if method == 0:
+            bad = result / ref > thresh
+        elif method == 1:
+            bad = result > thresh
+        elif method == 2:
+            bad = abs((result - ref) / ref) > thresh
+        elif method == 4:
+            bad = abs(result - ref) / ref > thresh
+        else:
+            bad = abs(result - ref) > thresh
+    if bad:
         ok = False
     if search_width != 0 and (x < dist or y < dist or x > search_width - dist or y > search_width - dist):
         ok = False
@@ -580,7 +644,7 @@ class OracleTracker:
             cx0, cy0, cw, ch = clip_rect(x0, y0, side, side, p.width, p.height)   # crop() clips to the image
             t8 = preprocess_crop(frame, cx0, cy0, cw, ch, p)
             self.tpl8.append(t8)
-            self.mideal.append(do_match_test(t8, self.backend))                    # LST4:566 (spot: per frame LST4:2050)
+            self.mideal.append(do_match_test(t8, self.backend, 2 if p.method == 0 else p.method))   # LST4:566
         self.dis = [(0.0, 0.0)] * 5
         self.spot0 = None
         rec = FrameRecord()
@@ -626,11 +690,12 @@ class OracleTracker:
         p = self.p
         cx, cy, cw, ch = clip_rect(wx, wy, ww, wh, p.width, p.height)
         win8 = preprocess_crop(frame, cx, cy, cw, ch, p)
-        coord, res = do_match_coord_res(win8, self.tpl8[k], p.sub_pixel, self.backend)
-        ix, iy, _ = max_loc_first(res)
+        coord, res = do_match_coord_res(win8, self.tpl8[k], p.sub_pixel, self.backend, p.method)
+        ix, iy, _ = best_loc_first(res, p.method)
         tm = TemplateMatch(x=coord[0], y=coord[1], score=coord[2], ix=ix, iy=iy,
                            wx=wx, wy=wy, ww=ww, wh=wh, s_used=s_used, evaluated=True)
-        tm.accepted = test_match_result(coord[2], self.mideal[k], coord[0], coord[1], 2 * s_used, p.templ_size)
+        tm.accepted = test_match_result(coord[2], self.mideal[k], coord[0], coord[1], 2 * s_used, p.templ_size,
+                                        method=p.method)
         return tm
 
     # -- analyseSlice: LST4:1302-2216 --------------------------------------------------

@@ -60,7 +60,8 @@ def test_version_and_no_gpu_is_loud(built_lib):
 def test_param_validation_mirrors_reference(built_lib):
     lib = N.load()
     ctx = C.c_void_p()
-    for kw, code in [(dict(method=3), N.LST_ERR_UNSUPPORTED),
+    for kw, code in [(dict(method=6), N.LST_ERR_INVALID),
+                     (dict(method=-1), N.LST_ERR_INVALID),
                      (dict(pixel_type=24), N.LST_ERR_UNSUPPORTED),
                      (dict(pixel_type=N.PIX_U16, match_intensity=0), N.LST_ERR_UNSUPPORTED),
                      (dict(templ_size=4), N.LST_ERR_UNSUPPORTED),

@@ -19,7 +19,7 @@ SUBPIX_TOL_CV2 = 1e-3     # north_star: sub-pixel positions / displacements with
 
 def _tracker(cfg, op, **kw):
     bits = {"u8": 8, "u16": 16, "f32": 32}[cfg.dtype]
-    return LaserSpotTrack4(cfg.width, cfg.height, bits, templSize=op.templ_size, sArea=op.s_area,
+    return LaserSpotTrack4(cfg.width, cfg.height, bits, method=op.method, templSize=op.templ_size, sArea=op.s_area,
                            markDist=op.mark_dist, subPixel=op.sub_pixel, matchIntensity=op.match_intensity,
                            doubling=op.doubling, maxSArea=op.max_s_area, range_mode=op.range_mode,
                            range_lo=op.range_lo, range_hi=op.range_hi, quant_mode=op.quant_mode, **kw)
@@ -193,7 +193,7 @@ def test_unsupported_like_reference(built_lib):
     with pytest.raises(LstError):
         LaserSpotTrack4(640, 480, 16, matchIntensity=False)     # null Mat in the reference, LST4:2510-2523
     with pytest.raises(LstError):
-        LaserSpotTrack4(640, 480, 8, method=3)
+        LaserSpotTrack4(640, 480, 8, method=6)
     with pytest.raises(LstError):
         LaserSpotTrack4(640, 480, 24)
     with LaserSpotTrack4(640, 480, 8) as t:
@@ -421,3 +421,43 @@ def test_both_match_engines_identical(stack_a):
         with _tracker(cfg2, op2, ncc_engine=engine) as t:
             t.set_reference(fr2[0], st2.ref_xy)
             util.compare_records(t.track(np.stack(fr2[1:])), w2, label=f"odd sizes engine {engine}")
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("S,T", [(96, 32), (75, 33), (150, 127)])
+def test_match_single_other_methods(built_lib, oracle_clib, method, S, T):
+    """the other five methods of the dialog (LST4:2381), score map bit-exact against
+    the exact oracle, min/max choice of LST4:2671-2679, and close to cv2 (relative to the map's scale:
+    OpenCV's float32 DFT numerator carries ~1e-6 relative noise on the raw-valued methods)."""
+    rng = np.random.default_rng(S * 1000 + T)
+    import cv2
+    base = cv2.GaussianBlur(rng.integers(0, 256, size=(S + 40, S + 40), dtype=np.uint8), (0, 0), 2.0)
+    win = np.ascontiguousarray(base[:S, :S])
+    tpl = np.ascontiguousarray(base[11:11 + T, 17:17 + T]) if S - T > 17 else np.ascontiguousarray(base[3:3 + T, 5:5 + T])
+    with LaserSpotTrack4(640, 480, 8) as t:
+        res, m = t.doMatch_coord_res(win, tpl, method, True, want_map=True)
+        exact = O.ncc_map_exact(win, tpl, method)
+        assert np.array_equal(m.view(np.uint32), exact.view(np.uint32)), f"method {method}: max abs {np.abs(m - exact).max()}"
+        want, _ = O.do_match_coord_res(win, tpl, True, "exact", method)
+        assert res == want, (res, want)
+        cvm = O.ncc_map_cv2(win, tpl, method)
+        scale = max(1.0, float(np.abs(cvm).max()))
+        assert float(np.abs(m.astype(np.float64) - cvm).max()) / scale <= SCORE_TOL_CV2
+        assert t.doMatch_test(tpl, method) == O.do_match_test(tpl, "exact", method)
+        # without the map (the tracking kernels' path): same peak
+        assert t.doMatch_coord_res(win, tpl, method, True) == want
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4])
+def test_track_other_methods(stack_a, method):
+    """Whole records for the other five methods, both match engines, against the oracle."""
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=False, method=method)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:21])
+    for engine in (1, 2):
+        with _tracker(cfg, op, ncc_engine=engine, max_batch=8) as t:
+            info = t.set_reference(frames[0], st.ref_xy)
+            assert list(info.mideal) == otr.mideal
+            util.compare_records(t.track(np.stack(frames[1:21])), want, label=f"method {method} engine {engine}")

@@ -175,3 +175,36 @@ def test_tracking_loop_golden(oracle_clib, name):
     # sanity against ground truth: tracked spot displacement follows the synthetic motion
     t = st.truth(n) - st.truth(0)
     assert abs(recs[-1].dX_pix - (t[0, 0] - t[1, 0])) < 0.15 and abs(recs[-1].dY_pix - (t[0, 1] - t[1, 1])) < 0.15
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4, 5])
+def test_all_methods_pinned_against_cv2(oracle_clib, method):
+    """common_matchTemplate restated for the six methods of the dialog (LST4:2381),
+    pinned against the OpenCV in this image.  Tolerance relative to the map's scale: cv2's numerator
+    is a float32 DFT."""
+    import cv2
+    rng = np.random.default_rng(40 + method)
+    for shape, tshape, blur in [((90, 100), (32, 32), 0), ((90, 100), (32, 32), 3), ((64, 70), (20, 33), 0)]:
+        win = rng.integers(0, 256, shape, dtype=np.uint8)
+        if blur:
+            win = cv2.GaussianBlur(win, (0, 0), blur)
+        tpl = win[20:20 + tshape[0], 30:30 + tshape[1]].copy() if blur == 0 and tshape == (32, 32) else \
+            rng.integers(0, 256, tshape, dtype=np.uint8)
+        a = O.ncc_map_exact(win, tpl, method)
+        b = O.ncc_map_cv2(win, tpl, method)
+        scale = max(1.0, float(np.abs(b).max()))
+        assert float(np.abs(a.astype(np.float64) - b).max()) / scale < 2e-4
+        assert O.best_loc_first(a, method)[:2] == O.best_loc_first(b, method)[:2]
+
+
+def test_match_result_all_methods():
+    """testMatchResult's per-method acceptance (LST4:1225-1255) with matchThreshold of LST4:147."""
+    T = O.test_match_result
+    assert T(0.09e6, 1.0e6, 30, 30, 64, 32, method=0) and not T(0.11e6, 1.0e6, 30, 30, 64, 32, method=0)
+    assert T(0.09, 123.0, 30, 30, 64, 32, method=1) and not T(0.11, 0.0, 30, 30, 64, 32, method=1)
+    assert T(0.96e6, 1.0e6, 30, 30, 64, 32, method=2) and not T(1.06e6, 1.0e6, 30, 30, 64, 32, method=2)
+    assert T(0.96, 1.0, 30, 30, 64, 32, method=3) and not T(0.94, 1.0, 30, 30, 64, 32, method=3)
+    assert T(0.81e6, 1.0e6, 30, 30, 64, 32, method=4) and not T(0.79e6, 1.0e6, 30, 30, 64, 32, method=4)
+    assert not T(0.96e6, 1.0e6, 1.0, 30, 64, 32, method=2)           # edge test is method-independent
+    # Java double division by a zero reference: x/0 -> inf (> thresh) for x > 0, 0/0 -> NaN (not > thresh)
+    assert not T(5.0, 0.0, 30, 30, 64, 32, method=0) and T(0.0, 0.0, 30, 30, 64, 32, method=0)

@@ -19,7 +19,7 @@ def oracle_params(cfg, **kw) -> O.Params:
 
 
 def native_params(op: O.Params, pixel_type: int, max_batch: int = 0) -> N.Params:
-    return N.default_params(op.width, op.height, pixel_type, templ_size=op.templ_size, s_area=op.s_area,
+    return N.default_params(op.width, op.height, pixel_type, method=op.method, templ_size=op.templ_size, s_area=op.s_area,
                             mark_dist=op.mark_dist, sub_pixel=int(op.sub_pixel),
                             match_intensity=int(op.match_intensity), range_mode=op.range_mode,
                             range_lo=op.range_lo, range_hi=op.range_hi, quant_mode=op.quant_mode,
