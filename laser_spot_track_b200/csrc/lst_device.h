@@ -28,7 +28,7 @@ struct Surface {
     const void *ptr;
     int32_t pitch_px;     // row pitch in pixels
     int32_t org_x, org_y; // slice coordinates of the surface's first pixel
-    int32_t pad;
+    int32_t rows;         // rows of the surface: [ptr, ptr + rows*pitch) is readable (the blur kernel's 128-bit loads stay inside)
 };
 
 // One region of interest gathered from every slice of a batch (same rectangle for all slices).

@@ -231,52 +231,204 @@ int launch_gather_rois(const void *const *mapped_frames, int n_frames, const Roi
 // ------------------------------------------------------------------------------------------------
 // crop -> float -> blur -> 8-bit
 // ------------------------------------------------------------------------------------------------
-// One line of ImageJ's GaussianBlur.convolveLine for output index i of a line of length n
-// (n >= 2*KR), float32, Java operation order.  IN(i) reads the line.
-#define LST_BLUR_AT(res, i, n, IN)                                            \
-    {                                                                         \
-        res = IN(i) * c_kern[0];                                              \
-        if ((i) < KR) res = res + c_ksum[(i)] * IN(0);                        \
-        if ((i) + KR >= (n)) res = res + c_ksum[(n) - (i)-1] * IN((n)-1);     \
-        _Pragma("unroll") for (int k_ = 1; k_ < KR; k_++)                     \
-        {                                                                     \
-            float v_ = 0.0f;                                                  \
-            if ((i)-k_ >= 0) v_ = v_ + IN((i)-k_);                            \
-            if ((i) + k_ < (n)) v_ = v_ + IN((i) + k_);                       \
-            res = res + c_kern[k_] * v_;                                      \
-        }                                                                     \
+// ImageJ's GaussianBlur.convolveLine, float32, Java operation order, for a run of NOUT consecutive
+// outputs whose inputs v[0 .. NOUT + 2*KR - 3] start KR-1 samples before the first output.  Samples
+// outside the line must be 0 in v: the reference adds only the in-range one of the two mirrored taps
+// (0 + x == x), and -- for the KR-1 outputs next to an end -- the replicated end sample times the
+// tail sum of the kernel *before* the tap loop.  i0 = line index of the first output, n = line length.
+template <int NOUT, bool EDGE>
+__device__ __forceinline__ void blur_run(const float *v, float *out, int i0, int n, float first, float last)
+{
+#pragma unroll
+    for (int j = 0; j < NOUT; j++) {
+        float res = v[KR - 1 + j] * c_kern[0];
+        if (EDGE) {
+            const int i = i0 + j;
+            if (i < KR) res = res + c_ksum[i] * first;
+            if (i + KR >= n && i < n) res = res + c_ksum[n - i - 1] * last;
+        }
+#pragma unroll
+        for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
+        out[j] = res;
     }
+}
+
+// ---- raw pixel staging --------------------------------------------------------------------------
+// Packed min/max of raw pixel words (u8 x 4, u16 x 2 or one float key per 32-bit word); wlo / whi are
+// the word with the bytes that do not count forced to 0xff / 0x00.
+template <int PIX>
+__device__ __forceinline__ void mm_word(uint32_t wlo, uint32_t whi, uint32_t &lo, uint32_t &hi)
+{
+    if (PIX == LST_PIX_U8) {
+        lo = __vminu4(lo, wlo);
+        hi = __vmaxu4(hi, whi);
+    } else if (PIX == LST_PIX_U16) {
+        lo = __vminu2(lo, wlo);
+        hi = __vmaxu2(hi, whi);
+    } else {
+        const uint32_t k = f32_key(__uint_as_float(whi));
+        lo = min(lo, k);
+        hi = max(hi, k);
+    }
+}
+template <int PIX>
+__device__ __forceinline__ void mm_finish(uint32_t &lo, uint32_t &hi)   // packed accumulators -> keys
+{
+    if (PIX == LST_PIX_U8) {
+        lo = min(min(lo & 0xffu, (lo >> 8) & 0xffu), min((lo >> 16) & 0xffu, lo >> 24));
+        hi = max(max(hi & 0xffu, (hi >> 8) & 0xffu), max((hi >> 16) & 0xffu, hi >> 24));
+    } else if (PIX == LST_PIX_U16) {
+        lo = min(lo & 0xffffu, lo >> 16);
+        hi = max(hi & 0xffffu, hi >> 16);
+    }
+}
+// bytes [s, e) of a 32-bit word as a mask (s, e clamped to 0..4)
+__device__ __forceinline__ uint32_t byte_range_mask(int s, int e)
+{
+    s = max(s, 0);
+    e = min(e, 4);
+    return e > s ? ((0xffffffffu >> (8 * (4 - (e - s)))) << (8 * s)) : 0u;
+}
+
+// Rows [row0, row0 + nrows) of the crop, byte columns [lo0, lo0 + 16*vpr) (lo0 may be negative), as 16-byte
+// vectors; a warp takes a row, a lane a vector.  The crop starts at an arbitrary pixel of the
+// surface, so a vector is fetched as the two aligned 128-bit words around it and realigned with
+// funnel shifts (the shift is the same for the whole row); bytes outside the crop row are masked
+// to 0.  Only when the aligned words would leave the surface is the vector assembled pixel by
+// pixel.  STORE: the pixels go to sraw[r][.] as floats; MINMAX: the in-crop pixels are folded into
+// the packed accumulators.
+template <int PIX, bool STORE, bool MINMAX>
+__device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, size_t row_pitch_bytes, int row0, int nrows,
+                                           int lo0, int vpr, int row_bytes, const uint8_t *surf_lo, const uint8_t *surf_hi,
+                                           float *sraw, int rwp, uint32_t &mlo, uint32_t &mhi)
+{
+    constexpr int ES = PIX == LST_PIX_U8 ? 1 : (PIX == LST_PIX_U16 ? 2 : 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < nrows; r += nwarps) {
+        const uint8_t *grow = crop00 + (size_t)(row0 + r) * row_pitch_bytes;
+        const uint8_t *p0 = grow + lo0;
+        const uint32_t a = (uint32_t)((uintptr_t)p0 & 15u);
+        const uint32_t bs = 8u * (a & 3u);
+        for (int q = lane; q < vpr; q += 32) {
+            const int lo = lo0 + 16 * q;                       // crop byte of this vector's first byte
+            uint32_t o[4] = {0u, 0u, 0u, 0u};
+            if (lo + 16 > 0 && lo < row_bytes) {
+                const uint8_t *pa = p0 + 16 * q - a;
+                if (pa >= surf_lo && pa + 32 <= surf_hi) {
+                    const uint4 v0 = __ldg((const uint4 *)pa), v1 = __ldg((const uint4 *)pa + 1);
+                    uint32_t w0 = v0.x, w1 = v0.y, w2 = v0.z, w3 = v0.w, w4 = v1.x, w5 = v1.y, w6 = v1.z, w7 = v1.w;
+                    if (a & 8u) w0 = w2, w1 = w3, w2 = w4, w3 = w5, w4 = w6, w5 = w7;
+                    if (a & 4u) w0 = w1, w1 = w2, w2 = w3, w3 = w4, w4 = w5;
+                    o[0] = __funnelshift_r(w0, w1, bs);
+                    o[1] = __funnelshift_r(w1, w2, bs);
+                    o[2] = __funnelshift_r(w2, w3, bs);
+                    o[3] = __funnelshift_r(w3, w4, bs);
+                    if (lo >= 0 && lo + 16 <= row_bytes) {
+                        if (MINMAX) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) mm_word<PIX>(o[j], o[j], mlo, mhi);
+                        }
+                    } else {
+                        const int b0 = -lo, b1 = row_bytes - lo;   // valid bytes of the vector: [b0, b1)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t m = byte_range_mask(b0 - 4 * j, b1 - 4 * j);
+                            o[j] &= m;
+                            if (MINMAX) {
+                                if (PIX != LST_PIX_F32) mm_word<PIX>(o[j] | ~m, o[j], mlo, mhi);
+                                else if (m) mm_word<PIX>(o[j], o[j], mlo, mhi);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int e = 0; e < 16 / ES; e++) {
+                        const int bo = lo + e * ES;            // crop byte offset of this pixel
+                        if (bo >= 0 && bo < row_bytes) {
+                            uint32_t v;
+                            if (PIX == LST_PIX_U8) v = grow[bo];
+                            else if (PIX == LST_PIX_U16) v = *(const uint16_t *)(grow + bo);
+                            else v = *(const uint32_t *)(grow + bo);
+                            const uint32_t sh = v << (8 * ((e * ES) & 3));
+                            const int wi = (e * ES) >> 2;
+                            o[0] |= wi == 0 ? sh : 0u, o[1] |= wi == 1 ? sh : 0u, o[2] |= wi == 2 ? sh : 0u, o[3] |= wi == 3 ? sh : 0u;
+                            if (MINMAX) {
+                                const uint32_t rep = PIX == LST_PIX_U8 ? v * 0x01010101u : (PIX == LST_PIX_U16 ? v * 0x00010001u : v);
+                                mm_word<PIX>(rep, rep, mlo, mhi);
+                            }
+                        }
+                    }
+                }
+            }
+            if (STORE) {
+                float *d = sraw + (size_t)r * rwp + q * (16 / ES);
+                if (PIX == LST_PIX_U8) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        ((float4 *)d)[j] = make_float4((float)(o[j] & 0xffu), (float)((o[j] >> 8) & 0xffu),
+                                                       (float)((o[j] >> 16) & 0xffu), (float)(o[j] >> 24));
+                } else if (PIX == LST_PIX_U16) {
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        ((float4 *)d)[j] = make_float4((float)(o[2 * j] & 0xffffu), (float)(o[2 * j] >> 16),
+                                                       (float)(o[2 * j + 1] & 0xffffu), (float)(o[2 * j + 1] >> 16));
+                } else {
+                    *(float4 *)d = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
+                }
+            }
+        }
+    }
+}
 
 // A CTA owns a column block (up to tile_w columns, the whole window for the named configurations) of
-// one window over its full height and walks it in strips of PRE_STRIP rows.  X-pass rows live in a
-// ring of PRE_RING rows indexed by (row mod PRE_RING), so the 12 rows two consecutive strips share
-// are computed once.  When the range convention needs the crop's min/max and the window is a
-// single column block, the CTA finds them itself first (no separate kernel).
+// one window over its full height and walks it in strips of PRE_STRIP rows:
+//   sraw [PRE_STRIP + KR-1][RWP]  the strip's new crop rows as floats, columns from cx0 - 8, zero outside
+//                                 the crop (so every run takes the same code path), fetched with
+//                                 128-bit loads (stage_rows);
+//   xp   [PRE_STRIP + 2(KR-1)][XWP] X-pass rows cy0-(KR-1) .. cy1+(KR-1)-1; the 2(KR-1) rows two strips
+//                                 share are moved to the front between strips, not recomputed.
+// X pass: a warp takes a run of 8 columns, its lanes consecutive rows (six 128-bit loads -> 8
+// results, two 128-bit stores; both pitches are odd multiples of 16 bytes: conflict-free).  Y pass:
+// a thread takes 8 rows of one column (20 loads at constant offsets -> 8 results), consecutive
+// threads own consecutive columns.  When the range convention needs the crop's min/max and the
+// window is a single column block, the CTA finds them itself first with the same 128-bit loads (no
+// separate kernel).
 #define PRE_STRIP 32
 #define PRE_RING (PRE_STRIP + 2 * (KR - 1))   // 44
+#define PRE_XRUN 8
+#define PRE_YRUN 8
+
+__host__ __device__ inline int pre_raw_pitch(int tile_w) { int v = tile_w + 32; return ((v >> 2) & 1) ? v : v + 4; }
+__host__ __device__ inline int pre_xp_pitch(int tile_w) { return ((tile_w >> 2) & 1) ? tile_w : tile_w + 4; }
 
 template <int PIX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512, 2)
 lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ surfaces, PreprocParams pp,
                const uint32_t *__restrict__ mm_keys, uint8_t *__restrict__ win8)
 {
-    extern __shared__ float smem_f[];
+    constexpr int ES = PIX == LST_PIX_U8 ? 1 : (PIX == LST_PIX_U16 ? 2 : 4);
+    extern __shared__ __align__(16) float smem_f[];
     __shared__ uint32_t s_mm[2];
     const DevTask t = tasks[blockIdx.y];
-    const int TW = pp.tile_w;
+    const int TW = pp.tile_w;                  // multiple of 16
     const int tiles_x = (t.w + TW - 1) / TW;
     if ((int)blockIdx.x >= tiles_x) return;
+    const int NT = blockDim.x;
     const int cx0 = blockIdx.x * TW;
     const int cx1 = min(cx0 + TW, t.w);
-    const int rx0 = max(cx0 - (KR - 1), 0), rx1 = min(cx1 + (KR - 1), t.w);
-    const int RWP = TW + 2 * (KR - 1) + 1;     // raw strip pitch (floats)
-    const int XWP = TW + 1;                    // x-pass ring pitch
-    float *raw = smem_f;                                            // [PRE_STRIP + KR - 1][RWP]
-    float *xp = smem_f + (size_t)(PRE_STRIP + KR - 1) * RWP;        // [PRE_RING][XWP]
+    const int ncw = cx1 - cx0;
+    const int nrun = (ncw + PRE_XRUN - 1) / PRE_XRUN;
+    const int RWP = pre_raw_pitch(TW), XWP = pre_xp_pitch(TW);
+    const int RB = cx0 - 8;                    // crop column held by sraw[.][0]
+    const int VPR = ((PRE_XRUN * nrun + 16) * ES + 15) >> 4;   // 16-byte vectors of a crop row the X pass needs
+    float *xp = smem_f;                                  // [PRE_RING][XWP]
+    float *sraw = smem_f + (size_t)PRE_RING * XWP;       // [PRE_STRIP + KR - 1][RWP]
     const Surface sf = surfaces[t.frame];
-    const void *fr = sf.ptr;
-    const int nrw = rx1 - rx0, ncw = cx1 - cx0;
-    const size_t src00 = (size_t)(t.y0 - sf.org_y) * sf.pitch_px + (t.x0 - sf.org_x);
+    const size_t row_pitch_bytes = (size_t)sf.pitch_px * ES;
+    const uint8_t *surf_lo = (const uint8_t *)sf.ptr, *surf_hi = surf_lo + (size_t)sf.rows * row_pitch_bytes;
+    const uint8_t *crop00 = surf_lo + ((size_t)(t.y0 - sf.org_y) * sf.pitch_px + (t.x0 - sf.org_x)) * ES;
+    const int row_bytes = t.w * ES;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = NT >> 5;
 
     float lo = pp.lo, hi = pp.hi;
     if (pp.range_per_task) {
@@ -287,20 +439,15 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
             }
             __syncthreads();
             uint32_t klo = 0xffffffffu, khi = 0u;
-            for (int r = threadIdx.x >> 5; r < t.h; r += 8) {
-                const size_t rowoff = src00 + (size_t)r * sf.pitch_px;
-#pragma unroll 8
-                for (int c = threadIdx.x & 31; c < t.w; c += 32) {
-                    uint32_t k = px_key<PIX>(fr, rowoff + c);
-                    klo = min(klo, k);
-                    khi = max(khi, k);
-                }
-            }
+            // vectors aligned to the crop's first pixel: only the last one of a row is partial
+            stage_rows<PIX, false, true>(crop00, row_pitch_bytes, 0, t.h, 0, (row_bytes + 15) >> 4, row_bytes, surf_lo, surf_hi,
+                                         nullptr, 0, klo, khi);
+            mm_finish<PIX>(klo, khi);
             for (int o = 16; o > 0; o >>= 1) {
                 klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
                 khi = max(khi, __shfl_xor_sync(0xffffffffu, khi, o));
             }
-            if ((threadIdx.x & 31) == 0) {
+            if (lane == 0) {
                 atomicMin(&s_mm[0], klo);
                 atomicMax(&s_mm[1], khi);
             }
@@ -313,127 +460,120 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
         }
     }
     const float scale = (pp.quant_mode == LST_QUANT_ROUND255 ? 255.0f : 256.0f) / (hi - lo);
+    const float qadd = pp.quant_mode == LST_QUANT_ROUND255 ? 0.5f : 0.0f;
     uint8_t *dst = win8 + t.win_off;
-    const int nsegx = (ncw + 3) >> 2;
+    // Y-pass items (8-row run sg, column cc) of this thread: idx = tid, tid + NT, ... without a division per item
+    const int ysg0 = threadIdx.x / ncw, ycc0 = threadIdx.x - ysg0 * ncw;
+    const int ydsg = NT / ncw, ydcc = NT - ydsg * ncw;
 
-    int xdone = 0;   // x-pass rows [0, xdone) are in the ring (the newest PRE_RING of them)
+    int xdone = 0;   // x-pass rows [0, xdone) have been computed
     for (int cy0 = 0; cy0 < t.h; cy0 += PRE_STRIP) {
         const int cy1 = min(cy0 + PRE_STRIP, t.h);
         const int need = min(cy1 + (KR - 1), t.h);          // x-pass rows needed up to here
         const int newr = need - xdone;                      // <= PRE_STRIP + KR - 1
-        // raw rows [xdone, need), columns [rx0, rx1)
-        for (int r = threadIdx.x >> 5; r < newr; r += 8) {
-            const size_t rowoff = src00 + (size_t)(xdone + r) * sf.pitch_px + rx0;
-#pragma unroll 8
-            for (int c = threadIdx.x & 31; c < nrw; c += 32) raw[r * RWP + c] = load_px<PIX>(fr, rowoff + c);
+        const int xrow0 = cy0 - (KR - 1);                   // crop row held by xp[0][.]
+        // raw rows [xdone, need), columns from RB, zero outside the crop
+        {
+            uint32_t d0 = 0, d1 = 0;
+            stage_rows<PIX, true, false>(crop00, row_pitch_bytes, xdone, newr, RB * ES, VPR, row_bytes, surf_lo, surf_hi, sraw,
+                                         RWP, d0, d1);
+        }
+        // the X-pass rows this strip shares with the previous one move to the front
+        if (cy0 > 0) {
+            const int n4 = XWP >> 2;
+            for (int r = warp; r < 2 * (KR - 1); r += nwarps)
+                for (int c = lane; c < n4; c += 32)
+                    ((float4 *)(xp + (size_t)r * XWP))[c] = ((const float4 *)(xp + (size_t)(PRE_STRIP + r) * XWP))[c];
         }
         __syncthreads();
-        // X pass of the new rows.  Interior runs of 4 columns (no edge replication) take 16 loads per
-        // 4 results; the few runs next to the crop's left/right border take the general form.  The two
-        // kinds are walked by separate loops so that no warp executes both paths.
-        {
-            int sg_lo = cx0 >= KR ? 0 : (KR - cx0 + 3) >> 2;
-            int lim = min(t.w - (KR + 4), cx1 - 4) - cx0;              // i0 - cx0 <= lim
-            int sg_hi = lim < 0 ? -1 : lim >> 2;                        // last interior run
-            if (sg_hi >= nsegx) sg_hi = nsegx - 1;
-            const int nint = sg_hi >= sg_lo ? sg_hi - sg_lo + 1 : 0;
-            for (int idx = threadIdx.x; idx < nint * newr; idx += blockDim.x) {
-                const int r = idx / nint, sg = sg_lo + (idx - r * nint);
-                const float *line = raw + r * RWP - rx0;   // line[i] = crop row pixel i
-                const int i0 = cx0 + 4 * sg;
-                float *dstx = xp + ((xdone + r) % PRE_RING) * XWP + 4 * sg;
-                float v[16];
+        // X pass of the new rows
+        for (int run = warp; run < nrun; run += nwarps) {
+            const int i0 = cx0 + PRE_XRUN * run;
+            const bool interior = i0 >= KR && i0 + PRE_XRUN - 1 + KR < t.w;
+            for (int r = lane; r < newr; r += 32) {
+                const float *line = sraw + (size_t)r * RWP;
+                float v[PRE_XRUN + 16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = line[i0 - (KR - 1) + j];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float res = v[KR - 1 + j] * c_kern[0];
-#pragma unroll
-                    for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
-                    dstx[j] = res;
+                for (int q = 0; q < (PRE_XRUN + 16) / 4; q++) {
+                    const float4 f = ((const float4 *)(line + PRE_XRUN * run))[q];      // crop columns i0 - 8 + 4q ..
+                    v[4 * q] = f.x, v[4 * q + 1] = f.y, v[4 * q + 2] = f.z, v[4 * q + 3] = f.w;
                 }
-            }
-            const int nedge = nsegx - nint;                              // runs [0, sg_lo) and (sg_hi, nsegx)
-            for (int idx = threadIdx.x; idx < nedge * 4 * newr; idx += blockDim.x) {
-                const int r = idx / (nedge * 4), e = idx - r * (nedge * 4);
-                const int es = e >> 2, j = e & 3;
-                const int sg = nint == 0 ? es : (es < sg_lo ? es : sg_hi + 1 + (es - sg_lo));
-                const int i = cx0 + 4 * sg + j;
-                if (i < cx1) {
-                    const float *line = raw + r * RWP - rx0;
-                    float res;
-#define IN_X(ii) line[(ii)]
-                    LST_BLUR_AT(res, i, t.w, IN_X)
-#undef IN_X
-                    xp[((xdone + r) % PRE_RING) * XWP + 4 * sg + j] = res;
-                }
+                float o[PRE_XRUN];
+                if (interior)
+                    blur_run<PRE_XRUN, false>(v + 8 - (KR - 1), o, i0, t.w, 0.0f, 0.0f);
+                else
+                    blur_run<PRE_XRUN, true>(v + 8 - (KR - 1), o, i0, t.w, line[0 - RB > 0 ? 0 - RB : 0],
+                                             line[t.w - 1 - RB < RWP ? t.w - 1 - RB : 0]);
+                float4 *dx = (float4 *)(xp + (size_t)(xdone + r - xrow0) * XWP + PRE_XRUN * run);
+#pragma unroll
+                for (int q = 0; q < PRE_XRUN / 4; q++) dx[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
             }
         }
         xdone = need;
         __syncthreads();
-        // Y pass + quantise of rows [cy0, cy1): a thread produces 4 consecutive rows of one column
-        // (consecutive threads own consecutive columns: conflict-free, coalesced stores).
+        // Y pass + quantise of rows [cy0, cy1)
         const int nch = cy1 - cy0;
-        const int nsegy = (nch + 3) >> 2;
-        for (int idx = threadIdx.x; idx < ncw * nsegy; idx += blockDim.x) {
-            const int sg = idx / ncw, cc = idx - sg * ncw;
-            const float *col = xp + cc;                // x-pass value at crop row i: col[(i % PRE_RING) * XWP]
-            const int i0 = cy0 + 4 * sg;
-            float out[4];
-            const int nout = min(4, cy1 - i0);
-            if (i0 >= KR && i0 + 3 + KR < t.h && nout == 4) {
-                float v[16];
-                int slot = (i0 - (KR - 1)) % PRE_RING;
+        const int nsegy = (nch + PRE_YRUN - 1) / PRE_YRUN;
+        for (int sg = ysg0, cc = ycc0; sg < nsegy;) {
+            const int i0 = cy0 + PRE_YRUN * sg;
+            const int nout = min(PRE_YRUN, cy1 - i0);
+            const float *col = xp + (size_t)(PRE_YRUN * sg) * XWP + cc;     // x-pass value at crop row i0 - (KR-1)
+            float v[PRE_YRUN + 2 * (KR - 1)], o[PRE_YRUN];
+            if (i0 >= KR && i0 + PRE_YRUN - 1 + KR < t.h) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    v[j] = col[slot * XWP];
-                    slot = slot + 1 == PRE_RING ? 0 : slot + 1;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float res = v[KR - 1 + j] * c_kern[0];
-#pragma unroll
-                    for (int k = 1; k < KR; k++) res = res + c_kern[k] * (v[KR - 1 + j - k] + v[KR - 1 + j + k]);
-                    out[j] = res;
-                }
+                for (int j = 0; j < PRE_YRUN + 2 * (KR - 1); j++) v[j] = col[j * XWP];
+                blur_run<PRE_YRUN, false>(v, o, i0, t.h, 0.0f, 0.0f);
             } else {
-                for (int j = 0; j < nout; j++) {
-                    const int i = i0 + j;
-                    float res;
-#define IN_Y(ii) col[((ii) % PRE_RING) * XWP]
-                    LST_BLUR_AT(res, i, t.h, IN_Y)
-#undef IN_Y
-                    out[j] = res;
-                }
-            }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j < nout) {
-                    float value = out[j] - lo;
-                    if (value < 0.0f) value = 0.0f;
-                    float q = value * scale;
-                    if (pp.quant_mode == LST_QUANT_ROUND255) q = q + 0.5f;
-                    int iv = __float2int_rz(q);            // Java (int): NaN -> 0, saturating
-                    iv = iv > 255 ? 255 : (iv < 0 ? 0 : iv);
-                    dst[(size_t)(i0 + j) * t.pitch + (cx0 + cc)] = (uint8_t)iv;
+                for (int j = 0; j < PRE_YRUN + 2 * (KR - 1); j++) {
+                    const int i = i0 - (KR - 1) + j;
+                    v[j] = (i >= 0 && i < t.h) ? col[j * XWP] : 0.0f;
                 }
+                blur_run<PRE_YRUN, true>(v, o, i0, t.h, xp[(size_t)(0 - xrow0 > 0 ? 0 - xrow0 : 0) * XWP + cc],
+                                         xp[(size_t)(t.h - 1 - xrow0 < PRE_RING ? t.h - 1 - xrow0 : 0) * XWP + cc]);
             }
+            uint8_t *d = dst + (size_t)i0 * t.pitch + (cx0 + cc);
+            uint32_t b[PRE_YRUN];
+#pragma unroll
+            for (int j = 0; j < PRE_YRUN; j++) {
+                // (int)(max(v - lo, 0) * scale + 0.5) clamped to 0..255, Java casts: NaN -> 0, saturating
+                const float q = fmaxf(o[j] - lo, 0.0f) * scale + qadd;
+                b[j] = min(__float2uint_rz(q), 255u);
+            }
+            if (nout == PRE_YRUN) {
+#pragma unroll
+                for (int j = 0; j < PRE_YRUN; j++, d += t.pitch) *d = (uint8_t)b[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < PRE_YRUN; j++, d += t.pitch)
+                    if (j < nout) *d = (uint8_t)b[j];
+            }
+            cc += ydcc;
+            sg += ydsg;
+            if (cc >= ncw) cc -= ncw, sg++;
         }
         // zero the pitch padding so the match kernel can load whole 16-byte words
         if (cx1 == t.w && t.pitch > t.w) {
             int padw = t.pitch - t.w;
-            for (int idx = threadIdx.x; idx < padw * nch; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < padw * nch; idx += NT) {
                 int r = idx / padw, c = idx - r * padw;
                 dst[(size_t)(cy0 + r) * t.pitch + t.w + c] = 0;
             }
         }
-        __syncthreads();   // the next strip overwrites raw and the oldest ring rows
+        __syncthreads();   // the next strip overwrites sraw and moves the ring
     }
 }
 
 static size_t preprocess_smem(const PreprocParams &pp)
 {
-    return ((size_t)(PRE_STRIP + KR - 1) * (pp.tile_w + 2 * (KR - 1) + 1) + (size_t)PRE_RING * (pp.tile_w + 1)) * sizeof(float);
+    return ((size_t)PRE_RING * pre_xp_pitch(pp.tile_w) + (size_t)(PRE_STRIP + KR - 1) * pre_raw_pitch(pp.tile_w)) * sizeof(float);
+}
+
+static int preprocess_threads(const PreprocParams &pp, int max_w)
+{
+    int w = max_w < pp.tile_w ? max_w : pp.tile_w;
+    int nt = (2 * w + 31) & ~31;     // Y pass: columns x 4 row runs per strip = two rounds; X pass: 32 rows x w/8 runs = two rounds
+    return nt < 128 ? 128 : (nt > 512 ? 512 : nt);
 }
 
 int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces,
@@ -442,17 +582,18 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
     int tiles = (max_w + pp.tile_w - 1) / pp.tile_w;
     size_t smem = preprocess_smem(pp);
     (void)max_h;
+    const int nt = preprocess_threads(pp, max_w);
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
         dim3 grid(tiles, n);
         const uint32_t *mm = mm_keys + 2 * base;
         if (pp.pixel_type == LST_PIX_U8)
-            lst_preprocess<LST_PIX_U8><<<grid, 256, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+            lst_preprocess<LST_PIX_U8><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         else if (pp.pixel_type == LST_PIX_U16)
-            lst_preprocess<LST_PIX_U16><<<grid, 256, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+            lst_preprocess<LST_PIX_U16><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         else
-            lst_preprocess<LST_PIX_F32><<<grid, 256, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+            lst_preprocess<LST_PIX_F32><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         launches++;
     }
     return launches;

@@ -171,14 +171,14 @@ int lst_ctx::ensure_frames(int n)
     return LST_OK;
 }
 
-static Surface whole_slice(const void *ptr, int width)
+static Surface whole_slice(const void *ptr, int width, int height)
 {
     Surface s;
     s.ptr = ptr;
     s.pitch_px = width;
     s.org_x = 0;
     s.org_y = 0;
-    s.pad = 0;
+    s.rows = height;
     return s;
 }
 
@@ -223,7 +223,7 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
         pp->range_per_task = 1;
     }
     int tw = (max_w + 7) & ~7;
-    pp->tile_w = tw < 192 ? tw : 192;   // whole window rows for the named configurations (S <= 192)
+    pp->tile_w = tw < 192 ? ((tw + 15) & ~15) : 192;   // whole window rows for the named configurations (S <= 192); multiple of 16
     pp->minmax_in_kernel = (pp->range_per_task && max_w <= pp->tile_w && (long)max_w * max_h <= 256L * 256) ? 1 : 0;
 }
 
@@ -652,7 +652,7 @@ int lst_set_reference(lst_ctx *c, const void *ref_frame, const float ref_xy[10],
     if (rc != LST_OK) return rc;
     CUC(c, cudaMemcpyAsync(c->d_ring[0], ref_frame, c->frame_bytes(), cudaMemcpyHostToDevice, c->s_compute));
     c->stats.h2d_bytes += (int64_t)c->frame_bytes();
-    c->h_surf[0] = whole_slice(c->d_ring[0], c->p.width);
+    c->h_surf[0] = whole_slice(c->d_ring[0], c->p.width, c->p.height);
     CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface), cudaMemcpyHostToDevice, c->s_compute));
     lst_task tasks[5];
     Rect crop[5];
@@ -955,15 +955,15 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
                     sf.pitch_px = r.w;
                     sf.org_x = r.x;
                     sf.org_y = r.y;
-                    sf.pad = 0;
+                    sf.rows = r.h;
                 }
-                c->h_surf[5 * nb + i] = whole_slice(mapped[f0 + i], c->p.width);   // zero-copy fallback
+                c->h_surf[5 * nb + i] = whole_slice(mapped[f0 + i], c->p.width, c->p.height);   // zero-copy fallback
             }
             nsurf = 6 * nb;
         } else if (!on_device) {
-            for (int i = 0; i < nb; i++) c->h_surf[i] = whole_slice(c->d_ring[half] + (size_t)i * fb, c->p.width);
+            for (int i = 0; i < nb; i++) c->h_surf[i] = whole_slice(c->d_ring[half] + (size_t)i * fb, c->p.width, c->p.height);
         } else {
-            for (int i = 0; i < nb; i++) c->h_surf[i] = whole_slice(src_of(f0 + i), c->p.width);
+            for (int i = 0; i < nb; i++) c->h_surf[i] = whole_slice(src_of(f0 + i), c->p.width, c->p.height);
         }
         if (launch_upload(c->d_surf, c->h_surf, sizeof(Surface) * nsurf, c->s_compute) < 0)
             return c->fail(LST_ERR_CUDA, "surface upload failed");
@@ -1228,7 +1228,7 @@ int lst_preprocess(lst_ctx *c, const void *frame, int32_t x0, int32_t y0, int32_
     rc = c->ensure_frames(1);
     if (rc != LST_OK) return rc;
     CUC(c, cudaMemcpyAsync(c->d_ring[1], frame, c->frame_bytes(), cudaMemcpyHostToDevice, c->s_compute));
-    c->h_surf[0] = whole_slice(c->d_ring[1], c->p.width);
+    c->h_surf[0] = whole_slice(c->d_ring[1], c->p.width, c->p.height);
     CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface), cudaMemcpyHostToDevice, c->s_compute));
     lst_task t;
     memset(&t, 0, sizeof(t));
