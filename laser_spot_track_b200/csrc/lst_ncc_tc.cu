@@ -366,6 +366,16 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
         // sums of this lane's row: [band][x][row in band] (see lst_box_sums), band = y / 32
         const size_t rowoff = t.sum_off + (size_t)(y0 / 32 + warp) * t.rw * 32 + lane;
         unsigned long long mybest = 0ull;
+        // While the tensor core works, pull this warp's window sums (written by lst_box_sums, long
+        // evicted from L2 by the time they are read) back into L2: one 128-byte line per (array, column).
+        if (y0 + 32 * warp < t.rh) {
+            const int ncols = min(nbc * TC_NB, t.rw - x0);
+            const size_t line0 = rowoff - lane + (size_t)x0 * 32;
+            for (int c = lane; c < 2 * ncols; c += 32) {
+                const uint32_t *pf = (c < ncols ? wsum : wsq) + line0 + (size_t)(c < ncols ? c : c - ncols) * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            }
+        }
         mbar_wait(&bar_done, 0);
         tc_fence_after();
         clk2 = clock64();
