@@ -2,6 +2,7 @@
 #include "lst_host.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -410,14 +411,83 @@ int resolve_batch(const ResolveInput &in, double dis_io[10], int64_t first_frame
     Resolver R(in, ex, n, st);
     double state[10];
     memcpy(state, dis_io, sizeof(state));
-    // pass 1: every frame speculated with the window origins of the state at batch start
-    {
+    // Speculation.  The windows of frame j are placed from the integer-truncated displacements left by
+    // frame j-1, which are unknown until the frames before it are matched.  Long batches are therefore
+    // speculated in two steps: (1a) every K-th frame is matched with the window origins of the state at
+    // batch start -- the target is still inside those windows unless it moved by more than sArea, so
+    // the positions found are the true ones; (1b) the states between the samples are interpolated
+    // linearly and every frame is matched with the windows those predicted states place.  Short
+    // batches skip (1a) and use the batch-start state for every frame.  Whatever the prediction, the
+    // exact walk below accepts a result only if its window is the one the true state places.
+    static const int kStride = [] {
+        const char *e = getenv("LST_SPEC_STRIDE");
+        int v = e ? atoi(e) : 8;
+        return v < 0 ? 0 : v;
+    }();
+    int passes = 0;
+    if (kStride >= 2 && n >= 4 * kStride) {
+        std::vector<int> samp;
+        for (int i = kStride - 1; i < n; i += kStride) samp.push_back(i);
+        if (samp.back() != n - 1) samp.push_back(n - 1);
+        double nd[10];
+        for (int i : samp) R.eval_frame(i, state, false, nullptr, nd);
+        int rc = R.run_pending(true);
+        if (rc != LST_OK) return rc;
+        passes++;
+        // states after the sample frames (valid when all five matches were accepted)
+        std::vector<double> sst(samp.size() * 10);
+        std::vector<char> ok(samp.size(), 0);
+        for (size_t m = 0; m < samp.size(); m++) {
+            int r = R.eval_frame(samp[m], state, false, nullptr, &sst[m * 10]);
+            ok[m] = r == 0;
+        }
+        R.pending.clear();      // only look-ups were meant; anything queued here is re-queued below if needed
+        R.pend_prev.clear();
+        std::fill(R.pend_head.begin(), R.pend_head.end(), -1);
+        // predicted state before frame j = state after frame j-1: cubic Hermite interpolation through the
+        // valid samples (anchor 0 = the batch-start state at frame -1), finite-difference tangents
+        std::vector<int> at;            // anchor frame indices
+        std::vector<const double *> ap; // anchor states
+        at.push_back(-1);
+        ap.push_back(state);
+        for (size_t m = 0; m < samp.size(); m++)
+            if (ok[m]) {
+                at.push_back(samp[m]);
+                ap.push_back(&sst[m * 10]);
+            }
+        const int na = (int)at.size();
+        int seg = 0;                    // anchors seg, seg+1 bracket prev
+        for (int j = 0; j < n; j++) {
+            const int prev = j - 1;
+            while (seg + 1 < na && at[seg + 1] <= prev) seg++;
+            double pred[10];
+            if (seg + 1 >= na || at[seg] == prev) {
+                memcpy(pred, ap[seg], sizeof(pred));      // on an anchor, or past the last one: hold
+            } else {
+                const double t1 = at[seg], t2 = at[seg + 1], h = t2 - t1, u = (prev - t1) / h;
+                const double u2 = u * u, u3 = u2 * u;
+                const double h00 = 2 * u3 - 3 * u2 + 1, h10 = u3 - 2 * u2 + u, h01 = -2 * u3 + 3 * u2, h11 = u3 - u2;
+                for (int c = 0; c < 10; c++) {
+                    const double p1 = ap[seg][c], p2 = ap[seg + 1][c];
+                    const double d = (p2 - p1) / h;
+                    const double m1 = seg > 0 ? (p2 - ap[seg - 1][c]) / (t2 - at[seg - 1]) : d;
+                    const double m2 = seg + 2 < na ? (ap[seg + 2][c] - p1) / (at[seg + 2] - t1) : d;
+                    pred[c] = h00 * p1 + h10 * h * m1 + h01 * p2 + h11 * h * m2;
+                }
+            }
+            R.eval_frame(j, pred, false, nullptr, nd);
+        }
+        rc = R.run_pending(true);
+        if (rc != LST_OK) return rc;
+        passes++;
+    } else {
         double nd[10];
         for (int j = 0; j < n; j++) R.eval_frame(j, state, false, nullptr, nd);
         int rc = R.run_pending(true);
         if (rc != LST_OK) return rc;
+        passes++;
     }
-    int first = 0, passes = 1;
+    int first = 0;
     while (first < n) {
         double walk[10];
         memcpy(walk, state, sizeof(walk));
