@@ -67,9 +67,13 @@ def bench_config(name: str, ring: int) -> StackConfig:
     return StackConfig(c.width, c.height, c.dtype, c.templ_size, c.s_area, n_frames=ring, motion="periodic", period=ring)
 
 
-# DRAM bytes per window of lst_ncc_match from the committed ncu --set full captures (profiles/):
-# config B: 66.9 MB for 2560 windows of 160x160 8-bit pixels (the window is read once; 25.6 KB algorithmic)
-NCU_DRAM_BYTES_PER_WINDOW = {("B", False): 66.9e6 / 2560, ("B", True): 67.5e6 / 2560}
+# DRAM bytes per window of the match kernel from the committed ncu --set full captures (profiles/):
+# lst_ncc_match (IDP.4A), config B: 66.9 MB for 2560 windows of 160x160 8-bit pixels (the window is
+#   read once; 25.6 KB algorithmic);
+# lst_ncc_tc (tensor core), config B: 752.7 MB read + 38.3 MB written for 4704 windows = 168 KB per
+#   window: the 8-bit window (25.6 KB), the window sums lst_box_sums left in HBM (2 x 4 B x 113^2 =
+#   102 KB, read once plus an L2 prefetch that is partly evicted again) and the Toeplitz table.
+NCU_DRAM_BYTES_PER_WINDOW = {("B", False): 66.9e6 / 2560, ("B", True): 790.98e6 / 4704}
 
 DEFAULTS = {  # frames per step, ring length, max_batch, cpu sample
     "A": (8192, 256, 2048, 512),

@@ -41,7 +41,7 @@ extern "C" {
 /* status codes */
 #define LST_OK               0
 #define LST_ERR_INVALID     -1   /* bad argument */
-#define LST_ERR_UNSUPPORTED -2   /* e.g. method != 5, 16-bit with matchIntensity=false (LST4:2510-2523) */
+#define LST_ERR_UNSUPPORTED -2   /* e.g. RGB slices, 16-bit with matchIntensity=false (LST4:2510-2523) */
 #define LST_ERR_CUDA        -3   /* no device / CUDA runtime error (see lst_last_error) */
 #define LST_ERR_NOMEM       -4
 #define LST_ERR_STATE       -5   /* call order (e.g. track before set_reference) */
@@ -70,7 +70,7 @@ typedef struct lst_params {
     int32_t struct_size;       /* sizeof(lst_params), for ABI evolution */
     int32_t width, height;     /* slice size (LST4:813-817 checks every slice against it) */
     int32_t pixel_type;        /* LST_PIX_* */
-    int32_t method;            /* only 5 (TM_CCOEFF_NORMED, default LST4:82) is accepted */
+    int32_t method;            /* 0..5 as in the dialog (LST4:2381); 5 = TM_CCOEFF_NORMED is the default (LST4:82) */
     int32_t templ_size;        /* templSize LST4:84 */
     int32_t s_area;            /* sArea LST4:83; 0 => whole-slice search (LST4:1316-1320) */
     int32_t sub_pixel;         /* LST4:89 */
