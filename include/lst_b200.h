@@ -86,7 +86,7 @@ typedef struct lst_params {
                                   copies, 2 = search regions gathered by a kernel from mapped host memory */
     double  mark_dist;         /* markDist LST4:85 */
     double  range_lo, range_hi;/* LST_RANGE_FIXED */
-    double  match_threshold;   /* matchThreshold[5] = 0.2, LST4:147 */
+    double  match_threshold;   /* 0 = matchThreshold[method] of LST4:147 ({0.1, 0.1, 0.05, 0.05, 0.2, 0.2}) */
     int32_t ncc_engine;        /* match kernel: 0 = auto (tensor cores when the template fits, else IDP.4A),
                                   1 = IDP.4A (lst_ncc_match), 2 = tensor cores (lst_ncc_tc); identical results */
     int32_t reserved1;
@@ -197,6 +197,27 @@ int lst_multi_get_state(const lst_multi *m, double dis[10]);
 int lst_multi_set_state(lst_multi *m, const double dis[10]);
 /* chunks tracked a second time because their speculated start state placed a window differently */
 int64_t lst_multi_retracked(const lst_multi *m);
+
+/* ---- slices as files --------------------------------------------------------
+ * The reference's virtual stack decodes one file per slice and opens it twice per frame
+ * (LST4:808-817, 831).  These entry points take the files themselves: a slice file is mapped once
+ * and only the rows of the five search regions are read and sent to the device.  Supported: classic
+ * TIFF, either byte order (big-endian samples are swapped on the device), one sample per pixel, 8/16-bit
+ * unsigned or 32-bit float, uncompressed strips; `pages` (nullable) selects a page of a multi-page
+ * file or a slice of an ImageJ stack file.  Other files: LST_ERR_UNSUPPORTED -- decode them and use
+ * lst_track_ptrs. */
+typedef struct lst_tiff_info {
+    int32_t width, height, bits, sample_format; /* sample_format: 1 unsigned integer, 3 IEEE float */
+    int32_t big_endian, rows_per_strip, n_strips;
+    int32_t imagej_images;                      /* "images=N" of an ImageJ description, else 0 */
+    int64_t first_strip_offset;
+} lst_tiff_info;
+/* host only, no GPU needed; err (nullable) receives a message */
+int lst_tiff_probe(const char *path, int32_t page, lst_tiff_info *out, char *err, int32_t err_cap);
+int lst_set_reference_file(lst_ctx *ctx, const char *path, int32_t page, const float ref_xy[10],
+                           lst_reference_info *out);
+int lst_track_files(lst_ctx *ctx, const char *const *paths, const int32_t *pages,
+                    int64_t first_frame_index, int32_t n_frames, lst_record *out);
 
 /* ---- the primitives, exposed like the reference's public statics ---------------------- */
 /* doMatch_coord_res(src, tpl, method, subPix, null) on the 8-bit images that reach OpenCV

@@ -66,6 +66,7 @@ struct PreprocParams {
     int quant_mode;        // LST_QUANT_*
     int tile_w;            // columns per CTA of the blur kernel (whole window when it fits)
     int minmax_in_kernel;  // the blur kernel finds the crop min/max itself (single column block)
+    int swap_bytes;        // the slices hold big-endian samples (files read by lst_track_files)
 };
 
 struct MatchParams {

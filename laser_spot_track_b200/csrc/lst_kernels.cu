@@ -54,6 +54,14 @@ __device__ __forceinline__ uint32_t px_key(const void *base, size_t idx)
     if (PIX == LST_PIX_U16) return ((const uint16_t *)base)[idx];
     return f32_key(((const float *)base)[idx]);
 }
+// the same for a slice whose samples are stored big-endian (TIFF "MM" files, lst_track_files)
+template <int PIX>
+__device__ __forceinline__ uint32_t px_key_swapped(const void *base, size_t idx)
+{
+    if (PIX == LST_PIX_U8) return ((const uint8_t *)base)[idx];
+    if (PIX == LST_PIX_U16) return __byte_perm((uint32_t)((const uint16_t *)base)[idx], 0, 0x3201);
+    return f32_key(__uint_as_float(__byte_perm(((const uint32_t *)base)[idx], 0, 0x0123)));
+}
 template <int PIX>
 __device__ __forceinline__ float key_to_float(uint32_t k)
 {
@@ -109,7 +117,7 @@ int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, c
 // ------------------------------------------------------------------------------------------------
 template <int PIX>
 __global__ void lst_minmax(const DevTask *__restrict__ tasks, const Surface *__restrict__ surfaces,
-                           uint32_t *__restrict__ mm_keys)
+                           uint32_t *__restrict__ mm_keys, int swap_bytes)
 {
     const DevTask t = tasks[blockIdx.y];
     const Surface sf = surfaces[t.frame];
@@ -118,7 +126,7 @@ __global__ void lst_minmax(const DevTask *__restrict__ tasks, const Surface *__r
     for (int r = blockIdx.x; r < t.h; r += gridDim.x) {
         size_t row = (size_t)(t.y0 - sf.org_y + r) * sf.pitch_px + (t.x0 - sf.org_x);
         for (int c = threadIdx.x; c < t.w; c += blockDim.x) {
-            uint32_t k = px_key<PIX>(fr, row + c);
+            uint32_t k = swap_bytes ? px_key_swapped<PIX>(fr, row + c) : px_key<PIX>(fr, row + c);
             lo = min(lo, k);
             hi = max(hi, k);
         }
@@ -143,11 +151,11 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *s
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
         dim3 grid(gx, n);
         if (pp.pixel_type == LST_PIX_U8)
-            lst_minmax<LST_PIX_U8><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base);
+            lst_minmax<LST_PIX_U8><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base, pp.swap_bytes);
         else if (pp.pixel_type == LST_PIX_U16)
-            lst_minmax<LST_PIX_U16><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base);
+            lst_minmax<LST_PIX_U16><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base, pp.swap_bytes);
         else
-            lst_minmax<LST_PIX_F32><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base);
+            lst_minmax<LST_PIX_F32><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base, pp.swap_bytes);
         launches++;
     }
     return launches;
@@ -300,7 +308,7 @@ __device__ __forceinline__ uint32_t byte_range_mask(int s, int e)
 template <int PIX, bool STORE, bool MINMAX>
 __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, size_t row_pitch_bytes, int row0, int nrows,
                                            int lo0, int vpr, int row_bytes, const uint8_t *surf_lo, const uint8_t *surf_hi,
-                                           float *sraw, int rwp, uint32_t &mlo, uint32_t &mhi)
+                                           float *sraw, int rwp, uint32_t &mlo, uint32_t &mhi, bool swap)
 {
     constexpr int ES = PIX == LST_PIX_U8 ? 1 : (PIX == LST_PIX_U16 ? 2 : 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -323,6 +331,10 @@ __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, s
                     o[1] = __funnelshift_r(w1, w2, bs);
                     o[2] = __funnelshift_r(w2, w3, bs);
                     o[3] = __funnelshift_r(w3, w4, bs);
+                    if (PIX != LST_PIX_U8 && swap) {   // big-endian samples (TIFF "MM")
+#pragma unroll
+                        for (int j = 0; j < 4; j++) o[j] = __byte_perm(o[j], 0, PIX == LST_PIX_U16 ? 0x2301 : 0x0123);
+                    }
                     if (lo >= 0 && lo + 16 <= row_bytes) {
                         if (MINMAX) {
 #pragma unroll
@@ -349,6 +361,7 @@ __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, s
                             if (PIX == LST_PIX_U8) v = grow[bo];
                             else if (PIX == LST_PIX_U16) v = *(const uint16_t *)(grow + bo);
                             else v = *(const uint32_t *)(grow + bo);
+                            if (PIX != LST_PIX_U8 && swap) v = PIX == LST_PIX_U16 ? __byte_perm(v, 0, 0x3201) : __byte_perm(v, 0, 0x0123);
                             const uint32_t sh = v << (8 * ((e * ES) & 3));
                             const int wi = (e * ES) >> 2;
                             o[0] |= wi == 0 ? sh : 0u, o[1] |= wi == 1 ? sh : 0u, o[2] |= wi == 2 ? sh : 0u, o[3] |= wi == 3 ? sh : 0u;
@@ -441,7 +454,7 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
             uint32_t klo = 0xffffffffu, khi = 0u;
             // vectors aligned to the crop's first pixel: only the last one of a row is partial
             stage_rows<PIX, false, true>(crop00, row_pitch_bytes, 0, t.h, 0, (row_bytes + 15) >> 4, row_bytes, surf_lo, surf_hi,
-                                         nullptr, 0, klo, khi);
+                                         nullptr, 0, klo, khi, pp.swap_bytes != 0);
             mm_finish<PIX>(klo, khi);
             for (int o = 16; o > 0; o >>= 1) {
                 klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
@@ -476,7 +489,7 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
         {
             uint32_t d0 = 0, d1 = 0;
             stage_rows<PIX, true, false>(crop00, row_pitch_bytes, xdone, newr, RB * ES, VPR, row_bytes, surf_lo, surf_hi, sraw,
-                                         RWP, d0, d1);
+                                         RWP, d0, d1, pp.swap_bytes != 0);
         }
         // the X-pass rows this strip shares with the previous one move to the front
         if (cy0 > 0) {

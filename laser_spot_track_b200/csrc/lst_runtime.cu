@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <future>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -16,11 +17,13 @@
 #include "../../include/lst_b200.h"
 #include "lst_device.h"
 #include "lst_host.h"
+#include "lst_tiff.h"
 
 using namespace lst;
 
 static thread_local std::string g_create_error;
 static const int kRoiMarginMax = 32;   // ROI ingest: the region ring is sized for this margin
+static const int kRetryWholeSlices = -100;   // internal: a window left the regions read from a slice file
 
 static double now_ms()
 {
@@ -81,6 +84,14 @@ struct lst_ctx : public Executor {
     int roi_margin_fixed = -1;   // LST_ROI_MARGIN pins it
     int roi_align_bytes = 16;
     std::unordered_map<const void *, const void *> mapped_cache;   // pinned host ptr -> device-visible ptr
+    // slices read from files (lst_track_files): pinned staging with the layout of the ROI ring
+    uint8_t *h_fstage[2] = {nullptr, nullptr};
+    size_t fstage_cap = 0;
+    uint8_t *h_fwhole = nullptr;   // whole slices of a sub-batch (fallback / whole-slice search)
+    size_t fwhole_cap = 0;
+    bool file_mode = false;        // the batch being resolved has no whole slice in memory to fall back to
+    bool swap_bytes = false;       // the slices being tracked hold big-endian samples
+    int file_threads = 8;
     // solve buffers
     int solve_cap = 0;
     double *d_dis10 = nullptr, *d_out5 = nullptr, *h_dis10 = nullptr, *h_out5 = nullptr;
@@ -225,6 +236,7 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
     int tw = (max_w + 7) & ~7;
     pp->tile_w = tw < 192 ? ((tw + 15) & ~15) : 192;   // whole window rows for the named configurations (S <= 192); multiple of 16
     pp->minmax_in_kernel = (pp->range_per_task && max_w <= pp->tile_w && (long)max_w * max_h <= 256L * 256) ? 1 : 0;
+    pp->swap_bytes = swap_bytes ? 1 : 0;
 }
 
 int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th, int method_override)
@@ -311,6 +323,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             if (c.x >= rr.x && c.y >= rr.y && c.x + c.w <= rr.x + rr.w && c.y + c.h <= rr.y + rr.h) {
                 d.frame = t.frame * 5 + t.tpl;
             } else {
+                if (file_mode) return kRetryWholeSlices;   // no slice in memory: the caller re-reads this batch whole
                 d.frame = 5 * roi_nb + t.frame;
                 stats.roi_fallback_tasks++;
                 stats.h2d_bytes += (int64_t)c.w * c.h * (int64_t)bpp() * 2;
@@ -795,10 +808,94 @@ static size_t plan_rois(const lst_ctx *c, const double dis[10], int nb, RoiDesc 
 // (ptrs); host memory unless on_device.  Host slices in pinned memory use the ROI ingest (only the
 // search regions cross PCIe, gathered by a kernel on the copy stream while the previous batch
 // computes); pageable slices and ingest_mode == 1 use whole-slice cudaMemcpyAsync into a ring.
-static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *const *ptrs, bool on_device,
-                      int64_t first_index, int32_t n_frames, lst_record *out)
+struct FileSource {
+    const char *const *paths;
+    const int32_t *pages;   // nullable: page 0 of every file
+    bool big_endian;
+};
+
+// Reads the regions `roi` of the slices [f0, f0 + nb) of a file source into `stage` (layout of the ROI
+// ring), several files at a time.  whole: the entire slice i goes to stage + i * frame_bytes instead.
+static int read_slices(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, const RoiDesc roi[5], bool whole, uint8_t *stage,
+                       std::string *err)
 {
-    if (!c || !out || n_frames < 0 || (!base && !ptrs)) return LST_ERR_INVALID;
+    const int nthreads = std::max(1, std::min(c->file_threads, nb));
+    std::vector<std::string> errs(nthreads);
+    std::vector<int> rcs(nthreads, LST_OK);
+    const int want_bits = c->p.pixel_type == LST_PIX_U8 ? 8 : (c->p.pixel_type == LST_PIX_U16 ? 16 : 32);
+    const size_t fb = c->frame_bytes();
+    auto work = [&](int ti) {
+        const int i0 = (int)((int64_t)nb * ti / nthreads), i1 = (int)((int64_t)nb * (ti + 1) / nthreads);
+        for (int i = i0; i < i1; i++) {
+            FileMap fm;
+            TiffLayout L;
+            int rc = fm.open(fs.paths[f0 + i], &errs[ti]);
+            if (rc == LST_OK) rc = tiff_parse(fm.data, fm.size, fs.pages ? fs.pages[f0 + i] : 0, &L, &errs[ti]);
+            if (rc == LST_OK && (L.width != c->p.width || L.height != c->p.height || L.bits != want_bits ||
+                                 (L.bits > 8 && L.big_endian != fs.big_endian))) {
+                errs[ti] = std::string("slice file differs from the stack's geometry or byte order: ") + fs.paths[f0 + i];
+                rc = LST_ERR_INVALID;   // all stack images must have the same size and type (LST4:393)
+            }
+            if (rc == LST_OK) {
+                if (whole) {
+                    rc = tiff_copy_rect(fm, L, 0, 0, L.width, L.height, stage + (size_t)i * fb, &errs[ti]);
+                } else {
+                    for (int k = 0; k < 5 && rc == LST_OK; k++)
+                        if (roi[k].w > 0 && roi[k].h > 0)
+                            rc = tiff_copy_rect(fm, L, roi[k].x, roi[k].y, roi[k].w, roi[k].h,
+                                                stage + roi[k].off + (size_t)i * roi[k].slice_bytes, &errs[ti]);
+                }
+            }
+            if (rc != LST_OK) {
+                rcs[ti] = rc;
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int ti = 1; ti < nthreads; ti++) th.emplace_back(work, ti);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int ti = 0; ti < nthreads; ti++)
+        if (rcs[ti] != LST_OK) {
+            if (err) *err = errs[ti];
+            return rcs[ti];
+        }
+    return LST_OK;
+}
+
+static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *const *ptrs, bool on_device,
+                      int64_t first_index, int32_t n_frames, lst_record *out, const FileSource *fs = nullptr);
+
+// Slices of a file source tracked through whole-slice reads (whole-slice search, or a batch whose
+// windows left the regions that had been read): sub-batches of whole slices in pinned memory go
+// through the ordinary host path.
+static int track_files_whole(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, int64_t first_index, lst_record *out)
+{
+    const size_t fb = c->frame_bytes();
+    const int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nb, ((size_t)256 << 20) / fb));
+    if ((size_t)sub * fb > c->fwhole_cap) {
+        if (c->h_fwhole) cudaFreeHost(c->h_fwhole);
+        c->h_fwhole = nullptr;
+        c->fwhole_cap = 0;
+        CUC(c, cudaHostAlloc((void **)&c->h_fwhole, (size_t)sub * fb, cudaHostAllocDefault));
+        c->fwhole_cap = (size_t)sub * fb;
+    }
+    for (int i = 0; i < nb; i += sub) {
+        const int m = std::min(sub, nb - i);
+        std::string err;
+        int rc = read_slices(c, fs, f0 + i, m, nullptr, true, c->h_fwhole, &err);
+        if (rc != LST_OK) return c->fail(rc, "%s", err.c_str());
+        rc = track_impl(c, c->h_fwhole, fb, nullptr, false, first_index + i, m, out + i);
+        if (rc != LST_OK) return rc;
+    }
+    return LST_OK;
+}
+
+static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *const *ptrs, bool on_device,
+                      int64_t first_index, int32_t n_frames, lst_record *out, const FileSource *fs)
+{
+    if (!c || !out || n_frames < 0 || (!base && !ptrs && !fs)) return LST_ERR_INVALID;
     if (!c->have_ref) return c->fail(LST_ERR_STATE, "lst_set_reference must be called before tracking");
     CUC(c, cudaSetDevice(c->device));
     if (n_frames == 0) return LST_OK;
@@ -810,6 +907,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     const size_t fb = c->frame_bytes();
     if (stride == 0) stride = fb;
     const int B = c->p.max_batch;
+    if (fs && c->p.s_area == 0) return track_files_whole(c, *fs, 0, n_frames, first_index, out);   // whole-slice search
     ResolveInput in;
     fill_resolve_input(c, &in);
     auto src_of = [&](int64_t i) -> const void * { return ptrs ? ptrs[i] : (const uint8_t *)base + (size_t)i * stride; };
@@ -828,9 +926,11 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     }
     const int nbatches = (int)bstart.size() - 1;
 
-    bool use_roi = !on_device && c->p.s_area > 0 && c->p.ingest_mode != 1;
+    bool use_roi = !on_device && c->p.s_area > 0 && (fs || c->p.ingest_mode != 1);
     std::vector<const void *> mapped;
-    if (use_roi) {
+    std::future<int> file_job[2];
+    std::string file_err[2];
+    if (use_roi && !fs) {
         mapped.resize(n_frames);
         for (int64_t i = 0; i < n_frames && use_roi; i++) {
             mapped[i] = mapped_host_ptr(c, src_of(i));
@@ -853,6 +953,15 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
         }
         rc = ensure_roi(c, (roi_block_max + 256) * (size_t)std::min<int64_t>(B, n_frames), B);
         if (rc != LST_OK) return rc;
+        if (fs && c->fstage_cap < c->roi_cap) {
+            for (int i = 0; i < 2; i++) {
+                if (c->h_fstage[i]) cudaFreeHost(c->h_fstage[i]);
+                c->h_fstage[i] = nullptr;
+            }
+            c->fstage_cap = 0;
+            for (int i = 0; i < 2; i++) CUC(c, cudaHostAlloc((void **)&c->h_fstage[i], c->roi_cap, cudaHostAllocDefault));
+            c->fstage_cap = c->roi_cap;
+        }
     }
     if (!on_device && !use_roi) {
         rc = ensure_ring(c, (size_t)std::min<int64_t>(B, n_frames) * fb);
@@ -866,6 +975,33 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
         if (use_roi) {
             size_t need = plan_rois(c, c->dis, nb, c->roi[half]);
             if (need > c->roi_cap) return c->fail(LST_ERR_STATE, "internal: ROI ring smaller than planned");
+            if (fs) {
+                // A reader thread maps the slice files, copies the rows of the five regions into the pinned
+                // staging half and then queues the (contiguous) copies to the device itself, so that
+                // they overlap the kernels of the batch being resolved.  Joined before the batch is used.
+                RoiDesc rois[5];
+                for (int k = 0; k < 5; k++) {
+                    rois[k] = c->roi[half][k];
+                    c->stats.h2d_bytes += (int64_t)(rois[k].slice_bytes * nb);
+                }
+                lst_ctx *cc = c;
+                const FileSource src = *fs;
+                std::string *errp = &file_err[half];
+                file_job[half] = std::async(std::launch::async, [cc, src, f0, nb, half, rois, errp]() -> int {
+                    int r = read_slices(cc, src, f0, nb, rois, false, cc->h_fstage[half], errp);
+                    if (r != LST_OK) return r;
+                    if (cudaSetDevice(cc->device) != cudaSuccess) return LST_ERR_CUDA;
+                    for (int k = 0; k < 5; k++) {
+                        const size_t bytes = (size_t)rois[k].slice_bytes * nb;
+                        if (bytes == 0) continue;
+                        if (cudaMemcpyAsync(cc->d_roi[half] + rois[k].off, cc->h_fstage[half] + rois[k].off, bytes,
+                                            cudaMemcpyHostToDevice, cc->s_copy) != cudaSuccess)
+                            return LST_ERR_CUDA;
+                    }
+                    return cudaEventRecord(cc->ev_copy[half], cc->s_copy) == cudaSuccess ? LST_OK : LST_ERR_CUDA;
+                });
+                return LST_OK;
+            }
             // Runs of equally spaced slices move with one strided 3-D DMA per region (copy engine: no SM
             // is taken from the kernels of the previous batch); irregularly placed slices (or
             // ingest_mode == 2) are gathered by a kernel reading the mapped host memory.
@@ -944,6 +1080,13 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
                 rc = enqueue_copy(b + 1);
                 if (rc != LST_OK) return rc;
             }
+            if (fs && file_job[half].valid()) {
+                rc = file_job[half].get();
+                if (rc != LST_OK) {
+                    if (file_job[half ^ 1].valid()) file_job[half ^ 1].wait();
+                    return c->fail(rc, "%s", file_err[half].empty() ? "reading slice files failed" : file_err[half].c_str());
+                }
+            }
             CUC(c, cudaStreamWaitEvent(c->s_compute, c->ev_copy[half], 0));
         }
         if (use_roi) {
@@ -957,7 +1100,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
                     sf.org_y = r.y;
                     sf.rows = r.h;
                 }
-                c->h_surf[5 * nb + i] = whole_slice(mapped[f0 + i], c->p.width, c->p.height);   // zero-copy fallback
+                c->h_surf[5 * nb + i] = whole_slice(fs ? nullptr : mapped[f0 + i], c->p.width, fs ? 0 : c->p.height);   // zero-copy fallback
             }
             nsurf = 6 * nb;
         } else if (!on_device) {
@@ -972,9 +1115,33 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
         c->roi_active = use_roi;
         c->roi_half = half;
         c->roi_nb = nb;
+        c->file_mode = fs != nullptr;
         rc = resolve_batch(in, c->dis, first_index + f0, nb, *c, out + f0, &c->stats);
         c->roi_active = false;
+        c->file_mode = false;
+        if (rc == kRetryWholeSlices && fs) {
+            // a window left the regions that were read: this batch again from whole slices.  The read-ahead
+            // of the next batch is drained first (the nested call reuses the copy stream and events) and
+            // re-planned afterwards from the state this batch leaves.
+            if (file_job[half ^ 1].valid()) file_job[half ^ 1].wait();
+            CUC(c, cudaStreamSynchronize(c->s_copy));
+            CUC(c, cudaStreamSynchronize(c->s_compute));
+            const int save_mode = c->p.ingest_mode;
+            c->p.ingest_mode = 1;
+            rc = track_files_whole(c, *fs, f0, nb, first_index + f0, out + f0);
+            c->p.ingest_mode = save_mode;
+            if (rc != LST_OK) return rc;
+            c->stats.roi_fallback_tasks += nb;
+            if (b + 1 < nbatches) {
+                rc = enqueue_copy(b + 1);
+                if (rc != LST_OK) return rc;
+            }
+            continue;
+        }
         if (rc != LST_OK) {
+            if (fs)
+                for (int h2 = 0; h2 < 2; h2++)
+                    if (file_job[h2].valid()) file_job[h2].wait();
             if (c->err.empty()) c->fail(rc, "resolver failed (%d)", rc);
             return rc;
         }
@@ -1018,6 +1185,87 @@ int lst_track_device_ptrs(lst_ctx *c, const void *const *dev_frame_ptrs, int64_t
                           lst_record *out)
 {
     return track_impl(c, nullptr, 0, dev_frame_ptrs, true, first_frame_index, n_frames, out);
+}
+
+// ---- slices as files -------------------------------------------------------------
+int lst_tiff_probe(const char *path, int32_t page, lst_tiff_info *out, char *err, int32_t err_cap)
+{
+    if (!path || !out) return LST_ERR_INVALID;
+    FileMap fm;
+    TiffLayout L;
+    std::string e;
+    int rc = fm.open(path, &e);
+    if (rc == LST_OK) rc = tiff_parse(fm.data, fm.size, page, &L, &e);
+    if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", e.c_str());
+    if (rc != LST_OK) return rc;
+    out->width = L.width;
+    out->height = L.height;
+    out->bits = L.bits;
+    out->sample_format = L.sample_format;
+    out->big_endian = L.big_endian ? 1 : 0;
+    out->rows_per_strip = L.rows_per_strip;
+    out->n_strips = (int32_t)L.strip_off.size();
+    out->imagej_images = L.imagej_images;
+    out->first_strip_offset = (int64_t)L.strip_off[0];
+    return LST_OK;
+}
+
+static int check_slice_file(lst_ctx *c, const char *path, int page, FileMap *fm, TiffLayout *L)
+{
+    std::string e;
+    int rc = fm->open(path, &e);
+    if (rc == LST_OK) rc = tiff_parse(fm->data, fm->size, page, L, &e);
+    if (rc != LST_OK) return c->fail(rc, "%s: %s", path, e.c_str());
+    const int want_bits = c->p.pixel_type == LST_PIX_U8 ? 8 : (c->p.pixel_type == LST_PIX_U16 ? 16 : 32);
+    if (L->width != c->p.width || L->height != c->p.height || L->bits != want_bits)
+        return c->fail(LST_ERR_INVALID, "%s is %dx%d %d-bit, the context was created for %dx%d %d-bit", path, L->width, L->height,
+                       L->bits, c->p.width, c->p.height, want_bits);
+    return LST_OK;
+}
+
+int lst_set_reference_file(lst_ctx *c, const char *path, int32_t page, const float ref_xy[10], lst_reference_info *out)
+{
+    if (!c || !path || !ref_xy) return LST_ERR_INVALID;
+    FileMap fm;
+    TiffLayout L;
+    int rc = check_slice_file(c, path, page, &fm, &L);
+    if (rc != LST_OK) return rc;
+    std::vector<uint8_t> px(c->frame_bytes());
+    std::string e;
+    rc = tiff_copy_rect(fm, L, 0, 0, L.width, L.height, px.data(), &e);
+    if (rc != LST_OK) return c->fail(rc, "%s: %s", path, e.c_str());
+    if (L.big_endian && L.bits == 16) {
+        for (size_t i = 0; i + 1 < px.size(); i += 2) std::swap(px[i], px[i + 1]);
+    } else if (L.big_endian && L.bits == 32) {
+        for (size_t i = 0; i + 3 < px.size(); i += 4) {
+            std::swap(px[i], px[i + 3]);
+            std::swap(px[i + 1], px[i + 2]);
+        }
+    }
+    return lst_set_reference(c, px.data(), ref_xy, out);
+}
+
+int lst_track_files(lst_ctx *c, const char *const *paths, const int32_t *pages, int64_t first_frame_index, int32_t n_frames,
+                    lst_record *out)
+{
+    if (!c || !paths || !out || n_frames < 0) return LST_ERR_INVALID;
+    if (n_frames == 0) return LST_OK;
+    // the first file fixes the byte order of the stack (every file is checked against it while reading)
+    FileSource fs;
+    fs.paths = paths;
+    fs.pages = pages;
+    {
+        FileMap fm;
+        TiffLayout L;
+        int rc = check_slice_file(c, paths[0], pages ? pages[0] : 0, &fm, &L);
+        if (rc != LST_OK) return rc;
+        fs.big_endian = L.big_endian;
+    }
+    if (const char *e = getenv("LST_FILE_THREADS")) c->file_threads = std::max(1, atoi(e));
+    c->swap_bytes = fs.big_endian && c->p.pixel_type != LST_PIX_U8;
+    int rc = track_impl(c, nullptr, 0, nullptr, false, first_frame_index, n_frames, out, &fs);
+    c->swap_bytes = false;
+    return rc;
 }
 
 // ---- several GPUs in one process ------------------------------------------------------------------

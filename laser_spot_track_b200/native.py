@@ -28,6 +28,7 @@ EXPORTS = [
     "lst_host_window_for", "lst_host_template_rect", "lst_host_resolve",
     "lst_multi_create", "lst_multi_destroy", "lst_multi_last_error", "lst_multi_set_reference", "lst_multi_track",
     "lst_multi_get_state", "lst_multi_set_state", "lst_multi_retracked",
+    "lst_tiff_probe", "lst_set_reference_file", "lst_track_files",
 ]
 
 
@@ -73,6 +74,12 @@ class Stats(C.Structure):
         ("ncc_kernel_ms", C.c_double), ("ncc_kernel_launches", C.c_int64), ("ncc_algorithmic_macs", C.c_double),
         ("roi_fallback_tasks", C.c_int64), ("device_wait_ms", C.c_double), ("host_ms", C.c_double),
     ]
+
+
+class TiffInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bits", C.c_int32), ("sample_format", C.c_int32),
+                ("big_endian", C.c_int32), ("rows_per_strip", C.c_int32), ("n_strips", C.c_int32),
+                ("imagej_images", C.c_int32), ("first_strip_offset", C.c_int64)]
 
 
 class Task(C.Structure):
@@ -131,6 +138,9 @@ def load() -> C.CDLL:
         "lst_measure_alu_peaks": ([C.c_int, dbl, P(dbl)], C.c_int),
         "lst_host_window_for": ([P(Params), P(i32), dbl, dbl, P(i32)], C.c_int),
         "lst_host_template_rect": ([P(Params), C.c_float, C.c_float, P(i32)], C.c_int),
+        "lst_tiff_probe": ([C.c_char_p, i32, P(TiffInfo), C.c_char_p, i32], C.c_int),
+        "lst_set_reference_file": ([vp, C.c_char_p, i32, P(C.c_float), P(ReferenceInfo)], C.c_int),
+        "lst_track_files": ([vp, P(C.c_char_p), P(i32), i64, i32, P(Record)], C.c_int),
         "lst_multi_create": ([P(Params), P(i32), i32, P(vp)], C.c_int),
         "lst_multi_destroy": ([vp], None),
         "lst_multi_last_error": ([vp], C.c_char_p),

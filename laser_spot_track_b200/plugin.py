@@ -21,6 +21,7 @@ Everything computes on the GPU through ``liblst_b200.so``; there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -145,6 +146,25 @@ class LaserSpotTrack4:
         ptrs = host_ptrs if isinstance(host_ptrs, C.Array) else (C.c_void_p * n)(*host_ptrs)
         out = (N.Record * n)() if out is None else out
         self._check(self._lib.lst_track_ptrs(self._ctx, ptrs, first_frame_index, n, out))
+        return out
+
+    # -- slices as files ---------------------------------------------------------------
+    def set_reference_file(self, path: str, ref_xy, page: int = 0) -> N.ReferenceInfo:
+        """``set_reference`` with the reference slice read from an uncompressed grey-scale TIFF file."""
+        xy = (C.c_float * 10)(*[float(v) for p in ref_xy for v in p])
+        info = N.ReferenceInfo()
+        self._check(self._lib.lst_set_reference_file(self._ctx, os.fsencode(path), int(page), xy, C.byref(info)))
+        return info
+
+    def track_files(self, paths, pages=None, first_frame_index: int = 1):
+        """Track the slices stored in ``paths`` (one uncompressed grey-scale TIFF per slice, or pages of
+        a multi-page / ImageJ stack file with ``pages``): what the reference's virtual stack feeds
+        analyseSlice (LST4:808-831).  Only the rows of the five search regions are read from each file."""
+        n = len(paths)
+        arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        pg = None if pages is None else (C.c_int32 * n)(*[int(p) for p in pages])
+        out = (N.Record * n)()
+        self._check(self._lib.lst_track_files(self._ctx, arr, pg, first_frame_index, n, out))
         return out
 
     def analyseSlice(self, slice_pixels: np.ndarray, frame_index: int = 0) -> N.Record:
@@ -299,6 +319,16 @@ class LaserSpotTrack4Multi:
     @property
     def retracked(self) -> int:
         return int(self._lib.lst_multi_retracked(self._m))
+
+
+def tiff_probe(path: str, page: int = 0) -> N.TiffInfo:
+    """Layout of a slice file as ``lst_track_files`` sees it (host only); raises LstError when unsupported."""
+    info = N.TiffInfo()
+    err = C.create_string_buffer(256)
+    rc = N.load().lst_tiff_probe(os.fsencode(path), int(page), C.byref(info), err, 256)
+    if rc != N.LST_OK:
+        raise LstError(rc, err.value.decode(errors="replace"))
+    return info
 
 
 def results_table(records, ref_info: Optional[N.ReferenceInfo] = None, time_step: float = 1.0,

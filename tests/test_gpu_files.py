@@ -1,0 +1,110 @@
+"""SURVEY 8f-N2 on the GPU: slices read from TIFF files (lst_track_files) give the records the oracle
+computes from the decoded arrays, for either byte order, strip layouts, multi-page files and the
+fallback to whole-slice reads."""
+import numpy as np
+import pytest
+
+from laser_spot_track_b200 import LaserSpotTrack4, LstError
+from laser_spot_track_b200.synth import StackConfig, SyntheticStack
+from oracle import lst_oracle as O
+
+import tiffio
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(cfg, st, frames, **kw):
+    op = util.oracle_params(cfg, **kw)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    return op, otr, otr.run(frames[1:])
+
+
+def _tracker(cfg, op, **kw):
+    bits = {"u8": 8, "u16": 16, "f32": 32}[cfg.dtype]
+    return LaserSpotTrack4(cfg.width, cfg.height, bits, templSize=op.templ_size, sArea=op.s_area, markDist=op.mark_dist,
+                           subPixel=op.sub_pixel, matchIntensity=op.match_intensity, **kw)
+
+
+@pytest.mark.parametrize("dtype,big_endian,rps", [("u16", False, None), ("u16", True, 7), ("u8", False, 5),
+                                                   ("f32", True, None), ("f32", False, 64)])
+def test_track_files_equals_oracle(built_lib, oracle_clib, tmp_path, dtype, big_endian, rps):
+    cfg = StackConfig(400, 300, dtype, 32, 24, 30)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 30)]
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    paths = []
+    for i, f in enumerate(frames):
+        p = tmp_path / f"s{i:04d}.tif"
+        tiffio.write_tiff(p, [f], big_endian=big_endian, rows_per_strip=rps)
+        paths.append(str(p))
+    with _tracker(cfg, op, max_batch=8) as t:
+        info = t.set_reference_file(paths[0], st.ref_xy)
+        assert list(info.mideal) == otr.mideal
+        got = t.track_files(paths[1:])
+        util.compare_records(got, want, label=f"files {dtype} be={big_endian} rps={rps}")
+        s = t.stats()
+        assert s.roi_fallback_tasks == 0
+        assert 0 < s.h2d_bytes < 0.8 * len(want) * frames[0].nbytes     # only the search regions travel
+
+
+def test_track_pages_of_one_file(built_lib, oracle_clib, tmp_path):
+    cfg = StackConfig(400, 300, "u16", 32, 24, 20)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 20)]
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    for name, kw in (("pages.tif", dict()), ("ijstack.tif", dict(imagej_stack=True, big_endian=True))):
+        p = str(tmp_path / name)
+        tiffio.write_tiff(p, frames, **kw)
+        with _tracker(cfg, op, max_batch=6) as t:
+            t.set_reference_file(p, st.ref_xy, page=0)
+            got = t.track_files([p] * 19, pages=list(range(1, 20)))
+            util.compare_records(got, want, label=name)
+
+
+def test_track_files_windows_leave_the_regions(built_lib, oracle_clib, tmp_path):
+    """A jump larger than the margin read around the search regions: the batch is re-read whole."""
+    cfg = StackConfig(400, 300, "u16", 32, 24, 24)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 24)]
+    for i in range(9, 24):
+        frames[i] = np.roll(frames[i], (15, -17), axis=(0, 1))
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    assert sum(w.status == 0 for w in want) >= 20
+    paths = []
+    for i, f in enumerate(frames):
+        p = tmp_path / f"j{i:04d}.tif"
+        tiffio.write_tiff(p, [f], big_endian=True)
+        paths.append(str(p))
+    with _tracker(cfg, op, max_batch=5) as t:
+        t.set_reference_file(paths[0], st.ref_xy)
+        got = t.track_files(paths[1:])
+        util.compare_records(got, want, label="files with a jump")
+        assert t.stats().roi_fallback_tasks > 0
+
+
+def test_track_files_whole_slice_search_and_errors(built_lib, oracle_clib, tmp_path):
+    cfg = StackConfig(200, 160, "u8", 24, 0, 6)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 6)]
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=False)
+    paths = []
+    for i, f in enumerate(frames):
+        p = tmp_path / f"w{i}.tif"
+        tiffio.write_tiff(p, [f])
+        paths.append(str(p))
+    with _tracker(cfg, op) as t:
+        t.set_reference_file(paths[0], st.ref_xy)
+        util.compare_records(t.track_files(paths[1:]), want, label="files, sArea=0")
+        # a slice of another size: "All stack images must have the same size and type" (LST4:393)
+        bad = tmp_path / "bad.tif"
+        tiffio.write_tiff(bad, [np.zeros((100, 100), np.uint8)])
+        with pytest.raises(LstError):
+            t.track_files([str(bad)])
+        with pytest.raises(LstError):
+            t.track_files([str(tmp_path / "missing.tif")])
+        comp = tmp_path / "lzw.tif"
+        tiffio.write_tiff(comp, [frames[1]], compression=5)
+        with pytest.raises(LstError):
+            t.track_files([str(comp)])
