@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames of the CPU baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the slices-from-TIFF-files leg (e2e_files)")
     ap.add_argument("--ingest", type=int, default=0, choices=[0, 1, 2], help="0 ROI DMA (default), 1 whole slices, 2 ROI gather kernel")
     ap.add_argument("--engine", default="auto", choices=["auto", "dp4a", "tc"], help="match kernel: tensor cores (default when the template fits) or IDP.4A")
     return ap.parse_args()
@@ -355,6 +356,49 @@ def main():
                "ingest": "pinned host ring of whole slices; only the five search regions (+8 px margin, 32-byte aligned) of "
                          "each slice cross PCIe, as strided 3-D DMA copies on a copy stream while the previous batch computes"}
 
+    # The same stack as files: one big-endian 16-bit TIFF per slice, as ImageJ writes them,
+    # in a temporary directory (page cache resident); lst_track_files maps each file and reads only the
+    # rows of the search regions.  Reported beside e2e; N = 1 only.
+    e2e_files = None
+    if not args.no_e2e and not args.no_files and world == 1:
+        import shutil
+        import struct
+        import tempfile
+        tdir = tempfile.mkdtemp(prefix="lst_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            def write_tiff(path, img):
+                h, w = img.shape
+                be = img.dtype.itemsize > 1
+                bo = ">" if be else "<"
+                raw = img.astype(img.dtype.newbyteorder(bo)).tobytes()
+                ent = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 1, img.dtype.itemsize * 8), (259, 3, 1, 1), (262, 3, 1, 1),
+                       (273, 4, 1, 8), (277, 3, 1, 1), (278, 4, 1, h), (279, 4, 1, len(raw)),
+                       (339, 3, 1, 3 if img.dtype.kind == "f" else 1)]
+                ifd = struct.pack(bo + "H", len(ent))
+                for tag, typ, cnt, val in ent:
+                    ifd += struct.pack(bo + "HHI", tag, typ, cnt) + (struct.pack(bo + "HH", val, 0) if typ == 3 else struct.pack(bo + "I", val))
+                ifd += struct.pack(bo + "I", 0)
+                with open(path, "wb") as f:
+                    f.write((b"MM" if be else b"II") + struct.pack(bo + "HI", 42, 8 + len(raw)) + raw + ifd)
+            files = []
+            for i in range(ring):
+                fp = os.path.join(tdir, f"slice{i:05d}.tif")
+                write_tiff(fp, st.frame(i))
+                files.append(fp)
+            paths = [files[i] for i in idx]
+
+            def step_files():
+                trk.track_files(paths, first_frame_index=1)
+
+            ms_f, wall_f, s_f = timed(step_files, K, 1)
+            e2e_files = {"value": F * K / (wall_f * 1e-3), "unit": UNIT, "ms_per_step": wall_f / K,
+                         "h2d_bytes_per_step": int(s_f.h2d_bytes // K), "file_bytes": int(os.path.getsize(files[0])),
+                         "reader_threads": int(os.environ.get("LST_FILE_THREADS", min(16, os.cpu_count() or 1))), "host_cores": os.cpu_count(),
+                         "what": "lst_track_files over %d paths per step cycling %d big-endian TIFF files in %s (page cache); "
+                                 "wall clock, includes mapping and parsing every file" % (F, ring, os.path.dirname(files[0]))}
+        finally:
+            shutil.rmtree(tdir, ignore_errors=True)
+
     value = world * F * K / (ms_dev * 1e-3)
     # roofline of the dominant kernel (the template match): exact u8 x u8 -> s32 multiply-accumulates
     win_macs = float((2 * cfg.s_area + 1) ** 2 * cfg.templ_size ** 2)
@@ -447,7 +491,7 @@ def main():
                              "ring smaller than L2; windows are re-read from HBM/L2 each pass",
                        "max_batch": args.max_batch or mb_d, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                        "accepted_frames_last_step": ok_frames},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(s_dev.kernel_launches),
+            "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
                          "chunks_retracked": sh_dev.retracked, "host_ms_per_step": s_dev.host_ms / K,

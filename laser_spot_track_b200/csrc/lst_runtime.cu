@@ -1261,7 +1261,11 @@ int lst_track_files(lst_ctx *c, const char *const *paths, const int32_t *pages, 
         if (rc != LST_OK) return rc;
         fs.big_endian = L.big_endian;
     }
-    if (const char *e = getenv("LST_FILE_THREADS")) c->file_threads = std::max(1, atoi(e));
+    {
+        unsigned hc = std::thread::hardware_concurrency();
+        c->file_threads = (int)std::min(16u, std::max(1u, hc));   // pread scales with the cores; the copy engine does the rest
+        if (const char *e = getenv("LST_FILE_THREADS")) c->file_threads = std::max(1, atoi(e));
+    }
     c->swap_bytes = fs.big_endian && c->p.pixel_type != LST_PIX_U8;
     int rc = track_impl(c, nullptr, 0, nullptr, false, first_frame_index, n_frames, out, &fs);
     c->swap_bytes = false;

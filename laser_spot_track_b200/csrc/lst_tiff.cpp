@@ -172,11 +172,12 @@ int FileMap::open(const char *path, std::string *err)
         return LST_ERR_INVALID;
     }
     void *p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-    ::close(fd);
     if (p == MAP_FAILED) {
+        ::close(fd);
         if (err) *err = std::string("cannot map ") + path;
         return LST_ERR_INVALID;
     }
+    this->fd = fd;
     data = (const uint8_t *)p;
     size = (uint64_t)st.st_size;
     return LST_OK;
@@ -185,6 +186,8 @@ int FileMap::open(const char *path, std::string *err)
 void FileMap::close()
 {
     if (data) munmap((void *)data, (size_t)size);
+    if (fd >= 0) ::close(fd);
+    fd = -1;
     data = nullptr;
     size = 0;
 }
@@ -194,11 +197,23 @@ int tiff_copy_rect(const FileMap &fm, const TiffLayout &L, int x0, int y0, int w
     if (x0 < 0 || y0 < 0 || w < 0 || h < 0 || x0 + w > L.width || y0 + h > L.height)
         return fail(err, LST_ERR_INVALID, "rectangle outside the TIFF image");
     const size_t bpp = (size_t)L.bits / 8, nb = (size_t)w * bpp;
-    if (w == L.width && L.strip_off.size() == 1) {   // whole rows of a single strip: one copy
-        memcpy(dst, fm.data + L.offset_of_row(y0), nb * (size_t)h);
+    auto rd = [&](uint8_t *d, uint64_t off, size_t len) -> bool {
+        while (len > 0) {
+            ssize_t k = pread(fm.fd, d, len, (off_t)off);
+            if (k <= 0) return false;
+            d += k;
+            off += (uint64_t)k;
+            len -= (size_t)k;
+        }
+        return true;
+    };
+    if (w == L.width && L.strip_off.size() == 1) {   // whole rows of a single strip: one read
+        if (!rd(dst, L.offset_of_row(y0), nb * (size_t)h)) return fail(err, LST_ERR_INVALID, "short read from the slice file");
         return LST_OK;
     }
-    for (int r = 0; r < h; r++) memcpy(dst + (size_t)r * nb, fm.data + L.offset_of_row(y0 + r) + (size_t)x0 * bpp, nb);
+    for (int r = 0; r < h; r++)
+        if (!rd(dst + (size_t)r * nb, L.offset_of_row(y0 + r) + (size_t)x0 * bpp, nb))
+            return fail(err, LST_ERR_INVALID, "short read from the slice file");
     return LST_OK;
 }
 

@@ -31,10 +31,13 @@ struct TiffLayout {
 // LST_ERR_UNSUPPORTED or LST_ERR_INVALID with a message.
 int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, std::string *err);
 
-// A read-only mapping of a file.
+// A read-only mapping of a file (used for the directory, which may lie anywhere in the file) plus the
+// descriptor: pixel rows are fetched with pread, which -- unlike page faults on a mapping -- does not
+// serialise the reader threads on the process's address-space lock.
 struct FileMap {
     const uint8_t *data = nullptr;
     uint64_t size = 0;
+    int fd = -1;
     int open(const char *path, std::string *err);
     void close();
     ~FileMap() { close(); }
