@@ -50,6 +50,7 @@ extern "C" {
 #define LST_PIX_U8   8
 #define LST_PIX_U16 16
 #define LST_PIX_F32 32
+#define LST_PIX_RGB 24          /* ColorProcessor pixels: one int32 0x00RRGGBB per pixel (DOES_RGB, LST4:172) */
 
 /* float -> 8-bit range convention of FloatProcessor.getBufferedImage (SURVEY.md 8c "known unknown") */
 #define LST_RANGE_DISPLAY 0      /* u8: [0,255]; u16/f32: crop's own pre-blur min/max (default) */
@@ -90,6 +91,7 @@ typedef struct lst_params {
     int32_t ncc_engine;        /* match kernel: 0 = auto (tensor cores when the template fits, else IDP.4A),
                                   1 = IDP.4A (lst_ncc_match), 2 = tensor cores (lst_ncc_tc); identical results */
     int32_t reserved1;
+    double  rgb_weights[3];    /* RGB -> grey weights of convertToGray32 (LST4:519-521); all 0 = ImageJ's default 1/3 each */
 } lst_params;
 
 /* One template's match in one frame: the double[3] of doMatch_coord_res plus context. */

@@ -101,6 +101,8 @@ int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_di
 // ingest of the *next* batch, and a 300 KB task list must not wait behind it.
 int launch_upload(void *dst_dev, const void *src_pinned_host, size_t bytes, cudaStream_t stream);
 int set_blur_kernel(const float kern[7], const float ksum[7]);
+// RGB -> grey weighting factors; like ColorProcessor.setWeightingFactors they are global (per device)
+int set_rgb_weights(const double w[3]);
 // picks band/tile split and the shared-memory pitch for lst_ncc_match
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes);
 int measure_alu_peaks(double ms_per_test, double out[3]);

@@ -38,9 +38,11 @@ int validate_params(const lst_params &p, std::string *err)
     if (p.struct_size != (int32_t)sizeof(lst_params)) return fail(LST_ERR_INVALID, "lst_params.struct_size mismatch");
     if (p.width <= 0 || p.height <= 0 || p.width > 32768 || p.height > 32768)
         return fail(LST_ERR_INVALID, "bad slice size");
-    if (p.pixel_type != LST_PIX_U8 && p.pixel_type != LST_PIX_U16 && p.pixel_type != LST_PIX_F32)
+    if (p.pixel_type != LST_PIX_U8 && p.pixel_type != LST_PIX_U16 && p.pixel_type != LST_PIX_F32 && p.pixel_type != LST_PIX_RGB)
         return fail(LST_ERR_UNSUPPORTED, "Unsupported image type");   // IJ.error text of LST4:2537
     if (p.method < 0 || p.method > 5) return fail(LST_ERR_INVALID, "matching method must be 0..5 (LST4:2381)");
+    if (p.pixel_type == LST_PIX_RGB && !p.match_intensity)
+        return fail(LST_ERR_UNSUPPORTED, "RGB stacks are matched on intensity only (matchIntensity=true): the 3-channel match is not on this path");
     if (p.pixel_type == LST_PIX_U16 && !p.match_intensity)
         return fail(LST_ERR_UNSUPPORTED,
                     "16-bit stacks need matchIntensity=true (the reference dereferences a null Mat, LST4:2510-2523)");

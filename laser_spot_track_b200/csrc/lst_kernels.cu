@@ -25,6 +25,7 @@ namespace lst {
 
 __constant__ float c_kern[KR];
 __constant__ float c_ksum[KR];
+__constant__ double c_rgbw[3] = {1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0};   // ColorProcessor weighting factors
 
 static void prefer_max_shared_everywhere();
 
@@ -40,9 +41,22 @@ int set_blur_kernel(const float kern[7], const float ksum[7])
 // helpers
 // ------------------------------------------------------------------------------------------------
 
+int set_rgb_weights(const double w[3])
+{
+    return cudaMemcpyToSymbol(c_rgbw, w, sizeof(double) * 3) == cudaSuccess ? 0 : -1;
+}
+
+// TypeConverter.convertRGBToByte [ImageJ, 3P-recall]: (byte)(r*rw + g*gw + b*bw + 0.5) in double
+__device__ __forceinline__ uint32_t rgb_gray(uint32_t c)
+{
+    const double r = (double)((c >> 16) & 0xffu), g = (double)((c >> 8) & 0xffu), b = (double)(c & 0xffu);
+    return (uint32_t)(int)(r * c_rgbw[0] + g * c_rgbw[1] + b * c_rgbw[2] + 0.5) & 0xffu;
+}
+
 template <int PIX>
 __device__ __forceinline__ float load_px(const void *base, size_t idx)
 {
+    if (PIX == LST_PIX_RGB) return (float)rgb_gray(((const uint32_t *)base)[idx]);
     if (PIX == LST_PIX_U8) return (float)((const uint8_t *)base)[idx];
     if (PIX == LST_PIX_U16) return (float)((const uint16_t *)base)[idx];
     return ((const float *)base)[idx];
@@ -50,6 +64,7 @@ __device__ __forceinline__ float load_px(const void *base, size_t idx)
 template <int PIX>
 __device__ __forceinline__ uint32_t px_key(const void *base, size_t idx)
 {
+    if (PIX == LST_PIX_RGB) return rgb_gray(((const uint32_t *)base)[idx]);
     if (PIX == LST_PIX_U8) return ((const uint8_t *)base)[idx];
     if (PIX == LST_PIX_U16) return ((const uint16_t *)base)[idx];
     return f32_key(((const float *)base)[idx]);
@@ -58,6 +73,7 @@ __device__ __forceinline__ uint32_t px_key(const void *base, size_t idx)
 template <int PIX>
 __device__ __forceinline__ uint32_t px_key_swapped(const void *base, size_t idx)
 {
+    if (PIX == LST_PIX_RGB) return rgb_gray(((const uint32_t *)base)[idx]);
     if (PIX == LST_PIX_U8) return ((const uint8_t *)base)[idx];
     if (PIX == LST_PIX_U16) return __byte_perm((uint32_t)((const uint16_t *)base)[idx], 0, 0x3201);
     return f32_key(__uint_as_float(__byte_perm(((const uint32_t *)base)[idx], 0, 0x0123)));
@@ -66,7 +82,7 @@ template <int PIX>
 __device__ __forceinline__ float key_to_float(uint32_t k)
 {
     if (PIX == LST_PIX_F32) return key_f32(k);
-    return (float)k;
+    return (float)k;   // u8, u16, grey value of an RGB pixel
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -154,6 +170,8 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *s
             lst_minmax<LST_PIX_U8><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base, pp.swap_bytes);
         else if (pp.pixel_type == LST_PIX_U16)
             lst_minmax<LST_PIX_U16><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base, pp.swap_bytes);
+        else if (pp.pixel_type == LST_PIX_RGB)
+            lst_minmax<LST_PIX_RGB><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base, pp.swap_bytes);
         else
             lst_minmax<LST_PIX_F32><<<grid, 128, 0, stream>>>(tasks + base, surfaces, mm_keys + 2 * base, pp.swap_bytes);
         launches++;
@@ -274,7 +292,7 @@ __device__ __forceinline__ void mm_word(uint32_t wlo, uint32_t whi, uint32_t &lo
         lo = __vminu2(lo, wlo);
         hi = __vmaxu2(hi, whi);
     } else {
-        const uint32_t k = f32_key(__uint_as_float(whi));
+        const uint32_t k = PIX == LST_PIX_RGB ? rgb_gray(whi) : f32_key(__uint_as_float(whi));
         lo = min(lo, k);
         hi = max(hi, k);
     }
@@ -331,7 +349,7 @@ __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, s
                     o[1] = __funnelshift_r(w1, w2, bs);
                     o[2] = __funnelshift_r(w2, w3, bs);
                     o[3] = __funnelshift_r(w3, w4, bs);
-                    if (PIX != LST_PIX_U8 && swap) {   // big-endian samples (TIFF "MM")
+                    if (PIX != LST_PIX_U8 && PIX != LST_PIX_RGB && swap) {   // big-endian samples (TIFF "MM")
 #pragma unroll
                         for (int j = 0; j < 4; j++) o[j] = __byte_perm(o[j], 0, PIX == LST_PIX_U16 ? 0x2301 : 0x0123);
                     }
@@ -347,7 +365,7 @@ __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, s
                             const uint32_t m = byte_range_mask(b0 - 4 * j, b1 - 4 * j);
                             o[j] &= m;
                             if (MINMAX) {
-                                if (PIX != LST_PIX_F32) mm_word<PIX>(o[j] | ~m, o[j], mlo, mhi);
+                                if (PIX != LST_PIX_F32 && PIX != LST_PIX_RGB) mm_word<PIX>(o[j] | ~m, o[j], mlo, mhi);
                                 else if (m) mm_word<PIX>(o[j], o[j], mlo, mhi);
                             }
                         }
@@ -361,7 +379,7 @@ __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, s
                             if (PIX == LST_PIX_U8) v = grow[bo];
                             else if (PIX == LST_PIX_U16) v = *(const uint16_t *)(grow + bo);
                             else v = *(const uint32_t *)(grow + bo);
-                            if (PIX != LST_PIX_U8 && swap) v = PIX == LST_PIX_U16 ? __byte_perm(v, 0, 0x3201) : __byte_perm(v, 0, 0x0123);
+                            if (PIX != LST_PIX_U8 && PIX != LST_PIX_RGB && swap) v = PIX == LST_PIX_U16 ? __byte_perm(v, 0, 0x3201) : __byte_perm(v, 0, 0x0123);
                             const uint32_t sh = v << (8 * ((e * ES) & 3));
                             const int wi = (e * ES) >> 2;
                             o[0] |= wi == 0 ? sh : 0u, o[1] |= wi == 1 ? sh : 0u, o[2] |= wi == 2 ? sh : 0u, o[3] |= wi == 3 ? sh : 0u;
@@ -385,6 +403,8 @@ __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, s
                     for (int j = 0; j < 2; j++)
                         ((float4 *)d)[j] = make_float4((float)(o[2 * j] & 0xffffu), (float)(o[2 * j] >> 16),
                                                        (float)(o[2 * j + 1] & 0xffffu), (float)(o[2 * j + 1] >> 16));
+                } else if (PIX == LST_PIX_RGB) {
+                    *(float4 *)d = make_float4((float)rgb_gray(o[0]), (float)rgb_gray(o[1]), (float)rgb_gray(o[2]), (float)rgb_gray(o[3]));
                 } else {
                     *(float4 *)d = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
                 }
@@ -605,6 +625,8 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
             lst_preprocess<LST_PIX_U8><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         else if (pp.pixel_type == LST_PIX_U16)
             lst_preprocess<LST_PIX_U16><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+        else if (pp.pixel_type == LST_PIX_RGB)
+            lst_preprocess<LST_PIX_RGB><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         else
             lst_preprocess<LST_PIX_F32><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
         launches++;
@@ -1092,6 +1114,7 @@ static void prefer_max_shared_everywhere()
     cudaFuncSetAttribute(lst_preprocess<LST_PIX_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(lst_preprocess<LST_PIX_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     const int mx = (int)cudaSharedmemCarveoutMaxShared;
@@ -1100,9 +1123,11 @@ static void prefer_max_shared_everywhere()
     cudaFuncSetAttribute(lst_minmax<LST_PIX_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_minmax<LST_PIX_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_minmax<LST_PIX_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_minmax<LST_PIX_RGB>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_preprocess<LST_PIX_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_preprocess<LST_PIX_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaFuncSetAttribute(lst_preprocess<LST_PIX_RGB>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_epilogue, cudaFuncAttributePreferredSharedMemoryCarveout, mx);

@@ -226,7 +226,8 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
         pp->range_per_task = 0;
         pp->lo = (float)p.range_lo;
         pp->hi = (float)p.range_hi;
-    } else if (p.range_mode == LST_RANGE_DISPLAY && p.pixel_type == LST_PIX_U8) {
+    } else if (p.range_mode == LST_RANGE_DISPLAY && (p.pixel_type == LST_PIX_U8 || p.pixel_type == LST_PIX_RGB)) {
+        // 8-bit and RGB images keep their 0..255 display range through convertToGray32
         pp->range_per_task = 0;
         pp->lo = 0.0f;
         pp->hi = 255.0f;
@@ -594,6 +595,11 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
     float kern[7], ksum[7];
     make_gaussian_kernel(kern, ksum);
     if (set_blur_kernel(kern, ksum) != 0) return bail(cudaGetLastError(), "blur kernel upload");
+    if (c->p.pixel_type == LST_PIX_RGB) {
+        double w[3] = {c->p.rgb_weights[0], c->p.rgb_weights[1], c->p.rgb_weights[2]};
+        if (w[0] == 0.0 && w[1] == 0.0 && w[2] == 0.0) w[0] = w[1] = w[2] = 1.0 / 3.0;   // ColorProcessor default
+        if (set_rgb_weights(w) != 0) return bail(cudaGetLastError(), "RGB weights upload");
+    }
     *out = c;
     return LST_OK;
 }
@@ -1212,6 +1218,7 @@ int lst_tiff_probe(const char *path, int32_t page, lst_tiff_info *out, char *err
 
 static int check_slice_file(lst_ctx *c, const char *path, int page, FileMap *fm, TiffLayout *L)
 {
+    if (c->p.pixel_type == LST_PIX_RGB) return c->fail(LST_ERR_UNSUPPORTED, "RGB slice files are not read here: decode them and use lst_track_ptrs");
     std::string e;
     int rc = fm->open(path, &e);
     if (rc == LST_OK) rc = tiff_parse(fm->data, fm->size, page, L, &e);

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liblst_b200.so")
 
 LST_OK, LST_ERR_INVALID, LST_ERR_UNSUPPORTED, LST_ERR_CUDA, LST_ERR_NOMEM, LST_ERR_STATE = 0, -1, -2, -3, -4, -5
-PIX_U8, PIX_U16, PIX_F32 = 8, 16, 32
+PIX_U8, PIX_U16, PIX_F32, PIX_RGB = 8, 16, 32, 24
 RANGE_DISPLAY, RANGE_CROP, RANGE_FIXED = 0, 1, 2
 QUANT_ROUND255, QUANT_TRUNC256 = 0, 1
 STATUS_OK, STATUS_SKIP, STATUS_STOP = 0, 1, 2
@@ -41,6 +41,7 @@ class Params(C.Structure):
         ("ingest_mode", C.c_int32),
         ("mark_dist", C.c_double), ("range_lo", C.c_double), ("range_hi", C.c_double),
         ("match_threshold", C.c_double), ("ncc_engine", C.c_int32), ("reserved1", C.c_int32),
+        ("rgb_weights", C.c_double * 3),
     ]
 
 
@@ -169,10 +170,13 @@ def default_params(width: int, height: int, pixel_type: int, **kw) -> Params:
     p.sub_pixel, p.match_intensity = 1, 1
     p.range_mode, p.quant_mode = RANGE_DISPLAY, QUANT_ROUND255
     p.doubling, p.auto_skip, p.max_s_area, p.max_batch = 0, 1, 500, 0
-    p.mark_dist, p.range_lo, p.range_hi, p.match_threshold = 100.0, 0.0, 255.0, 0.2
+    p.mark_dist, p.range_lo, p.range_hi = 100.0, 0.0, 255.0
+    p.match_threshold = 0.0   # 0 = matchThreshold[method] of LST4:147
     p.ncc_engine = 0
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)
+        if k == "rgb_weights":
+            v = (C.c_double * 3)(*[float(x) for x in (v or (0.0, 0.0, 0.0))])
         setattr(p, k, v)
     return p

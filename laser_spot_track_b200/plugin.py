@@ -28,7 +28,8 @@ import numpy as np
 
 from . import native as N
 
-_PIX = {8: (N.PIX_U8, np.uint8), 16: (N.PIX_U16, np.uint16), 32: (N.PIX_F32, np.float32)}
+_PIX = {8: (N.PIX_U8, np.uint8), 16: (N.PIX_U16, np.uint16), 32: (N.PIX_F32, np.float32),
+        24: (N.PIX_RGB, np.uint32)}   # 24: ColorProcessor pixels, 0x00RRGGBB per pixel; (h, w, 3) uint8 RGB arrays are packed
 TEMPLATE_NAMES = ("spot", "mark1", "mark2", "mark3", "mark4")
 RESULT_COLUMNS = ("Time", "Frame", "File", "dX_pix", "dY_pix", "X_abs", "Y_abs", "dL")   # LST4:867-875
 
@@ -47,7 +48,8 @@ class LaserSpotTrack4:
                  subPixel: bool = True, matchIntensity: bool = True, alwaysAutoSkip: bool = True,
                  doubling: bool = False, maxSArea: int = 500, range_mode: int = N.RANGE_DISPLAY,
                  range_lo: float = 0.0, range_hi: float = 255.0, quant_mode: int = N.QUANT_ROUND255,
-                 max_batch: int = 0, ingest_mode: int = 0, ncc_engine: int = 0):
+                 max_batch: int = 0, ingest_mode: int = 0, ncc_engine: int = 0, matchThreshold: float = 0.0,
+                 rgb_weights=None):
         if bit_depth not in _PIX:
             raise LstError(N.LST_ERR_UNSUPPORTED, "Unsupported image type")       # IJ.error, LST4:2537
         self._lib = N.load()
@@ -58,7 +60,8 @@ class LaserSpotTrack4:
             mark_dist=markDist, sub_pixel=int(subPixel), match_intensity=int(matchIntensity),
             auto_skip=int(alwaysAutoSkip), doubling=int(doubling), max_s_area=maxSArea,
             range_mode=range_mode, range_lo=range_lo, range_hi=range_hi, quant_mode=quant_mode,
-            max_batch=max_batch, ingest_mode=ingest_mode, ncc_engine=ncc_engine)
+            max_batch=max_batch, ingest_mode=ingest_mode, ncc_engine=ncc_engine, match_threshold=matchThreshold,
+            rgb_weights=rgb_weights)
         self._ctx = C.c_void_p()
         rc = self._lib.lst_create(C.byref(self.params), device, C.byref(self._ctx))
         if rc != N.LST_OK:
@@ -91,6 +94,8 @@ class LaserSpotTrack4:
             raise LstError(rc, self._lib.lst_last_error(self._ctx).decode())
 
     def _frame(self, a: np.ndarray) -> np.ndarray:
+        if self._np_dtype == np.uint32 and a.dtype == np.uint8 and a.shape[-1] == 3:
+            a = (a[..., 0].astype(np.uint32) << 16) | (a[..., 1].astype(np.uint32) << 8) | a[..., 2].astype(np.uint32)
         a = np.ascontiguousarray(a, dtype=self._np_dtype)
         if a.shape[-2:] != (self.height, self.width):
             raise LstError(N.LST_ERR_INVALID, "slice size differs from the stack's (LST4:813-817)")

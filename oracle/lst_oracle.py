@@ -73,6 +73,7 @@ class Params:
     doubling: bool = False         # search-area doubling recovery (LST4:1666-1735, 2058-2128); SURVEY 8f-N1
     auto_skip: bool = True         # headless policy: reject => skip the frame (LST4:2146-2148)
     max_s_area: int = 500          # maxSArea LST4:131
+    rgb_weights: Tuple[float, float, float] = (1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0)   # ColorProcessor weighting factors
 
 
 # --------------------------------------------------------------------------------------
@@ -237,6 +238,17 @@ def quantize_u8(blurred: np.ndarray, lo: float, hi: float, quant_mode: int) -> n
     return out
 
 
+def rgb_to_gray8(packed: np.ndarray, weights=(1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0)) -> np.ndarray:
+    """TypeConverter.convertRGBToByte [ImageJ, 3P-recall], the first half of convertToGray32 on a
+    ColorProcessor (LST4:519-521): (byte)(r*rw + g*gw + b*bw + 0.5) in double, pixels 0x00RRGGBB."""
+    c = packed.astype(np.uint32)
+    r = ((c >> 16) & 0xff).astype(np.float64)
+    g = ((c >> 8) & 0xff).astype(np.float64)
+    b = (c & 0xff).astype(np.float64)
+    v = r * weights[0] + g * weights[1] + b * weights[2] + 0.5
+    return (v.astype(np.int64) & 0xff).astype(np.uint8)
+
+
 def preprocess_crop(frame: np.ndarray, x0: int, y0: int, w: int, h: int, p: Params) -> np.ndarray:
     """crop -> [convertToGray32] -> blurGaussian(2,2,0.02) -> 8-bit, i.e. what reaches
     cv::matchTemplate for one window or template (LST4:1346-1347, 1456-1473, 2525-2535).
@@ -247,6 +259,13 @@ def preprocess_crop(frame: np.ndarray, x0: int, y0: int, w: int, h: int, p: Para
     unsupported here as there."""
     x0, y0, w, h = clip_rect(x0, y0, w, h, frame.shape[1], frame.shape[0])
     crop = frame[y0:y0 + h, x0:x0 + w]
+    if frame.dtype == np.uint32:
+        # RGB slice (DOES_RGB, LST4:172): matched on intensity; an 8-bit grey image from here on, whose
+        # 0..255 display range survives convertToGray32 like an 8-bit slice's
+        if not p.match_intensity:
+            raise ValueError("RGB stacks: only matchIntensity=true is on this path")
+        crop = rgb_to_gray8(crop, p.rgb_weights)
+        frame = crop
     if frame.dtype == np.uint8 and not p.match_intensity:
         lo, hi, qm = 0.0, 255.0, QUANT_ROUND255
     else:

@@ -195,7 +195,9 @@ def test_unsupported_like_reference(built_lib):
     with pytest.raises(LstError):
         LaserSpotTrack4(640, 480, 8, method=6)
     with pytest.raises(LstError):
-        LaserSpotTrack4(640, 480, 24)
+        LaserSpotTrack4(640, 480, 12)
+    with pytest.raises(LstError):
+        LaserSpotTrack4(640, 480, 24, matchIntensity=False)     # the 3-channel match is not on this path
     with LaserSpotTrack4(640, 480, 8) as t:
         with pytest.raises(LstError):
             t.track(np.zeros((1, 480, 640), np.uint8))            # no reference yet
@@ -461,3 +463,42 @@ def test_track_other_methods(stack_a, method):
             info = t.set_reference(frames[0], st.ref_xy)
             assert list(info.mideal) == otr.mideal
             util.compare_records(t.track(np.stack(frames[1:21])), want, label=f"method {method} engine {engine}")
+
+
+def _rgb_stack(cfg, n):
+    """An RGB stack (ColorProcessor pixels 0x00RRGGBB) whose grey value carries the synthetic scene."""
+    st = SyntheticStack(cfg)
+    frames = []
+    for i in range(n):
+        g = st.frame(i).astype(np.uint32)
+        r, b = (g * 3 // 4 + 17) & 0xff, (255 - g // 2) & 0xff
+        frames.append((r << 16) | (g << 8) | b)
+    return st, frames
+
+
+@pytest.mark.parametrize("weights", [None, (0.299, 0.587, 0.114)])
+def test_rgb_stack_matched_on_intensity(built_lib, oracle_clib, weights):
+    """DOES_RGB (LST4:172) with matchIntensity=true: convertToGray32 of a ColorProcessor,
+    then the 8-bit path.  Blurred 8-bit crops and whole records against the oracle."""
+    cfg = StackConfig(320, 240, "u8", 32, 20, 14)
+    st, frames = _rgb_stack(cfg, 14)
+    kw = dict(match_intensity=True)
+    if weights:
+        kw["rgb_weights"] = weights
+    op = util.oracle_params(cfg, **kw)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    assert sum(w.status == 0 for w in want) >= 10
+    extra = dict(rgb_weights=weights) if weights else {}
+    with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area, matchIntensity=True,
+                         max_batch=5, **extra) as t:
+        for (x0, y0, w, h) in [(0, 0, 72, 72), (101, 57, 75, 91), (248, 168, 72, 72)]:
+            got8 = t.preprocess(frames[3], x0, y0, w, h)
+            assert np.array_equal(got8, O.preprocess_crop(frames[3], x0, y0, w, h, op))
+        info = t.set_reference(frames[0], st.ref_xy)
+        assert list(info.mideal) == otr.mideal
+        util.compare_records(t.track(np.stack(frames[1:])), want, label="RGB")
+        # (h, w, 3) uint8 arrays are accepted as well
+        rgb3 = np.stack([(frames[5] >> 16) & 0xff, (frames[5] >> 8) & 0xff, frames[5] & 0xff], axis=-1).astype(np.uint8)
+        assert np.array_equal(t.preprocess(rgb3, 10, 10, 80, 80), O.preprocess_crop(frames[5], 10, 10, 80, 80, op))

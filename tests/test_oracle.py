@@ -208,3 +208,12 @@ def test_match_result_all_methods():
     assert not T(0.96e6, 1.0e6, 1.0, 30, 64, 32, method=2)           # edge test is method-independent
     # Java double division by a zero reference: x/0 -> inf (> thresh) for x > 0, 0/0 -> NaN (not > thresh)
     assert not T(5.0, 0.0, 30, 30, 64, 32, method=0) and T(0.0, 0.0, 30, 30, 64, 32, method=0)
+
+
+def test_rgb_to_gray8_is_imagej_unweighted_mean():
+    """convertRGBToByte with the default weights (1/3 each) and with the 'weighted' ones."""
+    px = np.array([[0x000000, 0xffffff, 0xff0000, 0x010101], [0x102030, 0x0000ff, 0xfefdfc, 0x808182]], np.uint32)
+    g = O.rgb_to_gray8(px)
+    assert g.tolist() == [[0, 255, 85, 1], [32, 85, 253, 129]]
+    gw = O.rgb_to_gray8(px, (0.299, 0.587, 0.114))
+    assert gw.tolist() == [[0, 255, 76, 1], [int(16 * 0.299 + 32 * 0.587 + 48 * 0.114 + 0.5), 29, 253, 129]]
