@@ -221,6 +221,16 @@ int lst_set_reference_file(lst_ctx *ctx, const char *path, int32_t page, const f
 int lst_track_files(lst_ctx *ctx, const char *const *paths, const int32_t *pages,
                     int64_t first_frame_index, int32_t n_frames, lst_record *out);
 
+/* ---- output side ------------------------------------------------------------
+ * The ResultsTable rows of LST4:864-875 for a whole batch of records in one call (the reference
+ * appends one row and rebuilds the plot per frame).  Skipped frames add no row (LST4:845).
+ * rows: n_records x 7 doubles {Time, Frame, dX_pix, dY_pix, X_abs, Y_abs, dL}; Time advances by
+ * time_step per analysed frame from time0 (the constant-step time base of LST4:2202-2215), Frame
+ * is the table's row counter continuing from first_row_number; src_index (nullable) receives the
+ * index of the record each row came from.  Returns the number of rows, or a negative status. */
+int64_t lst_results_rows(const lst_record *records, int64_t n_records, double time0, double time_step,
+                         int64_t first_row_number, double *rows, int64_t *src_index);
+
 /* ---- the primitives, exposed like the reference's public statics ---------------------- */
 /* doMatch_coord_res(src, tpl, method, subPix, null) on the 8-bit images that reach OpenCV
  * (LST4:2502-2563, 2665-2722); method 0..5 as in the dialog (LST4:2381).  out[3] = {x, y, score}

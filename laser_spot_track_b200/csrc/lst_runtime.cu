@@ -1193,6 +1193,31 @@ int lst_track_device_ptrs(lst_ctx *c, const void *const *dev_frame_ptrs, int64_t
     return track_impl(c, nullptr, 0, dev_frame_ptrs, true, first_frame_index, n_frames, out);
 }
 
+// ---- output side -------------------------------------------------------------------
+int64_t lst_results_rows(const lst_record *records, int64_t n_records, double time0, double time_step,
+                         int64_t first_row_number, double *rows, int64_t *src_index)
+{
+    if (!records || !rows || n_records < 0) return LST_ERR_INVALID;
+    int64_t n = 0;
+    double seconds = time0;
+    for (int64_t i = 0; i < n_records; i++) {
+        const lst_record &r = records[i];
+        if (r.status != LST_STATUS_OK) continue;   // `continue` of LST4:845: no row, no time step
+        seconds += time_step;
+        double *o = rows + n * 7;
+        o[0] = seconds;
+        o[1] = (double)(first_row_number + n);
+        o[2] = r.dX_pix;
+        o[3] = r.dY_pix;
+        o[4] = r.x_abs;
+        o[5] = r.y_abs;
+        o[6] = r.dL;
+        if (src_index) src_index[n] = i;
+        n++;
+    }
+    return n;
+}
+
 // ---- slices as files -------------------------------------------------------------
 int lst_tiff_probe(const char *path, int32_t page, lst_tiff_info *out, char *err, int32_t err_cap)
 {

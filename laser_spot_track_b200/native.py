@@ -28,7 +28,7 @@ EXPORTS = [
     "lst_host_window_for", "lst_host_template_rect", "lst_host_resolve",
     "lst_multi_create", "lst_multi_destroy", "lst_multi_last_error", "lst_multi_set_reference", "lst_multi_track",
     "lst_multi_get_state", "lst_multi_set_state", "lst_multi_retracked",
-    "lst_tiff_probe", "lst_set_reference_file", "lst_track_files",
+    "lst_tiff_probe", "lst_set_reference_file", "lst_track_files", "lst_results_rows",
 ]
 
 
@@ -139,6 +139,7 @@ def load() -> C.CDLL:
         "lst_measure_alu_peaks": ([C.c_int, dbl, P(dbl)], C.c_int),
         "lst_host_window_for": ([P(Params), P(i32), dbl, dbl, P(i32)], C.c_int),
         "lst_host_template_rect": ([P(Params), C.c_float, C.c_float, P(i32)], C.c_int),
+        "lst_results_rows": ([P(Record), i64, dbl, dbl, i64, P(dbl), P(i64)], C.c_int64),
         "lst_tiff_probe": ([C.c_char_p, i32, P(TiffInfo), C.c_char_p, i32], C.c_int),
         "lst_set_reference_file": ([vp, C.c_char_p, i32, P(C.c_float), P(ReferenceInfo)], C.c_int),
         "lst_track_files": ([vp, P(C.c_char_p), P(i32), i64, i32, P(Record)], C.c_int),

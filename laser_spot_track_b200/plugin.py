@@ -336,6 +336,19 @@ def tiff_probe(path: str, page: int = 0) -> N.TiffInfo:
     return info
 
 
+def results_rows(records, time0: float = 0.0, time_step: float = 1.0, first_row_number: int = 2):
+    """``lst_results_rows``: the numeric ResultsTable columns {Time, Frame, dX_pix, dY_pix, X_abs, Y_abs, dL}
+    of a whole ctypes array of records at once (LST4:864-875); returns (rows[n, 7], source index[n])."""
+    n = len(records)
+    rows = np.zeros((max(n, 1), 7), dtype=np.float64)
+    src = np.zeros(max(n, 1), dtype=np.int64)
+    k = N.load().lst_results_rows(records, n, float(time0), float(time_step), int(first_row_number),
+                                  rows.ctypes.data_as(C.POINTER(C.c_double)), src.ctypes.data_as(C.POINTER(C.c_int64)))
+    if k < 0:
+        raise LstError(int(k), "lst_results_rows failed")
+    return rows[:k], src[:k]
+
+
 def results_table(records, ref_info: Optional[N.ReferenceInfo] = None, time_step: float = 1.0,
                   file_label: str = "") -> List[dict]:
     """The ResultsTable rows the plugin's loop appends (LST4:707-718 row 0, LST4:864-875):

@@ -72,3 +72,20 @@ def test_param_validation_mirrors_reference(built_lib):
         for k, v in kw.items():
             setattr(p, k, v)
         assert lib.lst_create(C.byref(p), 0, C.byref(ctx)) == code, kw
+
+
+def test_results_rows_match_the_python_table(built_lib):
+    """one call fills the ResultsTable columns of LST4:864-875 for a batch; skipped
+    frames add no row and no time step (LST4:845)."""
+    from laser_spot_track_b200 import results_rows, results_table
+    recs = (N.Record * 6)()
+    for i, r in enumerate(recs):
+        r.status = N.STATUS_SKIP if i in (1, 4) else N.STATUS_OK
+        r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL = 0.5 * i, -0.25 * i, 10.0 + i, 20.0 - i, 0.125 * i
+    rows, src = results_rows(recs, time0=0.0, time_step=2.5, first_row_number=2)
+    assert src.tolist() == [0, 2, 3, 5]
+    want = results_table(recs, None, time_step=2.5)
+    assert len(rows) == len(want) == 4
+    for k, (row, w) in enumerate(zip(rows, want)):
+        assert row[0] == w["Time"] and row[1] == k + 2
+        assert (row[2], row[3], row[4], row[5], row[6]) == (w["dX_pix"], w["dY_pix"], w["X_abs"], w["Y_abs"], w["dL"])
