@@ -80,7 +80,7 @@ struct lst_ctx : public Executor {
     RoiDesc roi[2][5];     // per half: the rectangles gathered for that batch
     bool roi_active = false;   // the batch being resolved uses ROI surfaces
     int roi_half = 0, roi_nb = 0;
-    int roi_margin = 8;          // current margin; adapts to the excursion of the windows seen in the last batch
+    int roi_margin[5] = {8, 8, 8, 8, 8};   // current margin per region; adapts to the excursion of that template's windows in the last batch
     int roi_margin_fixed = -1;   // LST_ROI_MARGIN pins it
     int roi_align_bytes = 16;
     std::unordered_map<const void *, const void *> mapped_cache;   // pinned host ptr -> device-visible ptr
@@ -589,7 +589,10 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
         if (e && !strcmp(e, "tc")) eng = 2;
         c->ncc_engine = eng == 1 ? 0 : 1;      // internal: 1 = tensor cores wherever lst_ncc_tc applies
         tc_init_device();
-        if (const char *m = getenv("LST_ROI_MARGIN")) c->roi_margin = c->roi_margin_fixed = std::max(0, atoi(m));
+        if (const char *m = getenv("LST_ROI_MARGIN")) {
+            c->roi_margin_fixed = std::max(0, atoi(m));
+            for (int k = 0; k < 5; k++) c->roi_margin[k] = c->roi_margin_fixed;
+        }
         if (const char *a = getenv("LST_ROI_ALIGN")) c->roi_align_bytes = std::max(4, atoi(a));
     }
     float kern[7], ksum[7];
@@ -792,8 +795,8 @@ static size_t plan_rois(const lst_ctx *c, const double dis[10], int nb, RoiDesc 
     size_t off = 0;
     for (int k = 0; k < 5; k++) {
         Rect w = window_for(c->p, c->rect[k], jint(dis[2 * k]), jint(dis[2 * k + 1]), c->p.s_area, false, nullptr);
-        int x0 = w.x - c->roi_margin, y0 = w.y - c->roi_margin;
-        int x1 = w.x + w.w + c->roi_margin, y1 = w.y + w.h + c->roi_margin;
+        int x0 = w.x - c->roi_margin[k], y0 = w.y - c->roi_margin[k];
+        int x1 = w.x + w.w + c->roi_margin[k], y1 = w.y + w.h + c->roi_margin[k];
         x0 = x0 < 0 ? 0 : (x0 / ax) * ax;
         x1 = ((x1 + ax - 1) / ax) * ax;
         if (x1 > c->p.width) x1 = c->p.width;
@@ -950,7 +953,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     if (use_roi) {
         const int ax = c->roi_align_bytes / (int)c->bpp();
         for (int k = 0; k < 5; k++) {
-            const int mg = std::max(c->roi_margin, kRoiMarginMax);   // the margin adapts up to this
+            const int mg = std::max(c->roi_margin[k], kRoiMarginMax);   // the margin adapts up to this
             size_t w = (size_t)c->rect[k].w + 2 * c->p.s_area + 2 * mg + 2 * ax;
             size_t h = (size_t)c->rect[k].h + 2 * c->p.s_area + 2 * mg;
             w = std::min<size_t>(w, (size_t)c->p.width + ax);
@@ -1152,9 +1155,10 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
             return rc;
         }
         if (use_roi && c->roi_margin_fixed < 0) {
-            // adapt the margin: how far did the windows of this batch stray from where its regions were
-            // planned?  The next region plan gets that excursion + 3 px (4..kRoiMarginMax).
-            int exc = 0;
+            // adapt the margins: how far did each template's windows of this batch stray from where its
+            // region was planned?  The next plan gets that excursion + 3 px (4..kRoiMarginMax) per region:
+            // the marks of a rigid holder barely move while the spot may travel several pixels per batch.
+            int exc[5] = {0, 0, 0, 0, 0};
             for (int i = 0; i < nb; i++) {
                 const lst_record &r = out[f0 + i];
                 for (int k = 0; k < 5; k++) {
@@ -1163,10 +1167,10 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
                     int inner_x = r.tm[k].wx - rd.x, inner_y = r.tm[k].wy - rd.y;
                     int outer_x = rd.x + rd.w - (r.tm[k].wx + r.tm[k].ww), outer_y = rd.y + rd.h - (r.tm[k].wy + r.tm[k].wh);
                     int slack = std::min(std::min(inner_x, inner_y), std::min(outer_x, outer_y));   // < 0: fell outside
-                    exc = std::max(exc, c->roi_margin - slack);
+                    exc[k] = std::max(exc[k], c->roi_margin[k] - slack);
                 }
             }
-            c->roi_margin = std::min(kRoiMarginMax, std::max(4, exc + 3));
+            for (int k = 0; k < 5; k++) c->roi_margin[k] = std::min(kRoiMarginMax, std::max(4, exc[k] + 3));
         }
     }
     return LST_OK;
