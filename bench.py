@@ -350,6 +350,8 @@ def main():
         e2e = {"value": world * F * K / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(s_e2e.h2d_bytes // K), "d2h_bytes_per_step": int(s_e2e.d2h_bytes // K),
                "ms_per_step": ms_e2e / K, "roi_fallback_windows_per_step": int(s_e2e.roi_fallback_tasks // K),
+               "host_ms_per_step": s_e2e.host_ms / K, "device_wait_ms_per_step": s_e2e.device_wait_ms / K,
+               "passes_per_step": s_e2e.passes / K, "tasks_per_step": s_e2e.tasks / K,
                "pcie": {"achieved_gbs_per_gpu": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9,
                         "peak_gbs_per_gpu": pcie, "frac": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9 / pcie,
                         "how": "peak = 256 MB pinned cudaMemcpyAsync H2D, every rank at the same time, slowest rank"},
