@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames of the CPU baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanes", type=int, default=LANES_DEFAULT,
+                    help="tracking lanes per GPU (lst_multi_create with the device listed this many times): the host-side "
+                         "chain walk of one lane overlaps the kernels of the others")
     ap.add_argument("--no-files", action="store_true", help="skip the slices-from-TIFF-files leg (e2e_files)")
     ap.add_argument("--ingest", type=int, default=0, choices=[0, 1, 2], help="0 ROI DMA (default), 1 whole slices, 2 ROI gather kernel")
     ap.add_argument("--engine", default="auto", choices=["auto", "dp4a", "tc"], help="match kernel: tensor cores (default when the template fits) or IDP.4A")
@@ -75,6 +78,8 @@ def bench_config(name: str, ring: int) -> StackConfig:
 #   window: the 8-bit window (25.6 KB), the window sums lst_box_sums left in HBM (2 x 4 B x 113^2 =
 #   102 KB, read once plus an L2 prefetch that is partly evicted again) and the Toeplitz table.
 NCU_DRAM_BYTES_PER_WINDOW = {("B", False): 66.9e6 / 2560, ("B", True): 790.98e6 / 4704}
+
+LANES_DEFAULT = 4
 
 DEFAULTS = {  # frames per step, ring length, max_batch, cpu sample
     "A": (8192, 256, 2048, 512),
@@ -214,7 +219,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from laser_spot_track_b200 import LaserSpotTrack4, native as N
+    from laser_spot_track_b200 import LaserSpotTrack4, LaserSpotTrack4Multi, native as N
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the tracking path has no CPU fallback")
@@ -253,6 +258,13 @@ def main():
     dev_ring = trk.device_alloc(ring * fb)
     trk._check(lib.lst_device_upload(trk._ctx, C.c_void_p(dev_ring), host_ring, ring * fb))
     info = trk.set_reference(st.frame(0), st.ref_xy)
+    lanes = max(1, args.lanes)
+    runner = trk
+    if lanes > 1:
+        runner = LaserSpotTrack4Multi(cfg.width, cfg.height, bits, [local_rank] * lanes, templSize=cfg.templ_size,
+                                      sArea=cfg.s_area, max_batch=args.max_batch or mb_d,
+                                      ncc_engine={"auto": 0, "dp4a": 1, "tc": 2}[args.engine], ingest_mode=args.ingest)
+        runner.set_reference(st.frame(0), st.ref_xy)
 
     # this rank's chunk of each step: F consecutive slices of the (cyclic) stack, starting at slice 1
     idx = [(1 + j) % ring for j in range(F)]
@@ -270,28 +282,29 @@ def main():
             self.fn = fn
 
         def set_state(self, d):
-            trk.set_state(d)
+            runner.set_state(d)
 
         def get_state(self):
-            return trk.get_state()
+            return runner.get_state()
 
         def track(self, frames, first):
             return self.fn(frames, first, out)
 
     comm = TorchComm(host_group, "cpu") if world > 1 else None
-    sh_dev = ShardedTracker(_Adapter(trk.track_device_ptrs), comm)
-    sh_e2e = ShardedTracker(_Adapter(trk.track_host_ptrs), comm)
+    sh_dev = ShardedTracker(_Adapter(runner.track_device_ptrs), comm)
+    sh_e2e = ShardedTracker(_Adapter(runner.track_host_ptrs), comm)
 
     def step_device():
-        sh_dev.track_chunk(dev_ptrs, 1 + rank * F, trk.get_state())
+        sh_dev.track_chunk(dev_ptrs, 1 + rank * F, runner.get_state())
 
     def step_e2e():
-        sh_e2e.track_chunk(host_ptrs, 1 + rank * F, trk.get_state())
+        sh_e2e.track_chunk(host_ptrs, 1 + rank * F, runner.get_state())
 
-    def timed(step_fn, K, W):
+    def timed(step_fn, K, W, who=None):
+        who = who or runner
         for _ in range(W):
             step_fn()
-        trk.reset_stats()
+        who.reset_stats()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -306,7 +319,7 @@ def main():
         t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = trk.stats()
+        s = who.stats()
         return float(t[0]), float(t[1]), s
 
     K, W = args.steps, max(args.warmup, 0)
@@ -314,13 +327,23 @@ def main():
     peaks = (C.c_double * 3)()
     have_peaks = lib.lst_measure_alu_peaks(local_rank, 20.0, peaks) == 0
 
-    trk.set_kernel_timing(True)
+    if lanes == 1:
+        trk.set_kernel_timing(True)
     if rank == 0:
         sampler.start()
     ms_dev, wall_dev, s_dev = timed(step_device, K, W)
     clocks = sampler.stop() if rank == 0 else None
     ok_frames = sum(1 for r in out if r.status == 0)
     trk.set_kernel_timing(False)
+    # Per-launch kernel times need kernels that do not overlap: with several lanes the roofline numbers come
+    # from a second timed region of the same K steps on one lane (same kernels, same launches).
+    s_roof, ms_roof = s_dev, ms_dev
+    if lanes > 1:
+        def step_single():
+            trk.track_device_ptrs(dev_ptrs, 1 + rank * F, out)
+        trk.set_kernel_timing(True)
+        ms_roof, _, s_roof = timed(step_single, K, 1, trk)
+        trk.set_kernel_timing(False)
 
     def pcie_peak_gbs():
         """Measured host->device copy bandwidth of this rank (256 MB pinned cudaMemcpyAsync, all ranks
@@ -392,7 +415,7 @@ def main():
             def step_files():
                 trk.track_files(paths, first_frame_index=1)
 
-            ms_f, wall_f, s_f = timed(step_files, K, 1)
+            ms_f, wall_f, s_f = timed(step_files, K, 1, trk)
             e2e_files = {"value": F * K / (wall_f * 1e-3), "unit": UNIT, "ms_per_step": wall_f / K,
                          "h2d_bytes_per_step": int(s_f.h2d_bytes // K), "file_bytes": int(os.path.getsize(files[0])),
                          "reader_threads": int(os.environ.get("LST_FILE_THREADS", min(16, os.cpu_count() or 1))), "host_cores": os.cpu_count(),
@@ -404,8 +427,8 @@ def main():
     value = world * F * K / (ms_dev * 1e-3)
     # roofline of the dominant kernel (the template match): exact u8 x u8 -> s32 multiply-accumulates
     win_macs = float((2 * cfg.s_area + 1) ** 2 * cfg.templ_size ** 2)
-    macs_per_launch = s_dev.ncc_algorithmic_macs / max(s_dev.ncc_kernel_launches, 1)
-    kern_ms = s_dev.ncc_kernel_ms / max(s_dev.ncc_kernel_launches, 1)
+    macs_per_launch = s_roof.ncc_algorithmic_macs / max(s_roof.ncc_kernel_launches, 1)
+    kern_ms = s_roof.ncc_kernel_ms / max(s_roof.ncc_kernel_launches, 1)
     achieved = 2.0 * macs_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None
     dp4a_peak = 2.0 * peaks[0] / 1e12 if have_peaks else None
     imma_peak = 2.0 * peaks[2] / 1e12 if (have_peaks and peaks[2] > 0) else None
@@ -443,8 +466,11 @@ def main():
                           "(profiles/), per window, times the windows of an average launch",
         "ffma_peak_tflops": 2.0 * peaks[1] / 1e12 if have_peaks else None,
         "algorithmic_ops_per_launch": 2.0 * macs_per_launch, "avg_launch_ms": kern_ms,
-        "kernel_share_of_step": s_dev.ncc_kernel_ms / ms_dev if ms_dev > 0 else None,
-        "launches_timed": int(s_dev.ncc_kernel_launches),
+        "kernel_share_of_step": s_roof.ncc_kernel_ms / ms_roof if ms_roof > 0 else None,
+        "launches_timed": int(s_roof.ncc_kernel_launches),
+        "measured_with": "the timed region of `value`" if lanes == 1 else
+                         "a second timed region of the same %d steps on ONE lane (per-launch CUDA-event times need kernels that "
+                         "do not overlap; `value` runs %d lanes): %.0f frames/s" % (K, lanes, world * F * K / (ms_roof * 1e-3)),
         "window_bytes_per_frame": 5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 * (bits // 8),
         "hbm_view": {"peak_gbs": measured.get("hbm_gbs"),
                      "window_bytes_per_s": value * 5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 * (bits // 8) / 1e9},
@@ -491,7 +517,8 @@ def main():
                        "ring_frames": ring, "ring_bytes": ring * fb,
                        "l2": "inputs larger than L2 (ring of distinct slices cycled)" if ring * fb > 126e6 else
                              "ring smaller than L2; windows are re-read from HBM/L2 each pass",
-                       "max_batch": args.max_batch or mb_d, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                       "max_batch": args.max_batch or mb_d, "parallelism": f"frames sharded over {world} GPU(s), no collective" + (f"; {lanes} lanes per GPU" if lanes > 1 else ""),
+                       "lanes_per_gpu": lanes,
                        "accepted_frames_last_step": ok_frames},
             "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline,
@@ -501,6 +528,8 @@ def main():
             "wall_ms_per_step": wall_dev / K,
         }
         print(json.dumps(line), flush=True)
+    if runner is not trk:
+        runner.close()
     trk.device_free(dev_ring)
     lib.lst_free_pinned(host_ring)
     trk.close()

@@ -195,6 +195,14 @@ const char *lst_multi_last_error(const lst_multi *m);
 int lst_multi_set_reference(lst_multi *m, const void *ref_frame, const float ref_xy[10], lst_reference_info *out);
 int lst_multi_track(lst_multi *m, const void *const *frame_ptrs, int64_t first_frame_index, int32_t n_frames,
                     lst_record *out);
+/* the same with slices that already lie in device memory (every pointer readable from every device of m).
+ * A device may be listed more than once in lst_multi_create: each entry is a lane with its own host
+ * thread, streams and scratch, so the host-side chain walk of one lane overlaps the kernels of another. */
+int lst_multi_track_device(lst_multi *m, const void *const *dev_frame_ptrs, int64_t first_frame_index,
+                           int32_t n_frames, lst_record *out);
+/* sums over the contexts of m */
+int lst_multi_get_stats(const lst_multi *m, lst_stats *out);
+int lst_multi_reset_stats(lst_multi *m);
 int lst_multi_get_state(const lst_multi *m, double dis[10]);
 int lst_multi_set_state(lst_multi *m, const double dis[10]);
 /* chunks tracked a second time because their speculated start state placed a window differently */

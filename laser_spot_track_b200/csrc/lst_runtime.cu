@@ -1379,10 +1379,28 @@ int lst_multi_set_state(lst_multi *m, const double dis[10])
 }
 int64_t lst_multi_retracked(const lst_multi *m) { return m ? m->retracked : 0; }
 
+static int multi_track(lst_multi *m, const void *const *frame_ptrs, bool on_device, int64_t first_frame_index, int32_t n_frames,
+                       lst_record *out);
+
 int lst_multi_track(lst_multi *m, const void *const *frame_ptrs, int64_t first_frame_index, int32_t n_frames,
                     lst_record *out)
 {
+    return multi_track(m, frame_ptrs, false, first_frame_index, n_frames, out);
+}
+
+int lst_multi_track_device(lst_multi *m, const void *const *dev_frame_ptrs, int64_t first_frame_index, int32_t n_frames,
+                           lst_record *out)
+{
+    return multi_track(m, dev_frame_ptrs, true, first_frame_index, n_frames, out);
+}
+
+static int multi_track(lst_multi *m, const void *const *frame_ptrs, bool on_device, int64_t first_frame_index, int32_t n_frames,
+                       lst_record *out)
+{
     if (!m || !frame_ptrs || !out || n_frames < 0) return LST_ERR_INVALID;
+    auto track = [on_device](lst_ctx *c, const void *const *p, int64_t first, int32_t n, lst_record *o) {
+        return on_device ? lst_track_device_ptrs(c, p, first, n, o) : lst_track_ptrs(c, p, first, n, o);
+    };
     const int G = (int)m->ctx.size();
     if (n_frames == 0) return LST_OK;
     // contiguous chunks, sizes differing by at most one slice
@@ -1398,12 +1416,12 @@ int lst_multi_track(lst_multi *m, const void *const *frame_ptrs, int64_t first_f
             int li = std::min(m->lead_in, lo[r]);
             if (li > 0) {
                 std::vector<lst_record> tmp(li);
-                rcs[r] = lst_track_ptrs(c, frame_ptrs + lo[r] - li, first_frame_index + lo[r] - li, li, tmp.data());
+                rcs[r] = track(c, frame_ptrs + lo[r] - li, first_frame_index + lo[r] - li, li, tmp.data());
                 if (rcs[r] != LST_OK) return;
             }
         }
         lst_get_state(c, guess[r].data());
-        if (n > 0) rcs[r] = lst_track_ptrs(c, frame_ptrs + lo[r], first_frame_index + lo[r], n, out + lo[r]);
+        if (n > 0) rcs[r] = track(c, frame_ptrs + lo[r], first_frame_index + lo[r], n, out + lo[r]);
         lst_get_state(c, end[r].data());
     };
     {
@@ -1428,7 +1446,7 @@ int lst_multi_track(lst_multi *m, const void *const *frame_ptrs, int64_t first_f
         bool any_ok = false;
         if (!same_windows(verified, guess[r].data())) {
             lst_set_state(c, verified);
-            int rc = lst_track_ptrs(c, frame_ptrs + lo[r], first_frame_index + lo[r], n, out + lo[r]);
+            int rc = track(c, frame_ptrs + lo[r], first_frame_index + lo[r], n, out + lo[r]);
             if (rc != LST_OK) {
                 m->err = c->err;
                 return rc;
@@ -1450,6 +1468,38 @@ int lst_multi_track(lst_multi *m, const void *const *frame_ptrs, int64_t first_f
     }
     memcpy(m->dis, verified, sizeof(verified));
     for (lst_ctx *c : m->ctx) lst_set_state(c, verified);
+    return LST_OK;
+}
+
+int lst_multi_get_stats(const lst_multi *m, lst_stats *out)
+{
+    if (!m || !out) return LST_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    for (lst_ctx *c : m->ctx) {
+        lst_stats s;
+        int rc = lst_get_stats(c, &s);
+        if (rc != LST_OK) return rc;
+        out->frames += s.frames;
+        out->tasks += s.tasks;
+        out->respeculated += s.respeculated;
+        out->passes += s.passes;
+        out->kernel_launches += s.kernel_launches;
+        out->h2d_bytes += s.h2d_bytes;
+        out->d2h_bytes += s.d2h_bytes;
+        out->ncc_kernel_ms += s.ncc_kernel_ms;
+        out->ncc_kernel_launches += s.ncc_kernel_launches;
+        out->ncc_algorithmic_macs += s.ncc_algorithmic_macs;
+        out->roi_fallback_tasks += s.roi_fallback_tasks;
+        out->device_wait_ms += s.device_wait_ms;
+        out->host_ms += s.host_ms;
+    }
+    return LST_OK;
+}
+
+int lst_multi_reset_stats(lst_multi *m)
+{
+    if (!m) return LST_ERR_INVALID;
+    for (lst_ctx *c : m->ctx) lst_reset_stats(c);
     return LST_OK;
 }
 

@@ -27,7 +27,8 @@ EXPORTS = [
     "lst_get_stats", "lst_reset_stats", "lst_set_kernel_timing", "lst_measure_alu_peaks",
     "lst_host_window_for", "lst_host_template_rect", "lst_host_resolve",
     "lst_multi_create", "lst_multi_destroy", "lst_multi_last_error", "lst_multi_set_reference", "lst_multi_track",
-    "lst_multi_get_state", "lst_multi_set_state", "lst_multi_retracked",
+    "lst_multi_get_state", "lst_multi_set_state", "lst_multi_retracked", "lst_multi_track_device",
+    "lst_multi_get_stats", "lst_multi_reset_stats",
     "lst_tiff_probe", "lst_set_reference_file", "lst_track_files", "lst_results_rows",
 ]
 
@@ -148,6 +149,9 @@ def load() -> C.CDLL:
         "lst_multi_last_error": ([vp], C.c_char_p),
         "lst_multi_set_reference": ([vp, vp, P(C.c_float), P(ReferenceInfo)], C.c_int),
         "lst_multi_track": ([vp, P(vp), i64, i32, P(Record)], C.c_int),
+        "lst_multi_track_device": ([vp, P(vp), i64, i32, P(Record)], C.c_int),
+        "lst_multi_get_stats": ([vp, P(Stats)], C.c_int),
+        "lst_multi_reset_stats": ([vp], C.c_int),
         "lst_multi_get_state": ([vp, P(dbl)], C.c_int),
         "lst_multi_set_state": ([vp, P(dbl)], C.c_int),
         "lst_multi_retracked": ([vp], C.c_int64),

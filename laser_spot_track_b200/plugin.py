@@ -316,10 +316,38 @@ class LaserSpotTrack4Multi:
         self._check(self._lib.lst_multi_track(self._m, ptrs, first_frame_index, n, out))
         return out
 
+    def track_host_ptrs(self, host_ptrs, first_frame_index: int = 1, out=None):
+        n = len(host_ptrs)
+        ptrs = host_ptrs if isinstance(host_ptrs, C.Array) else (C.c_void_p * n)(*host_ptrs)
+        out = (N.Record * n)() if out is None else out
+        self._check(self._lib.lst_multi_track(self._m, ptrs, first_frame_index, n, out))
+        return out
+
+    def track_device_ptrs(self, dev_ptrs, first_frame_index: int = 1, out=None):
+        """Slices already in device memory; with a device listed twice in ``devices`` the two lanes overlap
+        each other's host-side chain walks on that GPU."""
+        n = len(dev_ptrs)
+        ptrs = dev_ptrs if isinstance(dev_ptrs, C.Array) else (C.c_void_p * n)(*dev_ptrs)
+        out = (N.Record * n)() if out is None else out
+        self._check(self._lib.lst_multi_track_device(self._m, ptrs, first_frame_index, n, out))
+        return out
+
     def get_state(self):
         d = (C.c_double * 10)()
         self._check(self._lib.lst_multi_get_state(self._m, d))
         return np.array(d[:])
+
+    def set_state(self, dis):
+        d = (C.c_double * 10)(*[float(v) for v in dis])
+        self._check(self._lib.lst_multi_set_state(self._m, d))
+
+    def stats(self) -> N.Stats:
+        s = N.Stats()
+        self._check(self._lib.lst_multi_get_stats(self._m, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        self._check(self._lib.lst_multi_reset_stats(self._m))
 
     @property
     def retracked(self) -> int:

@@ -502,3 +502,31 @@ def test_rgb_stack_matched_on_intensity(built_lib, oracle_clib, weights):
         # (h, w, 3) uint8 arrays are accepted as well
         rgb3 = np.stack([(frames[5] >> 16) & 0xff, (frames[5] >> 8) & 0xff, frames[5] & 0xff], axis=-1).astype(np.uint8)
         assert np.array_equal(t.preprocess(rgb3, 10, 10, 80, 80), O.preprocess_crop(frames[5], 10, 10, 80, 80, op))
+
+
+def test_lanes_on_one_device_with_device_resident_slices(stack_a):
+    """Several lanes on one GPU (the device listed more than once in lst_multi_create) over slices that
+    already lie in device memory: records identical to the sequential oracle, stats summed over lanes."""
+    import ctypes as C
+    from laser_spot_track_b200 import LaserSpotTrack4Multi
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=False)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    lib = N.load()
+    with _tracker(cfg, op) as single:
+        stack = np.ascontiguousarray(np.stack(frames[1:]))
+        fb = stack[0].nbytes
+        dev = single.device_alloc(stack.nbytes)
+        single._check(lib.lst_device_upload(single._ctx, C.c_void_p(dev), stack.ctypes.data, stack.nbytes))
+        ptrs = [dev + i * fb for i in range(len(stack))]
+        with LaserSpotTrack4Multi(cfg.width, cfg.height, 8, [0, 0, 0], templSize=op.templ_size, sArea=op.s_area,
+                                  markDist=op.mark_dist, matchIntensity=False, max_batch=7) as m:
+            m.set_reference(frames[0], st.ref_xy)
+            got = m.track_device_ptrs(ptrs)
+            util.compare_records(got, want, label="3 lanes, device slices")
+            s = m.stats()
+            assert s.frames >= len(want) and s.kernel_launches > 0
+            assert np.array_equal(m.get_state(), np.array([v for d in otr.dis for v in d]))
+        single.device_free(dev)
