@@ -129,8 +129,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 // The IDP.4A engine derives the sums of I and I^2 under the template footprint inside its CTAs; the
 // tensor-core engine wants its shared memory for operands and its warps for the epilogue, so the
 // sums are produced once per window by this kernel and read back (L2) by the epilogue.
-// CTA = 32 result rows of one window: vertical sliding sums per column, then one prefix scan per row
-// (warp shuffles) turns them into box sums: out[x] = P[x + tw - 1] - P[x - 1].
+// CTA = 32 result rows of one window: vertical sliding sums per column into shared memory, then
+// horizontal sliding sums with one row per lane.
 #define BS_ROWS 32
 
 __global__ void __launch_bounds__(256)
@@ -175,44 +175,31 @@ lst_box_sums(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
         }
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < nrows; r += 8) {
-        uint32_t *p1 = P1 + (size_t)r * wp, *p2 = P2 + (size_t)r * wp;
-        uint32_t c1 = 0, c2 = 0;
-        for (int b = 0; b < t.w; b += 32) {
-            const int c = b + lane;
-            uint32_t a1 = c < t.w ? p1[c] : 0u, a2 = c < t.w ? p2[c] : 0u;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t n1 = __shfl_up_sync(0xffffffffu, a1, o), n2 = __shfl_up_sync(0xffffffffu, a2, o);
-                if (lane >= o) {
-                    a1 += n1;
-                    a2 += n2;
-                }
-            }
-            a1 += c1;
-            a2 += c2;
-            if (c < t.w) {
-                p1[c] = a1;
-                p2[c] = a2;
-            }
-            c1 = __shfl_sync(0xffffffffu, a1, 31);
-            c2 = __shfl_sync(0xffffffffu, a2, 31);
-        }
-    }
-    __syncthreads();
-    // Output layout [band of 32 rows][x][row in band]: the epilogue of lst_ncc_tc owns one row per lane
-    // and walks x, so one warp load is 32 consecutive words.  Lanes = rows here too: the prefix arrays
-    // are read with stride wp (odd: conflict-free) and written 128 bytes at a time.
+    // Horizontal pass: lanes = the rows of the band, each warp a run of result columns.  A lane sums the
+    // first footprint of its run directly (tw loads) and slides from there: out[x+1] = out[x] + V[x+tw] - V[x].
+    // Rows are wp words apart (odd: conflict-free); a warp's store is 32 consecutive words of the
+    // output layout [band of 32 rows][x][row in band] -- the epilogue of lst_ncc_tc owns one row per
+    // lane and walks x, so its loads are 128 bytes per warp as well.
     {
-        uint32_t *o1 = wsum + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS;
-        uint32_t *o2 = wsq + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS;
-        const uint32_t *p1 = P1 + (size_t)lane * wp, *p2 = P2 + (size_t)lane * wp;
-        for (int x = warp; x < t.rw; x += 8) {
-            if (lane < nrows) {
-                uint32_t lo1 = x > 0 ? p1[x - 1] : 0u, lo2 = x > 0 ? p2[x - 1] : 0u;
-                o1[(size_t)x * BS_ROWS + lane] = p1[x + tw - 1] - lo1;
-                o2[(size_t)x * BS_ROWS + lane] = p2[x + tw - 1] - lo2;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        const int per = (t.rw + nwarps - 1) / nwarps;
+        const int x0 = warp * per, x1 = min(x0 + per, t.rw);
+        if (lane < nrows && x0 < x1) {
+            const uint32_t *p1 = P1 + (size_t)lane * wp, *p2 = P2 + (size_t)lane * wp;
+            uint32_t a1 = 0, a2 = 0;
+#pragma unroll 8
+            for (int u = 0; u < tw; u++) {
+                a1 += p1[x0 + u];
+                a2 += p2[x0 + u];
+            }
+            uint32_t *o1 = wsum + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS + lane;
+            uint32_t *o2 = wsq + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS + lane;
+            for (int x = x0;; x++) {
+                o1[(size_t)x * BS_ROWS] = a1;
+                o2[(size_t)x * BS_ROWS] = a2;
+                if (x + 1 >= x1) break;
+                a1 += p1[x + tw] - p1[x];
+                a2 += p2[x + tw] - p2[x];
             }
         }
     }
