@@ -80,7 +80,7 @@ struct MatchParams {
 };
 
 // launchers (all asynchronous on `stream`); each returns the number of kernels it launched or <0
-int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, cudaStream_t stream);
+int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, float *nbhd, cudaStream_t stream);
 int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *surfaces, const PreprocParams &pp,
                   uint32_t *mm_keys, cudaStream_t stream);
 int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces,
@@ -93,7 +93,8 @@ int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, 
                      const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *score_map,
                      const MatchParams &mp, cudaStream_t stream);
 int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls, const uint8_t *win8,
-                    const unsigned long long *best, DevResult *results, const MatchParams &mp, cudaStream_t stream);
+                    const unsigned long long *best, const float *nbhd, DevResult *results, const MatchParams &mp,
+                    cudaStream_t stream);
 int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_dist, const double *spot0,
                  double *out5, cudaStream_t stream);
 // Small host->device uploads on the compute stream go through a kernel reading pinned (mapped) host
@@ -117,7 +118,7 @@ int launch_box_sums(const DevTask *tasks, int n_tasks, int max_w, int max_rh, in
                     const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream);
 int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
                   const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
-                  unsigned long long *best, cudaStream_t stream);
+                  unsigned long long *best, float *nbhd, cudaStream_t stream);
 double measure_imma_peak(double ms_per_test);   // int8 tensor-core MAC/s (tcgen05.mma kind::i8)
 void tc_init_device();
 

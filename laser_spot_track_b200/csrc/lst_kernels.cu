@@ -112,19 +112,20 @@ int launch_upload(void *dst_dev, const void *src_pinned_host, size_t bytes, cuda
 // ------------------------------------------------------------------------------------------------
 // pass init
 // ------------------------------------------------------------------------------------------------
-__global__ void lst_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best)
+__global__ void lst_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, float *nbhd)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_tasks) {
         mm_keys[2 * i] = 0xffffffffu;
         mm_keys[2 * i + 1] = 0u;
         best[i] = 0ull;
+        nbhd[12 * i + 9] = 0.0f;   // "the match kernel left the 3x3 neighbourhood of the peak here"
     }
 }
 
-int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, cudaStream_t stream)
+int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, float *nbhd, cudaStream_t stream)
 {
-    lst_init_pass<<<(n_tasks + 255) / 256, 256, 0, stream>>>(n_tasks, mm_keys, best);
+    lst_init_pass<<<(n_tasks + 255) / 256, 256, 0, stream>>>(n_tasks, mm_keys, best, nbhd);
     return 1;
 }
 
@@ -1011,10 +1012,12 @@ int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(288)
 lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
-             const unsigned long long *__restrict__ best, DevResult *__restrict__ results, MatchParams mp)
+             const unsigned long long *__restrict__ best, const float *__restrict__ nbhd, DevResult *__restrict__ results,
+             MatchParams mp)
 {
     // nine warps: warp w recomputes the score of neighbour (w%3-1, w/3-1) of the peak exactly
-    // (correlation and window sums in integers, normalisation by ncc_score as in the match kernel)
+    // (correlation and window sums in integers, normalisation by ncc_score as in the match kernel) --
+    // unless the match kernel already left the nine scores (lst_ncc_tc, window owned by one CTA)
     __shared__ float nb[9];
     const DevTask t = tasks[blockIdx.x];
     const TplConst tc = tpls->c[t.tpl];
@@ -1025,7 +1028,11 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nx = ix + (warp % 3) - 1, ny = iy + (warp / 3) - 1;
     float sc = 0.0f;
-    if (nx >= 0 && nx < t.rw && ny >= 0 && ny < t.rh) {
+    const bool inside = nx >= 0 && nx < t.rw && ny >= 0 && ny < t.rh;
+    const bool have = nbhd[12 * (size_t)blockIdx.x + 9] != 0.0f;
+    if (have) {
+        if (inside) sc = nbhd[12 * (size_t)blockIdx.x + warp];
+    } else if (inside) {
         const uint8_t *w = win8 + t.win_off + (size_t)ny * t.pitch + nx;
         const uint8_t *tp = tpls->raw[t.tpl];
         uint32_t acc = 0, s = 0, q = 0;
@@ -1064,9 +1071,10 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
 }
 
 int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls, const uint8_t *win8,
-                    const unsigned long long *best, DevResult *results, const MatchParams &mp, cudaStream_t stream)
+                    const unsigned long long *best, const float *nbhd, DevResult *results, const MatchParams &mp,
+                    cudaStream_t stream)
 {
-    lst_epilogue<<<n_tasks, 288, 0, stream>>>(tasks, tpls, win8, best, results, mp);
+    lst_epilogue<<<n_tasks, 288, 0, stream>>>(tasks, tpls, win8, best, nbhd, results, mp);
     return 1;
 }
 

@@ -208,12 +208,22 @@ lst_box_sums(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
 // The exact (double-precision, OpenCV order) score of one candidate position, out of line: the
 // epilogue visits 32 positions with unrolled code and only a few of them get here, so the long
 // division / square-root sequences must not be replicated 32 times (instruction cache).
-__device__ __noinline__ unsigned long long tc_exact_key(uint32_t corr, const uint32_t *ws, const uint32_t *wq,
-                                                        const TplConst *tc, uint32_t idx)
+__device__ __noinline__ float tc_exact_score(uint32_t corr, const uint32_t *ws, const uint32_t *wq, const TplConst *tc)
 {
     const uint32_t s = __ldg(ws), sq = __ldg(wq);
-    const float sc = match_score(*tc, (double)corr, (double)s, (double)sq);
-    return pack_key(sc, idx, method_wants_min(tc->method));
+    return match_score(*tc, (double)corr, (double)s, (double)sq);
+}
+__device__ __forceinline__ unsigned long long tc_exact_key(uint32_t corr, const uint32_t *ws, const uint32_t *wq,
+                                                           const TplConst *tc, uint32_t idx)
+{
+    return pack_key(tc_exact_score(corr, ws, wq, tc), idx, method_wants_min(tc->method));
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
+{
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return r;
 }
 
 struct TcParams {
@@ -228,7 +238,7 @@ struct TcParams {
 __global__ void __launch_bounds__(TC_THREADS, 4)
 lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
            const uint32_t *__restrict__ wsum, const uint32_t *__restrict__ wsq, unsigned long long *__restrict__ best,
-           TcParams tp)
+           float *__restrict__ nbhd, TcParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem_tc[];
     __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done;
@@ -351,13 +361,15 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
         const uint32_t N = (uint32_t)(tw * th), tsum = tc.tsum;
         const long long Nflat = (long long)N + (long long)(N >> 5);
         // sums of this lane's row: [band][x][row in band] (see lst_box_sums), band = y / 32
-        const size_t rowoff = t.sum_off + (size_t)(y0 / 32 + warp) * t.rw * 32 + lane;
+        // (lanes whose row lies below the result map read the task's first row instead: their band may not
+        // exist in the sums buffer, and the last task's would lie beyond the allocation)
+        const size_t rowoff = row_ok ? t.sum_off + (size_t)(y0 / 32 + warp) * t.rw * 32 + lane : t.sum_off;
         unsigned long long mybest = 0ull;
         // While the tensor core works, pull this warp's window sums (written by lst_box_sums, long
         // evicted from L2 by the time they are read) back into L2: one 128-byte line per (array, column).
         if (y0 + 32 * warp < t.rh) {
             const int ncols = min(nbc * TC_NB, t.rw - x0);
-            const size_t line0 = rowoff - lane + (size_t)x0 * 32;
+            const size_t line0 = t.sum_off + (size_t)(y0 / 32 + warp) * t.rw * 32 + (size_t)x0 * 32;
             for (int c = lane; c < 2 * ncols; c += 32) {
                 const uint32_t *pf = (c < ncols ? wsum : wsq) + line0 + (size_t)(c < ncols ? c : c - ncols) * 32;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
@@ -371,7 +383,8 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
             tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(nb * TC_NB), corr);
             const int xb = x0 + TC_NB * nb;
             const int np = row_ok ? min(32, t.rw - xb) : 0;
-            const uint32_t *ws = wsum + rowoff + (size_t)xb * 32, *wq = wsq + rowoff + (size_t)xb * 32;
+            const int xs = xb < t.rw ? xb : 0;     // a block right of this (smaller) window's map: stay inside the buffer
+            const uint32_t *ws = wsum + rowoff + (size_t)xs * 32, *wq = wsq + rowoff + (size_t)xs * 32;
             // pass 1: float32 filter score of the 32 positions of this lane's row (all loads of a half
             // are issued before they are used), warp-wide maximum.  3e38 marks "nearly flat: always exact".
             float sf[32];
@@ -432,10 +445,32 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long b = s_best[0];
-        for (int w = 1; w < 4; w++) b = s_best[w] > b ? s_best[w] : b;
-        atomicMax(&best[blockIdx.y], b);
+    unsigned long long b = s_best[0];
+    for (int w = 1; w < 4; w++) b = s_best[w] > b ? s_best[w] : b;
+    if (threadIdx.x == 0) atomicMax(&best[blockIdx.y], b);
+    if (nbhd && gridDim.x == 1) {
+        // The window is this CTA's alone, so b is its final argmax and the 3x3 neighbourhood the sub-pixel
+        // fit needs (LST4:2681-2717) is still in TMEM: the lanes that own rows by-1..by+1 score the three
+        // columns bx-1..bx+1 exactly, and lst_epilogue does not have to recompute nine correlations.
+        if (warp < 4) {
+            tc_fence_after();
+            const uint32_t idx = 0xffffffffu - (uint32_t)(b & 0xffffffffull);
+            const int by = (int)(idx / (uint32_t)t.rw), bx = (int)(idx - (uint32_t)by * (uint32_t)t.rw);
+            const int y = 32 * warp + lane, dyi = y - by;
+            const size_t rowoff = t.sum_off + (size_t)warp * t.rw * 32 + lane;
+            float *o = nbhd + (size_t)blockIdx.y * 12;
+            for (int dxi = -1; dxi <= 1; dxi++) {
+                const int x = bx + dxi;
+                if (x < 0 || x >= t.rw) continue;
+                const uint32_t cv = tmem_ld1(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)x);
+                if (dyi >= -1 && dyi <= 1 && y < t.rh)
+                    o[(dyi + 1) * 3 + (dxi + 1)] = tc_exact_score(cv, wsum + rowoff + (size_t)x * 32, wsq + rowoff + (size_t)x * 32,
+                                                                  &tpls->c[t.tpl]);
+            }
+            if (threadIdx.x == 0) o[9] = 1.0f;
+        }
+        tc_fence_before();
+        __syncthreads();
     }
     if (warp == 4) {
         tc_fence_after();
@@ -485,7 +520,7 @@ int launch_box_sums(const DevTask *tasks, int n_tasks, int max_w, int max_rh, in
 
 int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
                   const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
-                  unsigned long long *best, cudaStream_t stream)
+                  unsigned long long *best, float *nbhd, cudaStream_t stream)
 {
     TcParams tp;
     size_t smem = tc_smem(tw, th, &tp, max_rw);
@@ -504,7 +539,8 @@ int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int
     for (int base = 0; base < n_tasks; base += 65535) {
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
         dim3 grid(xchunks * ytiles, n);
-        lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, best + base, tp);
+        lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, best + base,
+                                                       nbhd ? nbhd + (size_t)base * 12 : nullptr, tp);
         cudaError_t e = cudaPeekAtLastError();
         if (e != cudaSuccess)
             fprintf(stderr, "lst_ncc_tc launch failed: %s (grid %d x %d, smem %zu)\n", cudaGetErrorString(e), grid.x, grid.y, smem);

@@ -60,6 +60,7 @@ struct lst_ctx : public Executor {
     DevTask *d_tasks = nullptr, *h_tasks = nullptr;
     uint32_t *d_mm = nullptr;
     unsigned long long *d_best = nullptr;
+    float *d_nbhd = nullptr;      // [task][12]: 3x3 scores around the peak + flag, left by lst_ncc_tc
     DevResult *d_results = nullptr, *h_results = nullptr;
     uint8_t *d_win8 = nullptr;
     size_t win8_cap = 0;
@@ -164,6 +165,7 @@ int lst_ctx::ensure_tasks(int n)
     CU(regrow(&d_tasks, cap));
     CU(regrow(&d_mm, (size_t)cap * 2));
     CU(regrow(&d_best, cap));
+    CU(regrow(&d_nbhd, (size_t)cap * 12));
     CU(regrow(&d_results, cap));
     CU(regrow_host(&h_tasks, cap));
     CU(regrow_host(&h_results, cap));
@@ -366,7 +368,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         launches += up;
     }
     stats.h2d_bytes += (int64_t)sizeof(DevTask) * n;
-    launches += launch_init_pass(n, d_mm, d_best, s_compute);
+    launches += launch_init_pass(n, d_mm, d_best, d_nbhd, s_compute);
     if (!have_win8) {
         PreprocParams pp;
         preproc_params(&pp, max_w, max_h);
@@ -410,7 +412,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             if (bl >= 0) {
                 launches += bl;
                 if (timing) CU(cudaEventRecord(tl.e0, s_compute));   // time the match kernel alone
-                tcl = launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, d_best, s_compute);
+                tcl = launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, d_best, d_nbhd, s_compute);
             }
         }
         if (use_tc && tcl < 0) {
@@ -427,7 +429,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             CU(cudaEventRecord(tl.e1, s_compute));
             timed.push_back(tl);
         }
-        launches += launch_epilogue(d_tasks, n, d_tpls, d_win8, d_best, d_results, mp, s_compute);
+        launches += launch_epilogue(d_tasks, n, d_tpls, d_win8, d_best, d_nbhd, d_results, mp, s_compute);
         CU(cudaMemcpyAsync(h_results, d_results, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s_compute));
         stats.d2h_bytes += (int64_t)sizeof(DevResult) * n;
     }
@@ -622,6 +624,7 @@ void lst_destroy(lst_ctx *c)
     cudaFree(c->d_tasks);
     cudaFree(c->d_mm);
     cudaFree(c->d_best);
+    cudaFree(c->d_nbhd);
     cudaFree(c->d_results);
     cudaFree(c->d_win8);
     cudaFree(c->d_map);
