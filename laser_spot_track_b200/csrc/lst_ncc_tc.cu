@@ -232,6 +232,7 @@ struct TcParams {
     int ks;           // K steps (32 bytes) per column block
     int nb_per_cta;   // column blocks per CTA
     int vb;           // template rows (Toeplitz blocks) per ring stage
+    int group;        // column blocks per MMA group: the epilogue of a group overlaps the MMAs of the next
     unsigned long long *dbg;   // optional: per-CTA phase clocks (LST_TC_DEBUG)
 };
 
@@ -241,7 +242,7 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
            float *__restrict__ nbhd, TcParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem_tc[];
-    __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done;
+    __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done[TC_MAXNB];
     __shared__ uint32_t s_tmem;
     __shared__ unsigned long long s_best[4];
 
@@ -289,7 +290,7 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
         }
-        mbar_init(&bar_done, 1);
+        for (int g = 0; g < TC_MAXNB; g++) mbar_init(&bar_done[g], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -317,41 +318,49 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
             // ring producer and MMA issue in one thread: the copy for step st+1 goes out before the MMAs
             // of step st; its slot was last read by the MMAs of step st-2 (3 stages), long finished
             const uint8_t *table = tpls->toeplitz[t.tpl];
-            auto feed = [&](int st) {
-                const int s = st % TC_STAGES;
+            // The column blocks are worked off in groups of tp.group: all template rows for the blocks of group
+            // g, then the next group (the Toeplitz table streams through the ring once per group), so that the
+            // epilogue warps score group g while the tensor core is busy with group g + 1.
+            const int G = tp.group, ngroups = (nbc + G - 1) / G, total = ngroups * nsteps;
+            auto feed = [&](int gst) {                  // gst = global ring step: group * nsteps + step
+                const int s = gst % TC_STAGES, st = gst % nsteps;
                 const int nv = min(VB, th - st * VB);
-                if (st >= TC_STAGES) mbar_wait(&bar_empty[s], ((st / TC_STAGES) - 1) & 1);
+                if (gst >= TC_STAGES) mbar_wait(&bar_empty[s], ((gst / TC_STAGES) - 1) & 1);
                 mbar_expect_tx(&bar_full[s], bv_bytes * (uint32_t)nv);
                 bulk_g2s(sB + (size_t)s * st_bytes, table + (size_t)st * st_bytes, bv_bytes * (uint32_t)nv, &bar_full[s]);
             };
             feed(0);
-            uint32_t acc = 0;
-            int v = 0;
-            for (int st = 0; st < nsteps; st++) {
-                const int s = st % TC_STAGES;
-                const int nv = min(VB, th - st * VB);
-                if (st + 1 < nsteps) feed(st + 1);
-                mbar_wait(&bar_full[s], (st / TC_STAGES) & 1);
-                tc_fence_after();
-                uint64_t b_v = b_desc0 + (uint64_t)s * b_sstep;
-                for (int vv = 0; vv < nv; vv++, v++, b_v += b_vstep) {
-                    uint64_t a_nb = a_desc0 + (uint64_t)v;            // rows v .. v+127
-                    for (int nb = 0; nb < nbc; nb++, a_nb += a_kstep) {
-                        uint64_t a_d = a_nb, b_d = b_v;
-                        const uint32_t d = tmem + (uint32_t)(nb * TC_NB);
-                        mma_i8(d, a_d, b_d, idesc, acc);              // first k-step: overwrites D only for v == 0
+            int gst = 0;
+            for (int g = 0; g < ngroups; g++) {
+                const int nbg0 = g * G, nbg1 = min(nbc, nbg0 + G);
+                uint32_t acc = 0;
+                int v = 0;
+                for (int st = 0; st < nsteps; st++, gst++) {
+                    const int s = gst % TC_STAGES;
+                    const int nv = min(VB, th - st * VB);
+                    if (gst + 1 < total) feed(gst + 1);
+                    mbar_wait(&bar_full[s], (gst / TC_STAGES) & 1);
+                    tc_fence_after();
+                    uint64_t b_v = b_desc0 + (uint64_t)s * b_sstep;
+                    for (int vv = 0; vv < nv; vv++, v++, b_v += b_vstep) {
+                        uint64_t a_nb = a_desc0 + (uint64_t)v + (uint64_t)nbg0 * a_kstep;            // rows v .. v+127
+                        for (int nb = nbg0; nb < nbg1; nb++, a_nb += a_kstep) {
+                            uint64_t a_d = a_nb, b_d = b_v;
+                            const uint32_t d = tmem + (uint32_t)(nb * TC_NB);
+                            mma_i8(d, a_d, b_d, idesc, acc);              // first k-step: overwrites D only for v == 0
 #pragma unroll 1
-                        for (int ks = 1; ks < KS; ks++) {
-                            a_d += a_kstep;
-                            b_d += b_kstep;
-                            mma_i8(d, a_d, b_d, idesc, 1u);
+                            for (int ks = 1; ks < KS; ks++) {
+                                a_d += a_kstep;
+                                b_d += b_kstep;
+                                mma_i8(d, a_d, b_d, idesc, 1u);
+                            }
                         }
+                        acc = 1u;
                     }
-                    acc = 1u;
+                    tc_commit(&bar_empty[s]);     // the ring slot is free once these MMAs have read it
                 }
-                tc_commit(&bar_empty[s]);     // the ring slot is free once these MMAs have read it
+                tc_commit(&bar_done[g]);
             }
-            tc_commit(&bar_done);
         }
     } else {
         // ---- epilogue warps: rows 32*warp .. +31 of the tile (TMEM lanes of this warp) ----
@@ -375,10 +384,12 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
             }
         }
-        mbar_wait(&bar_done, 0);
-        tc_fence_after();
-        clk2 = clock64();
         for (int nb = 0; nb < nbc; nb++) {
+            if (nb % tp.group == 0) {
+                mbar_wait(&bar_done[nb / tp.group], 0);
+                tc_fence_after();
+                if (nb == 0) clk2 = clock64();
+            }
             uint32_t corr[32];
             tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(nb * TC_NB), corr);
             const int xb = x0 + TC_NB * nb;
@@ -486,6 +497,12 @@ static size_t tc_smem(int tw, int th, TcParams *tp, int max_rw)
     tp->rows_a = TC_M + th - 1;
     tp->kc_a = 2 * (tp->nb_per_cta - 1) + 2 * tp->ks;
     const size_t bv = (size_t)2 * tp->ks * TC_NB * 16;
+    static const int group_env = [] {
+        const char *e = getenv("LST_TC_GROUP");
+        return e ? atoi(e) : 0;
+    }();
+    tp->group = group_env > 0 ? group_env : 2;
+    if (tp->group > tp->nb_per_cta) tp->group = tp->nb_per_cta;
     tp->vb = (int)(6144 / bv);                        // ~6 KB per ring stage: 3 stages + the window stay under 56 KB
     if (tp->vb < 1) tp->vb = 1;
     if (tp->vb > th) tp->vb = th;
