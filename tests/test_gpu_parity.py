@@ -530,3 +530,33 @@ def test_lanes_on_one_device_with_device_resident_slices(stack_a):
             assert s.frames >= len(want) and s.kernel_launches > 0
             assert np.array_equal(m.get_state(), np.array([v for d in otr.dis for v in d]))
         single.device_free(dev)
+
+
+@pytest.mark.parametrize("dtype", ["u8", "u16", "f32"])
+def test_preprocess_random_rectangles_odd_pitch(built_lib, dtype):
+    """The blur kernel fetches crop rows as aligned 128-bit words and realigns them: a slice whose row
+    pitch is odd gives every row another alignment, and random rectangles give every crop another start.
+    Every byte must still equal the oracle's (incl. crops touching any border, widths from 14 pixels up,
+    the min/max range of the 16-bit / float conventions, and wide crops that the kernel tiles)."""
+    rng = np.random.default_rng({"u8": 1, "u16": 2, "f32": 3}[dtype])
+    W, H = 263, 211
+    if dtype == "u8":
+        fr = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    elif dtype == "u16":
+        fr = rng.integers(0, 65536, (H, W)).astype(np.uint16)
+    else:
+        fr = (rng.standard_normal((H, W)) * 1000.0).astype(np.float32)
+    import cv2
+    fr = cv2.GaussianBlur(fr.astype(np.float32), (0, 0), 1.5).astype(fr.dtype)     # some spatial structure
+    cfg = StackConfig(W, H, dtype, 32, 24, 1)
+    op = util.oracle_params(cfg, match_intensity=True)
+    with _tracker(cfg, op) as t:
+        rects = [(0, 0, W, H), (0, 0, 14, 14), (W - 14, H - 14, 14, 14), (1, 0, 262, 40), (3, 7, 200, 14)]
+        for _ in range(40):
+            w, h = int(rng.integers(14, 230)), int(rng.integers(14, 200))
+            rects.append((int(rng.integers(0, W - w + 1)), int(rng.integers(0, H - h + 1)), w, h))
+        for (x0, y0, w, h) in rects:
+            got = t.preprocess(fr, x0, y0, w, h)
+            want = O.preprocess_crop(fr, x0, y0, w, h, op)
+            bad = np.argwhere(got != want)
+            assert bad.size == 0, f"{dtype} rect {(x0, y0, w, h)}: {len(bad)} bytes differ, first {bad[:3]}"
