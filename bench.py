@@ -57,9 +57,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames of the CPU baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--lanes", type=int, default=LANES_DEFAULT,
+    ap.add_argument("--lanes", type=int, default=0,
                     help="tracking lanes per GPU (lst_multi_create with the device listed this many times): the host-side "
-                         "chain walk of one lane overlaps the kernels of the others")
+                         "chain walk of one lane overlaps the kernels of the others; 0 = up to %d, fewer when the host has "
+                         "less than one core per lane thread" % LANES_DEFAULT)
     ap.add_argument("--no-files", action="store_true", help="skip the slices-from-TIFF-files leg (e2e_files)")
     ap.add_argument("--ingest", type=int, default=0, choices=[0, 1, 2], help="0 ROI DMA (default), 1 whole slices, 2 ROI gather kernel")
     ap.add_argument("--engine", default="auto", choices=["auto", "dp4a", "tc"], help="match kernel: tensor cores (default when the template fits) or IDP.4A")
@@ -258,7 +259,8 @@ def main():
     dev_ring = trk.device_alloc(ring * fb)
     trk._check(lib.lst_device_upload(trk._ctx, C.c_void_p(dev_ring), host_ring, ring * fb))
     info = trk.set_reference(st.frame(0), st.ref_xy)
-    lanes = max(1, args.lanes)
+    # every lane is a host thread that waits on its stream: keep one host core per lane across the ranks of this node
+    lanes = args.lanes if args.lanes > 0 else max(1, min(LANES_DEFAULT, (os.cpu_count() or 8) // world))
     runner = trk
     if lanes > 1:
         runner = LaserSpotTrack4Multi(cfg.width, cfg.height, bits, [local_rank] * lanes, templSize=cfg.templ_size,
