@@ -426,6 +426,27 @@ def main():
         finally:
             shutil.rmtree(tdir, ignore_errors=True)
 
+    # The same stack in PAGEABLE host memory (what a JNI shim holding Java arrays hands over): the copy engine
+    # cannot gather from it, so reader threads pack the rows of the search regions into pinned staging.
+    e2e_pageable = None
+    if not args.no_e2e and world == 1:
+        page_ring = np.empty((ring, fb), dtype=np.uint8)
+        for i in range(ring):
+            page_ring[i] = st.frame(i).view(np.uint8).reshape(-1)
+        page_ptrs = (C.c_void_p * F)(*[page_ring[i].ctypes.data for i in idx])
+
+        def step_pageable():
+            sh_pg.track_chunk(page_ptrs, 1 + rank * F, runner.get_state())
+
+        sh_pg = ShardedTracker(_Adapter(runner.track_host_ptrs), comm)
+        ms_p, wall_p, s_p = timed(step_pageable, max(1, K // 2), 1)
+        kp = max(1, K // 2)
+        e2e_pageable = {"value": F * kp / (wall_p * 1e-3), "unit": UNIT, "ms_per_step": wall_p / kp,
+                        "h2d_bytes_per_step": int(s_p.h2d_bytes // kp),
+                        "what": "slices in pageable host memory; rows of the five search regions packed into pinned staging "
+                                "by reader threads, one contiguous DMA per region and batch (ingest_mode 0 on pageable memory)"}
+        del page_ptrs, page_ring
+
     value = world * F * K / (ms_dev * 1e-3)
     # roofline of the dominant kernel (the template match): exact u8 x u8 -> s32 multiply-accumulates
     win_macs = float((2 * cfg.s_area + 1) ** 2 * cfg.templ_size ** 2)
@@ -522,7 +543,7 @@ def main():
                        "max_batch": args.max_batch or mb_d, "parallelism": f"frames sharded over {world} GPU(s), no collective" + (f"; {lanes} lanes per GPU" if lanes > 1 else ""),
                        "lanes_per_gpu": lanes,
                        "accepted_frames_last_step": ok_frames},
-            "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "gpu_launches": int(s_dev.kernel_launches),
+            "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "e2e_pageable": e2e_pageable, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
                          "chunks_retracked": sh_dev.retracked, "host_ms_per_step": s_dev.host_ms / K,

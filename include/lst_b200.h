@@ -82,9 +82,11 @@ typedef struct lst_params {
     int32_t auto_skip;         /* alwaysAutoSkip; headless policy: rejected frame => LST_STATUS_SKIP */
     int32_t max_s_area;        /* maxSArea LST4:131 (0 = no limit) */
     int32_t max_batch;         /* frames resolved per device pass (0 = default) */
-    int32_t ingest_mode;       /* host slices: 0 = auto (pinned memory: only the search regions cross PCIe, as
-                                  strided 3-D DMA copies; pageable: whole-slice copies), 1 = always whole-slice
-                                  copies, 2 = search regions gathered by a kernel from mapped host memory */
+    int32_t ingest_mode;       /* host slices: 0 = auto (only the search regions cross PCIe: from pinned memory as
+                                  strided 3-D DMA copies, from pageable memory -- e.g. Java arrays held through
+                                  JNI -- packed into pinned staging by reader threads), 1 = always whole-slice
+                                  copies, 2 = search regions gathered by a kernel from mapped host memory,
+                                  3 = always packed by reader threads */
     double  mark_dist;         /* markDist LST4:85 */
     double  range_lo, range_hi;/* LST_RANGE_FIXED */
     double  match_threshold;   /* 0 = matchThreshold[method] of LST4:147 ({0.1, 0.1, 0.05, 0.05, 0.2, 0.2}) */

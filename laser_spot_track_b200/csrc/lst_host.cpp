@@ -54,7 +54,7 @@ int validate_params(const lst_params &p, std::string *err)
     if (p.range_mode < 0 || p.range_mode > 2 || p.quant_mode < 0 || p.quant_mode > 1)
         return fail(LST_ERR_INVALID, "bad range/quant mode");
     if (p.max_batch < 0) return fail(LST_ERR_INVALID, "bad max_batch");
-    if (p.ingest_mode < 0 || p.ingest_mode > 2) return fail(LST_ERR_INVALID, "bad ingest_mode");
+    if (p.ingest_mode < 0 || p.ingest_mode > 3) return fail(LST_ERR_INVALID, "bad ingest_mode");
     if (p.ncc_engine < 0 || p.ncc_engine > 2) return fail(LST_ERR_INVALID, "bad ncc_engine");
     return LST_OK;
 }

@@ -820,10 +820,17 @@ static size_t plan_rois(const lst_ctx *c, const double dis[10], int nb, RoiDesc 
 // (ptrs); host memory unless on_device.  Host slices in pinned memory use the ROI ingest (only the
 // search regions cross PCIe, gathered by a kernel on the copy stream while the previous batch
 // computes); pageable slices and ingest_mode == 1 use whole-slice cudaMemcpyAsync into a ring.
+// Slices that are not handed to the copy engine directly: files, or host memory whose search regions the
+// reader threads pack into pinned staging (pageable memory, e.g. Java arrays held through JNI; ingest_mode 3).
 struct FileSource {
-    const char *const *paths;
-    const int32_t *pages;   // nullable: page 0 of every file
-    bool big_endian;
+    const char *const *paths = nullptr;
+    const int32_t *pages = nullptr;   // nullable: page 0 of every file
+    bool big_endian = false;
+    const void *mem_base = nullptr;   // memory source: slice i at mem_ptrs[i] or mem_base + i * mem_stride
+    size_t mem_stride = 0;
+    const void *const *mem_ptrs = nullptr;
+    bool is_mem() const { return paths == nullptr; }
+    const uint8_t *mem(int64_t i) const { return mem_ptrs ? (const uint8_t *)mem_ptrs[i] : (const uint8_t *)mem_base + (size_t)i * mem_stride; }
 };
 
 // Reads the regions `roi` of the slices [f0, f0 + nb) of a file source into `stage` (layout of the ROI
@@ -839,6 +846,21 @@ static int read_slices(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, con
     auto work = [&](int ti) {
         const int i0 = (int)((int64_t)nb * ti / nthreads), i1 = (int)((int64_t)nb * (ti + 1) / nthreads);
         for (int i = i0; i < i1; i++) {
+            if (fs.is_mem()) {
+                const uint8_t *src = fs.mem(f0 + i);
+                const size_t bpp = c->bpp(), rowb = (size_t)c->p.width * bpp;
+                if (whole) {
+                    memcpy(stage + (size_t)i * fb, src, fb);
+                } else {
+                    for (int k = 0; k < 5; k++) {
+                        const size_t nbytes = (size_t)roi[k].w * bpp;
+                        uint8_t *dst = stage + roi[k].off + (size_t)i * roi[k].slice_bytes;
+                        const uint8_t *s0 = src + (size_t)roi[k].y * rowb + (size_t)roi[k].x * bpp;
+                        for (int r = 0; r < roi[k].h; r++) memcpy(dst + (size_t)r * nbytes, s0 + (size_t)r * rowb, nbytes);
+                    }
+                }
+                continue;
+            }
             FileMap fm;
             TiffLayout L;
             int rc = fm.open(fs.paths[f0 + i], &errs[ti]);
@@ -885,6 +907,15 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
 static int track_files_whole(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, int64_t first_index, lst_record *out)
 {
     const size_t fb = c->frame_bytes();
+    if (fs.is_mem()) {   // the slices are in memory already: the ordinary whole-slice path reads them in place
+        const int save_mode = c->p.ingest_mode;
+        c->p.ingest_mode = 1;
+        int rc = fs.mem_ptrs ? track_impl(c, nullptr, 0, fs.mem_ptrs + f0, false, first_index, nb, out)
+                             : track_impl(c, (const uint8_t *)fs.mem_base + (size_t)f0 * fs.mem_stride, fs.mem_stride, nullptr, false,
+                                          first_index, nb, out);
+        c->p.ingest_mode = save_mode;
+        return rc;
+    }
     const int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)nb, ((size_t)256 << 20) / fb));
     if ((size_t)sub * fb > c->fwhole_cap) {
         if (c->h_fwhole) cudaFreeHost(c->h_fwhole);
@@ -920,6 +951,26 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     if (stride == 0) stride = fb;
     const int B = c->p.max_batch;
     if (fs && c->p.s_area == 0) return track_files_whole(c, *fs, 0, n_frames, first_index, out);   // whole-slice search
+    if (!fs && !on_device && c->p.s_area > 0 && c->p.ingest_mode != 1 && c->p.ingest_mode != 2) {
+        // Host-packed ROI ingest: reader threads copy the rows of the search regions into pinned staging and
+        // one contiguous DMA per region follows.  Taken for pageable memory (the copy engine cannot gather
+        // from it; whole-slice copies would move 14x the bytes) and on request (ingest_mode 3, LST_HOST_PACK).
+        static const int force = [] {
+            const char *e = getenv("LST_HOST_PACK");
+            return e ? atoi(e) : 0;
+        }();
+        const void *first = ptrs ? ptrs[0] : base;
+        if (c->p.ingest_mode == 3 || force || !mapped_host_ptr(c, first)) {
+            FileSource ms;
+            ms.mem_base = base;
+            ms.mem_stride = stride;
+            ms.mem_ptrs = ptrs;
+            unsigned hc = std::thread::hardware_concurrency();
+            c->file_threads = (int)std::min(16u, std::max(1u, hc));
+            if (const char *e = getenv("LST_FILE_THREADS")) c->file_threads = std::max(1, atoi(e));
+            return track_impl(c, base, stride, ptrs, false, first_index, n_frames, out, &ms);
+        }
+    }
     ResolveInput in;
     fill_resolve_input(c, &in);
     auto src_of = [&](int64_t i) -> const void * { return ptrs ? ptrs[i] : (const uint8_t *)base + (size_t)i * stride; };

@@ -560,3 +560,23 @@ def test_preprocess_random_rectangles_odd_pitch(built_lib, dtype):
             want = O.preprocess_crop(fr, x0, y0, w, h, op)
             bad = np.argwhere(got != want)
             assert bad.size == 0, f"{dtype} rect {(x0, y0, w, h)}: {len(bad)} bytes differ, first {bad[:3]}"
+
+
+def test_pageable_slices_are_packed_by_reader_threads(stack_a):
+    """Pageable host slices (what a JNI shim holding Java arrays hands over) cannot be gathered by the copy
+    engine: reader threads pack the rows of the search regions into pinned staging (ingest_mode 0 and 3);
+    ingest_mode 1 still copies whole slices.  Same records either way, a fraction of the bytes."""
+    cfg, st, frames = stack_a
+    op = util.oracle_params(cfg, match_intensity=False)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    stack = np.stack(frames[1:])                      # ordinary (pageable) numpy memory
+    sent = {}
+    for mode in (0, 1, 3):
+        with _tracker(cfg, op, max_batch=16, ingest_mode=mode) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            util.compare_records(t.track(stack), want, label=f"pageable, ingest_mode {mode}")
+            sent[mode] = t.stats().h2d_bytes
+    assert sent[0] == sent[3] and sent[0] < 0.6 * sent[1]
+    assert sent[1] >= stack.nbytes
