@@ -261,6 +261,8 @@ def main():
     info = trk.set_reference(st.frame(0), st.ref_xy)
     # every lane is a host thread that waits on its stream: keep one host core per lane across the ranks of this node
     lanes = args.lanes if args.lanes > 0 else max(1, min(LANES_DEFAULT, (os.cpu_count() or 8) // world))
+    if args.lanes <= 0 and F // (args.max_batch or mb_d) < 4:
+        lanes = 1       # a lane should get several full batches; short steps (config D: 64 slices) stay on one
     runner = trk
     if lanes > 1:
         runner = LaserSpotTrack4Multi(cfg.width, cfg.height, bits, [local_rank] * lanes, templSize=cfg.templ_size,
