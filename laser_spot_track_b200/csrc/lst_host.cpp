@@ -421,11 +421,17 @@ int resolve_batch(const ResolveInput &in, double dis_io[10], int64_t first_frame
     // linearly and every frame is matched with the windows those predicted states place.  Short
     // batches skip (1a) and use the batch-start state for every frame.  Whatever the prediction, the
     // exact walk below accepts a result only if its window is the one the true state places.
-    static const int kStride = [] {
+    // The stride adapts when the caller keeps it between batches (ResolveInput::spec_stride): halved when
+    // more than 10 % of the windows needed a fix-up pass, doubled (up to 64) when fewer than 2 % did.
+    static const int kStrideEnv = [] {
         const char *e = getenv("LST_SPEC_STRIDE");
-        int v = e ? atoi(e) : 8;
-        return v < 0 ? 0 : v;
+        int v = e ? atoi(e) : -1;
+        return v;
     }();
+    const bool adaptive = kStrideEnv < 0 && in.spec_stride != nullptr;
+    int kStride = kStrideEnv >= 0 ? kStrideEnv : (in.spec_stride ? *in.spec_stride : 8);
+    if (kStride < 2 && kStrideEnv < 0) kStride = 8;
+    const int64_t respec_before = st ? st->respeculated : 0;
     int passes = 0;
     if (kStride >= 2 && n >= 4 * kStride) {
         std::vector<int> samp;
@@ -544,6 +550,11 @@ int resolve_batch(const ResolveInput &in, double dis_io[10], int64_t first_frame
     }
     memcpy(dis_io, state, sizeof(state));
     if (st) st->frames += n;
+    if (adaptive && st && n >= 16) {
+        const double frac = (double)(st->respeculated - respec_before) / (5.0 * n);
+        if (frac > 0.10 && kStride > 2) *in.spec_stride = kStride / 2;
+        else if (frac < 0.02 && kStride < 64 && n >= 4 * kStride) *in.spec_stride = kStride * 2;
+    }
     return LST_OK;
 }
 

@@ -52,6 +52,7 @@ struct ResolveInput {
     Rect rect[5];
     float ref_xy[10];
     double spot0[2];
+    int *spec_stride = nullptr;   // nullable: the caller's sampling stride of the speculation, adapted per batch
 };
 
 // Resolves n frames starting from displacement state dis_io (updated to the state after the

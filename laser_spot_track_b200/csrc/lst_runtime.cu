@@ -92,6 +92,7 @@ struct lst_ctx : public Executor {
     size_t fwhole_cap = 0;
     bool file_mode = false;        // the batch being resolved has no whole slice in memory to fall back to
     bool swap_bytes = false;       // the slices being tracked hold big-endian samples
+    int spec_stride = 8;           // sampling stride of the resolver's speculation (adapts per batch)
     int file_threads = 8;
     // solve buffers
     int solve_cap = 0;
@@ -740,6 +741,7 @@ static void fill_resolve_input(const lst_ctx *c, ResolveInput *in)
     memcpy(in->ref_xy, c->ref_xy, sizeof(in->ref_xy));
     in->spot0[0] = c->spot0[0];
     in->spot0[1] = c->spot0[1];
+    in->spec_stride = const_cast<int *>(&c->spec_stride);
 }
 
 static int ensure_roi(lst_ctx *c, size_t bytes_per_half, int n_ptrs)
