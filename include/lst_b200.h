@@ -36,12 +36,12 @@
 extern "C" {
 #endif
 
-#define LST_ABI_VERSION 1
+#define LST_ABI_VERSION 2
 
 /* status codes */
 #define LST_OK               0
 #define LST_ERR_INVALID     -1   /* bad argument */
-#define LST_ERR_UNSUPPORTED -2   /* e.g. RGB slices, 16-bit with matchIntensity=false (LST4:2510-2523) */
+#define LST_ERR_UNSUPPORTED -2   /* e.g. 16-bit or RGB stacks with matchIntensity=false (LST4:2510-2523), compressed slice files */
 #define LST_ERR_CUDA        -3   /* no device / CUDA runtime error (see lst_last_error) */
 #define LST_ERR_NOMEM       -4
 #define LST_ERR_STATE       -5   /* call order (e.g. track before set_reference) */
@@ -53,7 +53,7 @@ extern "C" {
 #define LST_PIX_RGB 24          /* ColorProcessor pixels: one int32 0x00RRGGBB per pixel (DOES_RGB, LST4:172) */
 
 /* float -> 8-bit range convention of FloatProcessor.getBufferedImage (SURVEY.md 8c "known unknown") */
-#define LST_RANGE_DISPLAY 0      /* u8: [0,255]; u16/f32: crop's own pre-blur min/max (default) */
+#define LST_RANGE_DISPLAY 0      /* u8 and RGB: [0,255]; u16/f32: crop's own pre-blur min/max (default) */
 #define LST_RANGE_CROP    1      /* always the crop's own pre-blur min/max */
 #define LST_RANGE_FIXED   2      /* [range_lo, range_hi] */
 #define LST_QUANT_ROUND255 0     /* (int)(v*255/(max-min) + 0.5f) */
