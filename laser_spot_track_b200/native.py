@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liblst_b200.so")
 
 LST_OK, LST_ERR_INVALID, LST_ERR_UNSUPPORTED, LST_ERR_CUDA, LST_ERR_NOMEM, LST_ERR_STATE = 0, -1, -2, -3, -4, -5
+ABI_VERSION = 2          # LST_ABI_VERSION of include/lst_b200.h
 PIX_U8, PIX_U16, PIX_F32, PIX_RGB = 8, 16, 32, 24
 RANGE_DISPLAY, RANGE_CROP, RANGE_FIXED = 0, 1, 2
 QUANT_ROUND255, QUANT_TRUNC256 = 0, 1
