@@ -215,17 +215,23 @@ int64_t lst_multi_retracked(const lst_multi *m);
  * (LST4:808-817, 831).  These entry points take the files themselves: a slice file is mapped once
  * and only the rows of the five search regions are read and sent to the device.  Supported: classic
  * TIFF, either byte order (big-endian samples are swapped on the device), one sample per pixel, 8/16-bit
- * unsigned or 32-bit float, uncompressed strips; `pages` (nullable) selects a page of a multi-page
- * file or a slice of an ImageJ stack file.  Other files: LST_ERR_UNSUPPORTED -- decode them and use
- * lst_track_ptrs. */
+ * unsigned or 32-bit float, strips that are uncompressed or PackBits / LZW / Deflate compressed (with
+ * or without the horizontal predictor; only the strips covering the search regions are decoded);
+ * `pages` (nullable) selects a page of a multi-page file or a slice of an ImageJ stack file.  Other
+ * files (JPEG, PNG, tiled or RGB TIFF ...): LST_ERR_UNSUPPORTED -- decode them and use lst_track_ptrs. */
 typedef struct lst_tiff_info {
     int32_t width, height, bits, sample_format; /* sample_format: 1 unsigned integer, 3 IEEE float */
     int32_t big_endian, rows_per_strip, n_strips;
     int32_t imagej_images;                      /* "images=N" of an ImageJ description, else 0 */
+    int32_t compression, predictor;             /* TIFF tags 259 and 317 */
     int64_t first_strip_offset;
 } lst_tiff_info;
 /* host only, no GPU needed; err (nullable) receives a message */
 int lst_tiff_probe(const char *path, int32_t page, lst_tiff_info *out, char *err, int32_t err_cap);
+/* host only: the pixels of the rectangle [x, x+w) x [y, y+h) of a slice file in native byte order,
+ * row pitch w * bits/8 (what the reader threads of lst_track_files fetch for one search region) */
+int lst_tiff_read_rect(const char *path, int32_t page, int32_t x, int32_t y, int32_t w, int32_t h, void *out,
+                       char *err, int32_t err_cap);
 int lst_set_reference_file(lst_ctx *ctx, const char *path, int32_t page, const float ref_xy[10],
                            lst_reference_info *out);
 int lst_track_files(lst_ctx *ctx, const char *const *paths, const int32_t *pages,

@@ -5,6 +5,6 @@ Only what the path needs: ``csrc/`` (CUDA kernels + the C ABI of include/lst_b20
 interface), ``sharded`` (frame sharding over several GPUs) and ``synth`` (seeded synthetic stacks).
 """
 from . import native  # noqa: F401
-from .plugin import LaserSpotTrack4, LaserSpotTrack4Multi, LstError, results_rows, results_table, tiff_probe  # noqa: F401
+from .plugin import LaserSpotTrack4, LaserSpotTrack4Multi, LstError, results_rows, results_table, tiff_probe, tiff_read  # noqa: F401
 
-__all__ = ["LaserSpotTrack4", "LaserSpotTrack4Multi", "LstError", "results_rows", "results_table", "tiff_probe", "native"]
+__all__ = ["LaserSpotTrack4", "LaserSpotTrack4Multi", "LstError", "results_rows", "results_table", "tiff_probe", "tiff_read", "native"]

@@ -876,10 +876,12 @@ static int read_slices(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, con
                 if (whole) {
                     rc = tiff_copy_rect(fm, L, 0, 0, L.width, L.height, stage + (size_t)i * fb, &errs[ti]);
                 } else {
-                    for (int k = 0; k < 5 && rc == LST_OK; k++)
+                    TiffRect q[5];
+                    int nq = 0;
+                    for (int k = 0; k < 5; k++)
                         if (roi[k].w > 0 && roi[k].h > 0)
-                            rc = tiff_copy_rect(fm, L, roi[k].x, roi[k].y, roi[k].w, roi[k].h,
-                                                stage + roi[k].off + (size_t)i * roi[k].slice_bytes, &errs[ti]);
+                            q[nq++] = TiffRect{roi[k].x, roi[k].y, roi[k].w, roi[k].h, stage + roi[k].off + (size_t)i * roi[k].slice_bytes};
+                    rc = tiff_copy_rects(fm, L, q, nq, &errs[ti]);
                 }
             }
             if (rc != LST_OK) {
@@ -1298,6 +1300,32 @@ int lst_tiff_probe(const char *path, int32_t page, lst_tiff_info *out, char *err
     out->n_strips = (int32_t)L.strip_off.size();
     out->imagej_images = L.imagej_images;
     out->first_strip_offset = (int64_t)L.strip_off[0];
+    out->compression = L.compression;
+    out->predictor = L.predictor;
+    return LST_OK;
+}
+
+int lst_tiff_read_rect(const char *path, int32_t page, int32_t x, int32_t y, int32_t w, int32_t h, void *out, char *err,
+                       int32_t err_cap)
+{
+    if (!path || !out) return LST_ERR_INVALID;
+    FileMap fm;
+    TiffLayout L;
+    std::string e;
+    int rc = fm.open(path, &e);
+    if (rc == LST_OK) rc = tiff_parse(fm.data, fm.size, page, &L, &e);
+    if (rc == LST_OK) rc = tiff_copy_rect(fm, L, x, y, w, h, (uint8_t *)out, &e);
+    if (err && err_cap > 0) snprintf(err, (size_t)err_cap, "%s", e.c_str());
+    if (rc != LST_OK) return rc;
+    uint8_t *px = (uint8_t *)out;
+    const size_t nbytes = (size_t)w * h * (L.bits / 8);
+    if (L.big_endian && L.bits == 16)
+        for (size_t i = 0; i + 1 < nbytes; i += 2) std::swap(px[i], px[i + 1]);
+    else if (L.big_endian && L.bits == 32)
+        for (size_t i = 0; i + 3 < nbytes; i += 4) {
+            std::swap(px[i], px[i + 3]);
+            std::swap(px[i + 1], px[i + 2]);
+        }
     return LST_OK;
 }
 

@@ -8,6 +8,9 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
 
 #include "../../include/lst_b200.h"
 
@@ -85,7 +88,8 @@ int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, st
     L.file_size = size;
     const uint16_t ne = r.u16(ifd);
     uint32_t compression = 1, photometric = 1, spp = 1, planar = 1, rps = 0xffffffffu;
-    uint64_t strips_entry = 0, desc_off = 0;
+    uint64_t strips_entry = 0, counts_entry = 0, desc_off = 0;
+    uint32_t predictor = 1;
     uint32_t nstrips = 0, desc_len = 0, bits = 1, fmt = 1;
     bool tiled = false;
     for (uint16_t e = 0; e < ne; e++) {
@@ -107,6 +111,8 @@ int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, st
                 nstrips = r.u32(en + 4);
                 break;
             case 277: if (entry_value(r, en, 0, &v)) spp = v; break;
+            case 279: counts_entry = en; break;
+            case 317: if (entry_value(r, en, 0, &v)) predictor = v; break;
             case 278: if (entry_value(r, en, 0, &v)) rps = v; break;
             case 284: if (entry_value(r, en, 0, &v)) planar = v; break;
             case 322: case 323: case 324: case 325: tiled = true; break;
@@ -117,7 +123,11 @@ int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, st
     (void)planar;
     if (L.width <= 0 || L.height <= 0) return fail(err, LST_ERR_INVALID, "TIFF without image size");
     if (tiled) return fail(err, LST_ERR_UNSUPPORTED, "tiled TIFF is not supported");
-    if (compression != 1) return fail(err, LST_ERR_UNSUPPORTED, "compressed TIFF is not supported (decode it and use lst_track_ptrs)");
+    if (compression != 1 && compression != 5 && compression != 8 && compression != 32946 && compression != 32773)
+        return fail(err, LST_ERR_UNSUPPORTED, "TIFF compression scheme is not supported (decode the file and use lst_track_ptrs)");
+    if (predictor != 1 && !(predictor == 2 && bits != 32))
+        return fail(err, LST_ERR_UNSUPPORTED, "TIFF predictor is not supported");
+    if (compression != 1 && !counts_entry) return fail(err, LST_ERR_INVALID, "compressed TIFF without strip byte counts");
     if (spp != 1) return fail(err, LST_ERR_UNSUPPORTED, "only one sample per pixel (RGB is not on this path, LST4:172)");
     if (photometric != 1) return fail(err, LST_ERR_UNSUPPORTED, "only BlackIsZero grey-scale TIFF is supported");
     if (!((bits == 8 && fmt == 1) || (bits == 16 && fmt == 1) || (bits == 32 && fmt == 3)))
@@ -149,10 +159,20 @@ int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, st
             return fail(err, LST_ERR_INVALID, "TIFF page index beyond the last directory");
         }
     }
+    L.compression = (int)compression;
+    L.predictor = (int)predictor;
+    L.strip_len.resize(want_strips);
     for (uint32_t i = 0; i < want_strips; i++) {
         const uint64_t rows = i + 1 < want_strips ? rps : (uint64_t)L.height - (uint64_t)i * rps;
-        if (!r.ok(L.strip_off[i], rows * L.row_bytes)) return fail(err, LST_ERR_INVALID, "TIFF pixel data outside the file");
+        uint32_t v = 0;
+        L.strip_len[i] = rows * L.row_bytes;
+        if (compression != 1) {
+            if (!entry_value(r, counts_entry, i, &v)) return fail(err, LST_ERR_INVALID, "bad TIFF strip byte counts");
+            L.strip_len[i] = v;
+        }
+        if (!r.ok(L.strip_off[i], L.strip_len[i])) return fail(err, LST_ERR_INVALID, "TIFF pixel data outside the file");
     }
+    if (walked < page && compression != 1) return fail(err, LST_ERR_INVALID, "TIFF page index beyond the last directory");
     *out = L;
     return LST_OK;
 }
@@ -192,10 +212,179 @@ void FileMap::close()
     size = 0;
 }
 
+namespace {
+
+bool read_at(int fd, uint8_t *d, uint64_t off, size_t len)
+{
+    while (len > 0) {
+        ssize_t k = pread(fd, d, len, (off_t)off);
+        if (k <= 0) return false;
+        d += k;
+        off += (uint64_t)k;
+        len -= (size_t)k;
+    }
+    return true;
+}
+
+// PackBits (TIFF 6.0 section 9)
+bool unpack_bits(const uint8_t *src, size_t n, uint8_t *dst, size_t want)
+{
+    size_t i = 0, o = 0;
+    while (i < n && o < want) {
+        const int8_t c = (int8_t)src[i++];
+        if (c >= 0) {
+            const size_t k = (size_t)c + 1;
+            if (i + k > n || o + k > want) return false;
+            memcpy(dst + o, src + i, k);
+            i += k;
+            o += k;
+        } else if (c != -128) {
+            const size_t k = (size_t)(1 - (int)c);
+            if (i >= n || o + k > want) return false;
+            memset(dst + o, src[i++], k);
+            o += k;
+        }
+    }
+    return o == want;
+}
+
+// TIFF LZW (section 13): MSB-first codes of 9..12 bits, ClearCode 256, EndOfInformation 257, the code
+// width grows one code early ("early change"), as every current writer does.
+bool unpack_lzw(const uint8_t *src, size_t n, uint8_t *dst, size_t want)
+{
+    struct Ent {
+        int32_t prev;
+        uint16_t len;
+        uint8_t first, last;
+    };
+    std::vector<Ent> tab(4096);
+    for (int i = 0; i < 256; i++) tab[i] = Ent{-1, 1, (uint8_t)i, (uint8_t)i};
+    int next = 258, width = 9, prev = -1;
+    uint64_t acc = 0;
+    int nbits = 0;
+    size_t i = 0, o = 0;
+    while (o < want) {
+        while (nbits < width && i < n) {
+            acc = (acc << 8) | src[i++];
+            nbits += 8;
+        }
+        if (nbits < width) break;
+        const int code = (int)((acc >> (nbits - width)) & ((1u << width) - 1));
+        nbits -= width;
+        if (code == 257) break;
+        if (code == 256) {
+            next = 258;
+            width = 9;
+            prev = -1;
+            continue;
+        }
+        int cur = code;
+        if (prev < 0) {
+            if (code >= 256) return false;
+        } else {
+            if (code > next || next >= 4096) return false;
+            // new entry = string(prev) + first char of string(cur) (or of string(prev) when cur is the entry itself)
+            const uint8_t fc = code < next ? tab[code].first : tab[prev].first;
+            tab[next] = Ent{prev, (uint16_t)(tab[prev].len + 1), tab[prev].first, fc};
+            next++;
+        }
+        const size_t len = tab[cur].len;
+        if (o + len > want) {
+            // the last string may run past the strip's rows when the writer padded: copy what fits
+            std::vector<uint8_t> tmp(len);
+            size_t k = len;
+            for (int e = cur; e >= 0; e = tab[e].prev) tmp[--k] = tab[e].last;
+            memcpy(dst + o, tmp.data(), want - o);
+            o = want;
+            break;
+        }
+        size_t k = o + len;
+        for (int e = cur; e >= 0; e = tab[e].prev) dst[--k] = tab[e].last;
+        o += len;
+        prev = cur;
+        if (next + 1 >= (1 << width) && width < 12) width++;
+    }
+    return o == want;
+}
+
+// One strip, decoded and with the predictor undone, as rows of L.row_bytes in the file's byte order.
+bool decode_strip(const FileMap &fm, const TiffLayout &L, int strip, std::vector<uint8_t> *raw, std::vector<uint8_t> *out)
+{
+    const int rows = std::min(L.rows_per_strip, L.height - strip * L.rows_per_strip);
+    const size_t want = (size_t)rows * L.row_bytes;
+    out->resize(want);
+    raw->resize(L.strip_len[strip]);
+    if (!read_at(fm.fd, raw->data(), L.strip_off[strip], raw->size())) return false;
+    bool ok = false;
+    if (L.compression == 32773) ok = unpack_bits(raw->data(), raw->size(), out->data(), want);
+    else if (L.compression == 5) ok = unpack_lzw(raw->data(), raw->size(), out->data(), want);
+    else {
+        uLongf got = (uLongf)want;
+        ok = uncompress(out->data(), &got, raw->data(), (uLong)raw->size()) == Z_OK && got == want;
+    }
+    if (!ok) return false;
+    if (L.predictor == 2) {
+        for (int r = 0; r < rows; r++) {
+            uint8_t *p = out->data() + (size_t)r * L.row_bytes;
+            if (L.bits == 8) {
+                for (int x = 1; x < L.width; x++) p[x] = (uint8_t)(p[x] + p[x - 1]);
+            } else {   // 16-bit samples in the file's byte order
+                const int hi = L.big_endian ? 0 : 1, lo = 1 - hi;
+                uint32_t acc = ((uint32_t)p[hi] << 8) | p[lo];
+                for (int x = 1; x < L.width; x++) {
+                    acc = (acc + (((uint32_t)p[2 * x + hi] << 8) | p[2 * x + lo])) & 0xffffu;
+                    p[2 * x + hi] = (uint8_t)(acc >> 8);
+                    p[2 * x + lo] = (uint8_t)acc;
+                }
+            }
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+int tiff_copy_rects(const FileMap &fm, const TiffLayout &L, const TiffRect *rects, int n, std::string *err)
+{
+    for (int k = 0; k < n; k++) {
+        const TiffRect &q = rects[k];
+        if (q.x < 0 || q.y < 0 || q.w < 0 || q.h < 0 || q.x + q.w > L.width || q.y + q.h > L.height)
+            return fail(err, LST_ERR_INVALID, "rectangle outside the TIFF image");
+    }
+    if (L.compression == 1) {
+        for (int k = 0; k < n; k++) {
+            int rc = tiff_copy_rect(fm, L, rects[k].x, rects[k].y, rects[k].w, rects[k].h, rects[k].dst, err);
+            if (rc != LST_OK) return rc;
+        }
+        return LST_OK;
+    }
+    // compressed: every strip that holds rows of a rectangle is decoded once
+    const size_t bpp = (size_t)L.bits / 8;
+    std::vector<uint8_t> raw, strip;
+    for (int s = 0; s < (int)L.strip_off.size(); s++) {
+        const int r0 = s * L.rows_per_strip, r1 = std::min(L.height, r0 + L.rows_per_strip);
+        bool needed = false;
+        for (int k = 0; k < n && !needed; k++) needed = rects[k].h > 0 && rects[k].w > 0 && rects[k].y < r1 && rects[k].y + rects[k].h > r0;
+        if (!needed) continue;
+        if (!decode_strip(fm, L, s, &raw, &strip)) return fail(err, LST_ERR_INVALID, "corrupt compressed TIFF strip");
+        for (int k = 0; k < n; k++) {
+            const TiffRect &q = rects[k];
+            const size_t nb = (size_t)q.w * bpp;
+            for (int y = std::max(q.y, r0); y < std::min(q.y + q.h, r1); y++)
+                memcpy(q.dst + (size_t)(y - q.y) * nb, strip.data() + (size_t)(y - r0) * L.row_bytes + (size_t)q.x * bpp, nb);
+        }
+    }
+    return LST_OK;
+}
+
 int tiff_copy_rect(const FileMap &fm, const TiffLayout &L, int x0, int y0, int w, int h, uint8_t *dst, std::string *err)
 {
     if (x0 < 0 || y0 < 0 || w < 0 || h < 0 || x0 + w > L.width || y0 + h > L.height)
         return fail(err, LST_ERR_INVALID, "rectangle outside the TIFF image");
+    if (L.compression != 1) {
+        TiffRect q{x0, y0, w, h, dst};
+        return tiff_copy_rects(fm, L, &q, 1, err);
+    }
     const size_t bpp = (size_t)L.bits / 8, nb = (size_t)w * bpp;
     auto rd = [&](uint8_t *d, uint64_t off, size_t len) -> bool {
         while (len > 0) {

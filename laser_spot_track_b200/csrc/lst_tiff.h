@@ -2,11 +2,13 @@
 // hands analyseSlice one decoded file per slice (LST4:808-817, 831) and opens each file twice.  Here a
 // slice file is mapped once and only the rows of the five search regions are touched.
 //
-// Supported: classic TIFF (II or MM), one sample per pixel, 8/16-bit unsigned or 32-bit float,
-// uncompressed, strips of any height; page p of a multi-page file by walking the IFD chain, or -- for
-// stacks written by ImageJ (one IFD, "images=N" in the ImageDescription, slices back to back) -- by
-// offset.  Anything else (compression, tiles, RGB, BigTIFF, WhiteIsZero) is LST_ERR_UNSUPPORTED: the
-// caller decodes such files itself and uses lst_track_ptrs.
+// Supported: classic TIFF (II or MM), one sample per pixel, 8/16-bit unsigned or 32-bit float, strips
+// of any height, uncompressed or compressed with PackBits, LZW or Deflate (with or without the
+// horizontal predictor, as libtiff / OpenCV write them): only the strips that cover the requested rows
+// are decoded; page p of a multi-page file by walking the IFD chain, or -- for stacks written by
+// ImageJ (one IFD, "images=N" in the ImageDescription, slices back to back) -- by offset.  Anything
+// else (JPEG-in-TIFF, tiles, RGB, BigTIFF, WhiteIsZero) is LST_ERR_UNSUPPORTED: the caller decodes such
+// files itself and uses lst_track_ptrs.
 #pragma once
 #include <stdint.h>
 #include <string>
@@ -21,6 +23,9 @@ struct TiffLayout {
     bool big_endian = false;
     int rows_per_strip = 0;
     std::vector<uint64_t> strip_off;   // file offset of every strip
+    std::vector<uint64_t> strip_len;   // stored (compressed) bytes of every strip
+    int compression = 1;     // 1 none, 5 LZW, 8 / 32946 Deflate, 32773 PackBits
+    int predictor = 1;       // 2: horizontal differencing of the samples
     uint64_t row_bytes = 0;
     uint64_t file_size = 0;
     int imagej_images = 0;   // "images=N" of an ImageJ ImageDescription (0 = none)
@@ -45,5 +50,12 @@ struct FileMap {
 
 // Copies the rectangle [x0, x0+w) x [y0, y0+h) (pixels) of the image into dst (row pitch w*bytes per pixel).
 int tiff_copy_rect(const FileMap &fm, const TiffLayout &L, int x0, int y0, int w, int h, uint8_t *dst, std::string *err);
+
+// Several rectangles of one image at once (every strip of a compressed file is decoded at most once).
+struct TiffRect {
+    int x, y, w, h;
+    uint8_t *dst;
+};
+int tiff_copy_rects(const FileMap &fm, const TiffLayout &L, const TiffRect *rects, int n, std::string *err);
 
 }  // namespace lst

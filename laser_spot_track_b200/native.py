@@ -30,7 +30,7 @@ EXPORTS = [
     "lst_multi_create", "lst_multi_destroy", "lst_multi_last_error", "lst_multi_set_reference", "lst_multi_track",
     "lst_multi_get_state", "lst_multi_set_state", "lst_multi_retracked", "lst_multi_track_device",
     "lst_multi_get_stats", "lst_multi_reset_stats",
-    "lst_tiff_probe", "lst_set_reference_file", "lst_track_files", "lst_results_rows",
+    "lst_tiff_probe", "lst_tiff_read_rect", "lst_set_reference_file", "lst_track_files", "lst_results_rows",
 ]
 
 
@@ -82,7 +82,8 @@ class Stats(C.Structure):
 class TiffInfo(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bits", C.c_int32), ("sample_format", C.c_int32),
                 ("big_endian", C.c_int32), ("rows_per_strip", C.c_int32), ("n_strips", C.c_int32),
-                ("imagej_images", C.c_int32), ("first_strip_offset", C.c_int64)]
+                ("imagej_images", C.c_int32), ("compression", C.c_int32), ("predictor", C.c_int32),
+                ("first_strip_offset", C.c_int64)]
 
 
 class Task(C.Structure):
@@ -143,6 +144,7 @@ def load() -> C.CDLL:
         "lst_host_template_rect": ([P(Params), C.c_float, C.c_float, P(i32)], C.c_int),
         "lst_results_rows": ([P(Record), i64, dbl, dbl, i64, P(dbl), P(i64)], C.c_int64),
         "lst_tiff_probe": ([C.c_char_p, i32, P(TiffInfo), C.c_char_p, i32], C.c_int),
+        "lst_tiff_read_rect": ([C.c_char_p, i32, i32, i32, i32, i32, vp, C.c_char_p, i32], C.c_int),
         "lst_set_reference_file": ([vp, C.c_char_p, i32, P(C.c_float), P(ReferenceInfo)], C.c_int),
         "lst_track_files": ([vp, P(C.c_char_p), P(i32), i64, i32, P(Record)], C.c_int),
         "lst_multi_create": ([P(Params), P(i32), i32, P(vp)], C.c_int),

@@ -364,6 +364,20 @@ def tiff_probe(path: str, page: int = 0) -> N.TiffInfo:
     return info
 
 
+def tiff_read(path: str, page: int = 0, rect=None) -> np.ndarray:
+    """The pixels of a slice file (or of the rectangle ``(x, y, w, h)`` of it) as the reader threads of
+    ``lst_track_files`` decode them: host only."""
+    info = tiff_probe(path, page)
+    x, y, w, h = rect if rect is not None else (0, 0, info.width, info.height)
+    dt = {8: np.uint8, 16: np.uint16, 32: np.float32}[info.bits]
+    out = np.zeros((h, w), dtype=dt)
+    err = C.create_string_buffer(256)
+    rc = N.load().lst_tiff_read_rect(os.fsencode(path), int(page), int(x), int(y), int(w), int(h), out.ctypes.data, err, 256)
+    if rc != N.LST_OK:
+        raise LstError(rc, err.value.decode(errors="replace"))
+    return out
+
+
 def results_rows(records, time0: float = 0.0, time_step: float = 1.0, first_row_number: int = 2):
     """``lst_results_rows``: the numeric ResultsTable columns {Time, Frame, dX_pix, dY_pix, X_abs, Y_abs, dL}
     of a whole ctypes array of records at once (LST4:864-875); returns (rows[n, 7], source index[n])."""

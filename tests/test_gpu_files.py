@@ -108,3 +108,23 @@ def test_track_files_whole_slice_search_and_errors(built_lib, oracle_clib, tmp_p
         tiffio.write_tiff(comp, [frames[1]], compression=5)
         with pytest.raises(LstError):
             t.track_files([str(comp)])
+
+
+@pytest.mark.parametrize("scheme", ["lzw", "deflate", "packbits"])
+def test_track_compressed_slice_files(built_lib, oracle_clib, tmp_path, scheme):
+    """Compressed slice files as libtiff writes them (cv2.imwrite): the reader threads decode only the strips
+    that cover the search regions; records equal the oracle's on the decoded arrays."""
+    import cv2
+    cfg = StackConfig(400, 300, "u16", 32, 24, 16)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 16)]
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    code = {"lzw": 5, "deflate": 8, "packbits": 32773}[scheme]
+    paths = []
+    for i, f in enumerate(frames):
+        p = str(tmp_path / f"z{i:03d}.tif")
+        assert cv2.imwrite(p, f, [cv2.IMWRITE_TIFF_COMPRESSION, code])
+        paths.append(p)
+    with _tracker(cfg, op, max_batch=6) as t:
+        t.set_reference_file(paths[0], st.ref_xy)
+        util.compare_records(t.track_files(paths[1:]), want, label=f"{scheme} files")

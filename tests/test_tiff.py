@@ -44,7 +44,7 @@ def test_probe_pages_and_imagej_stack(built_lib, tmp_path):
 
 def test_probe_rejects_what_the_path_cannot_read(built_lib, tmp_path):
     img = np.zeros((16, 16), np.uint8)
-    for kw in (dict(compression=5), dict(photometric=0)):
+    for kw in (dict(compression=7, fake_compression=True), dict(photometric=0)):      # 7: JPEG-in-TIFF
         p = tmp_path / "x.tif"
         tiffio.write_tiff(p, [img], **kw)
         with pytest.raises(LstError) as e:
@@ -69,3 +69,55 @@ def test_probe_rejects_what_the_path_cannot_read(built_lib, tmp_path):
     p.write_bytes(bytes(cut))
     with pytest.raises(LstError):
         tiff_probe(str(p))
+
+
+def _test_images(dtype):
+    rng = np.random.default_rng(11)
+    h, w = 97, 131
+    yy, xx = np.mgrid[0:h, 0:w]
+    top = 255 if dtype == np.uint8 else 65535
+    smooth = ((np.sin(xx / 9.0) + np.cos(yy / 7.0) + 2.0) / 4.0 * top).astype(dtype)           # compresses well
+    noisy = rng.integers(0, top + 1, (h, w)).astype(dtype)                                       # does not
+    flat = np.full((h, w), 7, dtype)                                                             # long runs
+    return [smooth, noisy, flat]
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+@pytest.mark.parametrize("scheme", ["lzw", "deflate", "packbits"])
+def test_compressed_strips_written_by_libtiff(built_lib, tmp_path, dtype, scheme):
+    """Slice files as libtiff (through cv2.imwrite) writes them: LZW / Deflate with the horizontal predictor,
+    PackBits, several strips.  Whole images and rectangles that straddle strips decode to the pixels."""
+    import cv2
+    from laser_spot_track_b200 import tiff_read
+    code = {"lzw": 5, "deflate": 8, "packbits": 32773}[scheme]
+    for k, img in enumerate(_test_images(dtype)):
+        p = str(tmp_path / f"{scheme}{k}.tif")
+        assert cv2.imwrite(p, img, [cv2.IMWRITE_TIFF_COMPRESSION, code])
+        info = tiff_probe(p)
+        assert info.compression == code and (info.width, info.height) == (img.shape[1], img.shape[0])
+        assert np.array_equal(tiff_read(p), img)
+        for rect in [(0, 0, 14, 14), (17, 40, 90, 33), (100, 60, 31, 37), (0, 96, 131, 1)]:
+            x, y, w, h = rect
+            assert np.array_equal(tiff_read(p, rect=rect), img[y:y + h, x:x + w]), (scheme, k, rect)
+
+
+@pytest.mark.parametrize("big_endian", [False, True])
+@pytest.mark.parametrize("compression,predictor", [(8, 1), (8, 2), (32773, 1), (32773, 2)])
+def test_compressed_strips_either_byte_order(built_lib, tmp_path, big_endian, compression, predictor):
+    from laser_spot_track_b200 import tiff_read
+    for dtype in (np.uint8, np.uint16):
+        for k, img in enumerate(_test_images(dtype)):
+            p = str(tmp_path / f"c{k}.tif")
+            tiffio.write_tiff(p, [img], big_endian=big_endian, rows_per_strip=13, compression=compression, predictor=predictor)
+            assert np.array_equal(tiff_read(p), img)
+            assert np.array_equal(tiff_read(p, rect=(5, 11, 100, 30)), img[11:41, 5:105])
+
+
+def test_corrupt_compressed_strip_is_an_error(built_lib, tmp_path):
+    from laser_spot_track_b200 import tiff_read
+    img = _test_images(np.uint16)[0]
+    p = tmp_path / "bad.tif"
+    tiffio.write_tiff(p, [img], compression=5, fake_compression=True)      # says LZW, holds raw bytes
+    tiff_probe(str(p))
+    with pytest.raises(LstError):
+        tiff_read(str(p))
