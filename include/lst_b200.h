@@ -217,8 +217,9 @@ int64_t lst_multi_retracked(const lst_multi *m);
  * TIFF, either byte order (big-endian samples are swapped on the device), one sample per pixel, 8/16-bit
  * unsigned or 32-bit float, strips that are uncompressed or PackBits / LZW / Deflate compressed (with
  * or without the horizontal predictor; only the strips covering the search regions are decoded);
- * `pages` (nullable) selects a page of a multi-page file or a slice of an ImageJ stack file.  Other
- * files (JPEG, PNG, tiled or RGB TIFF ...): LST_ERR_UNSUPPORTED -- decode them and use lst_track_ptrs. */
+ * `pages` (nullable) selects a page of a multi-page file or a slice of an ImageJ stack file.  Grey 8/16-bit
+ * PNG files (not interlaced) are read as well.  Other files (JPEG, tiled or RGB TIFF / PNG ...):
+ * LST_ERR_UNSUPPORTED -- decode them and use lst_track_ptrs. */
 typedef struct lst_tiff_info {
     int32_t width, height, bits, sample_format; /* sample_format: 1 unsigned integer, 3 IEEE float */
     int32_t big_endian, rows_per_strip, n_strips;

@@ -61,8 +61,50 @@ bool entry_value(const Reader &r, uint64_t entry, uint32_t i, uint32_t *out)
 
 }  // namespace
 
+static int png_parse(const uint8_t *d, uint64_t n, int page, TiffLayout *out, std::string *err)
+{
+    if (page != 0) return fail(err, LST_ERR_INVALID, "a PNG file holds one image");
+    TiffLayout L;
+    L.png = true;
+    L.big_endian = true;   // PNG samples are in network byte order
+    L.file_size = n;
+    uint64_t o = 8;
+    bool have_hdr = false, done = false;
+    while (!done && o + 12 <= n) {
+        const uint32_t len = ((uint32_t)d[o] << 24) | ((uint32_t)d[o + 1] << 16) | ((uint32_t)d[o + 2] << 8) | d[o + 3];
+        const uint8_t *ty = d + o + 4;
+        if (o + 12 + (uint64_t)len > n) return fail(err, LST_ERR_INVALID, "PNG chunk outside the file");
+        if (!memcmp(ty, "IHDR", 4)) {
+            if (len < 13) return fail(err, LST_ERR_INVALID, "bad PNG header");
+            const uint8_t *h = d + o + 8;
+            L.width = (int)(((uint32_t)h[0] << 24) | ((uint32_t)h[1] << 16) | ((uint32_t)h[2] << 8) | h[3]);
+            L.height = (int)(((uint32_t)h[4] << 24) | ((uint32_t)h[5] << 16) | ((uint32_t)h[6] << 8) | h[7]);
+            L.bits = h[8];
+            if (h[9] != 0) return fail(err, LST_ERR_UNSUPPORTED, "only grey-scale PNG is supported (RGB / palette / alpha are not on this path)");
+            if (L.bits != 8 && L.bits != 16) return fail(err, LST_ERR_UNSUPPORTED, "only 8- and 16-bit PNG samples are supported");
+            if (h[12] != 0) return fail(err, LST_ERR_UNSUPPORTED, "interlaced PNG is not supported");
+            have_hdr = true;
+        } else if (!memcmp(ty, "IDAT", 4)) {
+            L.strip_off.push_back(o + 8);
+            L.strip_len.push_back(len);
+        } else if (!memcmp(ty, "IEND", 4)) {
+            done = true;
+        }
+        o += 12 + (uint64_t)len;
+    }
+    if (!have_hdr || L.width <= 0 || L.height <= 0 || L.strip_off.empty()) return fail(err, LST_ERR_INVALID, "PNG without header or image data");
+    L.sample_format = 1;
+    L.row_bytes = (uint64_t)L.width * (L.bits / 8);
+    L.rows_per_strip = L.height;
+    L.compression = 8;
+    *out = L;
+    return LST_OK;
+}
+
 int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, std::string *err)
 {
+    static const uint8_t kPngSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (data && size >= 8 && !memcmp(data, kPngSig, 8)) return png_parse(data, size, page, out, err);
     if (!data || size < 8 || page < 0) return fail(err, LST_ERR_INVALID, "not a TIFF file (too short)");
     Reader r{data, size, false};
     if (data[0] == 'I' && data[1] == 'I') r.be = false;
@@ -350,6 +392,67 @@ int tiff_copy_rects(const FileMap &fm, const TiffLayout &L, const TiffRect *rect
         const TiffRect &q = rects[k];
         if (q.x < 0 || q.y < 0 || q.w < 0 || q.h < 0 || q.x + q.w > L.width || q.y + q.h > L.height)
             return fail(err, LST_ERR_INVALID, "rectangle outside the TIFF image");
+    }
+    if (L.png) {
+        // one zlib stream over all IDAT chunks; rows are filtered against the row above, so the image is
+        // inflated from the top down to the last row any rectangle needs
+        int last = -1;
+        for (int k = 0; k < n; k++)
+            if (rects[k].w > 0 && rects[k].h > 0) last = std::max(last, rects[k].y + rects[k].h - 1);
+        if (last < 0) return LST_OK;
+        const size_t bpp = (size_t)L.bits / 8, rb = (size_t)L.row_bytes;
+        std::vector<uint8_t> rows(2 * (rb + 1), 0);
+        uint8_t *cur = rows.data(), *prv = rows.data() + rb + 1;
+        z_stream z;
+        memset(&z, 0, sizeof(z));
+        if (inflateInit(&z) != Z_OK) return fail(err, LST_ERR_INVALID, "zlib initialisation failed");
+        size_t chunk = 0;
+        bool ok = true;
+        for (int y = 0; y <= last && ok; y++) {
+            z.next_out = cur;
+            z.avail_out = (uInt)(rb + 1);
+            while (z.avail_out > 0 && ok) {
+                if (z.avail_in == 0) {
+                    if (chunk >= L.strip_off.size()) {
+                        ok = false;
+                        break;
+                    }
+                    z.next_in = (Bytef *)(fm.data + L.strip_off[chunk]);
+                    z.avail_in = (uInt)L.strip_len[chunk];
+                    chunk++;
+                }
+                const int zr = inflate(&z, Z_NO_FLUSH);
+                if (zr != Z_OK && zr != Z_STREAM_END) ok = false;
+                if (zr == Z_STREAM_END && z.avail_out > 0) ok = false;
+            }
+            if (!ok) break;
+            uint8_t *p = cur + 1;
+            const uint8_t *up = prv + 1;
+            switch (cur[0]) {
+                case 0: break;
+                case 1: for (size_t i = bpp; i < rb; i++) p[i] = (uint8_t)(p[i] + p[i - bpp]); break;
+                case 2: for (size_t i = 0; i < rb; i++) p[i] = (uint8_t)(p[i] + up[i]); break;
+                case 3:
+                    for (size_t i = 0; i < rb; i++) p[i] = (uint8_t)(p[i] + (((i >= bpp ? p[i - bpp] : 0) + up[i]) >> 1));
+                    break;
+                case 4:
+                    for (size_t i = 0; i < rb; i++) {
+                        const int a = i >= bpp ? p[i - bpp] : 0, b = up[i], c = i >= bpp ? up[i - bpp] : 0;
+                        const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c);
+                        p[i] = (uint8_t)(p[i] + (pa <= pb && pa <= pc ? a : (pb <= pc ? b : c)));
+                    }
+                    break;
+                default: ok = false; break;
+            }
+            for (int k = 0; k < n && ok; k++) {
+                const TiffRect &q = rects[k];
+                if (q.w > 0 && y >= q.y && y < q.y + q.h) memcpy(q.dst + (size_t)(y - q.y) * q.w * bpp, p + (size_t)q.x * bpp, (size_t)q.w * bpp);
+            }
+            std::swap(cur, prv);
+        }
+        inflateEnd(&z);
+        if (!ok) return fail(err, LST_ERR_INVALID, "corrupt PNG image data");
+        return LST_OK;
     }
     if (L.compression == 1) {
         for (int k = 0; k < n; k++) {

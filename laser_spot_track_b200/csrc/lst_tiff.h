@@ -29,10 +29,13 @@ struct TiffLayout {
     uint64_t row_bytes = 0;
     uint64_t file_size = 0;
     int imagej_images = 0;   // "images=N" of an ImageJ ImageDescription (0 = none)
+    bool png = false;        // a PNG file (grey 8/16-bit, not interlaced): strip_off/strip_len list its IDAT chunks
     uint64_t offset_of_row(int y) const { return strip_off[(size_t)(y / rows_per_strip)] + (uint64_t)(y % rows_per_strip) * row_bytes; }
 };
 
-// Parses page `page` of a TIFF image that lies in memory (a mapping of the file).  Returns LST_OK,
+// Parses page `page` of a TIFF image that lies in memory (a mapping of the file); a PNG signature is
+// recognised and handed to the PNG parser (grey-scale 8/16-bit, not interlaced; samples are big-endian
+// by definition, so they take the same device-side swap as "MM" TIFFs).  Returns LST_OK,
 // LST_ERR_UNSUPPORTED or LST_ERR_INVALID with a message.
 int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, std::string *err);
 

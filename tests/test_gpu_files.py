@@ -128,3 +128,20 @@ def test_track_compressed_slice_files(built_lib, oracle_clib, tmp_path, scheme):
     with _tracker(cfg, op, max_batch=6) as t:
         t.set_reference_file(paths[0], st.ref_xy)
         util.compare_records(t.track_files(paths[1:]), want, label=f"{scheme} files")
+
+
+def test_track_png_slice_files(built_lib, oracle_clib, tmp_path):
+    """16-bit grey PNG slices (network byte order: swapped on the device like big-endian TIFFs)."""
+    import cv2
+    cfg = StackConfig(400, 300, "u16", 32, 24, 12)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 12)]
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    paths = []
+    for i, f in enumerate(frames):
+        p = str(tmp_path / f"p{i:03d}.png")
+        assert cv2.imwrite(p, f)
+        paths.append(p)
+    with _tracker(cfg, op, max_batch=5) as t:
+        t.set_reference_file(paths[0], st.ref_xy)
+        util.compare_records(t.track_files(paths[1:]), want, label="png files")

@@ -121,3 +121,27 @@ def test_corrupt_compressed_strip_is_an_error(built_lib, tmp_path):
     tiff_probe(str(p))
     with pytest.raises(LstError):
         tiff_read(str(p))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_grey_png_slices(built_lib, tmp_path, dtype):
+    """Grey 8/16-bit PNG slices (cv2.imwrite -> libpng: every row filter type occurs): whole image and
+    rectangles; RGB / interlaced PNG is rejected."""
+    import cv2
+    from laser_spot_track_b200 import tiff_read
+    for k, img in enumerate(_test_images(dtype)):
+        for level in (1, 9):
+            p = str(tmp_path / f"g{k}_{level}.png")
+            assert cv2.imwrite(p, img, [cv2.IMWRITE_PNG_COMPRESSION, level])
+            info = tiff_probe(p)
+            assert (info.width, info.height, info.bits) == (img.shape[1], img.shape[0], img.dtype.itemsize * 8)
+            assert np.array_equal(tiff_read(p), img)
+            assert np.array_equal(tiff_read(p, rect=(17, 40, 90, 33)), img[40:73, 17:107])
+            assert np.array_equal(tiff_read(p, rect=(0, 0, 14, 14)), img[:14, :14])
+    rgb = str(tmp_path / "rgb.png")
+    assert cv2.imwrite(rgb, np.zeros((20, 20, 3), np.uint8))
+    with pytest.raises(LstError) as e:
+        tiff_probe(rgb)
+    assert e.value.code == N.LST_ERR_UNSUPPORTED
+    with pytest.raises(LstError):
+        tiff_probe(p, 1)
