@@ -480,6 +480,17 @@ def main():
                     "roofline is given as dp4a_engine_peak",
             "dp4a_engine_peak": dp4a_peak, "achieved_over_dp4a_peak": (achieved / dp4a_peak) if (achieved and dp4a_peak) else None,
         }
+        # The bound that applies to this embedding: an M128 K32 tcgen05.mma.kind::i8 with operands in shared
+        # memory takes >= 42 cycles for any N <= 64 (tools/tc_rate.cu on this GPU), and a window needs
+        # th * ceil(R/32) * ceil((31 + tw)/32) of them.
+        R = 2 * cfg.s_area + 1
+        mmas_per_window = cfg.templ_size * ((R + 31) // 32) * ((31 + cfg.templ_size + 31) // 32)
+        windows_per_launch = macs_per_launch / max(win_macs, 1)
+        sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+        floor_ms = windows_per_launch * mmas_per_window * 42.0 / (148 * sm_hz * 1e6) * 1e3
+        roofline["mma_issue_floor"] = {"cycles_per_mma": 42, "mmas_per_window": mmas_per_window, "floor_ms_per_launch": floor_ms,
+                                       "frac_of_floor": floor_ms / kern_ms if kern_ms > 0 else None,
+                                       "source": "tools/tc_rate.cu, profiles/README.md"}
     else:
         peak = dp4a_peak
         roofline = {
