@@ -51,6 +51,7 @@ def track_fixture(name, cfg, n, **kw):
     recs = tr.run(frames[1:])
     a = records_to_arrays(recs)
     np.savez_compressed(os.path.join(HERE, name), cfg=np.array([cfg.width, cfg.height, cfg.templ_size, cfg.s_area, n]),
+                        method=int(op.method),
                         dtype=cfg.dtype, ref_xy=np.array(st.ref_xy), rects=np.array(tr.rects), mideal=np.array(tr.mideal),
                         ref_out=np.array([ref.dX_pix, ref.dY_pix, ref.x_abs, ref.y_abs, ref.dL]),
                         match_intensity=int(op.match_intensity), frame_crc=np.array([int(f.astype(np.int64).sum()) for f in frames]), **a)
@@ -76,6 +77,27 @@ def match_fixture():
     print("match_kat ok")
 
 
+def methods_fixture():
+    """the other five methods of the dialog: cv2's own maps and min/max locations on fixed
+    8-bit inputs, plus the oracle's exact maps."""
+    import cv2
+    cv2.setNumThreads(1)
+    rng = np.random.default_rng(20260120)
+    base = cv2.GaussianBlur(rng.integers(0, 256, size=(130, 130), dtype=np.uint8), (0, 0), 2.0)
+    win = np.ascontiguousarray(base[:100, :110])
+    tpl = np.ascontiguousarray(base[31:63, 40:72])
+    out = dict(win=win, tpl=tpl)
+    for m in range(6):
+        cvm = O.ncc_map_cv2(win, tpl, m)
+        out[f"cv2map{m}"] = cvm
+        out[f"exactmap{m}"] = O.ncc_map_exact(win, tpl, m)
+        mn, mx, mnl, mxl = cv2.minMaxLoc(cvm)
+        out[f"cv2best{m}"] = np.array([mnl[0], mnl[1], mn] if m in (0, 1) else [mxl[0], mxl[1], mx])
+        out[f"self{m}"] = np.array([O.do_match_test(tpl, "exact", m), O.do_match_test(tpl, "cv2", m)])
+    np.savez_compressed(os.path.join(HERE, "match_methods_kat.npz"), **out)
+    print("match_methods_kat ok")
+
+
 def blur_fixture():
     rng = np.random.default_rng(7)
     img8 = rng.integers(0, 256, size=(40, 52), dtype=np.uint8)
@@ -92,5 +114,8 @@ def blur_fixture():
 if __name__ == "__main__":
     track_fixture("track_a_u8.npz", StackConfig(640, 480, "u8", 32, 32, 200), 40, match_intensity=False)
     track_fixture("track_small_u16.npz", StackConfig(480, 400, "u16", 48, 56, 24), 12)
+    for m in (0, 1, 2, 3, 4):
+        track_fixture(f"track_method{m}_u8.npz", StackConfig(640, 480, "u8", 32, 32, 200), 16, match_intensity=False, method=m)
     match_fixture()
+    methods_fixture()
     blur_fixture()

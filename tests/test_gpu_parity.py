@@ -266,17 +266,17 @@ def test_roi_ingest_margin_exceeded(built_lib, oracle_clib):
         N.load().lst_free_pinned(ptr)
 
 
-@pytest.mark.parametrize("name", ["track_a_u8.npz", "track_small_u16.npz"])
+@pytest.mark.parametrize("name", ["track_a_u8.npz", "track_small_u16.npz"] + [f"track_method{m}_u8.npz" for m in range(5)])
 def test_golden_fixtures_on_gpu(built_lib, name):
     """The CUDA path against the committed fixtures (no oracle at run time)."""
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
     w, h, T, s, n = [int(v) for v in g["cfg"]]
-    cfg = StackConfig(w, h, str(g["dtype"]), T, s, 200 if name.startswith("track_a") else 24)
+    cfg = StackConfig(w, h, str(g["dtype"]), T, s, 24 if name.startswith("track_small") else 200)
     st = SyntheticStack(cfg)
     frames = [st.frame(i) for i in range(n + 1)]
     bits = {"u8": 8, "u16": 16}[cfg.dtype]
-    with LaserSpotTrack4(w, h, bits, templSize=T, sArea=s, matchIntensity=bool(g["match_intensity"])) as t:
+    with LaserSpotTrack4(w, h, bits, method=int(g["method"]), templSize=T, sArea=s, matchIntensity=bool(g["match_intensity"])) as t:
         info = t.set_reference(frames[0], st.ref_xy)
         assert np.array_equal(np.array([list(r) for r in info.rect]), g["rects"])
         assert list(info.mideal) == g["mideal"].tolist()
@@ -580,3 +580,20 @@ def test_pageable_slices_are_packed_by_reader_threads(stack_a):
             sent[mode] = t.stats().h2d_bytes
     assert sent[0] == sent[3] and sent[0] < 0.6 * sent[1]
     assert sent[1] >= stack.nbytes
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4, 5])
+def test_match_methods_golden_on_gpu(built_lib, method):
+    """The CUDA score maps and peaks against the frozen vectors of tests/golden/match_methods_kat.npz
+    (exact maps bit for bit; cv2's own maps within its float32-DFT noise) -- no oracle at run time."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "match_methods_kat.npz"))
+    win, tpl = g["win"], g["tpl"]
+    with LaserSpotTrack4(640, 480, 8) as t:
+        res, m = t.doMatch_coord_res(win, tpl, method, False, want_map=True)
+        assert np.array_equal(m.view(np.uint32), g[f"exactmap{method}"].view(np.uint32))
+        cvm = g[f"cv2map{method}"]
+        scale = max(1.0, float(np.abs(cvm).max()))
+        assert float(np.abs(m.astype(np.float64) - cvm).max()) / scale < SCORE_TOL_CV2
+        assert (res[0], res[1]) == (g[f"cv2best{method}"][0], g[f"cv2best{method}"][1])
+        assert t.doMatch_test(tpl, method) == g[f"self{method}"][0]

@@ -152,15 +152,18 @@ def test_match_result_thresholds():
 
 
 # ---- the loop, against the frozen fixtures --------------------------------------------------------
-@pytest.mark.parametrize("name", ["track_a_u8.npz", "track_small_u16.npz"])
+GOLDEN_TRACKS = ["track_a_u8.npz", "track_small_u16.npz"] + [f"track_method{m}_u8.npz" for m in range(5)]
+
+
+@pytest.mark.parametrize("name", GOLDEN_TRACKS)
 def test_tracking_loop_golden(oracle_clib, name):
     g = np.load(os.path.join(G, name))
     w, h, T, s, n = [int(v) for v in g["cfg"]]
-    cfg = StackConfig(w, h, str(g["dtype"]), T, s, 200 if name.startswith("track_a") else 24)
+    cfg = StackConfig(w, h, str(g["dtype"]), T, s, 24 if name.startswith("track_small") else 200)
     st = SyntheticStack(cfg)
     frames = [st.frame(i) for i in range(n + 1)]
     assert [int(f.astype(np.int64).sum()) for f in frames] == g["frame_crc"].tolist(), "synthetic generator changed"
-    op = O.Params(w, h, T, s, match_intensity=bool(g["match_intensity"]))
+    op = O.Params(w, h, T, s, match_intensity=bool(g["match_intensity"]), method=int(g["method"]))
     tr = O.OracleTracker(op)
     ref = tr.set_reference(frames[0], st.ref_xy)
     assert np.array_equal(np.array(tr.rects), g["rects"]) and tr.mideal == g["mideal"].tolist()
@@ -172,6 +175,8 @@ def test_tracking_loop_golden(oracle_clib, name):
         assert [t.score for t in r.tm] == g["scores"][i].tolist()
         assert [(t.x, t.y) for t in r.tm] == [tuple(p) for p in g["pos"][i]]
         assert [r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL] == g["out"][i].tolist()
+    if int(g["method"]) != 5:
+        return
     # sanity against ground truth: tracked spot displacement follows the synthetic motion
     t = st.truth(n) - st.truth(0)
     assert abs(recs[-1].dX_pix - (t[0, 0] - t[1, 0])) < 0.15 and abs(recs[-1].dY_pix - (t[0, 1] - t[1, 1])) < 0.15
@@ -217,3 +222,20 @@ def test_rgb_to_gray8_is_imagej_unweighted_mean():
     assert g.tolist() == [[0, 255, 85, 1], [32, 85, 253, 129]]
     gw = O.rgb_to_gray8(px, (0.299, 0.587, 0.114))
     assert gw.tolist() == [[0, 255, 76, 1], [int(16 * 0.299 + 32 * 0.587 + 48 * 0.114 + 0.5), 29, 253, 129]]
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4, 5])
+def test_methods_golden(oracle_clib, method):
+    """Frozen vectors of SURVEY 8f-N3: cv2's own result map, its min/max location and the 1x1 self match
+    for every method, on fixed 8-bit inputs (tests/golden/match_methods_kat.npz)."""
+    g = np.load(os.path.join(G, "match_methods_kat.npz"))
+    win, tpl = g["win"], g["tpl"]
+    exact = O.ncc_map_exact(win, tpl, method)
+    assert np.array_equal(exact.view(np.uint32), g[f"exactmap{method}"].view(np.uint32))
+    cvm = g[f"cv2map{method}"]
+    scale = max(1.0, float(np.abs(cvm).max()))
+    assert float(np.abs(exact.astype(np.float64) - cvm).max()) / scale < 1e-4
+    x, y, v = O.best_loc_first(exact, method)
+    assert (x, y) == (int(g[f"cv2best{method}"][0]), int(g[f"cv2best{method}"][1]))
+    assert abs(v - g[f"cv2best{method}"][2]) / scale < 1e-4
+    assert O.do_match_test(tpl, "exact", method) == g[f"self{method}"][0]
