@@ -508,6 +508,9 @@ def main():
         "algorithmic_ops_per_launch": 2.0 * macs_per_launch, "avg_launch_ms": kern_ms,
         "kernel_share_of_step": s_roof.ncc_kernel_ms / ms_roof if ms_roof > 0 else None,
         "launches_timed": int(s_roof.ncc_kernel_launches),
+        "kernel_ms_per_step": {"lst_preprocess": s_roof.preprocess_ms / K, "lst_box_sums": s_roof.box_sums_ms / K,
+                               "match": s_roof.ncc_kernel_ms / K, "lst_epilogue": s_roof.epilogue_ms / K,
+                               "step": ms_roof / K},
         "measured_with": "the timed region of `value`" if lanes == 1 else
                          "a second timed region of the same %d steps on ONE lane (per-launch CUDA-event times need kernels that "
                          "do not overlap; `value` runs %d lanes): %.0f frames/s" % (K, lanes, world * F * K / (ms_roof * 1e-3)),

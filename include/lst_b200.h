@@ -139,6 +139,9 @@ typedef struct lst_stats {
     int64_t roi_fallback_tasks;/* ROI ingest: windows read straight from pinned host memory (margin exceeded) */
     double  device_wait_ms;    /* host time blocked in stream synchronisation (device busy) */
     double  host_ms;           /* host time inside the tracking entry points, total */
+    double  preprocess_ms;     /* CUDA-event time of lst_preprocess (+ lst_minmax), lst_box_sums and lst_epilogue over the */
+    double  box_sums_ms;       /* same timed passes as ncc_kernel_ms (if timing on) */
+    double  epilogue_ms;
 } lst_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------- */

@@ -31,7 +31,8 @@ static double now_ms()
 }
 
 struct TimedLaunch {
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0, e1;            // around the match kernel
+    cudaEvent_t ea, eb, ec;        // before lst_preprocess, before lst_box_sums (or the match kernel), after lst_epilogue
     double macs;
 };
 
@@ -288,8 +289,10 @@ void lst_ctx::drain_timers()
             stats.ncc_kernel_launches += 1;
             stats.ncc_algorithmic_macs += t.macs;
         }
-        event_pool.push_back(t.e0);
-        event_pool.push_back(t.e1);
+        if (cudaEventElapsedTime(&ms, t.ea, t.eb) == cudaSuccess) stats.preprocess_ms += ms;
+        if (cudaEventElapsedTime(&ms, t.eb, t.e0) == cudaSuccess) stats.box_sums_ms += ms;
+        if (cudaEventElapsedTime(&ms, t.e1, t.ec) == cudaSuccess) stats.epilogue_ms += ms;
+        for (cudaEvent_t e : {t.e0, t.e1, t.ea, t.eb, t.ec}) event_pool.push_back(e);
     }
     timed.clear();
 }
@@ -370,6 +373,19 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     }
     stats.h2d_bytes += (int64_t)sizeof(DevTask) * n;
     launches += launch_init_pass(n, d_mm, d_best, d_nbhd, s_compute);
+    TimedLaunch tl;
+    const bool timed_pass = timing && !preprocess_only && !have_win8;
+    if (timed_pass) {
+        for (cudaEvent_t *e : {&tl.e0, &tl.e1, &tl.ea, &tl.eb, &tl.ec}) {
+            if (!event_pool.empty()) {
+                *e = event_pool.back();
+                event_pool.pop_back();
+            } else {
+                CU(cudaEventCreate(e));
+            }
+        }
+        CU(cudaEventRecord(tl.ea, s_compute));
+    }
     if (!have_win8) {
         PreprocParams pp;
         preproc_params(&pp, max_w, max_h);
@@ -384,17 +400,9 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         mp.templ_size = p.templ_size;
         mp.thresh = p.match_threshold;
         if (smem > 200 * 1024) return fail(LST_ERR_UNSUPPORTED, "match tile needs %zu bytes of shared memory", smem);
-        TimedLaunch tl;
-        if (timing) {
-            for (cudaEvent_t *e : {&tl.e0, &tl.e1}) {
-                if (!event_pool.empty()) {
-                    *e = event_pool.back();
-                    event_pool.pop_back();
-                } else {
-                    CU(cudaEventCreate(e));
-                }
-            }
+        if (timed_pass) {
             tl.macs = macs;
+            CU(cudaEventRecord(tl.eb, s_compute));
             CU(cudaEventRecord(tl.e0, s_compute));
         }
         bool use_tc = ncc_engine == 1 && !map_out_host && tc_supported(max_tw, max_th);
@@ -412,7 +420,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             int bl = launch_box_sums(d_tasks, n, max_w, max_rh, max_th, d_tpls, d_win8, d_wsum, d_wsq, s_compute);
             if (bl >= 0) {
                 launches += bl;
-                if (timing) CU(cudaEventRecord(tl.e0, s_compute));   // time the match kernel alone
+                if (timed_pass) CU(cudaEventRecord(tl.e0, s_compute));   // time the match kernel alone
                 tcl = launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, d_best, d_nbhd, s_compute);
             }
         }
@@ -426,11 +434,12 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         else
             launches += launch_ncc_match(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_best,
                                          map_out_host ? d_map : nullptr, mp, s_compute);
-        if (timing) {
-            CU(cudaEventRecord(tl.e1, s_compute));
+        if (timed_pass) CU(cudaEventRecord(tl.e1, s_compute));
+        launches += launch_epilogue(d_tasks, n, d_tpls, d_win8, d_best, d_nbhd, d_results, mp, s_compute);
+        if (timed_pass) {
+            CU(cudaEventRecord(tl.ec, s_compute));
             timed.push_back(tl);
         }
-        launches += launch_epilogue(d_tasks, n, d_tpls, d_win8, d_best, d_nbhd, d_results, mp, s_compute);
         CU(cudaMemcpyAsync(h_results, d_results, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s_compute));
         stats.d2h_bytes += (int64_t)sizeof(DevResult) * n;
     }
@@ -1576,6 +1585,9 @@ int lst_multi_get_stats(const lst_multi *m, lst_stats *out)
         out->roi_fallback_tasks += s.roi_fallback_tasks;
         out->device_wait_ms += s.device_wait_ms;
         out->host_ms += s.host_ms;
+        out->preprocess_ms += s.preprocess_ms;
+        out->box_sums_ms += s.box_sums_ms;
+        out->epilogue_ms += s.epilogue_ms;
     }
     return LST_OK;
 }

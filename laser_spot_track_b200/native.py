@@ -76,6 +76,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ncc_kernel_ms", C.c_double), ("ncc_kernel_launches", C.c_int64), ("ncc_algorithmic_macs", C.c_double),
         ("roi_fallback_tasks", C.c_int64), ("device_wait_ms", C.c_double), ("host_ms", C.c_double),
+        ("preprocess_ms", C.c_double), ("box_sums_ms", C.c_double), ("epilogue_ms", C.c_double),
     ]
 
 
