@@ -597,3 +597,27 @@ def test_match_methods_golden_on_gpu(built_lib, method):
         assert float(np.abs(m.astype(np.float64) - cvm).max()) / scale < SCORE_TOL_CV2
         assert (res[0], res[1]) == (g[f"cv2best{method}"][0], g[f"cv2best{method}"][1])
         assert t.doMatch_test(tpl, method) == g[f"self{method}"][0]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_random_geometries_both_engines(built_lib, oracle_clib, seed):
+    """Random template sizes (14..90), search areas and slice sizes: the tensor-core engine sees different
+    numbers of K-steps, column blocks and partial blocks, windows clipped by the borders, result maps
+    split over several CTAs (R > 128); both engines must reproduce the oracle's records."""
+    rng = np.random.default_rng(1000 + seed)
+    T = int(rng.integers(14, 91))
+    s = int(rng.integers(6, 80))
+    W = int(rng.integers(max(260, 3 * T + 2 * s + 40), 520))
+    H = int(rng.integers(max(220, 3 * T + 2 * s + 40), 440))
+    dtype = ["u8", "u16"][seed % 2]
+    cfg = StackConfig(W, H, dtype, T, s, 6)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 6)]
+    op = util.oracle_params(cfg, match_intensity=(dtype == "u16") or bool(seed % 3 == 0))
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    for engine in (1, 2):
+        with _tracker(cfg, op, ncc_engine=engine, max_batch=3) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            util.compare_records(t.track(np.stack(frames[1:])), want, label=f"seed {seed} T={T} s={s} {W}x{H} {dtype} engine {engine}")
