@@ -245,6 +245,7 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
     __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done[TC_MAXNB];
     __shared__ uint32_t s_tmem;
     __shared__ unsigned long long s_best[4];
+    __shared__ uint32_t s_fmax;    // orderable key of the largest filter score any warp of the CTA has seen so far
 
     const long long clk0 = clock64();
     const DevTask t = tasks[blockIdx.y];
@@ -290,6 +291,7 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
         }
+        s_fmax = 0u;
         for (int g = 0; g < TC_MAXNB; g++) mbar_init(&bar_done[g], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -428,9 +430,13 @@ lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ t
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-            // pass 2: OpenCV's double-precision score for the candidates only
+            // pass 2: OpenCV's double-precision score for the candidates only.  A candidate must come within
+            // TC_EPS of the largest filter score seen anywhere in the CTA so far (every position within TC_EPS
+            // of the final maximum passes this, whenever it is visited), not just of this block's.
             const uint32_t rowidx = (uint32_t)y * (uint32_t)t.rw;
-            const float thr = tmax - TC_EPS;
+            if (lane == 0 && tmax > -3.0e38f) atomicMax(&s_fmax, f32_key(tmax));
+            __syncwarp();
+            const float thr = fmaxf(tmax, key_f32(*(volatile uint32_t *)&s_fmax)) - TC_EPS;
 #pragma unroll
             for (int p = 0; p < 32; p++) {
                 if (sf[p] >= thr && p < np) {
