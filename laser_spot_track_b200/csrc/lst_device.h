@@ -55,7 +55,7 @@ struct DevTemplates {
     TplConst c[kMaxTpl];
     const uint32_t *packed[kMaxTpl];    // [th][kw] words, see build_packed_template
     const uint8_t *raw[kMaxTpl];        // [th][tw] bytes
-    const uint8_t *toeplitz[kMaxTpl];   // tensor-core engine: [th][2*KS][32][16] bytes, see tc_build_table
+    const uint8_t *toeplitz[kMaxTpl];   // tensor-core engine: [th][2][nd*32][16] bytes, see tc_build_table
 };
 
 struct PreprocParams {
@@ -108,17 +108,16 @@ int set_rgb_weights(const double w[3]);
 void plan_match(int max_rw, int max_rh, int tw, int th, int n_tasks, MatchParams *mp, size_t *smem_bytes);
 int measure_alu_peaks(double ms_per_test, double out[3]);
 
-// Tensor-core engine of the match (lst_ncc_tc.cu): Toeplitz table of a template and the launcher.
-// table[v][kc][n][j] = T[v][16*kc + j - n] (0 outside the template), kc < 2*KS, n < 32, j < 16.
-int tc_ksteps(int tw);                                  // KS = ceil((31 + tw) / 32)
+// Tensor-core engine of the match (lst_ncc_tc.cu): Toeplitz table of a template and the launcher of the
+// persistent kernel (window sums, correlation, normalisation and argmax fused).
+// table[v][kc][n][j] = T[v][32*d + 16*kc + j - nn], row n = (nd-1-d)*32 + nn (0 outside the template), kc < 2, j < 16.
+int tc_nd(int tw);                                      // nd = ceil((31 + tw) / 32) band blocks per template row
 size_t tc_table_bytes(int tw, int th);
 void tc_build_table(const uint8_t *tpl8, int tw, int th, uint8_t *out);
 bool tc_supported(int tw, int th);
-int launch_box_sums(const DevTask *tasks, int n_tasks, int max_w, int max_rh, int th, const DevTemplates *tpls,
-                    const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream);
-int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                  const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
-                  unsigned long long *best, float *nbhd, cudaStream_t stream);
+// every window of the pass has row pitch `pitch` and starts at a multiple of it in win8 (total_rows rows in all)
+int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th, int pitch, long long total_rows,
+                  const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *nbhd, cudaStream_t stream);
 double measure_imma_peak(double ms_per_test);   // int8 tensor-core MAC/s (tcgen05.mma kind::i8)
 void tc_init_device();
 

@@ -1,52 +1,68 @@
 // lst_ncc_tc.cu -- tensor-core engine of the template match: the exact integer cross-correlation as
-// an implicit (Toeplitz) GEMM on tcgen05.mma kind::i8 (u8 x u8 -> s32, exact), accumulators in TMEM.
+// an implicit (Toeplitz) GEMM on tcgen05.mma kind::i8 (u8 x u8 -> s32, exact), accumulators in TMEM,
+// fused with the window sums, the normalisation and the argmax in ONE persistent kernel.
 //
-//   out[y][x] = sum_v sum_c W[y+v][c] * T[v][c-x]
+//   out[y][x] = sum_v sum_c W[y+v][c] * T[v][c-x]                       (matchTemplate, LST4:2560)
 //
-// For a tile of 128 result rows x (up to 4 blocks of) 32 result columns:
-//   A operand  = the 8-bit window in shared memory as [16-byte column chunk][row][16 B]: 8 consecutive
-//                rows of one chunk are a 128-byte core matrix *for any starting row*, so "rows y+v" is
-//                just a start address advanced by v*16 bytes in the shared-memory descriptor;
-//   B operand  = for template row v the Toeplitz block B_v[n][k] = T[v][k-n] (32 x (31+tw) bytes), the
-//                same for every 32-column block; all B_v of a template form a table in global memory
-//                (built once per template) and stream through a 4-stage shared-memory ring with
-//                cp.async.bulk (TMA engine) completing on mbarriers;
-//   D          = 128 lanes x 32 columns of TMEM per column block, accumulated over v and the K steps.
-// One elected thread issues the MMAs, one thread feeds the ring, four warps run the epilogue:
-// window sums from vertical sliding sums, float32 filter, OpenCV's double-precision normalisation
-// for the candidates, first-maximum argmax -- the same arithmetic as the IDP.4A engine
-// (lst_ncc_match), so both engines return identical bits.
+// Work item = one tile (128 result rows x up to 4 blocks of 32 result columns) of one window.  One CTA
+// per SM walks the items of a pass (item = blockIdx.x, + gridDim.x, ...) with these roles:
+//
+//   warp 8   window loader   the tile's window rows come in by TMA (cp.async.bulk.tensor.2d, one box of
+//                            16 bytes x rows per 16-byte column chunk) as [chunk][row][16 B]: 8 consecutive
+//                            rows of one chunk are a 128-byte core matrix *for any starting row*, so the A
+//                            operand "rows y+v" is a start address advanced by v*16 bytes in the descriptor;
+//   warp 9   table feeder    for template row v the Toeplitz band B_v = [D_nd-1; ..; D_0], D_d[n][k] =
+//                            T[v][32d + k - n] (32 x 32 bytes each), streams from global memory (L2) through a
+//                            ring with cp.async.bulk completing on mbarriers;
+//   warp 10  MMA issuer      for every 32-byte K step j of the window one MMA covers all the column blocks
+//                            b = j-nd+1 .. j it contributes to (N = 32..128), D = 128 TMEM lanes x 128 columns,
+//                            two accumulator sets so that the MMAs of item i+1 run under the epilogue of item i;
+//   warps 0-7 workers        (a) vertical sliding sums of I and I^2 per window column, straight from the staged
+//                            window, into shared memory ([column][row], what cv::integral gives matchTemplate);
+//                            (b) epilogue: lane = result row walks x, sliding the horizontal sums, float32
+//                            filter score, OpenCV's double-precision normalisation for the candidates only,
+//                            first-maximum argmax; when the window is one tile also the nine scores around
+//                            the peak for the sub-pixel fit (LST4:2681-2717), read back from TMEM.
+//
+// No window sum ever goes through global memory; the same arithmetic as the IDP.4A engine (lst_ncc_match),
+// so both engines return identical bits.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/lst_b200.h"
 #include "lst_device.h"
 
 namespace lst {
 
-#define TC_M 128          // result rows per CTA (TMEM lanes)
-#define TC_NB 32          // result columns per MMA (N)
-#define TC_MAXNB 4        // column blocks per CTA (128 TMEM columns)
-#define TC_STAGES 3
-#define TC_THREADS 160    // warps 0-3 epilogue, warp 4: one thread feeds the ring (TMA) and issues the MMAs; TMEM alloc
+#define TC_M 128          // result rows per tile (TMEM lanes)
+#define TC_NB 32          // result columns per column block
+#define TC_MAXNB 4        // column blocks per tile (128 TMEM columns per accumulator set)
+#define TC_MAXSTAGES 8
+#define TC_WORKERS 256    // warps 0-7
+#define TC_THREADS 352    // + warp 8 window loader, warp 9 table feeder, warp 10 MMA issuer / TMEM owner
 #define TC_EPS 1e-5f
 
-int tc_ksteps(int tw) { return (TC_NB - 1 + tw + 31) / 32; }
-size_t tc_table_bytes(int tw, int th) { return (size_t)th * 2 * tc_ksteps(tw) * TC_NB * 16; }
+int tc_nd(int tw) { return (tw + 31 + 31) / 32; }                       // Toeplitz sub-blocks per template row
+size_t tc_table_bytes(int tw, int th) { return (size_t)th * tc_nd(tw) * 1024; }
 bool tc_supported(int tw, int th) { return tw >= 1 && th >= 1 && tw <= 181 && th <= 181; }   // s32 accumulators
 
+// table[v][kc][n][j] = T[v][32*d + 16*kc + j - nn] for row n = (nd-1-d)*32 + nn, kc < 2, j < 16 (0 outside the template)
 void tc_build_table(const uint8_t *tpl8, int tw, int th, uint8_t *out)
 {
-    const int kc2 = 2 * tc_ksteps(tw);
+    const int nd = tc_nd(tw);
     for (int v = 0; v < th; v++)
-        for (int kc = 0; kc < kc2; kc++)
-            for (int n = 0; n < TC_NB; n++)
+        for (int kc = 0; kc < 2; kc++)
+            for (int n = 0; n < nd * 32; n++)
                 for (int j = 0; j < 16; j++) {
-                    int u = 16 * kc + j - n;
-                    out[(((size_t)v * kc2 + kc) * TC_NB + n) * 16 + j] = (u >= 0 && u < tw) ? tpl8[v * tw + u] : 0;
+                    const int d = nd - 1 - n / 32, nn = n % 32;
+                    const int u = 32 * d + 16 * kc + j - nn;
+                    out[(((size_t)v * 2 + kc) * (nd * 32) + n) * 16 + j] = (u >= 0 && u < tw) ? tpl8[v * tw + u] : 0;
                 }
 }
 
@@ -70,6 +86,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -81,6 +101,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 2-D tiled TMA load: box {16 bytes, rows} of the pass's 8-bit window buffer -> [row][16 B] in shared memory
+__device__ __forceinline__ void tma_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -88,6 +116,7 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory"); }
 
 // shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1):
 // 8 rows x 16 B core matrices; LBO = bytes between the two K halves, SBO = bytes between 8-row groups
@@ -96,7 +125,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, K-major, N = 32, M = 128
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, K-major
 __device__ __forceinline__ uint32_t instr_desc_u8(int m, int n)
 {
     return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -112,111 +141,14 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// ---- window sums for the tensor-core engine ------------------------------------------------------
-// The IDP.4A engine derives the sums of I and I^2 under the template footprint inside its CTAs; the
-// tensor-core engine wants its shared memory for operands and its warps for the epilogue, so the
-// sums are produced once per window by this kernel and read back (L2) by the epilogue.
-// CTA = 32 result rows of one window: vertical sliding sums per column into shared memory, then
-// horizontal sliding sums with one row per lane.
-#define BS_ROWS 32
-
-__global__ void __launch_bounds__(256)
-lst_box_sums(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
-             uint32_t *__restrict__ wsum, uint32_t *__restrict__ wsq, int wp)
-{
-    extern __shared__ __align__(16) uint8_t smem_bs[];
-    const DevTask t = tasks[blockIdx.y];
-    const int tw = tpls->c[t.tpl].tw, th = tpls->c[t.tpl].th;
-    const int y0 = blockIdx.x * BS_ROWS;
-    if (y0 >= t.rh) return;
-    const int nrows = min(BS_ROWS, t.rh - y0);
-    const int trows = nrows + th - 1;
-    uint32_t *P2 = (uint32_t *)smem_bs;                 // [BS_ROWS][wp]  sums of squares, then prefix
-    uint32_t *P1 = P2 + (size_t)BS_ROWS * wp;           // [BS_ROWS][wp]  sums, then prefix
-    uint8_t *tile = (uint8_t *)(P1 + (size_t)BS_ROWS * wp);   // [trows][pitch]
-    const int pitch = t.pitch;
-    {
-        const uint8_t *src = win8 + t.win_off + (size_t)y0 * pitch;
-        const int vec = pitch / 16;
-        for (int i = threadIdx.x; i < trows * vec; i += blockDim.x) {
-            int r = i / vec, c = (i - r * vec) * 16;
-            *(uint4 *)(tile + (size_t)r * pitch + c) = *(const uint4 *)(src + (size_t)r * pitch + c);
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < t.w; c += blockDim.x) {
-        uint32_t s = 0, q = 0;
-        for (int v = 0; v < th; v++) {
-            uint32_t p = tile[(size_t)v * pitch + c];
-            s += p;
-            q += p * p;
-        }
-        P1[c] = s;
-        P2[c] = q;
-        for (int r = 1; r < nrows; r++) {
-            uint32_t a = tile[(size_t)(r + th - 1) * pitch + c], b = tile[(size_t)(r - 1) * pitch + c];
-            s += a - b;
-            q += a * a - b * b;
-            P1[(size_t)r * wp + c] = s;
-            P2[(size_t)r * wp + c] = q;
-        }
-    }
-    __syncthreads();
-    // Horizontal pass: lanes = the rows of the band, each warp a run of result columns.  A lane sums the
-    // first footprint of its run directly (tw loads) and slides from there: out[x+1] = out[x] + V[x+tw] - V[x].
-    // Rows are wp words apart (odd: conflict-free); a warp's store is 32 consecutive words of the
-    // output layout [band of 32 rows][x][row in band] -- the epilogue of lst_ncc_tc owns one row per
-    // lane and walks x, so its loads are 128 bytes per warp as well.
-    {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-        const int per = (t.rw + nwarps - 1) / nwarps;
-        const int x0 = warp * per, x1 = min(x0 + per, t.rw);
-        if (lane < nrows && x0 < x1) {
-            const uint32_t *p1 = P1 + (size_t)lane * wp, *p2 = P2 + (size_t)lane * wp;
-            uint32_t a1 = 0, a2 = 0;
-#pragma unroll 8
-            for (int u = 0; u < tw; u++) {
-                a1 += p1[x0 + u];
-                a2 += p2[x0 + u];
-            }
-            uint32_t *o1 = wsum + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS + lane;
-            uint32_t *o2 = wsq + t.sum_off + (size_t)blockIdx.x * t.rw * BS_ROWS + lane;
-            for (int x = x0;; x++) {
-                o1[(size_t)x * BS_ROWS] = a1;
-                o2[(size_t)x * BS_ROWS] = a2;
-                if (x + 1 >= x1) break;
-                a1 += p1[x + tw] - p1[x];
-                a2 += p2[x + tw] - p2[x];
-            }
-        }
-    }
-}
-
-// The exact (double-precision, OpenCV order) score of one candidate position, out of line: the
-// epilogue visits 32 positions with unrolled code and only a few of them get here, so the long
-// division / square-root sequences must not be replicated 32 times (instruction cache).
-__device__ __noinline__ float tc_exact_score(uint32_t corr, const uint32_t *ws, const uint32_t *wq, const TplConst *tc)
-{
-    const uint32_t s = __ldg(ws), sq = __ldg(wq);
-    return match_score(*tc, (double)corr, (double)s, (double)sq);
-}
-__device__ __forceinline__ unsigned long long tc_exact_key(uint32_t corr, const uint32_t *ws, const uint32_t *wq,
-                                                           const TplConst *tc, uint32_t idx)
-{
-    return pack_key(tc_exact_score(corr, ws, wq, tc), idx, method_wants_min(tc->method));
 }
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
 {
@@ -225,368 +157,587 @@ __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr)
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     return r;
 }
+__device__ __forceinline__ float rsqrt_fast(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t dcol_addr(uint32_t tmem, int acc, int q4, int col)
+{
+    return tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(acc * 128 + col);      // TMEM address: lane << 16 | column
+}
+__device__ __forceinline__ void o_flag(float *nbhd, int task) { nbhd[(size_t)task * 12 + 9] = 1.0f; }
+
+// The exact (double-precision, OpenCV order) score of one candidate position, out of line: the
+// epilogue visits 16 positions with unrolled code and only a few of them get here, so the long
+// division / square-root sequences must not be replicated (instruction cache).
+__device__ __noinline__ float tc_exact_score(uint32_t corr, uint32_t s, uint32_t sq, const TplConst *tc)
+{
+    return match_score(*tc, (double)corr, (double)s, (double)sq);
+}
 
 struct TcParams {
-    int rows_a;       // window rows staged per CTA: TC_M + max_th - 1
-    int kc_a;         // 16-byte column chunks staged per CTA
-    int ks;           // K steps (32 bytes) per column block
-    int nb_per_cta;   // column blocks per CTA
-    int vb;           // template rows (Toeplitz blocks) per ring stage
-    int group;        // column blocks per MMA group: the epilogue of a group overlaps the MMAs of the next
-    unsigned long long *dbg;   // optional: per-CTA phase clocks (LST_TC_DEBUG)
+    int n_items;       // tasks * tiles_x * tiles_y
+    int tiles_x, tiles_y;
+    int nbc;           // column blocks per tile
+    int tile_rows;     // result rows per tile (<= 128; the MMA always computes 128)
+    int rows_alloc;    // window rows of an A buffer: 127 + max_th, rounded up to a multiple of 8
+    int rows_load;     // window rows loaded per tile: tile_rows + max_th - 1
+    int rows_box1;     // rows of the first TMA box (<= 256); a second box takes the rest
+    int kc_a;          // 16-byte column chunks of an A buffer
+    int n_abuf;        // 1 or 2 window buffers
+    int vr;            // row pitch (in elements) of a column of the vertical sums: odd, >= tile_rows
+    int vcols;         // columns of the vertical sums: 32 * nbc + max_tw
+    int stages, vb;    // ring: stages, template rows per stage
+    int stage_bytes;
+    int single_tile;   // every window of the pass is one tile: the kernel also leaves the 3x3 scores around the peak
+    unsigned long long *dbg;   // optional per-CTA phase clocks (LST_TC_DEBUG)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 4)
-lst_ncc_tc(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
-           const uint32_t *__restrict__ wsum, const uint32_t *__restrict__ wsq, unsigned long long *__restrict__ best,
-           float *__restrict__ nbhd, TcParams tp)
+// what every role needs to know about a work item
+struct TcItem {
+    int task, tpl;
+    int x0, y0;        // tile origin in the result map
+    int rw_t, rh_t;    // valid result columns / rows of this tile
+    int nbe;           // column blocks with valid columns
+    int nk;            // 32-byte K steps of the window the tile needs
+    int tw, th, nd;
+    int row_base;      // first row of the window in the pass's window buffer (win_off / pitch)
+    int rw;            // result-map width of the task
+};
+
+// returns 0 = nothing to do for this tile, 1 = match it, 2 = flat template (method 5): the map is all ones
+__device__ __forceinline__ int tc_decode(int item, const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls,
+                                         const TcParams &tp, TcItem *it)
+{
+    const int tpt = tp.tiles_x * tp.tiles_y;
+    const int task = item / tpt, tile = item - task * tpt;
+    const int ty = tile / tp.tiles_x, tx = tile - ty * tp.tiles_x;
+    const DevTask *t = tasks + task;
+    const int rw = t->rw, rh = t->rh, tpl = t->tpl;
+    it->task = task;
+    it->tpl = tpl;
+    it->x0 = tx * tp.nbc * TC_NB;
+    it->y0 = ty * tp.tile_rows;
+    if (it->x0 >= rw || it->y0 >= rh) return 0;
+    const TplConst *c = &tpls->c[tpl];
+    if (c->flat && c->method == 5) return tile == 0 ? 2 : 0;
+    it->tw = c->tw;
+    it->th = c->th;
+    it->nd = (it->tw + 62) >> 5;
+    it->rw = rw;
+    it->rw_t = min(tp.nbc * TC_NB, rw - it->x0);
+    it->rh_t = min(tp.tile_rows, rh - it->y0);
+    it->nbe = (it->rw_t + TC_NB - 1) / TC_NB;
+    it->nk = ((it->rw_t + it->tw - 2) >> 5) + 1;
+    it->row_base = (int)(t->win_off / (uint64_t)t->pitch);
+    return 1;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+           const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, unsigned long long *__restrict__ best,
+           float *__restrict__ nbhd, const TcParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem_tc[];
-    __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_done[TC_MAXNB];
+    __shared__ __align__(8) uint64_t a_full[2], a_free[2], acc_full[2], acc_free[2], r_full[TC_MAXSTAGES], r_empty[TC_MAXSTAGES];
     __shared__ uint32_t s_tmem;
-    __shared__ unsigned long long s_best[4];
-    __shared__ uint32_t s_fmax;    // orderable key of the largest filter score any warp of the CTA has seen so far
+    __shared__ unsigned long long s_best[8];
+    __shared__ uint32_t s_fmax;    // orderable key of the largest filter score any warp has seen in the current item
 
-    const long long clk0 = clock64();
-    const DevTask t = tasks[blockIdx.y];
-    const TplConst tc = tpls->c[t.tpl];
-    const int tw = tc.tw, th = tc.th;
-    const int nb_total = (t.rw + TC_NB - 1) / TC_NB;
-    const int xchunks = (nb_total + tp.nb_per_cta - 1) / tp.nb_per_cta;
-    const int ytiles = (t.rh + TC_M - 1) / TC_M;
-    if ((int)blockIdx.x >= xchunks * ytiles) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (tc.flat && tc.method == 5) {   // templSdv^2 < DBL_EPSILON: OpenCV fills the result with 1 -> first position wins
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&best[blockIdx.y], pack_key(1.0f, 0u));
-        return;
-    }
-    const int xc = blockIdx.x % xchunks, yt = blockIdx.x / xchunks;
-    const int nb0 = xc * tp.nb_per_cta;
-    const int nbc = min(tp.nb_per_cta, nb_total - nb0);     // column blocks of this CTA
-    const int x0 = nb0 * TC_NB, y0 = yt * TC_M;
-    const int ROWS = tp.rows_a, KCA = tp.kc_a, KS = tp.ks;
-    const uint32_t bv_bytes = (uint32_t)(2 * KS * TC_NB * 16);   // one Toeplitz block B_v
-    const int VB = tp.vb;                                        // blocks per ring stage
-    const uint32_t st_bytes = bv_bytes * (uint32_t)VB;
-    const int nsteps = (th + VB - 1) / VB;
+    const size_t a_bytes = (size_t)tp.kc_a * tp.rows_alloc * 16;
+    uint8_t *sA = smem_tc;                                                  // [n_abuf][kc_a][rows_alloc][16]
+    uint8_t *sB = sA + (size_t)tp.n_abuf * a_bytes;                         // [stages][stage_bytes]
+    uint32_t *V2 = (uint32_t *)(sB + (size_t)tp.stages * tp.stage_bytes);   // [vcols + 1][vr]  sums of I^2 over th rows
+    uint16_t *V1 = (uint16_t *)(V2 + (size_t)(tp.vcols + 1) * tp.vr);       // [vcols + 1][vr]  sums of I
 
-    uint8_t *sA = smem_tc;                                          // [KCA][ROWS][16]
-    uint8_t *sB = sA + (size_t)KCA * ROWS * 16;                     // [TC_STAGES][VB][2*KS][32][16]
-
-    // ---- stage the window: rows [y0, y0 + ROWS), byte columns [x0, x0 + 16*KCA), zero filled ----
-    {
-        const uint8_t *src = win8 + t.win_off;
-        const int total = KCA * ROWS;
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int kc = i / ROWS, r = i - kc * ROWS;      // consecutive threads -> consecutive rows: conflict-free stores
-            const int gx = x0 + 16 * kc, gy = y0 + r;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (gy < t.h && gx < t.pitch) v = *(const uint4 *)(src + (size_t)gy * t.pitch + gx);
-            *(uint4 *)(sA + ((size_t)kc * ROWS + r) * 16) = v;
-        }
-        fence_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
-    }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) {
-            mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_free[i], 2);       // the MMAs that read the buffer + the workers' vertical sums
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_free[i], 1);
         }
-        s_fmax = 0u;
-        for (int g = 0; g < TC_MAXNB; g++) mbar_init(&bar_done[g], 1);
+        for (int s = 0; s < TC_MAXSTAGES; s++) {
+            mbar_init(&r_full[s], 1);
+            mbar_init(&r_empty[s], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(128u));
+    if (warp == 10) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const long long clk1 = clock64();
-    long long clk2 = clk1, clk3 = clk1;
 
-    if (warp == 4) {
+    if (warp == 8) {
+        // ---- window loader ----
+        if (lane == 0) {
+            int k = 0;
+            for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
+                TcItem it;
+                if (tc_decode(item, tasks, tpls, tp, &it) != 1) continue;
+                const int buf = tp.n_abuf == 2 ? (k & 1) : 0, u = tp.n_abuf == 2 ? (k >> 1) : k;
+                if (u > 0) mbar_wait(&a_free[buf], (u - 1) & 1);
+                const int nch = 2 * it.nk;                       // chunks this tile needs
+                mbar_expect_tx(&a_full[buf], (uint32_t)(nch * tp.rows_load * 16));
+                uint8_t *dst = sA + (size_t)buf * a_bytes;
+                const int r0 = it.row_base + it.y0;
+                for (int kc = 0; kc < nch; kc++) {
+                    tma_2d(dst + (size_t)kc * tp.rows_alloc * 16, &map1, it.x0 + 16 * kc, r0, &a_full[buf]);
+                    if (tp.rows_load > tp.rows_box1)
+                        tma_2d(dst + ((size_t)kc * tp.rows_alloc + tp.rows_box1) * 16, &map2, it.x0 + 16 * kc, r0 + tp.rows_box1,
+                               &a_full[buf]);
+                }
+                k++;
+            }
+        }
+    } else if (warp == 9) {
+        // ---- Toeplitz table feeder ----
+        if (lane == 0) {
+            int g = 0;
+            for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
+                TcItem it;
+                if (tc_decode(item, tasks, tpls, tp, &it) != 1) continue;
+                const uint8_t *table = tpls->toeplitz[it.tpl];
+                const uint32_t row_bytes = (uint32_t)it.nd * 1024u;
+                for (int v = 0; v < it.th; v += tp.vb, g++) {
+                    const int s = g % tp.stages;
+                    if (g >= tp.stages) mbar_wait(&r_empty[s], ((g / tp.stages) - 1) & 1);
+                    const uint32_t bytes = row_bytes * (uint32_t)min(tp.vb, it.th - v);
+                    mbar_expect_tx(&r_full[s], bytes);
+                    bulk_g2s(sB + (size_t)s * tp.stage_bytes, table + (size_t)v * row_bytes, bytes, &r_full[s]);
+                }
+            }
+        }
+    } else if (warp == 10) {
         // ---- MMA issuer ----
         // One thread issues everything, so the loop body must be a handful of instructions: the
         // descriptors are 64-bit integers whose low field is (address >> 4), advanced by plain adds.
         if (lane == 0) {
-            const uint32_t idesc = instr_desc_u8(TC_M, TC_NB);
-            const uint64_t a_desc0 = smem_desc(smem_u32(sA), (uint32_t)ROWS * 16, 128);
-            const uint64_t b_desc0 = smem_desc(smem_u32(sB), TC_NB * 16, 128);
-            const uint64_t a_kstep = (uint64_t)(2 * ROWS);            // two 16-byte column chunks, in 16-byte units
-            const uint64_t b_kstep = (uint64_t)(2 * TC_NB);
-            const uint64_t b_vstep = (uint64_t)(bv_bytes >> 4), b_sstep = (uint64_t)(st_bytes >> 4);
-            // ring producer and MMA issue in one thread: the copy for step st+1 goes out before the MMAs
-            // of step st; its slot was last read by the MMAs of step st-2 (3 stages), long finished
-            const uint8_t *table = tpls->toeplitz[t.tpl];
-            // The column blocks are worked off in groups of tp.group: all template rows for the blocks of group
-            // g, then the next group (the Toeplitz table streams through the ring once per group), so that the
-            // epilogue warps score group g while the tensor core is busy with group g + 1.
-            const int G = tp.group, ngroups = (nbc + G - 1) / G, total = ngroups * nsteps;
-            auto feed = [&](int gst) {                  // gst = global ring step: group * nsteps + step
-                const int s = gst % TC_STAGES, st = gst % nsteps;
-                const int nv = min(VB, th - st * VB);
-                if (gst >= TC_STAGES) mbar_wait(&bar_empty[s], ((gst / TC_STAGES) - 1) & 1);
-                mbar_expect_tx(&bar_full[s], bv_bytes * (uint32_t)nv);
-                bulk_g2s(sB + (size_t)s * st_bytes, table + (size_t)st * st_bytes, bv_bytes * (uint32_t)nv, &bar_full[s]);
-            };
-            feed(0);
-            int gst = 0;
-            for (int g = 0; g < ngroups; g++) {
-                const int nbg0 = g * G, nbg1 = min(nbc, nbg0 + G);
-                uint32_t acc = 0;
+            const uint32_t idesc0 = instr_desc_u8(TC_M, 0);
+            int k = 0, g = 0;
+            for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
+                TcItem it;
+                if (tc_decode(item, tasks, tpls, tp, &it) != 1) continue;
+                const int buf = tp.n_abuf == 2 ? (k & 1) : 0, ua = tp.n_abuf == 2 ? (k >> 1) : k;
+                const int acc = k & 1, uc = k >> 1;
+                mbar_wait(&a_full[buf], ua & 1);
+                if (uc > 0) mbar_wait(&acc_free[acc], (uc - 1) & 1);
+                tc_fence_after();
+                const uint64_t a_desc0 = smem_desc(smem_u32(sA + (size_t)buf * a_bytes), (uint32_t)tp.rows_alloc * 16, 128);
+                const uint64_t a_kstep = (uint64_t)(2 * tp.rows_alloc);        // two 16-byte column chunks, in 16-byte units
+                const uint32_t b_lbo = (uint32_t)it.nd * 32 * 16;               // the second K half of a band: nd*32 rows further
+                const uint64_t b_vstep = (uint64_t)(it.nd * 64);               // one template row of the table, in 16-byte units
+                const uint32_t dcol = tmem + (uint32_t)(acc * 128);
+                const int nd = it.nd, nbe = it.nbe, nk = it.nk;
                 int v = 0;
-                for (int st = 0; st < nsteps; st++, gst++) {
-                    const int s = gst % TC_STAGES;
-                    const int nv = min(VB, th - st * VB);
-                    if (gst + 1 < total) feed(gst + 1);
-                    mbar_wait(&bar_full[s], (gst / TC_STAGES) & 1);
+                for (; v < it.th; g++) {
+                    const int s = g % tp.stages;
+                    const int nv = min(tp.vb, it.th - v);
+                    mbar_wait(&r_full[s], (g / tp.stages) & 1);
                     tc_fence_after();
-                    uint64_t b_v = b_desc0 + (uint64_t)s * b_sstep;
+                    uint64_t b_v = smem_desc(smem_u32(sB + (size_t)s * tp.stage_bytes), b_lbo, 128);
                     for (int vv = 0; vv < nv; vv++, v++, b_v += b_vstep) {
-                        uint64_t a_nb = a_desc0 + (uint64_t)v + (uint64_t)nbg0 * a_kstep;            // rows v .. v+127
-                        for (int nb = nbg0; nb < nbg1; nb++, a_nb += a_kstep) {
-                            uint64_t a_d = a_nb, b_d = b_v;
-                            const uint32_t d = tmem + (uint32_t)(nb * TC_NB);
-                            mma_i8(d, a_d, b_d, idesc, acc);              // first k-step: overwrites D only for v == 0
-#pragma unroll 1
-                            for (int ks = 1; ks < KS; ks++) {
-                                a_d += a_kstep;
-                                b_d += b_kstep;
-                                mma_i8(d, a_d, b_d, idesc, 1u);
+                        uint64_t a_d = a_desc0 + (uint64_t)v;                  // rows v .. v+127
+                        if (v == 0) {
+                            // first template row: column block j gets its first contribution from K step j and
+                            // must be overwritten, the blocks left of it accumulate
+                            for (int j = 0; j < nk; j++, a_d += a_kstep) {
+                                const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
+                                const uint64_t b_d = b_v + (uint64_t)((nd - 1 - (j - b_lo)) * 32);
+                                const int nold = (b_hi == j ? b_hi : b_hi + 1) - b_lo;    // blocks that already hold a partial sum
+                                if (nold > 0)
+                                    mma_i8(dcol + (uint32_t)(32 * b_lo), a_d, b_d, idesc0 | ((uint32_t)(nold * 4) << 17), 1u);
+                                if (b_hi == j)
+                                    mma_i8(dcol + (uint32_t)(32 * j), a_d, b_d + (uint64_t)(nold * 32), idesc0 | (4u << 17), 0u);
+                            }
+                        } else {
+                            for (int j = 0; j < nk; j++, a_d += a_kstep) {
+                                const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
+                                const uint64_t b_d = b_v + (uint64_t)((nd - 1 - (j - b_lo)) * 32);
+                                mma_i8(dcol + (uint32_t)(32 * b_lo), a_d, b_d, idesc0 | ((uint32_t)((b_hi - b_lo + 1) * 4) << 17), 1u);
                             }
                         }
-                        acc = 1u;
                     }
-                    tc_commit(&bar_empty[s]);     // the ring slot is free once these MMAs have read it
+                    tc_commit(&r_empty[s]);     // the ring slot is free once these MMAs have read it
                 }
-                tc_commit(&bar_done[g]);
+                tc_commit(&a_free[buf]);
+                tc_commit(&acc_full[acc]);
+                k++;
             }
         }
     } else {
-        // ---- epilogue warps: rows 32*warp .. +31 of the tile (TMEM lanes of this warp) ----
-        const int yy = 32 * warp + lane;                  // row of the tile owned by this lane
-        const int y = y0 + yy;
-        const bool row_ok = y < t.rh;
-        const uint32_t N = (uint32_t)(tw * th), tsum = tc.tsum;
-        const long long Nflat = (long long)N + (long long)(N >> 5);
-        // sums of this lane's row: [band][x][row in band] (see lst_box_sums), band = y / 32
-        // (lanes whose row lies below the result map read the task's first row instead: their band may not
-        // exist in the sums buffer, and the last task's would lie beyond the allocation)
-        const size_t rowoff = row_ok ? t.sum_off + (size_t)(y0 / 32 + warp) * t.rw * 32 + lane : t.sum_off;
-        unsigned long long mybest = 0ull;
-        // While the tensor core works, pull this warp's window sums (written by lst_box_sums, long
-        // evicted from L2 by the time they are read) back into L2: one 128-byte line per (array, column).
-        if (y0 + 32 * warp < t.rh) {
-            const int ncols = min(nbc * TC_NB, t.rw - x0);
-            const size_t line0 = t.sum_off + (size_t)(y0 / 32 + warp) * t.rw * 32 + (size_t)x0 * 32;
-            for (int c = lane; c < 2 * ncols; c += 32) {
-                const uint32_t *pf = (c < ncols ? wsum : wsq) + line0 + (size_t)(c < ncols ? c : c - ncols) * 32;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-            }
-        }
-        for (int nb = 0; nb < nbc; nb++) {
-            if (nb % tp.group == 0) {
-                mbar_wait(&bar_done[nb / tp.group], 0);
-                tc_fence_after();
-                if (nb == 0) clk2 = clock64();
-            }
-            uint32_t corr[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(nb * TC_NB), corr);
-            const int xb = x0 + TC_NB * nb;
-            const int np = row_ok ? min(32, t.rw - xb) : 0;
-            const int xs = xb < t.rw ? xb : 0;     // a block right of this (smaller) window's map: stay inside the buffer
-            const uint32_t *ws = wsum + rowoff + (size_t)xs * 32, *wq = wsq + rowoff + (size_t)xs * 32;
-            // pass 1: float32 filter score of the 32 positions of this lane's row (all loads of a half
-            // are issued before they are used), warp-wide maximum.  3e38 marks "nearly flat: always exact".
-            float sf[32];
-            float tmax = -3.0e38f;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t sv[16], qv[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int p = 16 * h + i;
-                    const int pc = p < np ? p : 0;            // clamped: the load is always legal
-                    sv[i] = __ldg(ws + pc * 32);
-                    qv[i] = __ldg(wq + pc * 32);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int p = 16 * h + i;
-                    // 32 x 32 -> 64-bit products (IMAD.WIDE.U32): every factor fits 32 bits
-                    const long long A = (long long)((unsigned long long)N * corr[p]) - (long long)((unsigned long long)sv[i] * tsum);
-                    const long long B = (long long)((unsigned long long)N * qv[i]) - (long long)((unsigned long long)sv[i] * sv[i]);
-                    float f;
-                    if (p >= np) f = -3.0e38f;
-                    else if (2 * B <= Nflat || tc.method != 5) f = 3.0e38f;   // other methods: every position exact
-                    else {
-                        f = (float)A * rsqrtf((float)B) * tc.inv_sqrt_c;
-                        tmax = fmaxf(tmax, f);
+        // ---- workers: vertical sums, then the epilogue of the item ----
+        const int tid = threadIdx.x;
+        const int q4 = warp & 3, hh = warp >> 2;         // TMEM lane quarter (rows 32*q4 ..), column half
+        const int row = 32 * q4 + lane;
+        long long clk_wait = 0, clk_v = 0, clk_e = 0;
+        int k = 0;
+        for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
+            TcItem it;
+            const int kind = tc_decode(item, tasks, tpls, tp, &it);
+            if (kind == 2 && tid == 0) atomicMax(&best[it.task], pack_key(1.0f, 0u));   // templSdv^2 < DBL_EPSILON: all ones, first wins
+            if (kind != 1) continue;
+            const TplConst *tcp = &tpls->c[it.tpl];
+            const int buf = tp.n_abuf == 2 ? (k & 1) : 0, ua = tp.n_abuf == 2 ? (k >> 1) : k;
+            const int acc = k & 1, uc = k >> 1;
+            const int tw = it.tw, th = it.th, VR = tp.vr;
+            const long long c0 = clock64();
+            mbar_wait(&a_full[buf], ua & 1);
+            const long long c1 = clock64();
+            // (a) vertical sliding sums: a thread owns a window column (and a segment of the tile's rows)
+            {
+                const int ncv = it.rw_t + tw - 1;
+                int nseg = TC_WORKERS / ncv;
+                nseg = nseg < 1 ? 1 : (nseg > 4 ? 4 : nseg);
+                if (it.rh_t < 16 * nseg) nseg = 1;
+                const int seg_rows = (it.rh_t + nseg - 1) / nseg;
+                const uint8_t *A = sA + (size_t)buf * a_bytes;
+                for (int w = tid; w < ncv * nseg; w += TC_WORKERS) {
+                    const int sg = w / ncv, c = w - sg * ncv;
+                    const int r0 = sg * seg_rows, r1 = min(r0 + seg_rows, it.rh_t);
+                    const uint8_t *p = A + ((size_t)(c >> 4) * tp.rows_alloc) * 16 + (c & 15);
+                    uint32_t s = 0, q = 0;
+                    const uint8_t *pv = p + (size_t)r0 * 16;
+#pragma unroll 4
+                    for (int v = 0; v < th; v++) {
+                        const uint32_t px = pv[v * 16];
+                        s += px;
+                        q += px * px;
                     }
-                    sf[p] = f;
+                    uint16_t *o1 = V1 + (size_t)c * VR;
+                    uint32_t *o2 = V2 + (size_t)c * VR;
+                    if (r0 < r1) {
+                        o1[r0] = (uint16_t)s;
+                        o2[r0] = q;
+                    }
+                    const uint8_t *pn = p + (size_t)(r0 + th) * 16, *po = p + (size_t)r0 * 16;
+#pragma unroll 4
+                    for (int r = r0 + 1; r < r1; r++, pn += 16, po += 16) {
+                        const int a = *pn, b = *po;
+                        const int d = a - b, sm = a + b;
+                        s += (uint32_t)d;
+                        q += (uint32_t)(d * sm);
+                        o1[r] = (uint16_t)s;
+                        o2[r] = q;
+                    }
                 }
             }
+            if (tid == 0) s_fmax = 0u;
+            worker_bar();
+            if (tid == 0) mbar_arrive(&a_free[buf]);
+            const long long c2 = clock64();
+            mbar_wait(&acc_full[acc], uc & 1);
+            tc_fence_after();
+            const long long c3 = clock64();
+            // (b) epilogue: rows 32*q4 .. +31 (TMEM lanes of this warp), column blocks of this warp's half
+            const bool row_ok = row < it.rh_t;
+            const int vrow = row_ok ? row : 0;
+            const int y = it.y0 + row;
+            const uint32_t N = (uint32_t)(tw * th);
+            const int ntsum = -(int)tcp->tsum;
+            const long long Nflat = (long long)N + (long long)(N >> 5);
+            const int method = tcp->method;
+            const bool want_min = method_wants_min(method);
+            const float eps_g = method == 5 ? TC_EPS / tcp->inv_sqrt_c : 0.0f;   // the filter compares A / sqrt(B); score = that * inv_sqrt_c
+            const int nbh = (it.nbe + 1) >> 1;
+            const int nb0 = hh == 0 ? 0 : nbh, nb1 = hh == 0 ? nbh : it.nbe;
+            unsigned long long mybest = 0ull;
+            if (nb0 < nb1) {
+                const uint16_t *v1 = V1 + vrow;
+                const uint32_t *v2 = V2 + vrow;
+                // horizontal sums under the template footprint at the first column of this warp's range
+                uint32_t S = 0, Q = 0;
+                {
+                    const int xs = TC_NB * nb0;
+#pragma unroll 4
+                    for (int u = 0; u < tw; u++) {
+                        S += v1[(size_t)(xs + u) * VR];
+                        Q += v2[(size_t)(xs + u) * VR];
+                    }
+                }
+                const uint32_t rowidx = (uint32_t)y * (uint32_t)it.rw + (uint32_t)it.x0;
+#pragma unroll 1
+                for (int nb = nb0; nb < nb1; nb++) {
+#pragma unroll 1
+                    for (int h = 0; h < 2; h++) {
+                        const int xb = TC_NB * nb + 16 * h;            // tile column of position 0 of this half block
+                        uint32_t corr[16];
+                        tmem_ld16(dcol_addr(tmem, acc, q4, xb), corr);
+                        const int np = row_ok ? min(16, it.rw_t - xb) : 0;
+                        uint32_t Sx[16], Qx[16];
+                        float g[16];
+                        float tmax = -3.0e38f;
+                        const uint16_t *p1 = v1 + (size_t)xb * VR;
+                        const uint32_t *p2 = v2 + (size_t)xb * VR;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-            // pass 2: OpenCV's double-precision score for the candidates only.  A candidate must come within
-            // TC_EPS of the largest filter score seen anywhere in the CTA so far (every position within TC_EPS
-            // of the final maximum passes this, whenever it is visited), not just of this block's.
-            const uint32_t rowidx = (uint32_t)y * (uint32_t)t.rw;
-            if (lane == 0 && tmax > -3.0e38f) atomicMax(&s_fmax, f32_key(tmax));
-            __syncwarp();
-            const float thr = fmaxf(tmax, key_f32(*(volatile uint32_t *)&s_fmax)) - TC_EPS;
+                        for (int i = 0; i < 16; i++) {
+                            Sx[i] = S;
+                            Qx[i] = Q;
+                            // 32 x 32 -> 64-bit products (IMAD.WIDE): every factor fits 31 bits
+                            const long long A = (long long)(int)N * (long long)(int)corr[i] + (long long)(int)S * (long long)ntsum;
+                            const long long B = (long long)((unsigned long long)N * Q) - (long long)((unsigned long long)S * S);
+                            float f;
+                            if (i >= np) f = -3.0e38f;
+                            else if (2 * B <= Nflat || method != 5) f = 3.0e38f;   // nearly flat window, other methods: always exact
+                            else {
+                                f = (float)A * rsqrt_fast((float)B);
+                                tmax = fmaxf(tmax, f);
+                            }
+                            g[i] = f;
+                            S += (uint32_t)p1[(size_t)(i + tw) * VR] - (uint32_t)p1[(size_t)i * VR];
+                            Q += p2[(size_t)(i + tw) * VR] - p2[(size_t)i * VR];
+                        }
 #pragma unroll
-            for (int p = 0; p < 32; p++) {
-                if (sf[p] >= thr && p < np) {
-                    const unsigned long long key =
-                        tc_exact_key(corr[p], ws + p * 32, wq + p * 32, &tpls->c[t.tpl], rowidx + (uint32_t)(xb + p));
-                    mybest = key > mybest ? key : mybest;
+                        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+                        // OpenCV's double-precision score for the candidates only.  A candidate must come within
+                        // eps of the largest filter score seen anywhere in the tile so far (every position within eps
+                        // of the final maximum passes this, whenever it is visited), not just of this block's.
+                        if (lane == 0 && tmax > -3.0e38f) atomicMax(&s_fmax, f32_key(tmax));
+                        __syncwarp();
+                        const float thr = fmaxf(tmax, key_f32(*(volatile uint32_t *)&s_fmax)) - eps_g;
+                        float lmax = g[0];
+#pragma unroll
+                        for (int i = 1; i < 16; i++) lmax = fmaxf(lmax, g[i]);
+                        if (lmax >= thr) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                if (g[i] >= thr && i < np) {
+                                    const float sc = tc_exact_score(corr[i], Sx[i], Qx[i], tcp);
+                                    const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(xb + i), want_min);
+                                    mybest = key > mybest ? key : mybest;
+                                }
+                            }
+                        }
+                    }
                 }
             }
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);
+                mybest = other > mybest ? other : mybest;
+            }
+            if (lane == 0) s_best[warp] = mybest;
+            worker_bar();
+            unsigned long long b = s_best[0];
+#pragma unroll
+            for (int w = 1; w < 8; w++) b = s_best[w] > b ? s_best[w] : b;
+            if (tp.single_tile) {
+                // The window is this tile alone, so b is its final argmax and the 3x3 neighbourhood the sub-pixel
+                // fit needs (LST4:2681-2717) is still in TMEM: the lanes that own rows by-1..by+1 score the three
+                // columns bx-1..bx+1 exactly, and lst_epilogue does not have to recompute nine correlations.
+                if (tid == 0) best[it.task] = b;
+                if (hh == 0 && nbhd) {
+                    const uint32_t idx = 0xffffffffu - (uint32_t)(b & 0xffffffffull);
+                    const int by = (int)(idx / (uint32_t)it.rw), bx = (int)(idx - (uint32_t)by * (uint32_t)it.rw);
+                    const int dyi = row - by;
+                    if (by + 1 >= 32 * q4 && by - 1 < 32 * q4 + 32) {       // warp-uniform: this quarter holds one of the rows
+                        float *o = nbhd + (size_t)it.task * 12;
+                        for (int dxi = -1; dxi <= 1; dxi++) {
+                            const int x = bx + dxi;
+                            if (x < 0 || x >= it.rw) continue;
+                            const uint32_t cv = tmem_ld1(dcol_addr(tmem, acc, q4, x));
+                            uint32_t S = 0, Q = 0;
+                            for (int u = 0; u < tw; u++) {
+                                S += V1[(size_t)(x + u) * VR + vrow];
+                                Q += V2[(size_t)(x + u) * VR + vrow];
+                            }
+                            if (dyi >= -1 && dyi <= 1 && row_ok) o[(dyi + 1) * 3 + (dxi + 1)] = tc_exact_score(cv, S, Q, tcp);
+                        }
+                    }
+                    if (tid == 0) o_flag(nbhd, it.task);
+                }
+            } else if (tid == 0) {
+                atomicMax(&best[it.task], b);
+            }
+            tc_fence_before();
+            worker_bar();
+            if (tid == 0) mbar_arrive(&acc_free[acc]);
+            const long long c4 = clock64();
+            clk_wait += (c1 - c0) + (c3 - c2);
+            clk_v += c2 - c1;
+            clk_e += c4 - c3;
+            k++;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);
-            mybest = other > mybest ? other : mybest;
-        }
-        if (lane == 0) s_best[warp] = mybest;
-        clk3 = clock64();
-        if (tp.dbg && threadIdx.x == 0 && blockIdx.y < 4096) {
-            unsigned long long *d = tp.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 4;
-            d[0] = (unsigned long long)(clk1 - clk0);
-            d[1] = (unsigned long long)(clk2 - clk1);
-            d[2] = (unsigned long long)(clk3 - clk2);
-            d[3] = (unsigned long long)clk0;
+        if (tp.dbg && tid == 0) {
+            unsigned long long *d = tp.dbg + (size_t)blockIdx.x * 4;
+            d[0] = (unsigned long long)clk_wait;
+            d[1] = (unsigned long long)clk_v;
+            d[2] = (unsigned long long)clk_e;
+            d[3] = (unsigned long long)k;
         }
     }
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
-    unsigned long long b = s_best[0];
-    for (int w = 1; w < 4; w++) b = s_best[w] > b ? s_best[w] : b;
-    if (threadIdx.x == 0) atomicMax(&best[blockIdx.y], b);
-    if (nbhd && gridDim.x == 1) {
-        // The window is this CTA's alone, so b is its final argmax and the 3x3 neighbourhood the sub-pixel
-        // fit needs (LST4:2681-2717) is still in TMEM: the lanes that own rows by-1..by+1 score the three
-        // columns bx-1..bx+1 exactly, and lst_epilogue does not have to recompute nine correlations.
-        if (warp < 4) {
-            tc_fence_after();
-            const uint32_t idx = 0xffffffffu - (uint32_t)(b & 0xffffffffull);
-            const int by = (int)(idx / (uint32_t)t.rw), bx = (int)(idx - (uint32_t)by * (uint32_t)t.rw);
-            const int y = 32 * warp + lane, dyi = y - by;
-            const size_t rowoff = t.sum_off + (size_t)warp * t.rw * 32 + lane;
-            float *o = nbhd + (size_t)blockIdx.y * 12;
-            for (int dxi = -1; dxi <= 1; dxi++) {
-                const int x = bx + dxi;
-                if (x < 0 || x >= t.rw) continue;
-                const uint32_t cv = tmem_ld1(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)x);
-                if (dyi >= -1 && dyi <= 1 && y < t.rh)
-                    o[(dyi + 1) * 3 + (dxi + 1)] = tc_exact_score(cv, wsum + rowoff + (size_t)x * 32, wsq + rowoff + (size_t)x * 32,
-                                                                  &tpls->c[t.tpl]);
-            }
-            if (threadIdx.x == 0) o[9] = 1.0f;
-        }
-        tc_fence_before();
-        __syncthreads();
-    }
-    if (warp == 4) {
+    if (warp == 10) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
     }
 }
 
-static size_t tc_smem(int tw, int th, TcParams *tp, int max_rw)
+// ---- host side: tile plan, tensor maps, launch -----------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
 {
-    const int nb_total = (max_rw + TC_NB - 1) / TC_NB;
-    tp->nb_per_cta = nb_total < TC_MAXNB ? nb_total : TC_MAXNB;
-    tp->ks = tc_ksteps(tw);
-    tp->rows_a = TC_M + th - 1;
-    tp->kc_a = 2 * (tp->nb_per_cta - 1) + 2 * tp->ks;
-    const size_t bv = (size_t)2 * tp->ks * TC_NB * 16;
-    static const int group_env = [] {
-        const char *e = getenv("LST_TC_GROUP");
-        return e ? atoi(e) : 0;
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return (EncodeTiledFn)p;
     }();
-    tp->group = group_env > 0 ? group_env : 2;
-    if (tp->group > tp->nb_per_cta) tp->group = tp->nb_per_cta;
-    tp->vb = (int)(6144 / bv);                        // ~6 KB per ring stage: 3 stages + the window stay under 56 KB
-    if (tp->vb < 1) tp->vb = 1;
-    if (tp->vb > th) tp->vb = th;
-    return (size_t)tp->kc_a * tp->rows_a * 16 + (size_t)TC_STAGES * tp->vb * bv + 64;
+    return fn;
 }
+
+// The pass's 8-bit windows as one 2-D byte image [total_rows][pitch]; box = {16 bytes, rows}.
+static bool make_window_map(CUtensorMap *map, const uint8_t *win8, int pitch, long long total_rows, int box_rows)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)total_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)win8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static const size_t kTcSmemMax = 227 * 1024 - 2048;    // dynamic part; the static barriers and the 128-byte alignment take the rest
+
+// Picks the tile shape and the shared-memory split for a pass; returns the dynamic shared-memory size, 0 = does not fit.
+static size_t tc_plan(int max_rw, int max_rh, int tw, int th, TcParams *tp)
+{
+    static const int env_nbc = [] { const char *e = getenv("LST_TC_NBC"); return e ? atoi(e) : 0; }();
+    static const int env_abuf = [] { const char *e = getenv("LST_TC_ABUF"); return e ? atoi(e) : 0; }();
+    const int nd = tc_nd(tw);
+    const int nb_total = (max_rw + TC_NB - 1) / TC_NB;
+    tp->tile_rows = max_rh < TC_M ? max_rh : TC_M;
+    tp->rows_alloc = (TC_M - 1 + th + 7) & ~7;     // chunk columns start 128-byte aligned (TMA destination)
+    tp->rows_load = tp->tile_rows + th - 1;
+    tp->rows_box1 = tp->rows_load < 256 ? tp->rows_load : 256;
+    tp->vr = tp->tile_rows | 1;
+    const size_t row_bytes = (size_t)nd * 1024;
+    for (int nbc = nb_total < TC_MAXNB ? nb_total : TC_MAXNB; nbc >= 1; nbc = nbc > 2 ? 2 : nbc - 1) {
+        if (env_nbc > 0 && nbc > env_nbc) continue;
+        for (int nab = 2; nab >= 1; nab--) {
+            if (env_abuf > 0 && nab > env_abuf) continue;
+            const int nk = nbc + nd - 1;
+            tp->nbc = nbc;
+            tp->kc_a = 2 * nk;
+            tp->n_abuf = nab;
+            tp->vcols = TC_NB * nbc + tw;
+            const size_t a = (size_t)tp->kc_a * tp->rows_alloc * 16 * nab;
+            const size_t v = (size_t)(tp->vcols + 1) * tp->vr * 6 + 16;
+            if (a + v + 2 * row_bytes > kTcSmemMax) continue;
+            // ring: template rows per stage ~6 KB, as many stages as fit (the table streams from L2: ~1 us of latency to cover)
+            int vb = (int)(6144 / row_bytes);
+            if (vb < 1) vb = 1;
+            if (vb > th) vb = th;
+            int stages = (int)((kTcSmemMax - a - v) / (vb * row_bytes));
+            if (stages < 2) {
+                vb = 1;
+                stages = (int)((kTcSmemMax - a - v) / row_bytes);
+            }
+            if (stages > TC_MAXSTAGES) stages = TC_MAXSTAGES;
+            if (stages < 2) continue;
+            tp->vb = vb;
+            tp->stages = stages;
+            tp->stage_bytes = (int)(vb * row_bytes);
+            return a + (size_t)stages * tp->stage_bytes + v;
+        }
+    }
+    return 0;
+}
+
+static std::mutex g_tc_mutex;
+struct TcDeviceState {
+    int sms = 0;
+    bool attr_ok = false;
+    unsigned long long *dbg = nullptr;
+};
+static TcDeviceState g_tc_dev[64];
+static int g_tc_debug = -1;
 
 void tc_init_device()
 {
-    cudaError_t e = cudaFuncSetAttribute(lst_ncc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_tc_mutex);
+    if (g_tc_debug < 0) g_tc_debug = getenv("LST_TC_DEBUG") ? 1 : 0;
+    if (dev < 0 || dev >= 64) return;
+    TcDeviceState &d = g_tc_dev[dev];
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(lst_ncc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemMax);
     if (e != cudaSuccess) fprintf(stderr, "lst_ncc_tc: MaxDynamicSharedMemorySize: %s\n", cudaGetErrorString(e));
-    cudaFuncSetAttribute(lst_ncc_tc, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(lst_box_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
-    cudaFuncSetAttribute(lst_box_sums, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    d.attr_ok = e == cudaSuccess;
+    e = cudaFuncSetAttribute(lst_ncc_tc, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) fprintf(stderr, "lst_ncc_tc: PreferredSharedMemoryCarveout: %s\n", cudaGetErrorString(e));
+    if (g_tc_debug && !d.dbg) cudaMalloc((void **)&d.dbg, 1024 * 4 * sizeof(unsigned long long));
     cudaGetLastError();
 }
 
-int launch_box_sums(const DevTask *tasks, int n_tasks, int max_w, int max_rh, int th, const DevTemplates *tpls,
-                    const uint8_t *win8, uint32_t *wsum, uint32_t *wsq, cudaStream_t stream)
+// All windows of the pass lie in win8 with the same row pitch, window k at row win_off / pitch (run_group lays them
+// out so); total_rows = rows of the whole buffer.  Returns the number of kernels launched, < 0 = not applicable.
+int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th, int pitch, long long total_rows,
+                  const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *nbhd, cudaStream_t stream)
 {
-    const int wp = ((max_w + 15) & ~15) | 1;
-    const size_t bs_smem = (size_t)2 * BS_ROWS * wp * 4 + (size_t)(BS_ROWS + th - 1) * ((max_w + 15) & ~15) + 16;
-    if (bs_smem > 226 * 1024) return -1;
-    int launches = 0;
-    for (int base = 0; base < n_tasks; base += 65535) {
-        int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
-        dim3 bgrid((max_rh + BS_ROWS - 1) / BS_ROWS, n);
-        lst_box_sums<<<bgrid, 256, bs_smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, wp);
-        launches++;
-    }
-    return launches;
-}
-
-int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
-                  const DevTemplates *tpls, const uint8_t *win8, const uint32_t *wsum, const uint32_t *wsq,
-                  unsigned long long *best, float *nbhd, cudaStream_t stream)
-{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !g_tc_dev[dev].attr_ok) return -1;
+    const TcDeviceState &ds = g_tc_dev[dev];
     TcParams tp;
-    size_t smem = tc_smem(tw, th, &tp, max_rw);
-    if (smem > 226 * 1024) return -1;
-    static unsigned long long *dbg = nullptr;
-    static int dbg_on = -1;
-    if (dbg_on < 0) {
-        dbg_on = getenv("LST_TC_DEBUG") ? 1 : 0;
-        if (dbg_on) cudaMalloc((void **)&dbg, 4096 * 16 * 4 * sizeof(unsigned long long));
+    memset(&tp, 0, sizeof(tp));
+    const size_t smem = tc_plan(max_rw, max_rh, tw, th, &tp);
+    if (smem == 0) return -1;
+    tp.tiles_x = ((max_rw + TC_NB - 1) / TC_NB + tp.nbc - 1) / tp.nbc;
+    tp.tiles_y = (max_rh + tp.tile_rows - 1) / tp.tile_rows;
+    tp.single_tile = tp.tiles_x * tp.tiles_y == 1 ? 1 : 0;
+    const long long items = (long long)n_tasks * tp.tiles_x * tp.tiles_y;
+    if (items > 0x7fffffffLL) return -1;
+    tp.n_items = (int)items;
+    tp.dbg = g_tc_debug ? ds.dbg : nullptr;
+    CUtensorMap map1, map2;
+    if (!make_window_map(&map1, win8, pitch, total_rows, tp.rows_box1)) return -1;
+    const int rows2 = tp.rows_load - tp.rows_box1;
+    if (!make_window_map(&map2, win8, pitch, total_rows, rows2 > 0 ? rows2 : 1)) return -1;
+    const int grid = (int)(items < ds.sms ? items : ds.sms);
+    if (grid < 1) return 0;
+    if (tp.dbg) cudaMemsetAsync(tp.dbg, 0, (size_t)grid * 32, stream);
+    lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(map1, map2, tasks, tpls, best, nbhd, tp);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "lst_ncc_tc launch failed: %s (grid %d, smem %zu)\n", cudaGetErrorString(e), grid, smem);
+        return -1;
     }
-    tp.dbg = dbg_on ? dbg : nullptr;
-    const int nb_total = (max_rw + TC_NB - 1) / TC_NB;
-    const int xchunks = (nb_total + tp.nb_per_cta - 1) / tp.nb_per_cta;
-    const int ytiles = (max_rh + TC_M - 1) / TC_M;
-    int launches = 0;
-    for (int base = 0; base < n_tasks; base += 65535) {
-        int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
-        dim3 grid(xchunks * ytiles, n);
-        lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(tasks + base, tpls, win8, wsum, wsq, best + base,
-                                                       nbhd ? nbhd + (size_t)base * 12 : nullptr, tp);
-        cudaError_t e = cudaPeekAtLastError();
-        if (e != cudaSuccess)
-            fprintf(stderr, "lst_ncc_tc launch failed: %s (grid %d x %d, smem %zu)\n", cudaGetErrorString(e), grid.x, grid.y, smem);
-        launches++;
-    }
-    if (dbg_on && n_tasks >= 1024) {
+    if (tp.dbg && n_tasks >= 1024) {
         cudaStreamSynchronize(stream);
-        const int ncta = xchunks * ytiles * (n_tasks < 4096 ? n_tasks : 4096);
-        unsigned long long *h = (unsigned long long *)malloc((size_t)ncta * 32);
-        cudaMemcpy(h, dbg, (size_t)ncta * 32, cudaMemcpyDeviceToHost);
-        double a = 0, b = 0, c = 0;
-        for (int i = 0; i < ncta; i++) {
+        unsigned long long h[1024 * 4];
+        cudaMemcpy(h, tp.dbg, (size_t)grid * 32, cudaMemcpyDeviceToHost);
+        double a = 0, b = 0, c = 0, k = 0;
+        for (int i = 0; i < grid; i++) {
             a += (double)h[4 * i];
             b += (double)h[4 * i + 1];
             c += (double)h[4 * i + 2];
+            k += (double)h[4 * i + 3];
         }
-        fprintf(stderr, "lst_ncc_tc phases (cycles, mean over %d CTAs): stage %.0f  mma-wait %.0f  epilogue %.0f  smem %zu\n", ncta,
-                a / ncta, b / ncta, c / ncta, smem);
-        free(h);
+        fprintf(stderr,
+                "lst_ncc_tc workers (cycles per item, mean over %d CTAs, %.0f items): wait %.0f  vertical sums %.0f  epilogue %.0f | "
+                "nbc %d abuf %d stages %d x %d B smem %zu\n",
+                grid, k, a / k, b / k, c / k, tp.nbc, tp.n_abuf, tp.stages, tp.stage_bytes, smem);
     }
-    return launches;
+    return 1;
 }
-
 
 // ---- int8 tensor-core peak (roofline denominator of lst_ncc_tc) ------------------------------------
 // One CTA per SM issues `iters` x 2 tcgen05.mma kind::i8 of M128 N256 K32 from (uninitialised) shared

@@ -32,7 +32,7 @@ static double now_ms()
 
 struct TimedLaunch {
     cudaEvent_t e0, e1;            // around the match kernel
-    cudaEvent_t ea, eb, ec;        // before lst_preprocess, before lst_box_sums (or the match kernel), after lst_epilogue
+    cudaEvent_t ea, eb, ec;        // before lst_preprocess, before the match kernel, after lst_epilogue
     double macs;
 };
 
@@ -67,8 +67,6 @@ struct lst_ctx : public Executor {
     size_t win8_cap = 0;
     float *d_map = nullptr;
     size_t map_cap = 0;
-    uint32_t *d_wsum = nullptr, *d_wsq = nullptr;   // tensor-core engine: window sums per result position
-    size_t sum_cap = 0;
     // surface table (where each task's pixels live) + slice ring (whole-slice ingest)
     int frame_cap = 0;
     Surface *d_surf = nullptr, *h_surf = nullptr;
@@ -317,6 +315,16 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         for (int k = 0; k < kMaxTpl; k++) cnt[k + 1] += cnt[k];
         for (int i = 0; i < n; i++) order[cnt[std::min(std::max(tasks[i].tpl, 0), kMaxTpl - 1)]++] = i;
     }
+    // The tensor-core engine reads the 8-bit windows by TMA as one 2-D byte image: every window of the pass gets
+    // the same row pitch (the widest window's) and starts at a multiple of it.
+    const bool tc_layout = ncc_engine == 1 && !preprocess_only && !map_out_host;
+    int pass_pitch = 0;
+    if (tc_layout)
+        for (int i = 0; i < n; i++) {
+            const lst_task &t = tasks[i];
+            Rect c = have_win8 ? Rect{0, 0, t.ww, t.wh} : clip_rect(t.wx, t.wy, t.ww, t.wh, p.width, p.height);
+            pass_pitch = std::max(pass_pitch, (c.w + 15) & ~15);
+        }
     for (int i = 0; i < n; i++) {
         const lst_task &t = tasks[order[i]];
         DevTask &d = h_tasks[i];
@@ -341,7 +349,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         d.y0 = c.y;
         d.w = c.w;
         d.h = c.h;
-        d.pitch = (c.w + 15) & ~15;
+        d.pitch = tc_layout ? pass_pitch : (c.w + 15) & ~15;
         d.s_used = t.s_used;
         if (c.w < 2 * kBlurRadius || c.h < 2 * kBlurRadius)
             if (!have_win8) return fail(LST_ERR_UNSUPPORTED, "window %dx%d smaller than the blur support", c.w, c.h);
@@ -358,8 +366,8 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         }
         d.win_off = win_off;
         d.sum_off = sum_off;
-        win_off += ((size_t)d.pitch * d.h + 255) & ~(size_t)255;
-        sum_off += (size_t)d.rw * (((size_t)d.rh + 31) & ~(size_t)31);   // banded layout of the window sums pads rows to 32
+        win_off += tc_layout ? (size_t)d.pitch * d.h : (((size_t)d.pitch * d.h + 255) & ~(size_t)255);
+        sum_off += (size_t)d.rw * d.rh;
         max_w = std::max(max_w, d.w);
         max_h = std::max(max_h, d.h);
     }
@@ -405,25 +413,13 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             CU(cudaEventRecord(tl.eb, s_compute));
             CU(cudaEventRecord(tl.e0, s_compute));
         }
-        bool use_tc = ncc_engine == 1 && !map_out_host && tc_supported(max_tw, max_th);
+        bool use_tc = tc_layout && tc_supported(max_tw, max_th);
         if (use_tc)
             for (int i = 0; i < n && use_tc; i++) use_tc = h_tpls.toeplitz[h_tasks[i].tpl] != nullptr;
-        if (use_tc && sum_off + 32 > sum_cap) {
-            CU(cudaStreamSynchronize(s_compute));
-            size_t cap = std::max(sum_off + 32, sum_cap + sum_cap / 2);
-            CU(regrow(&d_wsum, cap));
-            CU(regrow(&d_wsq, cap));
-            sum_cap = cap;
-        }
         int tcl = -1;
-        if (use_tc) {
-            int bl = launch_box_sums(d_tasks, n, max_w, max_rh, max_th, d_tpls, d_win8, d_wsum, d_wsq, s_compute);
-            if (bl >= 0) {
-                launches += bl;
-                if (timed_pass) CU(cudaEventRecord(tl.e0, s_compute));   // time the match kernel alone
-                tcl = launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_wsum, d_wsq, d_best, d_nbhd, s_compute);
-            }
-        }
+        if (use_tc)
+            tcl = launch_ncc_tc(d_tasks, n, max_rw, max_rh, max_tw, max_th, pass_pitch, (long long)(win_off / (size_t)pass_pitch), d_tpls,
+                                d_win8, d_best, d_nbhd, s_compute);
         if (use_tc && tcl < 0) {
             static bool warned = false;
             if (!warned) fprintf(stderr, "lst_b200: tensor-core match engine not applicable to this window/template size; using IDP.4A\n");
@@ -483,7 +479,7 @@ int lst_ctx::compute(const lst_task *tasks, int n, lst_task_result *results)
         while (j < n) {
             const lst_task &t = tasks[j];
             size_t pitch = (t.ww + 15) & ~15;
-            size_t need = pitch * t.wh + 256 + (ncc_engine == 1 ? 2 * sizeof(uint32_t) * ((size_t)t.ww * t.wh + 32) : 0);
+            size_t need = pitch * t.wh + 256;
             if (j > i && bytes + need > scratch_limit) break;
             bytes += need;
             j++;
@@ -638,8 +634,6 @@ void lst_destroy(lst_ctx *c)
     cudaFree(c->d_results);
     cudaFree(c->d_win8);
     cudaFree(c->d_map);
-    cudaFree(c->d_wsum);
-    cudaFree(c->d_wsq);
     cudaFree(c->d_surf);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_roi[i]);
