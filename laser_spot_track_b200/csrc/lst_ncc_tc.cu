@@ -44,9 +44,17 @@ namespace lst {
 #define TC_NB 32          // result columns per column block
 #define TC_MAXNB 4        // column blocks per tile (128 TMEM columns per accumulator set)
 #define TC_MAXSTAGES 8
+#define TC_MAXK 10        // K steps of a tile: nbc + nd - 1 <= 4 + 7 - 1
 #define TC_WORKERS 256    // warps 0-7
-#define TC_THREADS 352    // + warp 8 window loader, warp 9 table feeder, warp 10 MMA issuer / TMEM owner
+#ifndef TC_NISS
+#define TC_NISS 2
+#endif
+#define TC_NISS_DOC         // MMA issuer warps: they share the template rows of every ring stage
+#define TC_THREADS (320 + 32 * TC_NISS)   // + warp 8 window loader, warp 9 table feeder, warps 10.. MMA issuers (warp 10 owns the TMEM allocation)
 #define TC_EPS 1e-5f
+#ifndef TC_CVT
+#define TC_CVT 0
+#endif
 
 int tc_nd(int tw) { return (tw + 31 + 31) / 32; }                       // Toeplitz sub-blocks per template row
 size_t tc_table_bytes(int tw, int th) { return (size_t)th * tc_nd(tw) * 1024; }
@@ -141,6 +149,86 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
+// The MMA warp runs its loops convergent (all 32 lanes, uniform values -> uniform registers, no R2UR / waterfall
+// loop per MMA); only the instruction itself is predicated on the elected lane.
+__device__ __forceinline__ void mma_i8_pred(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t leader)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pred(uint64_t *bar, uint32_t leader)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred;
+}
+// int64 -> float32 without I2F.S64 (a slow conversion-unit instruction): |v| as two 32-bit halves through the
+// pipelined 32-bit conversions; relative error <= 2^-23
+__device__ __forceinline__ float i64_to_f32(long long v)
+{
+#if TC_CVT == 0
+    return (float)v;
+#elif TC_CVT == 1
+    const long long sgn = v >> 63;
+    const unsigned long long a = (unsigned long long)((v ^ sgn) - sgn);
+    const float f = (float)(uint32_t)(a >> 32) * 4294967296.0f + (float)(uint32_t)a;
+    return __uint_as_float(__float_as_uint(f) | ((uint32_t)(sgn) & 0x80000000u));
+#else
+    return (float)(int)(v >> 32) * 4294967296.0f + (float)(uint32_t)v;
+#endif
+}
+__device__ __forceinline__ float u64_to_f32(unsigned long long a)
+{
+#if TC_CVT == 0
+    return (float)(long long)a;
+#else
+    return (float)(uint32_t)(a >> 32) * 4294967296.0f + (float)(uint32_t)a;
+#endif
+}
+// waits of the two feeder threads: they have the highest warp ids of their schedulers, which the arbiter
+// prefers -- a hot spin would take issue slots from the workers, so they sleep between polls
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 {
     asm volatile(
@@ -188,12 +276,14 @@ struct TcParams {
     int rows_box1;     // rows of the first TMA box (<= 256); a second box takes the rest
     int kc_a;          // 16-byte column chunks of an A buffer
     int n_abuf;        // 1 or 2 window buffers
-    int vr;            // row pitch (in elements) of a column of the vertical sums: odd, >= tile_rows
     int vcols;         // columns of the vertical sums: 32 * nbc + max_tw
+    int p1, p2;        // row pitches of the vertical sums V1 (u16 elements) / V2 (u32 elements): rows 16-byte aligned,
+                       // pitch in words = 4 mod 8, so that 32 lanes owning 32 rows load 128-bit words conflict-free
     int stages, vb;    // ring: stages, template rows per stage
     int stage_bytes;
     int single_tile;   // every window of the pass is one tile: the kernel also leaves the 3x3 scores around the peak
     unsigned long long *dbg;   // optional per-CTA phase clocks (LST_TC_DEBUG)
+    int mode;          // experiments (LST_TC_MODE): 1 = workers skip their work, 2 = no MMAs issued, 4 = workers skip the vertical sums, 8 = skip the epilogue
 };
 
 // what every role needs to know about a work item
@@ -242,7 +332,7 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
            float *__restrict__ nbhd, const TcParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem_tc[];
-    __shared__ __align__(8) uint64_t a_full[2], a_free[2], acc_full[2], acc_free[2], r_full[TC_MAXSTAGES], r_empty[TC_MAXSTAGES];
+    __shared__ __align__(8) uint64_t a_full[2], a_free[2], acc_full[2], acc_free[2], row0_done[2], r_full[TC_MAXSTAGES], r_empty[TC_MAXSTAGES];
     __shared__ uint32_t s_tmem;
     __shared__ unsigned long long s_best[8];
     __shared__ uint32_t s_fmax;    // orderable key of the largest filter score any warp has seen in the current item
@@ -251,19 +341,20 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
     const size_t a_bytes = (size_t)tp.kc_a * tp.rows_alloc * 16;
     uint8_t *sA = smem_tc;                                                  // [n_abuf][kc_a][rows_alloc][16]
     uint8_t *sB = sA + (size_t)tp.n_abuf * a_bytes;                         // [stages][stage_bytes]
-    uint32_t *V2 = (uint32_t *)(sB + (size_t)tp.stages * tp.stage_bytes);   // [vcols + 1][vr]  sums of I^2 over th rows
-    uint16_t *V1 = (uint16_t *)(V2 + (size_t)(tp.vcols + 1) * tp.vr);       // [vcols + 1][vr]  sums of I
+    uint32_t *V2 = (uint32_t *)(sB + (size_t)tp.stages * tp.stage_bytes);   // [tile_rows][p2]  sums of I^2 over th rows, per window column
+    uint16_t *V1 = (uint16_t *)(V2 + (size_t)tp.tile_rows * tp.p2);         // [tile_rows][p1]  sums of I
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
             mbar_init(&a_full[i], 1);
-            mbar_init(&a_free[i], 2);       // the MMAs that read the buffer + the workers' vertical sums
-            mbar_init(&acc_full[i], 1);
+            mbar_init(&a_free[i], TC_NISS + 1);       // the MMAs that read the buffer (every issuer) + the workers' vertical sums
+            mbar_init(&acc_full[i], TC_NISS);
+            mbar_init(&row0_done[i], 1);
             mbar_init(&acc_free[i], 1);
         }
         for (int s = 0; s < TC_MAXSTAGES; s++) {
             mbar_init(&r_full[s], 1);
-            mbar_init(&r_empty[s], 1);
+            mbar_init(&r_empty[s], TC_NISS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -284,7 +375,7 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                 TcItem it;
                 if (tc_decode(item, tasks, tpls, tp, &it) != 1) continue;
                 const int buf = tp.n_abuf == 2 ? (k & 1) : 0, u = tp.n_abuf == 2 ? (k >> 1) : k;
-                if (u > 0) mbar_wait(&a_free[buf], (u - 1) & 1);
+                if (u > 0) mbar_wait_sleep(&a_free[buf], (u - 1) & 1);
                 const int nch = 2 * it.nk;                       // chunks this tile needs
                 mbar_expect_tx(&a_full[buf], (uint32_t)(nch * tp.rows_load * 16));
                 uint8_t *dst = sA + (size_t)buf * a_bytes;
@@ -309,68 +400,138 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                 const uint32_t row_bytes = (uint32_t)it.nd * 1024u;
                 for (int v = 0; v < it.th; v += tp.vb, g++) {
                     const int s = g % tp.stages;
-                    if (g >= tp.stages) mbar_wait(&r_empty[s], ((g / tp.stages) - 1) & 1);
+                    if (g >= tp.stages) mbar_wait_sleep(&r_empty[s], ((g / tp.stages) - 1) & 1);
                     const uint32_t bytes = row_bytes * (uint32_t)min(tp.vb, it.th - v);
                     mbar_expect_tx(&r_full[s], bytes);
                     bulk_g2s(sB + (size_t)s * tp.stage_bytes, table + (size_t)v * row_bytes, bytes, &r_full[s]);
                 }
             }
         }
-    } else if (warp == 10) {
-        // ---- MMA issuer ----
-        // One thread issues everything, so the loop body must be a handful of instructions: the
-        // descriptors are 64-bit integers whose low field is (address >> 4), advanced by plain adds.
-        if (lane == 0) {
+    } else if (warp >= 10) {
+        // ---- MMA issuers ----
+        // One thread issues everything, so the work per MMA must be a handful of instructions: per item the
+        // descriptors of the K steps are set up once in registers (the loops over j are fully unrolled); per template
+        // row the A descriptors advance by one row (+1 in 16-byte units) and the B descriptors by one table row --
+        // 32-bit adds on the low words, the start-address field never carries out of its 14 bits.
+        // The loop over the items runs convergent: all lanes decode the item and its shape goes through a warp
+        // reduction, whose result ptxas knows to be uniform -- the descriptors then live in uniform registers and a
+        // UTCIMMA costs a couple of uniform adds instead of five R2UR transfers.  One elected lane issues an item's MMAs.
+        // A single thread cannot issue faster than one MMA per ~125 cycles (descriptor moves into uniform registers), so
+        // TC_NISS warps share the work: issuer i takes the template rows i, i + TC_NISS, .. of every ring stage.  The
+        // accumulation is integer, so the order in which the tensor core takes their MMAs does not matter -- except that
+        // template row 0 (issuer 0), which overwrites the accumulators, must come first (row0_done).
+        {
+            const int iss = warp - 10;
+            const uint32_t tmem_u = (uint32_t)__reduce_max_sync(0xffffffffu, tmem);
             const uint32_t idesc0 = instr_desc_u8(TC_M, 0);
             int k = 0, g = 0;
+            long long m_wa = 0, m_wc = 0, m_wr = 0, m_tot = 0;
+            const uint32_t b_hi32 = (uint32_t)(smem_desc(0, 0, 128) >> 32);
             for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
                 TcItem it;
-                if (tc_decode(item, tasks, tpls, tp, &it) != 1) continue;
+                const int kind0 = tc_decode(item, tasks, tpls, tp, &it);
+                const uint32_t pk = __reduce_max_sync(0xffffffffu, (uint32_t)kind0 | (kind0 == 1 ? ((uint32_t)it.nd << 2) | ((uint32_t)it.nbe << 5) |
+                                                                                                       ((uint32_t)it.nk << 8) | ((uint32_t)it.th << 12)
+                                                                                                 : 0u));
+                if ((pk & 3u) != 1u) continue;
+                const int nd = (int)((pk >> 2) & 7u), nbe = (int)((pk >> 5) & 7u), nk = (int)((pk >> 8) & 15u), th = (int)(pk >> 12);
                 const int buf = tp.n_abuf == 2 ? (k & 1) : 0, ua = tp.n_abuf == 2 ? (k >> 1) : k;
                 const int acc = k & 1, uc = k >> 1;
-                mbar_wait(&a_full[buf], ua & 1);
-                if (uc > 0) mbar_wait(&acc_free[acc], (uc - 1) & 1);
-                tc_fence_after();
                 const uint64_t a_desc0 = smem_desc(smem_u32(sA + (size_t)buf * a_bytes), (uint32_t)tp.rows_alloc * 16, 128);
-                const uint64_t a_kstep = (uint64_t)(2 * tp.rows_alloc);        // two 16-byte column chunks, in 16-byte units
-                const uint32_t b_lbo = (uint32_t)it.nd * 32 * 16;               // the second K half of a band: nd*32 rows further
-                const uint64_t b_vstep = (uint64_t)(it.nd * 64);               // one template row of the table, in 16-byte units
-                const uint32_t dcol = tmem + (uint32_t)(acc * 128);
-                const int nd = it.nd, nbe = it.nbe, nk = it.nk;
-                int v = 0;
-                for (; v < it.th; g++) {
-                    const int s = g % tp.stages;
-                    const int nv = min(tp.vb, it.th - v);
-                    mbar_wait(&r_full[s], (g / tp.stages) & 1);
+                const uint32_t a_hi32 = (uint32_t)(a_desc0 >> 32);
+                const uint32_t b_lbo = (uint32_t)nd * 32 * 16;                  // the second K half of a band: nd*32 rows further
+                const uint32_t b_vstep = (uint32_t)(nd * 64);                  // one template row of the table, in 16-byte units
+                const uint32_t dcol = tmem_u + (uint32_t)(acc * 128);
+                const uint32_t a_kstep = (uint32_t)(2 * tp.rows_alloc);        // two 16-byte column chunks per K step
+                const int nsteps = (th + tp.vb - 1) / tp.vb;
+                if (elect_one()) {
+                    const long long t0 = clock64();
+                    mbar_wait(&a_full[buf], ua & 1);
+                    const long long t1 = clock64();
+                    if (uc > 0) mbar_wait(&acc_free[acc], (uc - 1) & 1);
+                    if (iss != 0) mbar_wait(&row0_done[acc], uc & 1);
+                    const long long t2 = clock64();
+                    m_wa += t1 - t0;
+                    m_wc += t2 - t1;
                     tc_fence_after();
-                    uint64_t b_v = smem_desc(smem_u32(sB + (size_t)s * tp.stage_bytes), b_lbo, 128);
-                    for (int vv = 0; vv < nv; vv++, v++, b_v += b_vstep) {
-                        uint64_t a_d = a_desc0 + (uint64_t)v;                  // rows v .. v+127
-                        if (v == 0) {
-                            // first template row: column block j gets its first contribution from K step j and
-                            // must be overwritten, the blocks left of it accumulate
-                            for (int j = 0; j < nk; j++, a_d += a_kstep) {
-                                const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
-                                const uint64_t b_d = b_v + (uint64_t)((nd - 1 - (j - b_lo)) * 32);
-                                const int nold = (b_hi == j ? b_hi : b_hi + 1) - b_lo;    // blocks that already hold a partial sum
-                                if (nold > 0)
-                                    mma_i8(dcol + (uint32_t)(32 * b_lo), a_d, b_d, idesc0 | ((uint32_t)(nold * 4) << 17), 1u);
-                                if (b_hi == j)
-                                    mma_i8(dcol + (uint32_t)(32 * j), a_d, b_d + (uint64_t)(nold * 32), idesc0 | (4u << 17), 0u);
+                    int v = 0, gg = g;
+                    for (; v < th; gg++) {
+                        const int s = gg % tp.stages;
+                        const int nv = min(tp.vb, th - v);
+                        const long long t3 = clock64();
+                        mbar_wait(&r_full[s], (gg / tp.stages) & 1);
+                        m_wr += clock64() - t3;
+                        tc_fence_after();
+                        uint32_t b_v = (uint32_t)smem_desc(smem_u32(sB + (size_t)s * tp.stage_bytes), b_lbo, 128);
+                        if (tp.mode & 16) {
+                            // experiment: K step outer, template rows of the stage inner (consecutive MMAs with the same D range)
+#pragma unroll
+                            for (int j = 0; j < TC_MAXK; j++) {
+                                if (j < nk) {
+                                    const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
+                                    const uint32_t dc = dcol + (uint32_t)(32 * b_lo);
+                                    for (int vv = 0; vv < nv; vv++) {
+                                        const uint64_t a_d = ((uint64_t)a_hi32 << 32) | ((uint32_t)a_desc0 + (uint32_t)(v + vv) + (uint32_t)j * a_kstep);
+                                        const uint64_t b_d = ((uint64_t)b_hi32 << 32) | (b_v + (uint32_t)vv * b_vstep + (uint32_t)((nd - 1 - (j - b_lo)) * 32));
+                                        if (v + vv == 0 && j < nbe) {
+                                            const uint32_t nold = (uint32_t)(j - b_lo);
+                                            if (nold > 0) mma_i8(dc, a_d, b_d, idesc0 | (nold << 19), 1u);
+                                            mma_i8(dcol + (uint32_t)(32 * j), a_d, b_d + (uint64_t)(nold * 32u), idesc0 | (1u << 19), 0u);
+                                        } else {
+                                            mma_i8(dc, a_d, b_d, idesc0 | ((uint32_t)(b_hi - b_lo + 1) << 19), 1u);
+                                        }
+                                    }
+                                }
                             }
-                        } else {
-                            for (int j = 0; j < nk; j++, a_d += a_kstep) {
-                                const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
-                                const uint64_t b_d = b_v + (uint64_t)((nd - 1 - (j - b_lo)) * 32);
-                                mma_i8(dcol + (uint32_t)(32 * b_lo), a_d, b_d, idesc0 | ((uint32_t)((b_hi - b_lo + 1) * 4) << 17), 1u);
+                            v += nv;
+                        } else
+                        for (int vv = 0; vv < nv; vv++, v++, b_v += b_vstep) {
+                            if (vv % TC_NISS != iss) continue;
+                            // K step j feeds the column blocks b_lo = max(0, j-nd+1) .. b_hi = min(nbe-1, j); its band starts
+                            // (nd-1-(j-b_lo)) blocks into the table row.  In the first template row column block j gets its first
+                            // contribution from K step j and must be overwritten, the blocks left of it accumulate.
+                            uint32_t a_lo = (uint32_t)a_desc0 + (uint32_t)v;
+#pragma unroll
+                            for (int j = 0; j < TC_MAXK; j++) {
+                                if (j < nk && !(tp.mode & 2)) {
+                                    const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
+                                    const uint64_t a_d = ((uint64_t)a_hi32 << 32) | a_lo;
+                                    const uint64_t b_d = ((uint64_t)b_hi32 << 32) | (b_v + (uint32_t)((nd - 1 - (j - b_lo)) * 32));
+                                    const uint32_t dc = dcol + (uint32_t)(32 * b_lo);
+                                    if (v == 0 && j < nbe) {
+                                        const uint32_t nold = (uint32_t)(j - b_lo);       // blocks that already hold a partial sum
+                                        if (nold > 0) mma_i8(dc, a_d, b_d, idesc0 | (nold << 19), 1u);
+                                        mma_i8(dcol + (uint32_t)(32 * j), a_d, b_d + (uint64_t)(nold * 32u), idesc0 | (1u << 19), 0u);
+                                    } else {
+                                        mma_i8(dc, a_d, b_d, idesc0 | ((uint32_t)(b_hi - b_lo + 1) << 19), 1u);
+                                    }
+                                }
+                                a_lo += a_kstep;
+                            }
+                            if (v == 0 && TC_NISS > 1) {
+                                tc_fence_before();
+                                mbar_arrive(&row0_done[acc]);
                             }
                         }
+                        tc_commit(&r_empty[s]);     // the ring slot is free once these MMAs have read it
                     }
-                    tc_commit(&r_empty[s]);     // the ring slot is free once these MMAs have read it
+                    tc_commit(&a_free[buf]);
+                    tc_commit(&acc_full[acc]);
+                    m_tot += clock64() - t0;
                 }
-                tc_commit(&a_free[buf]);
-                tc_commit(&acc_full[acc]);
+                __syncwarp();
+                g += nsteps;
                 k++;
+            }
+            // whichever lane was elected holds the clocks
+            m_wa = __reduce_max_sync(0xffffffffu, (unsigned)min(m_wa, 0xffffffffLL)), m_wc = __reduce_max_sync(0xffffffffu, (unsigned)min(m_wc, 0xffffffffLL));
+            m_wr = __reduce_max_sync(0xffffffffu, (unsigned)min(m_wr, 0xffffffffLL)), m_tot = __reduce_max_sync(0xffffffffu, (unsigned)min(m_tot, 0xffffffffLL));
+            if (tp.dbg && lane == 0 && iss == 0) {
+                unsigned long long *d = tp.dbg + (size_t)blockIdx.x * 8 + 4;
+                d[0] = (unsigned long long)m_wa;
+                d[1] = (unsigned long long)m_wc;
+                d[2] = (unsigned long long)m_wr;
+                d[3] = (unsigned long long)m_tot;
             }
         }
     } else {
@@ -378,7 +539,8 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
         const int tid = threadIdx.x;
         const int q4 = warp & 3, hh = warp >> 2;         // TMEM lane quarter (rows 32*q4 ..), column half
         const int row = 32 * q4 + lane;
-        long long clk_wait = 0, clk_v = 0, clk_e = 0;
+        const int P1 = tp.p1, P2 = tp.p2;                // row pitches of V1 (in u16) and V2 (in u32)
+        long long clk_wait = 0, clk_v = 0, clk_e = 0, clk_e1 = 0, clk_e2 = 0, clk_e3 = 0;
         int k = 0;
         for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
             TcItem it;
@@ -388,12 +550,12 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             const TplConst *tcp = &tpls->c[it.tpl];
             const int buf = tp.n_abuf == 2 ? (k & 1) : 0, ua = tp.n_abuf == 2 ? (k >> 1) : k;
             const int acc = k & 1, uc = k >> 1;
-            const int tw = it.tw, th = it.th, VR = tp.vr;
+            const int tw = it.tw, th = it.th;
             const long long c0 = clock64();
             mbar_wait(&a_full[buf], ua & 1);
             const long long c1 = clock64();
-            // (a) vertical sliding sums: a thread owns a window column (and a segment of the tile's rows)
-            {
+            // (a) vertical sliding sums: a thread owns a window column (and a segment of the tile's rows); V[row][column]
+            if (!(tp.mode & 5)) {
                 const int ncv = it.rw_t + tw - 1;
                 int nseg = TC_WORKERS / ncv;
                 nseg = nseg < 1 ? 1 : (nseg > 4 ? 4 : nseg);
@@ -406,27 +568,28 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                     const uint8_t *p = A + ((size_t)(c >> 4) * tp.rows_alloc) * 16 + (c & 15);
                     uint32_t s = 0, q = 0;
                     const uint8_t *pv = p + (size_t)r0 * 16;
-#pragma unroll 4
+#pragma unroll 8
                     for (int v = 0; v < th; v++) {
                         const uint32_t px = pv[v * 16];
                         s += px;
                         q += px * px;
                     }
-                    uint16_t *o1 = V1 + (size_t)c * VR;
-                    uint32_t *o2 = V2 + (size_t)c * VR;
+                    uint16_t *o1 = V1 + (size_t)r0 * P1 + c;
+                    uint32_t *o2 = V2 + (size_t)r0 * P2 + c;
                     if (r0 < r1) {
-                        o1[r0] = (uint16_t)s;
-                        o2[r0] = q;
+                        *o1 = (uint16_t)s;
+                        *o2 = q;
                     }
                     const uint8_t *pn = p + (size_t)(r0 + th) * 16, *po = p + (size_t)r0 * 16;
 #pragma unroll 4
-                    for (int r = r0 + 1; r < r1; r++, pn += 16, po += 16) {
+                    for (int r = r0 + 1; r < r1; r++) {
                         const int a = *pn, b = *po;
+                        pn += 16, po += 16, o1 += P1, o2 += P2;
                         const int d = a - b, sm = a + b;
                         s += (uint32_t)d;
                         q += (uint32_t)(d * sm);
-                        o1[r] = (uint16_t)s;
-                        o2[r] = q;
+                        *o1 = (uint16_t)s;
+                        *o2 = q;
                     }
                 }
             }
@@ -443,57 +606,100 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             const int y = it.y0 + row;
             const uint32_t N = (uint32_t)(tw * th);
             const int ntsum = -(int)tcp->tsum;
-            const long long Nflat = (long long)N + (long long)(N >> 5);
+            const float Bflat = (float)(((long long)N + (long long)(N >> 5)) >> 1);   // 2*B <= N + N/32: a nearly flat window
             const int method = tcp->method;
             const bool want_min = method_wants_min(method);
             const float eps_g = method == 5 ? TC_EPS / tcp->inv_sqrt_c : 0.0f;   // the filter compares A / sqrt(B); score = that * inv_sqrt_c
             const int nbh = (it.nbe + 1) >> 1;
             const int nb0 = hh == 0 ? 0 : nbh, nb1 = hh == 0 ? nbh : it.nbe;
+            const bool al = ((tw & 7) == 0);               // the columns tw further on are 16-byte aligned as well
             unsigned long long mybest = 0ull;
-            if (nb0 < nb1) {
-                const uint16_t *v1 = V1 + vrow;
-                const uint32_t *v2 = V2 + vrow;
+            if (nb0 < nb1 && 32 * q4 < it.rh_t && !(tp.mode & 9)) {
+                const uint16_t *v1 = V1 + (size_t)vrow * P1;
+                const uint32_t *v2 = V2 + (size_t)vrow * P2;
                 // horizontal sums under the template footprint at the first column of this warp's range
                 uint32_t S = 0, Q = 0;
                 {
                     const int xs = TC_NB * nb0;
-#pragma unroll 4
-                    for (int u = 0; u < tw; u++) {
-                        S += v1[(size_t)(xs + u) * VR];
-                        Q += v2[(size_t)(xs + u) * VR];
+                    int u = 0;
+                    for (; u + 8 <= tw; u += 8) {           // xs is a multiple of 32: 16-byte aligned vectors
+                        const uint4 a4 = *(const uint4 *)(v2 + xs + u), b4 = *(const uint4 *)(v2 + xs + u + 4);
+                        const uint4 c4 = *(const uint4 *)(v1 + xs + u);
+                        Q += (a4.x + a4.y) + (a4.z + a4.w) + (b4.x + b4.y) + (b4.z + b4.w);
+                        S += (c4.x & 0xffffu) + (c4.x >> 16) + (c4.y & 0xffffu) + (c4.y >> 16) + (c4.z & 0xffffu) + (c4.z >> 16) +
+                             (c4.w & 0xffffu) + (c4.w >> 16);
+                    }
+                    for (; u < tw; u++) {
+                        S += v1[xs + u];
+                        Q += v2[xs + u];
                     }
                 }
+                clk_e1 += clock64() - c3;
                 const uint32_t rowidx = (uint32_t)y * (uint32_t)it.rw + (uint32_t)it.x0;
+                const int xend = min(TC_NB * nb1, it.rw_t);
 #pragma unroll 1
-                for (int nb = nb0; nb < nb1; nb++) {
-#pragma unroll 1
-                    for (int h = 0; h < 2; h++) {
-                        const int xb = TC_NB * nb + 16 * h;            // tile column of position 0 of this half block
-                        uint32_t corr[16];
-                        tmem_ld16(dcol_addr(tmem, acc, q4, xb), corr);
-                        const int np = row_ok ? min(16, it.rw_t - xb) : 0;
-                        uint32_t Sx[16], Qx[16];
-                        float g[16];
+                for (int xb = TC_NB * nb0; xb < xend; xb += 16) {
+                    uint32_t corr[16];
+                    tmem_ld16(dcol_addr(tmem, acc, q4, xb), corr);
+                    const int np = row_ok ? min(16, it.rw_t - xb) : 0;
+                    // differences of the vertical sums tw columns apart: 128-bit loads when the alignment allows
+                    int d1[16], d2[16];
+                    {
+                        uint32_t o1[8], o2[16];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 t4 = *(const uint4 *)(v2 + xb + 4 * j);
+                            o2[4 * j] = t4.x, o2[4 * j + 1] = t4.y, o2[4 * j + 2] = t4.z, o2[4 * j + 3] = t4.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const uint4 t4 = *(const uint4 *)(v1 + xb + 8 * j);
+                            o1[4 * j] = t4.x, o1[4 * j + 1] = t4.y, o1[4 * j + 2] = t4.z, o1[4 * j + 3] = t4.w;
+                        }
+                        if (al) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint4 t4 = *(const uint4 *)(v2 + xb + tw + 4 * j);
+                                d2[4 * j] = (int)(t4.x - o2[4 * j]), d2[4 * j + 1] = (int)(t4.y - o2[4 * j + 1]);
+                                d2[4 * j + 2] = (int)(t4.z - o2[4 * j + 2]), d2[4 * j + 3] = (int)(t4.w - o2[4 * j + 3]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                const uint4 t4 = *(const uint4 *)(v1 + xb + tw + 8 * j);
+                                const uint32_t n4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    d1[8 * j + 2 * e] = (int)(n4[e] & 0xffffu) - (int)(o1[4 * j + e] & 0xffffu);
+                                    d1[8 * j + 2 * e + 1] = (int)(n4[e] >> 16) - (int)(o1[4 * j + e] >> 16);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                d2[i] = (int)(v2[xb + tw + i] - o2[i]);
+                                d1[i] = (int)v1[xb + tw + i] - (int)((i & 1) ? (o1[i >> 1] >> 16) : (o1[i >> 1] & 0xffffu));
+                            }
+                        }
+                    }
+                    uint32_t Sx[16], Qx[16];
+                    float g[16];
+                    if (method == 5) {
                         float tmax = -3.0e38f;
-                        const uint16_t *p1 = v1 + (size_t)xb * VR;
-                        const uint32_t *p2 = v2 + (size_t)xb * VR;
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
                             Sx[i] = S;
                             Qx[i] = Q;
                             // 32 x 32 -> 64-bit products (IMAD.WIDE): every factor fits 31 bits
                             const long long A = (long long)(int)N * (long long)(int)corr[i] + (long long)(int)S * (long long)ntsum;
-                            const long long B = (long long)((unsigned long long)N * Q) - (long long)((unsigned long long)S * S);
-                            float f;
-                            if (i >= np) f = -3.0e38f;
-                            else if (2 * B <= Nflat || method != 5) f = 3.0e38f;   // nearly flat window, other methods: always exact
-                            else {
-                                f = (float)A * rsqrt_fast((float)B);
-                                tmax = fmaxf(tmax, f);
-                            }
-                            g[i] = f;
-                            S += (uint32_t)p1[(size_t)(i + tw) * VR] - (uint32_t)p1[(size_t)i * VR];
-                            Q += p2[(size_t)(i + tw) * VR] - p2[(size_t)i * VR];
+                            const long long B = (long long)((unsigned long long)N * Q) + (long long)(int)S * (long long)(-(int)S);
+                            const float Bf = u64_to_f32((unsigned long long)B);
+                            const float f = i64_to_f32(A) * rsqrt_fast(Bf);
+                            const bool valid = i < np;
+                            const bool flat = Bf <= Bflat;                      // exact: both sides are integers below 2^24 when it matters
+                            g[i] = valid ? (flat ? 3.0e38f : f) : -3.0e38f;    // 3e38: nearly flat window -> always scored exactly
+                            tmax = fmaxf(tmax, (valid && !flat) ? f : -3.0e38f);
+                            S += (uint32_t)d1[i];
+                            Q += (uint32_t)d2[i];
                         }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
@@ -516,15 +722,31 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                                 }
                             }
                         }
+                    } else {
+                        // the other five methods: every position is scored with OpenCV's formula
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            if (i < np) {
+                                const float sc = tc_exact_score(corr[i], S, Q, tcp);
+                                const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(xb + i), want_min);
+                                mybest = key > mybest ? key : mybest;
+                            }
+                            S += (uint32_t)d1[i];
+                            Q += (uint32_t)d2[i];
+                        }
                     }
                 }
             }
+            const long long c3b = clock64();
             for (int o = 16; o > 0; o >>= 1) {
                 unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);
                 mybest = other > mybest ? other : mybest;
             }
             if (lane == 0) s_best[warp] = mybest;
             worker_bar();
+            const long long c3c = clock64();
+            clk_e2 += c3b - c3;
+            clk_e3 += c3c - c3b;
             unsigned long long b = s_best[0];
 #pragma unroll
             for (int w = 1; w < 8; w++) b = s_best[w] > b ? s_best[w] : b;
@@ -536,20 +758,48 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                 if (hh == 0 && nbhd) {
                     const uint32_t idx = 0xffffffffu - (uint32_t)(b & 0xffffffffull);
                     const int by = (int)(idx / (uint32_t)it.rw), bx = (int)(idx - (uint32_t)by * (uint32_t)it.rw);
-                    const int dyi = row - by;
-                    if (by + 1 >= 32 * q4 && by - 1 < 32 * q4 + 32) {       // warp-uniform: this quarter holds one of the rows
-                        float *o = nbhd + (size_t)it.task * 12;
-                        for (int dxi = -1; dxi <= 1; dxi++) {
-                            const int x = bx + dxi;
-                            if (x < 0 || x >= it.rw) continue;
-                            const uint32_t cv = tmem_ld1(dcol_addr(tmem, acc, q4, x));
-                            uint32_t S = 0, Q = 0;
-                            for (int u = 0; u < tw; u++) {
-                                S += V1[(size_t)(x + u) * VR + vrow];
-                                Q += V2[(size_t)(x + u) * VR + vrow];
+                    const int ra = max(max(by - 1, 0), 32 * q4), rb = min(min(by + 1, it.rh_t - 1), 32 * q4 + 31);
+                    if (ra <= rb) {       // warp-uniform: this quarter holds some of the rows by-1 .. by+1
+                        // correlations of this lane's row at columns bx-1 .. bx+1
+                        uint32_t cv[3];
+#pragma unroll
+                        for (int d = 0; d < 3; d++) cv[d] = tmem_ld1(dcol_addr(tmem, acc, q4, min(max(bx - 1 + d, 0), TC_NB * TC_MAXNB - 1)));
+                        // Window sums of the up to nine positions: for a row the lanes add the tw + 2 vertical sums of columns
+                        // bx-1 .. bx+tw in parallel (full sum F), then S(bx-1) = F - c[tw] - c[tw+1], S(bx) = F - c[0] - c[tw+1],
+                        // S(bx+1) = F - c[0] - c[1].  Lane 3*(r-by+1) + d keeps the values of position (r, bx-1+d).
+                        uint32_t myS = 0, myQ = 0, myC = 0;
+                        for (int r = ra; r <= rb; r++) {
+                            const uint16_t *w1 = V1 + (size_t)r * P1;
+                            const uint32_t *w2 = V2 + (size_t)r * P2;
+                            uint32_t f1 = 0, f2 = 0;
+                            for (int c = lane; c < tw + 2; c += 32) {
+                                const int col = bx - 1 + c;
+                                if (col >= 0 && col < it.rw + tw - 1) f1 += w1[col], f2 += w2[col];
                             }
-                            if (dyi >= -1 && dyi <= 1 && row_ok) o[(dyi + 1) * 3 + (dxi + 1)] = tc_exact_score(cv, S, Q, tcp);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+                                f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+                            }
+                            const int cl[4] = {bx - 1, bx, bx - 1 + tw, bx + tw};
+                            uint32_t e1[4], e2[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const bool ok = cl[e] >= 0 && cl[e] < it.rw + tw - 1;
+                                e1[e] = ok ? w1[cl[e]] : 0u;
+                                e2[e] = ok ? w2[cl[e]] : 0u;
+                            }
+                            const uint32_t s3[3] = {f1 - e1[2] - e1[3], f1 - e1[0] - e1[3], f1 - e1[0] - e1[1]};
+                            const uint32_t q3[3] = {f2 - e2[2] - e2[3], f2 - e2[0] - e2[3], f2 - e2[0] - e2[1]};
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                const uint32_t c_rd = __shfl_sync(0xffffffffu, cv[d], r & 31);
+                                if (lane == 3 * (r - by + 1) + d) myS = s3[d], myQ = q3[d], myC = c_rd;
+                            }
                         }
+                        const int dy = lane / 3 - 1, dx = lane - 3 * (lane / 3) - 1;
+                        if (lane < 9 && by + dy >= ra && by + dy <= rb && bx + dx >= 0 && bx + dx < it.rw)
+                            nbhd[(size_t)it.task * 12 + lane] = tc_exact_score(myC, myS, myQ, tcp);
                     }
                     if (tid == 0) o_flag(nbhd, it.task);
                 }
@@ -566,11 +816,15 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             k++;
         }
         if (tp.dbg && tid == 0) {
-            unsigned long long *d = tp.dbg + (size_t)blockIdx.x * 4;
+            unsigned long long *d = tp.dbg + (size_t)blockIdx.x * 8;
             d[0] = (unsigned long long)clk_wait;
             d[1] = (unsigned long long)clk_v;
             d[2] = (unsigned long long)clk_e;
             d[3] = (unsigned long long)k;
+            unsigned long long *d2 = tp.dbg + (size_t)(1024 + blockIdx.x) * 8;
+            d2[0] = (unsigned long long)clk_e1;
+            d2[1] = (unsigned long long)clk_e2;
+            d2[2] = (unsigned long long)clk_e3;
         }
     }
     __syncwarp();
@@ -626,7 +880,6 @@ static size_t tc_plan(int max_rw, int max_rh, int tw, int th, TcParams *tp)
     tp->rows_alloc = (TC_M - 1 + th + 7) & ~7;     // chunk columns start 128-byte aligned (TMA destination)
     tp->rows_load = tp->tile_rows + th - 1;
     tp->rows_box1 = tp->rows_load < 256 ? tp->rows_load : 256;
-    tp->vr = tp->tile_rows | 1;
     const size_t row_bytes = (size_t)nd * 1024;
     for (int nbc = nb_total < TC_MAXNB ? nb_total : TC_MAXNB; nbc >= 1; nbc = nbc > 2 ? 2 : nbc - 1) {
         if (env_nbc > 0 && nbc > env_nbc) continue;
@@ -637,17 +890,21 @@ static size_t tc_plan(int max_rw, int max_rh, int tw, int th, TcParams *tp)
             tp->kc_a = 2 * nk;
             tp->n_abuf = nab;
             tp->vcols = TC_NB * nbc + tw;
+            tp->p2 = (tp->vcols + 3) & ~3;
+            if ((tp->p2 & 7) != 4) tp->p2 += 4;
+            tp->p1 = (tp->vcols + 7) & ~7;
+            if ((tp->p1 & 15) != 8) tp->p1 += 8;
             const size_t a = (size_t)tp->kc_a * tp->rows_alloc * 16 * nab;
-            const size_t v = (size_t)(tp->vcols + 1) * tp->vr * 6 + 16;
-            if (a + v + 2 * row_bytes > kTcSmemMax) continue;
+            const size_t v = (size_t)tp->tile_rows * ((size_t)tp->p2 * 4 + (size_t)tp->p1 * 2) + 16;
+            if (a + v + 2 * TC_NISS * row_bytes > kTcSmemMax) continue;
             // ring: template rows per stage ~6 KB, as many stages as fit (the table streams from L2: ~1 us of latency to cover)
-            int vb = (int)(6144 / row_bytes);
-            if (vb < 1) vb = 1;
-            if (vb > th) vb = th;
+            static const int env_vb = [] { const char *e = getenv("LST_TC_VB"); return e ? atoi(e) : 0; }();
+            int vb = (env_vb > 0 ? env_vb : (int)(6144 / row_bytes)) / TC_NISS * TC_NISS;
+            if (vb < TC_NISS) vb = TC_NISS;
             int stages = (int)((kTcSmemMax - a - v) / (vb * row_bytes));
             if (stages < 2) {
-                vb = 1;
-                stages = (int)((kTcSmemMax - a - v) / row_bytes);
+                vb = TC_NISS;
+                stages = (int)((kTcSmemMax - a - v) / (vb * row_bytes));
             }
             if (stages > TC_MAXSTAGES) stages = TC_MAXSTAGES;
             if (stages < 2) continue;
@@ -683,7 +940,7 @@ void tc_init_device()
     d.attr_ok = e == cudaSuccess;
     e = cudaFuncSetAttribute(lst_ncc_tc, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) fprintf(stderr, "lst_ncc_tc: PreferredSharedMemoryCarveout: %s\n", cudaGetErrorString(e));
-    if (g_tc_debug && !d.dbg) cudaMalloc((void **)&d.dbg, 1024 * 4 * sizeof(unsigned long long));
+    if (g_tc_debug && !d.dbg) cudaMalloc((void **)&d.dbg, 2048 * 8 * sizeof(unsigned long long));
     cudaGetLastError();
 }
 
@@ -707,34 +964,40 @@ int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int
     if (items > 0x7fffffffLL) return -1;
     tp.n_items = (int)items;
     tp.dbg = g_tc_debug ? ds.dbg : nullptr;
+    {
+        static const int mode = [] { const char *e = getenv("LST_TC_MODE"); return e ? atoi(e) : 0; }();
+        tp.mode = mode;
+    }
     CUtensorMap map1, map2;
     if (!make_window_map(&map1, win8, pitch, total_rows, tp.rows_box1)) return -1;
     const int rows2 = tp.rows_load - tp.rows_box1;
     if (!make_window_map(&map2, win8, pitch, total_rows, rows2 > 0 ? rows2 : 1)) return -1;
     const int grid = (int)(items < ds.sms ? items : ds.sms);
     if (grid < 1) return 0;
-    if (tp.dbg) cudaMemsetAsync(tp.dbg, 0, (size_t)grid * 32, stream);
+    if (tp.dbg) cudaMemsetAsync(tp.dbg, 0, (size_t)2048 * 64, stream);
     lst_ncc_tc<<<grid, TC_THREADS, smem, stream>>>(map1, map2, tasks, tpls, best, nbhd, tp);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
         fprintf(stderr, "lst_ncc_tc launch failed: %s (grid %d, smem %zu)\n", cudaGetErrorString(e), grid, smem);
         return -1;
     }
-    if (tp.dbg && n_tasks >= 1024) {
+    static int dbg_prints = 0;
+    if (tp.dbg && n_tasks >= 1024 && dbg_prints++ < 2) {
         cudaStreamSynchronize(stream);
-        unsigned long long h[1024 * 4];
-        cudaMemcpy(h, tp.dbg, (size_t)grid * 32, cudaMemcpyDeviceToHost);
-        double a = 0, b = 0, c = 0, k = 0;
+        static unsigned long long h[2048 * 8];
+        cudaMemcpy(h, tp.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        double a[8] = {0}, e[3] = {0};
         for (int i = 0; i < grid; i++) {
-            a += (double)h[4 * i];
-            b += (double)h[4 * i + 1];
-            c += (double)h[4 * i + 2];
-            k += (double)h[4 * i + 3];
+            for (int j = 0; j < 8; j++) a[j] += (double)h[8 * i + j];
+            for (int j = 0; j < 3; j++) e[j] += (double)h[8 * (1024 + i) + j];
         }
+        const double k = a[3];
         fprintf(stderr,
-                "lst_ncc_tc workers (cycles per item, mean over %d CTAs, %.0f items): wait %.0f  vertical sums %.0f  epilogue %.0f | "
-                "nbc %d abuf %d stages %d x %d B smem %zu\n",
-                grid, k, a / k, b / k, c / k, tp.nbc, tp.n_abuf, tp.stages, tp.stage_bytes, smem);
+                "lst_ncc_tc (cycles per item, mean over %d CTAs, %.0f items): workers wait %.0f vsums %.0f epilogue %.0f | mma wait-window %.0f "
+                "wait-acc %.0f wait-table %.0f total %.0f | nbc %d abuf %d stages %d x %d B smem %zu | epilogue warp 0: init %.0f, to end of chunks %.0f, "
+                "barrier %.0f\n",
+                grid, k, a[0] / k, a[1] / k, a[2] / k, a[4] / k, a[5] / k, a[6] / k, a[7] / k, tp.nbc, tp.n_abuf, tp.stages, tp.stage_bytes,
+                smem, e[0] / k, e[1] / k, e[2] / k);
     }
     return 1;
 }

@@ -211,6 +211,11 @@ static int run_case(const Geo &g, int verify, int time_iters)
 int main(int argc, char **argv)
 {
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    if (argc > 1 && !strcmp(argv[1], "time")) {
+        tc_init_device();
+        run_case(Geo{160, 160, 48, 48, 4704, 5, 0}, 0, 20);
+        return 0;
+    }
     tc_init_device();
     int fails = 0;
     // w, h, tw, th, n, method, mixed
