@@ -93,8 +93,10 @@ LST_HD float match_score(const TplConst &c, double corr, double wsum, double wsq
 // methods 0 and 1 look for the minimum of the map, the others for the maximum (LST4:2671-2679)
 LST_HD bool method_wants_min(int method) { return method == 0 || method == 1; }
 
-// 3x3 quadratic sub-pixel fit, LST4:2681-2717.  nb = 3x3 neighbourhood (row-major, centre nb[4])
-// read as float32 and computed in double.  border != 0 => peak on the map border => (0,0).
+// 3x3 quadratic sub-pixel fit, LST4:2681-2717.  nb = 3x3 neighbourhood (row-major, centre nb[4]).
+// FloatIndexer.get returns a Java float: the four-term sum of fxy and the differences of fx / fy are float32
+// operations (one rounding each) that are promoted only by the division by the double constant; fxx and fyy are
+// promoted by the 2.0 * term from the start.  border != 0 => peak on the map border => (0,0).
 LST_HD void subpixel_fit(const float *nb, int border, double *dx, double *dy)
 {
     *dx = 0.0;
@@ -103,9 +105,13 @@ LST_HD void subpixel_fit(const float *nb, int border, double *dx, double *dy)
     double c = (double)nb[4];
     double fxx = (double)nb[3] - 2.0 * c + (double)nb[5];
     double fyy = (double)nb[1] - 2.0 * c + (double)nb[7];
-    double fxy = ((double)nb[8] + (double)nb[0] - (double)nb[2] - (double)nb[6]) / 4.0;
-    double fx = ((double)nb[5] - (double)nb[3]) / 2.0;
-    double fy = ((double)nb[7] - (double)nb[1]) / 2.0;
+    float sxy = nb[8] + nb[0];
+    sxy = sxy - nb[2];
+    sxy = sxy - nb[6];
+    double fxy = (double)sxy / 4.0;
+    float dfx = nb[5] - nb[3], dfy = nb[7] - nb[1];
+    double fx = (double)dfx / 2.0;
+    double fy = (double)dfy / 2.0;
     double denom = fxy * fxy - fxx * fyy;
     if (denom == 0.0) return;
     double ddx = (fyy * fx - fxy * fy) / denom;

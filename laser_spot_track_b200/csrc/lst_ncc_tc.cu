@@ -326,6 +326,78 @@ __device__ __forceinline__ int tc_decode(int item, const DevTask *__restrict__ t
     return 1;
 }
 
+// What the MMA issuer needs for one item.
+struct TcIssue {
+    uint64_t a_desc0;
+    uint32_t a_kstep, b_hi32, b_lbo, b_vstep, dcol, idesc0;
+    int th, g, iss, stages, vb, stage_bytes, nd, nbe, nk, issue;
+    uint8_t *sB;
+    uint64_t *r_full, *r_empty, *row0;
+};
+
+// Issues the MMAs of one item (the template rows this issuer owns).  K step j feeds the column blocks b_lo = max(0, j-nd+1)
+// .. b_hi = min(nbe-1, j); its band starts (nd-1-(j-b_lo)) blocks into the table row.  In the first template row column
+// block j gets its first contribution from K step j and must be overwritten, the blocks left of it accumulate.
+// ND, NBE > 0: the band shape is a compile-time constant, so the column ranges, band offsets and instruction descriptors
+// of the K steps are immediates and an MMA costs two adds; ND = 0: any shape.  Returns the cycles spent waiting for the ring.
+template <int ND, int NBE>
+__device__ __forceinline__ long long tc_issue_item(const TcIssue &q)
+{
+    const int nd = ND > 0 ? ND : q.nd, nbe = ND > 0 ? NBE : q.nbe, nk = ND > 0 ? ND + NBE - 1 : q.nk;
+    constexpr int KMAX = ND > 0 ? ND + NBE - 1 : TC_MAXK;
+    const uint32_t a_hi32 = (uint32_t)(q.a_desc0 >> 32);
+    long long waited = 0;
+    int v = 0, gg = q.g;
+    for (; v < q.th; gg++) {
+        const int s = gg % q.stages;
+        const int nv = min(q.vb, q.th - v);
+        const long long t3 = clock64();
+        mbar_wait(&q.r_full[s], (gg / q.stages) & 1);
+        waited += clock64() - t3;
+        tc_fence_after();
+        uint32_t b_v = (uint32_t)smem_desc(smem_u32(q.sB + (size_t)s * q.stage_bytes), q.b_lbo, 128);
+        for (int vv = 0; vv < nv; vv++, v++, b_v += q.b_vstep) {
+            if (vv % TC_NISS != q.iss) continue;
+            const uint32_t a_lo = (uint32_t)q.a_desc0 + (uint32_t)v;
+            if (!q.issue) {
+                if (v == 0 && TC_NISS > 1) mbar_arrive(q.row0);
+            } else if (v == 0) {
+#pragma unroll
+                for (int j = 0; j < KMAX; j++) {
+                    if (j < nk) {
+                        const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
+                        const uint64_t a_d = ((uint64_t)a_hi32 << 32) | (a_lo + (uint32_t)j * q.a_kstep);
+                        const uint64_t b_d = ((uint64_t)q.b_hi32 << 32) | (b_v + (uint32_t)((nd - 1 - (j - b_lo)) * 32));
+                        if (j < nbe) {
+                            const uint32_t nold = (uint32_t)(j - b_lo);       // blocks that already hold a partial sum
+                            if (nold > 0) mma_i8(q.dcol + (uint32_t)(32 * b_lo), a_d, b_d, q.idesc0 | (nold << 19), 1u);
+                            mma_i8(q.dcol + (uint32_t)(32 * j), a_d, b_d + (uint64_t)(nold * 32u), q.idesc0 | (1u << 19), 0u);
+                        } else {
+                            mma_i8(q.dcol + (uint32_t)(32 * b_lo), a_d, b_d, q.idesc0 | ((uint32_t)(b_hi - b_lo + 1) << 19), 1u);
+                        }
+                    }
+                }
+                if (TC_NISS > 1) {
+                    tc_fence_before();
+                    mbar_arrive(q.row0);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < KMAX; j++) {
+                    if (j < nk) {
+                        const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
+                        mma_i8(q.dcol + (uint32_t)(32 * b_lo), ((uint64_t)a_hi32 << 32) | (a_lo + (uint32_t)j * q.a_kstep),
+                               ((uint64_t)q.b_hi32 << 32) | (b_v + (uint32_t)((nd - 1 - (j - b_lo)) * 32)),
+                               q.idesc0 | ((uint32_t)(b_hi - b_lo + 1) << 19), 1u);
+                    }
+                }
+            }
+        }
+        tc_commit(&q.r_empty[s]);     // the ring slot is free once these MMAs have read it
+    }
+    return waited;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
            const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, unsigned long long *__restrict__ best,
@@ -454,67 +526,19 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                     m_wa += t1 - t0;
                     m_wc += t2 - t1;
                     tc_fence_after();
-                    int v = 0, gg = g;
-                    for (; v < th; gg++) {
-                        const int s = gg % tp.stages;
-                        const int nv = min(tp.vb, th - v);
-                        const long long t3 = clock64();
-                        mbar_wait(&r_full[s], (gg / tp.stages) & 1);
-                        m_wr += clock64() - t3;
-                        tc_fence_after();
-                        uint32_t b_v = (uint32_t)smem_desc(smem_u32(sB + (size_t)s * tp.stage_bytes), b_lbo, 128);
-                        if (tp.mode & 16) {
-                            // experiment: K step outer, template rows of the stage inner (consecutive MMAs with the same D range)
-#pragma unroll
-                            for (int j = 0; j < TC_MAXK; j++) {
-                                if (j < nk) {
-                                    const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
-                                    const uint32_t dc = dcol + (uint32_t)(32 * b_lo);
-                                    for (int vv = 0; vv < nv; vv++) {
-                                        const uint64_t a_d = ((uint64_t)a_hi32 << 32) | ((uint32_t)a_desc0 + (uint32_t)(v + vv) + (uint32_t)j * a_kstep);
-                                        const uint64_t b_d = ((uint64_t)b_hi32 << 32) | (b_v + (uint32_t)vv * b_vstep + (uint32_t)((nd - 1 - (j - b_lo)) * 32));
-                                        if (v + vv == 0 && j < nbe) {
-                                            const uint32_t nold = (uint32_t)(j - b_lo);
-                                            if (nold > 0) mma_i8(dc, a_d, b_d, idesc0 | (nold << 19), 1u);
-                                            mma_i8(dcol + (uint32_t)(32 * j), a_d, b_d + (uint64_t)(nold * 32u), idesc0 | (1u << 19), 0u);
-                                        } else {
-                                            mma_i8(dc, a_d, b_d, idesc0 | ((uint32_t)(b_hi - b_lo + 1) << 19), 1u);
-                                        }
-                                    }
-                                }
-                            }
-                            v += nv;
-                        } else
-                        for (int vv = 0; vv < nv; vv++, v++, b_v += b_vstep) {
-                            if (vv % TC_NISS != iss) continue;
-                            // K step j feeds the column blocks b_lo = max(0, j-nd+1) .. b_hi = min(nbe-1, j); its band starts
-                            // (nd-1-(j-b_lo)) blocks into the table row.  In the first template row column block j gets its first
-                            // contribution from K step j and must be overwritten, the blocks left of it accumulate.
-                            uint32_t a_lo = (uint32_t)a_desc0 + (uint32_t)v;
-#pragma unroll
-                            for (int j = 0; j < TC_MAXK; j++) {
-                                if (j < nk && !(tp.mode & 2)) {
-                                    const int b_lo = max(0, j - nd + 1), b_hi = min(nbe - 1, j);
-                                    const uint64_t a_d = ((uint64_t)a_hi32 << 32) | a_lo;
-                                    const uint64_t b_d = ((uint64_t)b_hi32 << 32) | (b_v + (uint32_t)((nd - 1 - (j - b_lo)) * 32));
-                                    const uint32_t dc = dcol + (uint32_t)(32 * b_lo);
-                                    if (v == 0 && j < nbe) {
-                                        const uint32_t nold = (uint32_t)(j - b_lo);       // blocks that already hold a partial sum
-                                        if (nold > 0) mma_i8(dc, a_d, b_d, idesc0 | (nold << 19), 1u);
-                                        mma_i8(dcol + (uint32_t)(32 * j), a_d, b_d + (uint64_t)(nold * 32u), idesc0 | (1u << 19), 0u);
-                                    } else {
-                                        mma_i8(dc, a_d, b_d, idesc0 | ((uint32_t)(b_hi - b_lo + 1) << 19), 1u);
-                                    }
-                                }
-                                a_lo += a_kstep;
-                            }
-                            if (v == 0 && TC_NISS > 1) {
-                                tc_fence_before();
-                                mbar_arrive(&row0_done[acc]);
-                            }
-                        }
-                        tc_commit(&r_empty[s]);     // the ring slot is free once these MMAs have read it
-                    }
+                    TcIssue q;
+                    q.a_desc0 = a_desc0, q.a_kstep = a_kstep, q.b_hi32 = b_hi32, q.b_lbo = b_lbo, q.b_vstep = b_vstep, q.dcol = dcol;
+                    q.idesc0 = idesc0, q.th = th, q.g = g, q.iss = iss, q.stages = tp.stages, q.vb = tp.vb, q.stage_bytes = tp.stage_bytes;
+                    q.sB = sB, q.r_full = r_full, q.r_empty = r_empty, q.row0 = &row0_done[acc], q.nd = nd, q.nbe = nbe, q.nk = nk;
+                    q.issue = !(tp.mode & 2);
+                    // the loops are specialised for the band shapes of the named configurations (compile-time column ranges)
+                    long long wr;
+                    if (nd == 3 && nbe == 4) wr = tc_issue_item<3, 4>(q);          // templates of 33..64 columns, four column blocks (config B)
+                    else if (nd == 2 && nbe == 3) wr = tc_issue_item<2, 3>(q);     // templates up to 32 columns, three blocks (config A)
+                    else if (nd == 3 && nbe == 2) wr = tc_issue_item<3, 2>(q);     // 64-column templates, two blocks (config C tiles)
+                    else if (nd == 5 && nbe == 2) wr = tc_issue_item<5, 2>(q);     // 128-column templates, two blocks (config D tiles)
+                    else wr = tc_issue_item<0, 0>(q);
+                    m_wr += wr;
                     tc_commit(&a_free[buf]);
                     tc_commit(&acc_full[acc]);
                     m_tot += clock64() - t0;
@@ -554,42 +578,51 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             const long long c0 = clock64();
             mbar_wait(&a_full[buf], ua & 1);
             const long long c1 = clock64();
-            // (a) vertical sliding sums: a thread owns a window column (and a segment of the tile's rows); V[row][column]
+            // (a) vertical sliding sums: a thread owns two adjacent window columns (16-bit loads) over a segment of the
+            //     tile's rows; V1 / V2 are [row][column], so a pair is one 32-bit / one 64-bit store
             if (!(tp.mode & 5)) {
                 const int ncv = it.rw_t + tw - 1;
-                int nseg = TC_WORKERS / ncv;
-                nseg = nseg < 1 ? 1 : (nseg > 4 ? 4 : nseg);
-                if (it.rh_t < 16 * nseg) nseg = 1;
-                const int seg_rows = (it.rh_t + nseg - 1) / nseg;
+                // work item = (16-byte column chunk, row segment, pair within the chunk): the lanes of a warp read one or two
+                // chunks at different rows -- chunk columns are a multiple of 128 bytes apart (all in the same four banks),
+                // rows 16 bytes
+                const int nchunk = (ncv + 15) >> 4;
+                int nseg = TC_WORKERS / (8 * nchunk);
+                nseg = nseg < 1 ? 1 : (nseg > 6 ? 6 : nseg);
+                if (it.rh_t < 8 * nseg) nseg = it.rh_t >= 8 ? it.rh_t / 8 : 1;
+                int seg_rows = (it.rh_t + nseg - 1) / nseg;
+                if ((seg_rows & 7) == 0 && nseg > 1) seg_rows++;          // segments start in different banks
                 const uint8_t *A = sA + (size_t)buf * a_bytes;
-                for (int w = tid; w < ncv * nseg; w += TC_WORKERS) {
-                    const int sg = w / ncv, c = w - sg * ncv;
+                for (int w = tid; w < 8 * nchunk * nseg; w += TC_WORKERS) {
+                    const int rest = w >> 3, ch = rest / nseg, sg = rest - ch * nseg, c = 16 * ch + 2 * (w & 7);
                     const int r0 = sg * seg_rows, r1 = min(r0 + seg_rows, it.rh_t);
+                    if (r0 >= r1 || c >= ncv) continue;
                     const uint8_t *p = A + ((size_t)(c >> 4) * tp.rows_alloc) * 16 + (c & 15);
-                    uint32_t s = 0, q = 0;
+                    uint32_t s0 = 0, s1 = 0, q0 = 0, q1 = 0;
                     const uint8_t *pv = p + (size_t)r0 * 16;
 #pragma unroll 8
                     for (int v = 0; v < th; v++) {
-                        const uint32_t px = pv[v * 16];
-                        s += px;
-                        q += px * px;
+                        const uint32_t px = *(const uint16_t *)(pv + v * 16);
+                        const uint32_t a0 = px & 0xffu, a1 = px >> 8;
+                        s0 += a0, s1 += a1;
+                        q0 += a0 * a0, q1 += a1 * a1;
                     }
-                    uint16_t *o1 = V1 + (size_t)r0 * P1 + c;
-                    uint32_t *o2 = V2 + (size_t)r0 * P2 + c;
-                    if (r0 < r1) {
-                        *o1 = (uint16_t)s;
-                        *o2 = q;
-                    }
+                    uint32_t *o1 = (uint32_t *)(V1 + (size_t)r0 * P1 + c);
+                    uint2 *o2 = (uint2 *)(V2 + (size_t)r0 * P2 + c);
+                    *o1 = s0 | (s1 << 16);
+                    *o2 = make_uint2(q0, q1);
                     const uint8_t *pn = p + (size_t)(r0 + th) * 16, *po = p + (size_t)r0 * 16;
 #pragma unroll 4
                     for (int r = r0 + 1; r < r1; r++) {
-                        const int a = *pn, b = *po;
-                        pn += 16, po += 16, o1 += P1, o2 += P2;
-                        const int d = a - b, sm = a + b;
-                        s += (uint32_t)d;
-                        q += (uint32_t)(d * sm);
-                        *o1 = (uint16_t)s;
-                        *o2 = q;
+                        const uint32_t wn = *(const uint16_t *)pn, wo = *(const uint16_t *)po;
+                        pn += 16, po += 16;
+                        o1 = (uint32_t *)((uint16_t *)o1 + P1);
+                        o2 = (uint2 *)((uint32_t *)o2 + P2);
+                        const int a0 = wn & 0xffu, a1 = wn >> 8, b0 = wo & 0xffu, b1 = wo >> 8;
+                        const int d0 = a0 - b0, d1 = a1 - b1;
+                        s0 += (uint32_t)d0, s1 += (uint32_t)d1;
+                        q0 += (uint32_t)(d0 * (a0 + b0)), q1 += (uint32_t)(d1 * (a1 + b1));
+                        *o1 = s0 | (s1 << 16);
+                        *o2 = make_uint2(q0, q1);
                     }
                 }
             }
@@ -681,26 +714,42 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                             }
                         }
                     }
-                    uint32_t Sx[16], Qx[16];
                     float g[16];
                     if (method == 5) {
-                        float tmax = -3.0e38f;
+                        // Fast path: the filter score f = A / sqrt(B) of the 16 positions with nothing but the arithmetic --
+                        // no validity or flatness selects.  A lane whose chunk is partial (np < 16) or holds a nearly flat
+                        // footprint (2B <= N + N/32; OpenCV's double formula decides those) redoes its positions below.
+                        const uint32_t S0 = S, Q0 = Q;
+                        float tmax = -3.0e38f, bmin = 3.0e38f;
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            Sx[i] = S;
-                            Qx[i] = Q;
                             // 32 x 32 -> 64-bit products (IMAD.WIDE): every factor fits 31 bits
                             const long long A = (long long)(int)N * (long long)(int)corr[i] + (long long)(int)S * (long long)ntsum;
                             const long long B = (long long)((unsigned long long)N * Q) + (long long)(int)S * (long long)(-(int)S);
                             const float Bf = u64_to_f32((unsigned long long)B);
                             const float f = i64_to_f32(A) * rsqrt_fast(Bf);
-                            const bool valid = i < np;
-                            const bool flat = Bf <= Bflat;                      // exact: both sides are integers below 2^24 when it matters
-                            g[i] = valid ? (flat ? 3.0e38f : f) : -3.0e38f;    // 3e38: nearly flat window -> always scored exactly
-                            tmax = fmaxf(tmax, (valid && !flat) ? f : -3.0e38f);
+                            g[i] = f;
+                            tmax = fmaxf(tmax, f);          // a NaN (B = 0) is ignored here and caught by bmin
+                            bmin = fminf(bmin, Bf);
                             S += (uint32_t)d1[i];
                             Q += (uint32_t)d2[i];
                         }
+                        bool special = false;               // this lane has positions that are always scored exactly
+                        if (np < 16 || bmin <= Bflat) {
+                            tmax = -3.0e38f;
+                            uint32_t Sr = S0, Qr = Q0;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                const long long B = (long long)((unsigned long long)N * Qr) + (long long)(int)Sr * (long long)(-(int)Sr);
+                                const bool flat = u64_to_f32((unsigned long long)B) <= Bflat;      // exact: integers below 2^24 when it matters
+                                if (i >= np) g[i] = -3.0e38f;
+                                else if (flat) g[i] = 3.0e38f, special = true;
+                                else tmax = fmaxf(tmax, g[i]);
+                                Sr += (uint32_t)d1[i];
+                                Qr += (uint32_t)d2[i];
+                            }
+                        }
+                        const float lane_max = tmax;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
                         // OpenCV's double-precision score for the candidates only.  A candidate must come within
@@ -709,17 +758,17 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                         if (lane == 0 && tmax > -3.0e38f) atomicMax(&s_fmax, f32_key(tmax));
                         __syncwarp();
                         const float thr = fmaxf(tmax, key_f32(*(volatile uint32_t *)&s_fmax)) - eps_g;
-                        float lmax = g[0];
-#pragma unroll
-                        for (int i = 1; i < 16; i++) lmax = fmaxf(lmax, g[i]);
-                        if (lmax >= thr) {
+                        if (lane_max >= thr || special) {
+                            uint32_t Sr = S0, Qr = Q0;
 #pragma unroll
                             for (int i = 0; i < 16; i++) {
                                 if (g[i] >= thr && i < np) {
-                                    const float sc = tc_exact_score(corr[i], Sx[i], Qx[i], tcp);
+                                    const float sc = tc_exact_score(corr[i], Sr, Qr, tcp);
                                     const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(xb + i), want_min);
                                     mybest = key > mybest ? key : mybest;
                                 }
+                                Sr += (uint32_t)d1[i];
+                                Qr += (uint32_t)d2[i];
                             }
                         }
                     } else {
@@ -750,24 +799,29 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             unsigned long long b = s_best[0];
 #pragma unroll
             for (int w = 1; w < 8; w++) b = s_best[w] > b ? s_best[w] : b;
+            // The window is this tile alone (single_tile): b is its final argmax and the 3x3 neighbourhood the sub-pixel fit
+            // needs (LST4:2681-2717) is still in TMEM.  The warps that own rows by-1..by+1 collect the correlations and the
+            // window sums of the up to nine positions now, release the accumulator and the vertical sums, and score the
+            // positions afterwards (registers only) -- lst_epilogue does not have to recompute nine correlations.
+            uint32_t myS = 0, myQ = 0, myC = 0;
+            bool nb_mine = false;
             if (tp.single_tile) {
-                // The window is this tile alone, so b is its final argmax and the 3x3 neighbourhood the sub-pixel
-                // fit needs (LST4:2681-2717) is still in TMEM: the lanes that own rows by-1..by+1 score the three
-                // columns bx-1..bx+1 exactly, and lst_epilogue does not have to recompute nine correlations.
                 if (tid == 0) best[it.task] = b;
                 if (hh == 0 && nbhd) {
                     const uint32_t idx = 0xffffffffu - (uint32_t)(b & 0xffffffffull);
-                    const int by = (int)(idx / (uint32_t)it.rw), bx = (int)(idx - (uint32_t)by * (uint32_t)it.rw);
+                    int by = __float2int_rz(__fmul_rn((float)idx, __frcp_rn((float)it.rw)));      // idx < 2^24: off by one at most
+                    int bx = (int)idx - by * it.rw;
+                    if (bx >= it.rw) by++, bx -= it.rw;
+                    if (bx < 0) by--, bx += it.rw;
                     const int ra = max(max(by - 1, 0), 32 * q4), rb = min(min(by + 1, it.rh_t - 1), 32 * q4 + 31);
                     if (ra <= rb) {       // warp-uniform: this quarter holds some of the rows by-1 .. by+1
                         // correlations of this lane's row at columns bx-1 .. bx+1
                         uint32_t cv[3];
 #pragma unroll
                         for (int d = 0; d < 3; d++) cv[d] = tmem_ld1(dcol_addr(tmem, acc, q4, min(max(bx - 1 + d, 0), TC_NB * TC_MAXNB - 1)));
-                        // Window sums of the up to nine positions: for a row the lanes add the tw + 2 vertical sums of columns
-                        // bx-1 .. bx+tw in parallel (full sum F), then S(bx-1) = F - c[tw] - c[tw+1], S(bx) = F - c[0] - c[tw+1],
-                        // S(bx+1) = F - c[0] - c[1].  Lane 3*(r-by+1) + d keeps the values of position (r, bx-1+d).
-                        uint32_t myS = 0, myQ = 0, myC = 0;
+                        // Window sums: for a row the lanes add the tw + 2 vertical sums of columns bx-1 .. bx+tw in parallel
+                        // (full sum F), then S(bx-1) = F - c[tw] - c[tw+1], S(bx) = F - c[0] - c[tw+1], S(bx+1) = F - c[0] - c[1].
+                        // Lane 3*(r-by+1) + d keeps the values of position (r, bx-1+d).
                         for (int r = ra; r <= rb; r++) {
                             const uint16_t *w1 = V1 + (size_t)r * P1;
                             const uint32_t *w2 = V2 + (size_t)r * P2;
@@ -798,10 +852,8 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                             }
                         }
                         const int dy = lane / 3 - 1, dx = lane - 3 * (lane / 3) - 1;
-                        if (lane < 9 && by + dy >= ra && by + dy <= rb && bx + dx >= 0 && bx + dx < it.rw)
-                            nbhd[(size_t)it.task * 12 + lane] = tc_exact_score(myC, myS, myQ, tcp);
+                        nb_mine = lane < 9 && by + dy >= ra && by + dy <= rb && bx + dx >= 0 && bx + dx < it.rw;
                     }
-                    if (tid == 0) o_flag(nbhd, it.task);
                 }
             } else if (tid == 0) {
                 atomicMax(&best[it.task], b);
@@ -809,6 +861,8 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             tc_fence_before();
             worker_bar();
             if (tid == 0) mbar_arrive(&acc_free[acc]);
+            if (nb_mine) nbhd[(size_t)it.task * 12 + lane] = tc_exact_score(myC, myS, myQ, tcp);
+            if (tp.single_tile && nbhd && tid == 0) o_flag(nbhd, it.task);
             const long long c4 = clock64();
             clk_wait += (c1 - c0) + (c3 - c2);
             clk_v += c2 - c1;

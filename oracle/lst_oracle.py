@@ -465,16 +465,20 @@ def max_loc_first(res: np.ndarray):
 # the reference's own arithmetic
 # --------------------------------------------------------------------------------------
 def subpixel_fit(res: np.ndarray, x: int, y: int) -> Tuple[float, float]:
-    """3x3 quadratic fit, LST4:2681-2717 (values read as float32, computed in double)."""
+    """3x3 quadratic fit, LST4:2681-2717.  FloatIndexer.get returns a Java float, so the four-term sum of fxy and the
+    differences of fx / fy are float32 operations (one rounding each, left to right) promoted to double only by the
+    division by 4.0 / 2.0; fxx and fyy are promoted from the start by the 2.0 * term (LST4:2694-2699)."""
     rows, cols = res.shape
     if x == 0 or x == cols - 1 or y == 0 or y == rows - 1:
         return 0.0, 0.0
+    f = lambda yy, xx: np.float32(res[yy, xx])
     r = lambda yy, xx: float(res[yy, xx])
     fxx = r(y, x - 1) - 2.0 * r(y, x) + r(y, x + 1)
     fyy = r(y - 1, x) - 2.0 * r(y, x) + r(y + 1, x)
-    fxy = (r(y + 1, x + 1) + r(y - 1, x - 1) - r(y - 1, x + 1) - r(y + 1, x - 1)) / 4.0
-    fx = (r(y, x + 1) - r(y, x - 1)) / 2.0
-    fy = (r(y + 1, x) - r(y - 1, x)) / 2.0
+    with np.errstate(all="ignore"):
+        fxy = float(np.float32(np.float32(np.float32(f(y + 1, x + 1) + f(y - 1, x - 1)) - f(y - 1, x + 1)) - f(y + 1, x - 1))) / 4.0
+        fx = float(np.float32(f(y, x + 1) - f(y, x - 1))) / 2.0
+        fy = float(np.float32(f(y + 1, x) - f(y - 1, x))) / 2.0
     denom = fxy * fxy - fxx * fyy
     if denom == 0.0:
         return 0.0, 0.0
