@@ -7,11 +7,11 @@
 // Work item = one tile (128 result rows x up to 4 blocks of 32 result columns) of one window.  One CTA
 // per SM walks the items of a pass (item = blockIdx.x, + gridDim.x, ...) with these roles:
 //
-//   warp 8   window loader   the tile's window rows come in by TMA (cp.async.bulk.tensor.2d, one box of
+//   warp 8   window loader   (lane 0) the tile's window rows come in by TMA (cp.async.bulk.tensor.2d, one box of
 //                            16 bytes x rows per 16-byte column chunk) as [chunk][row][16 B]: 8 consecutive
 //                            rows of one chunk are a 128-byte core matrix *for any starting row*, so the A
 //                            operand "rows y+v" is a start address advanced by v*16 bytes in the descriptor;
-//   warp 9   table feeder    for template row v the Toeplitz band B_v = [D_nd-1; ..; D_0], D_d[n][k] =
+//   warp 8   table feeder    (lane 1) for template row v the Toeplitz band B_v = [D_nd-1; ..; D_0], D_d[n][k] =
 //                            T[v][32d + k - n] (32 x 32 bytes each), streams from global memory (L2) through a
 //                            ring with cp.async.bulk completing on mbarriers;
 //   warp 10  MMA issuer      for every 32-byte K step j of the window one MMA covers all the column blocks
@@ -21,8 +21,11 @@
 //                            window, into shared memory ([column][row], what cv::integral gives matchTemplate);
 //                            (b) epilogue: lane = result row walks x, sliding the horizontal sums, float32
 //                            filter score, OpenCV's double-precision normalisation for the candidates only,
-//                            first-maximum argmax; when the window is one tile also the nine scores around
-//                            the peak for the sub-pixel fit (LST4:2681-2717), read back from TMEM.
+//                            first-maximum argmax; when the window is one tile they also copy what the nine
+//                            scores around the peak need (correlations from TMEM, three rows of vertical sums)
+//                            into a small stash before they release the accumulator;
+//   warp 9   neighbourhood   turns a stash into the nine exact scores for the sub-pixel fit (LST4:2681-2717)
+//                            while the workers are already busy with the next item.
 //
 // No window sum ever goes through global memory; the same arithmetic as the IDP.4A engine (lst_ncc_match),
 // so both engines return identical bits.
@@ -50,8 +53,14 @@ namespace lst {
 #define TC_NISS 2
 #endif
 #define TC_NISS_DOC         // MMA issuer warps: they share the template rows of every ring stage
-#define TC_THREADS (320 + 32 * TC_NISS)   // + warp 8 window loader, warp 9 table feeder, warps 10.. MMA issuers (warp 10 owns the TMEM allocation)
+#define TC_NBW 9                           // the neighbourhood warp
+// 12 warps = 3 per scheduler: a 13th would cap every thread at 128 registers (the register file is per scheduler).
+#define TC_THREADS (320 + 32 * TC_NISS)   // + warp 8: window loader (lane 0) and table feeder (lane 1), warp 9: neighbourhood warp, warps 10..: MMA issuers (warp 10 owns the TMEM allocation)
 #define TC_EPS 1e-5f
+#ifndef TC_VUNROLL
+#define TC_VUNROLL 4
+#endif
+constexpr int kVUnroll = TC_VUNROLL;   // unrolling of the vertical sliding sums
 #ifndef TC_CVT
 #define TC_CVT 0
 #endif
@@ -266,6 +275,120 @@ __device__ __noinline__ float tc_exact_score(uint32_t corr, uint32_t s, uint32_t
     return match_score(*tc, (double)corr, (double)s, (double)sq);
 }
 
+
+// Differences of the vertical sums tw columns apart for 16 consecutive columns from xb (what the horizontal sliding sums of
+// a result row add per step): 128-bit loads when the alignment allows (al: tw is a multiple of 8).
+__device__ __forceinline__ void tc_load_diffs(const uint16_t *v1, const uint32_t *v2, int xb, int tw, bool al, int (&d1)[16], int (&d2)[16])
+{
+    uint32_t o1[8], o2[16];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint4 t4 = *(const uint4 *)(v2 + xb + 4 * j);
+        o2[4 * j] = t4.x, o2[4 * j + 1] = t4.y, o2[4 * j + 2] = t4.z, o2[4 * j + 3] = t4.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint4 t4 = *(const uint4 *)(v1 + xb + 8 * j);
+        o1[4 * j] = t4.x, o1[4 * j + 1] = t4.y, o1[4 * j + 2] = t4.z, o1[4 * j + 3] = t4.w;
+    }
+    if (al) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint4 t4 = *(const uint4 *)(v2 + xb + tw + 4 * j);
+            d2[4 * j] = (int)(t4.x - o2[4 * j]), d2[4 * j + 1] = (int)(t4.y - o2[4 * j + 1]);
+            d2[4 * j + 2] = (int)(t4.z - o2[4 * j + 2]), d2[4 * j + 3] = (int)(t4.w - o2[4 * j + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint4 t4 = *(const uint4 *)(v1 + xb + tw + 8 * j);
+            const uint32_t n4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                d1[8 * j + 2 * e] = (int)(n4[e] & 0xffffu) - (int)(o1[4 * j + e] & 0xffffu);
+                d1[8 * j + 2 * e + 1] = (int)(n4[e] >> 16) - (int)(o1[4 * j + e] >> 16);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            d2[i] = (int)(v2[xb + tw + i] - o2[i]);
+            d1[i] = (int)v1[xb + tw + i] - (int)((i & 1) ? (o1[i >> 1] >> 16) : (o1[i >> 1] & 0xffffu));
+        }
+    }
+}
+
+// the float32 filter score A / sqrt(B) of one position (TM_CCOEFF_NORMED up to the template's constant factor); the two
+// passes of the epilogue must get the same bits, so both call this
+__device__ __forceinline__ float tc_filter(uint32_t N, int ntsum, uint32_t corr, uint32_t S, uint32_t Q, float *Bf_out)
+{
+    // 32 x 32 -> 64-bit products (IMAD.WIDE): every factor fits 31 bits
+    const long long A = (long long)(int)N * (long long)(int)corr + (long long)(int)S * (long long)ntsum;
+    const long long B = (long long)((unsigned long long)N * Q) + (long long)(int)S * (long long)(-(int)S);
+    const float Bf = u64_to_f32((unsigned long long)B);
+    *Bf_out = Bf;
+    return i64_to_f32(A) * rsqrt_fast(Bf);
+}
+
+// Second pass of the TM_CCOEFF_NORMED epilogue over one 16-column chunk of this lane's row (out of line: one or two warps
+// of an item get here).  Every valid position whose filter score reaches thr -- and every nearly flat one, which OpenCV's
+// double formula must decide -- is scored exactly; returns the lane's best key.
+__device__ __noinline__ unsigned long long tc_second_pass(const uint16_t *v1, const uint32_t *v2, uint32_t taddr, int xb, int np, int tw,
+                                                          uint32_t N, int ntsum, float Bflat, float thr, uint32_t idx0, const TplConst *tcp)
+{
+    uint32_t corr[16];
+    tmem_ld16(taddr, corr);
+    uint32_t S = 0, Q = 0;
+#pragma unroll 1
+    for (int u = 0; u < tw; u++) {
+        S += v1[xb + u];
+        Q += v2[xb + u];
+    }
+    unsigned long long mybest = 0ull;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float Bf;
+        const float f = tc_filter(N, ntsum, corr[i], S, Q, &Bf);
+        if (i < np && (Bf <= Bflat || f >= thr)) {
+            const float sc = tc_exact_score(corr[i], S, Q, tcp);
+            const unsigned long long key = pack_key(sc, idx0 + (uint32_t)i, false);
+            mybest = key > mybest ? key : mybest;
+        }
+        S += (uint32_t)v1[xb + tw + i] - (uint32_t)v1[xb + i];
+        Q += v2[xb + tw + i] - v2[xb + i];
+    }
+    return mybest;
+}
+
+// Light second pass over one chunk (TM_CCOEFF_NORMED): the filter scores again, from the sums the first pass had at the start
+// of the chunk; the positions that can be the maximum go to the CTA's candidate list instead of being scored on the spot.
+#define TC_MAXCAND 8
+__device__ __forceinline__ void tc_collect(const uint16_t *v1, const uint32_t *v2, uint32_t taddr, int xb, int np, int tw, bool al, uint32_t N,
+                                           int ntsum, float Bflat, float thr, uint32_t idx0, uint32_t S, uint32_t Q, uint32_t *s_ncand,
+                                           uint4 *s_cand)
+{
+    uint32_t corr[16];
+    tmem_ld16(taddr, corr);
+    int d1[16], d2[16];
+    tc_load_diffs(v1, v2, xb, tw, al, d1, d2);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float Bf;
+        const float f = tc_filter(N, ntsum, corr[i], S, Q, &Bf);
+        if (i < np && (Bf <= Bflat || f >= thr)) {
+            const uint32_t slot = atomicAdd(s_ncand, 1u);
+            if (slot < TC_MAXCAND) s_cand[slot] = make_uint4(idx0 + (uint32_t)i, corr[i], S, Q);
+        }
+        S += (uint32_t)d1[i];
+        Q += (uint32_t)d2[i];
+    }
+}
+
+#ifdef TC_ISS_SLEEP
+#define MBAR_WAIT_ISS mbar_wait_sleep
+#else
+#define MBAR_WAIT_ISS mbar_wait
+#endif
+
 struct TcParams {
     int n_items;       // tasks * tiles_x * tiles_y
     int tiles_x, tiles_y;
@@ -326,6 +449,16 @@ __device__ __forceinline__ int tc_decode(int item, const DevTask *__restrict__ t
     return 1;
 }
 
+// What the workers leave for the neighbourhood warp: the peak, the nine correlations around it and rows by-1 .. by+1 of
+// the vertical sums at columns bx-1 .. bx+tw (0 outside the window).
+#define TC_STASH_COLS 192                 // >= tw + 2 for every supported template (tw <= 181)
+struct TcStash {
+    int task, tpl, by, bx, rw, rh, tw, need_best;    // need_best: the peak's exact score has not been computed yet
+    uint32_t corr[12];
+    uint32_t v2[3][TC_STASH_COLS];
+    uint16_t v1[3][TC_STASH_COLS];
+};
+
 // What the MMA issuer needs for one item.
 struct TcIssue {
     uint64_t a_desc0;
@@ -352,7 +485,7 @@ __device__ __forceinline__ long long tc_issue_item(const TcIssue &q)
         const int s = gg % q.stages;
         const int nv = min(q.vb, q.th - v);
         const long long t3 = clock64();
-        mbar_wait(&q.r_full[s], (gg / q.stages) & 1);
+        MBAR_WAIT_ISS(&q.r_full[s], (gg / q.stages) & 1);
         waited += clock64() - t3;
         tc_fence_after();
         uint32_t b_v = (uint32_t)smem_desc(smem_u32(q.sB + (size_t)s * q.stage_bytes), q.b_lbo, 128);
@@ -408,6 +541,11 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
     __shared__ uint32_t s_tmem;
     __shared__ unsigned long long s_best[8];
     __shared__ uint32_t s_fmax;    // orderable key of the largest filter score any warp has seen in the current item
+    __shared__ __align__(8) uint64_t nb_full[2], nb_free[2];
+    __shared__ __align__(16) TcStash s_stash[2];
+    __shared__ uint32_t s_ncand;   // positions of the current item that can be its maximum (may exceed TC_MAXCAND)
+    __shared__ __align__(16) uint4 s_cand[TC_MAXCAND];   // {map index, correlation, sum I, sum I^2}
+    __shared__ __align__(16) TcItem s_item[2];     // the item whose window is in A buffer [i]; task < 0 = no more items
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t a_bytes = (size_t)tp.kc_a * tp.rows_alloc * 16;
@@ -423,6 +561,8 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             mbar_init(&acc_full[i], TC_NISS);
             mbar_init(&row0_done[i], 1);
             mbar_init(&acc_free[i], 1);
+            mbar_init(&nb_full[i], 1);
+            mbar_init(&nb_free[i], 1);
         }
         for (int s = 0; s < TC_MAXSTAGES; s++) {
             mbar_init(&r_full[s], 1);
@@ -440,14 +580,26 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
     const uint32_t tmem = s_tmem;
 
     if (warp == 8) {
-        // ---- window loader ----
+        // ---- window loader: the only role that decodes items (divisions, dependent global loads); the others read the
+        //      decoded item next to its window once the window has landed ----
         if (lane == 0) {
             int k = 0;
-            for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
+            for (int item = blockIdx.x;; item += gridDim.x) {
                 TcItem it;
-                if (tc_decode(item, tasks, tpls, tp, &it) != 1) continue;
+                int kind = -1;
+                if (item < tp.n_items) {
+                    kind = tc_decode(item, tasks, tpls, tp, &it);
+                    if (kind == 2) atomicMax(&best[it.task], pack_key(1.0f, 0u));   // templSdv^2 < DBL_EPSILON: all ones, first wins
+                    if (kind != 1) continue;
+                }
                 const int buf = tp.n_abuf == 2 ? (k & 1) : 0, u = tp.n_abuf == 2 ? (k >> 1) : k;
                 if (u > 0) mbar_wait_sleep(&a_free[buf], (u - 1) & 1);
+                if (kind < 0) {
+                    s_item[buf].task = -1;
+                    mbar_arrive(&a_full[buf]);
+                    break;
+                }
+                s_item[buf] = it;
                 const int nch = 2 * it.nk;                       // chunks this tile needs
                 mbar_expect_tx(&a_full[buf], (uint32_t)(nch * tp.rows_load * 16));
                 uint8_t *dst = sA + (size_t)buf * a_bytes;
@@ -460,14 +612,16 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                 }
                 k++;
             }
-        }
-    } else if (warp == 9) {
-        // ---- Toeplitz table feeder ----
-        if (lane == 0) {
+        } else if (lane == 1) {
+            // ---- Toeplitz table feeder: the other side of the same branch, so the two lanes block on their barriers and
+            //      progress independently of each other (independent thread scheduling) ----
             int g = 0;
-            for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
-                TcItem it;
-                if (tc_decode(item, tasks, tpls, tp, &it) != 1) continue;
+            for (int k = 0;; k++) {
+                const int buf = tp.n_abuf == 2 ? (k & 1) : 0, ua = tp.n_abuf == 2 ? (k >> 1) : k;
+                mbar_wait_sleep(&a_full[buf], ua & 1);
+                const int tpl_k = s_item[buf].task < 0 ? -1 : s_item[buf].tpl;
+                if (tpl_k < 0) break;
+                struct { int tpl, th, nd; } it = {tpl_k, s_item[buf].th, s_item[buf].nd};
                 const uint8_t *table = tpls->toeplitz[it.tpl];
                 const uint32_t row_bytes = (uint32_t)it.nd * 1024u;
                 for (int v = 0; v < it.th; v += tp.vb, g++) {
@@ -499,13 +653,16 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             int k = 0, g = 0;
             long long m_wa = 0, m_wc = 0, m_wr = 0, m_tot = 0;
             const uint32_t b_hi32 = (uint32_t)(smem_desc(0, 0, 128) >> 32);
-            for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
-                TcItem it;
-                const int kind0 = tc_decode(item, tasks, tpls, tp, &it);
-                const uint32_t pk = __reduce_max_sync(0xffffffffu, (uint32_t)kind0 | (kind0 == 1 ? ((uint32_t)it.nd << 2) | ((uint32_t)it.nbe << 5) |
-                                                                                                       ((uint32_t)it.nk << 8) | ((uint32_t)it.th << 12)
-                                                                                                 : 0u));
-                if ((pk & 3u) != 1u) continue;
+            for (;;) {
+                // all lanes wait for the window, read the item beside it and make its shape warp-uniform
+                {
+                    const int buf_w = tp.n_abuf == 2 ? (k & 1) : 0, ua_w = tp.n_abuf == 2 ? (k >> 1) : k;
+                    MBAR_WAIT_ISS(&a_full[buf_w], ua_w & 1);
+                }
+                const TcItem &sit = s_item[tp.n_abuf == 2 ? (k & 1) : 0];
+                const uint32_t pk = __reduce_max_sync(0xffffffffu, sit.task < 0 ? 0u : 1u | ((uint32_t)sit.nd << 2) | ((uint32_t)sit.nbe << 5) |
+                                                                                          ((uint32_t)sit.nk << 8) | ((uint32_t)sit.th << 12));
+                if ((pk & 3u) != 1u) break;
                 const int nd = (int)((pk >> 2) & 7u), nbe = (int)((pk >> 5) & 7u), nk = (int)((pk >> 8) & 15u), th = (int)(pk >> 12);
                 const int buf = tp.n_abuf == 2 ? (k & 1) : 0, ua = tp.n_abuf == 2 ? (k >> 1) : k;
                 const int acc = k & 1, uc = k >> 1;
@@ -520,8 +677,8 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                     const long long t0 = clock64();
                     mbar_wait(&a_full[buf], ua & 1);
                     const long long t1 = clock64();
-                    if (uc > 0) mbar_wait(&acc_free[acc], (uc - 1) & 1);
-                    if (iss != 0) mbar_wait(&row0_done[acc], uc & 1);
+                    if (uc > 0) MBAR_WAIT_ISS(&acc_free[acc], (uc - 1) & 1);
+                    if (iss != 0) MBAR_WAIT_ISS(&row0_done[acc], uc & 1);
                     const long long t2 = clock64();
                     m_wa += t1 - t0;
                     m_wc += t2 - t1;
@@ -558,26 +715,72 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                 d[3] = (unsigned long long)m_tot;
             }
         }
+    } else if (warp == TC_NBW) {
+        // ---- neighbourhood warp: the nine exact scores around the peak of a single-tile window ----
+        if (tp.single_tile && nbhd) {
+            for (int k = 0;; k++) {
+                const TcStash *st = &s_stash[k & 1];
+                mbar_wait_sleep(&nb_full[k & 1], (k >> 1) & 1);
+                if (st->task < 0) break;        // the workers have seen the end of the items
+                const int by = st->by, bx = st->bx, tw = st->tw;
+                // Window sums of a row: the lanes add the tw + 2 vertical sums of columns bx-1 .. bx+tw (full sum F), then
+                // S(bx-1) = F - c[tw] - c[tw+1], S(bx) = F - c[0] - c[tw+1], S(bx+1) = F - c[0] - c[1].
+                uint32_t myS = 0, myQ = 0;
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++) {
+                    uint32_t f1 = 0, f2 = 0;
+                    for (int c = lane; c < tw + 2; c += 32) f1 += st->v1[dy][c], f2 += st->v2[dy][c];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+                        f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+                    }
+                    const uint32_t a1 = st->v1[dy][0], b1 = st->v1[dy][1], c1 = st->v1[dy][tw], d1 = st->v1[dy][tw + 1];
+                    const uint32_t a2 = st->v2[dy][0], b2 = st->v2[dy][1], c2 = st->v2[dy][tw], d2 = st->v2[dy][tw + 1];
+                    if (lane == 3 * dy) myS = f1 - c1 - d1, myQ = f2 - c2 - d2;
+                    if (lane == 3 * dy + 1) myS = f1 - a1 - d1, myQ = f2 - a2 - d2;
+                    if (lane == 3 * dy + 2) myS = f1 - a1 - b1, myQ = f2 - a2 - b2;
+                }
+                const int dy = lane / 3 - 1, dx = lane - 3 * (lane / 3) - 1;
+                if (lane < 9 && by + dy >= 0 && by + dy < st->rh && bx + dx >= 0 && bx + dx < st->rw) {
+                    const float sc = tc_exact_score(st->corr[lane], myS, myQ, &tpls->c[st->tpl]);
+                    nbhd[(size_t)st->task * 12 + lane] = sc;
+                    if (lane == 4 && st->need_best) best[st->task] = pack_key(sc, (uint32_t)(by * st->rw + bx), false);
+                }
+                const int task = st->task;
+                __syncwarp();
+                if (lane == 0) {
+                    o_flag(nbhd, task);
+                    mbar_arrive(&nb_free[k & 1]);
+                }
+            }
+        }
     } else {
         // ---- workers: vertical sums, then the epilogue of the item ----
         const int tid = threadIdx.x;
         const int q4 = warp & 3, hh = warp >> 2;         // TMEM lane quarter (rows 32*q4 ..), column half
         const int row = 32 * q4 + lane;
         const int P1 = tp.p1, P2 = tp.p2;                // row pitches of V1 (in u16) and V2 (in u32)
-        long long clk_wait = 0, clk_v = 0, clk_e = 0, clk_e1 = 0, clk_e2 = 0, clk_e3 = 0;
+        long long clk_wait = 0, clk_v = 0, clk_e = 0, clk_e1 = 0, clk_e2 = 0, clk_e3 = 0, clk_e4 = 0, clk_e5 = 0, clk_p1 = 0;
+        const bool do_nb = tp.single_tile && nbhd != nullptr;
         int k = 0;
-        for (int item = blockIdx.x; item < tp.n_items; item += gridDim.x) {
-            TcItem it;
-            const int kind = tc_decode(item, tasks, tpls, tp, &it);
-            if (kind == 2 && tid == 0) atomicMax(&best[it.task], pack_key(1.0f, 0u));   // templSdv^2 < DBL_EPSILON: all ones, first wins
-            if (kind != 1) continue;
-            const TplConst *tcp = &tpls->c[it.tpl];
+        for (;;) {
             const int buf = tp.n_abuf == 2 ? (k & 1) : 0, ua = tp.n_abuf == 2 ? (k >> 1) : k;
             const int acc = k & 1, uc = k >> 1;
-            const int tw = it.tw, th = it.th;
             const long long c0 = clock64();
             mbar_wait(&a_full[buf], ua & 1);
             const long long c1 = clock64();
+            const TcItem it = s_item[buf];      // decoded by the window loader
+            if (it.task < 0) {
+                if (do_nb && tid == 0) {        // tell the neighbourhood warp
+                    if (k >= 2) mbar_wait(&nb_free[k & 1], ((k >> 1) - 1) & 1);
+                    s_stash[k & 1].task = -1;
+                    mbar_arrive(&nb_full[k & 1]);
+                }
+                break;
+            }
+            const TplConst *tcp = &tpls->c[it.tpl];
+            const int tw = it.tw, th = it.th;
             // (a) vertical sliding sums: a thread owns two adjacent window columns (16-bit loads) over a segment of the
             //     tile's rows; V1 / V2 are [row][column], so a pair is one 32-bit / one 64-bit store
             if (!(tp.mode & 5)) {
@@ -611,7 +814,7 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                     *o1 = s0 | (s1 << 16);
                     *o2 = make_uint2(q0, q1);
                     const uint8_t *pn = p + (size_t)(r0 + th) * 16, *po = p + (size_t)r0 * 16;
-#pragma unroll 4
+#pragma unroll kVUnroll
                     for (int r = r0 + 1; r < r1; r++) {
                         const uint32_t wn = *(const uint16_t *)pn, wo = *(const uint16_t *)po;
                         pn += 16, po += 16;
@@ -626,7 +829,7 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                     }
                 }
             }
-            if (tid == 0) s_fmax = 0u;
+            if (tid == 0) s_fmax = 0u, s_ncand = 0u;
             worker_bar();
             if (tid == 0) mbar_arrive(&a_free[buf]);
             const long long c2 = clock64();
@@ -647,7 +850,10 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             const int nb0 = hh == 0 ? 0 : nbh, nb1 = hh == 0 ? nbh : it.nbe;
             const bool al = ((tw & 7) == 0);               // the columns tw further on are 16-byte aligned as well
             unsigned long long mybest = 0ull;
-            if (nb0 < nb1 && 32 * q4 < it.rh_t && !(tp.mode & 9)) {
+            float runmax = -3.0e38f, cm0 = -3.0e38f, cm1 = -3.0e38f, cm2 = -3.0e38f, cm3 = -3.0e38f;   // first-pass maxima: lane, lane's chunks
+            uint32_t sc0 = 0, sc1 = 0, sc2 = 0, sc3 = 0, qc0 = 0, qc1 = 0, qc2 = 0, qc3 = 0;           // window sums at the start of the lane's chunks
+            const bool epi_active = nb0 < nb1 && 32 * q4 < it.rh_t && !(tp.mode & 9);
+            if (epi_active) {
                 const uint16_t *v1 = V1 + (size_t)vrow * P1;
                 const uint32_t *v2 = V2 + (size_t)vrow * P2;
                 // horizontal sums under the template footprint at the first column of this warp's range
@@ -670,107 +876,55 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                 clk_e1 += clock64() - c3;
                 const uint32_t rowidx = (uint32_t)y * (uint32_t)it.rw + (uint32_t)it.x0;
                 const int xend = min(TC_NB * nb1, it.rw_t);
+                int ci = 0;
 #pragma unroll 1
-                for (int xb = TC_NB * nb0; xb < xend; xb += 16) {
+                for (int xb = TC_NB * nb0; xb < xend; xb += 16, ci++) {
                     uint32_t corr[16];
                     tmem_ld16(dcol_addr(tmem, acc, q4, xb), corr);
                     const int np = row_ok ? min(16, it.rw_t - xb) : 0;
-                    // differences of the vertical sums tw columns apart: 128-bit loads when the alignment allows
                     int d1[16], d2[16];
-                    {
-                        uint32_t o1[8], o2[16];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint4 t4 = *(const uint4 *)(v2 + xb + 4 * j);
-                            o2[4 * j] = t4.x, o2[4 * j + 1] = t4.y, o2[4 * j + 2] = t4.z, o2[4 * j + 3] = t4.w;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 2; j++) {
-                            const uint4 t4 = *(const uint4 *)(v1 + xb + 8 * j);
-                            o1[4 * j] = t4.x, o1[4 * j + 1] = t4.y, o1[4 * j + 2] = t4.z, o1[4 * j + 3] = t4.w;
-                        }
-                        if (al) {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const uint4 t4 = *(const uint4 *)(v2 + xb + tw + 4 * j);
-                                d2[4 * j] = (int)(t4.x - o2[4 * j]), d2[4 * j + 1] = (int)(t4.y - o2[4 * j + 1]);
-                                d2[4 * j + 2] = (int)(t4.z - o2[4 * j + 2]), d2[4 * j + 3] = (int)(t4.w - o2[4 * j + 3]);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 2; j++) {
-                                const uint4 t4 = *(const uint4 *)(v1 + xb + tw + 8 * j);
-                                const uint32_t n4[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    d1[8 * j + 2 * e] = (int)(n4[e] & 0xffffu) - (int)(o1[4 * j + e] & 0xffffu);
-                                    d1[8 * j + 2 * e + 1] = (int)(n4[e] >> 16) - (int)(o1[4 * j + e] >> 16);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                d2[i] = (int)(v2[xb + tw + i] - o2[i]);
-                                d1[i] = (int)v1[xb + tw + i] - (int)((i & 1) ? (o1[i >> 1] >> 16) : (o1[i >> 1] & 0xffffu));
-                            }
-                        }
-                    }
-                    float g[16];
+                    tc_load_diffs(v1, v2, xb, tw, al, d1, d2);
                     if (method == 5) {
-                        // Fast path: the filter score f = A / sqrt(B) of the 16 positions with nothing but the arithmetic --
-                        // no validity or flatness selects.  A lane whose chunk is partial (np < 16) or holds a nearly flat
-                        // footprint (2B <= N + N/32; OpenCV's double formula decides those) redoes its positions below.
+                        // First pass: the filter score f = A / sqrt(B) of the 16 positions with nothing but the arithmetic -- no
+                        // validity or flatness selects, no exact scores: only the lane's maximum per chunk is kept.  A lane whose
+                        // chunk is partial (np < 16) or holds a nearly flat footprint (2B <= N + N/32; OpenCV's double formula
+                        // decides those) redoes its maximum below.
                         const uint32_t S0 = S, Q0 = Q;
                         float tmax = -3.0e38f, bmin = 3.0e38f;
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            // 32 x 32 -> 64-bit products (IMAD.WIDE): every factor fits 31 bits
-                            const long long A = (long long)(int)N * (long long)(int)corr[i] + (long long)(int)S * (long long)ntsum;
-                            const long long B = (long long)((unsigned long long)N * Q) + (long long)(int)S * (long long)(-(int)S);
-                            const float Bf = u64_to_f32((unsigned long long)B);
-                            const float f = i64_to_f32(A) * rsqrt_fast(Bf);
-                            g[i] = f;
+                            float Bf;
+                            const float f = tc_filter(N, ntsum, corr[i], S, Q, &Bf);
                             tmax = fmaxf(tmax, f);          // a NaN (B = 0) is ignored here and caught by bmin
                             bmin = fminf(bmin, Bf);
                             S += (uint32_t)d1[i];
                             Q += (uint32_t)d2[i];
                         }
-                        bool special = false;               // this lane has positions that are always scored exactly
-                        if (np < 16 || bmin <= Bflat) {
+                        float cmv = tmax;                   // what the second pass compares with the threshold
+                        if (!row_ok) {                      // a lane below the map: nothing to offer (and no reason to redo anything)
+                            tmax = cmv = -3.0e38f;
+                        } else if (np < 16 || bmin <= Bflat) {
                             tmax = -3.0e38f;
+                            bool special = false;           // a valid, nearly flat position: always scored exactly
                             uint32_t Sr = S0, Qr = Q0;
 #pragma unroll
                             for (int i = 0; i < 16; i++) {
-                                const long long B = (long long)((unsigned long long)N * Qr) + (long long)(int)Sr * (long long)(-(int)Sr);
-                                const bool flat = u64_to_f32((unsigned long long)B) <= Bflat;      // exact: integers below 2^24 when it matters
-                                if (i >= np) g[i] = -3.0e38f;
-                                else if (flat) g[i] = 3.0e38f, special = true;
-                                else tmax = fmaxf(tmax, g[i]);
-                                Sr += (uint32_t)d1[i];
-                                Qr += (uint32_t)d2[i];
-                            }
-                        }
-                        const float lane_max = tmax;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-                        // OpenCV's double-precision score for the candidates only.  A candidate must come within
-                        // eps of the largest filter score seen anywhere in the tile so far (every position within eps
-                        // of the final maximum passes this, whenever it is visited), not just of this block's.
-                        if (lane == 0 && tmax > -3.0e38f) atomicMax(&s_fmax, f32_key(tmax));
-                        __syncwarp();
-                        const float thr = fmaxf(tmax, key_f32(*(volatile uint32_t *)&s_fmax)) - eps_g;
-                        if (lane_max >= thr || special) {
-                            uint32_t Sr = S0, Qr = Q0;
-#pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                if (g[i] >= thr && i < np) {
-                                    const float sc = tc_exact_score(corr[i], Sr, Qr, tcp);
-                                    const unsigned long long key = pack_key(sc, rowidx + (uint32_t)(xb + i), want_min);
-                                    mybest = key > mybest ? key : mybest;
+                                float Bf;
+                                const float f = tc_filter(N, ntsum, corr[i], Sr, Qr, &Bf);
+                                if (i < np) {
+                                    if (Bf <= Bflat) special = true;      // exact: integers below 2^24 when it matters
+                                    else tmax = fmaxf(tmax, f);
                                 }
                                 Sr += (uint32_t)d1[i];
                                 Qr += (uint32_t)d2[i];
                             }
+                            cmv = special ? 3.0e38f : tmax;
                         }
+                        runmax = fmaxf(runmax, tmax);
+                        if (ci == 0) cm0 = cmv, sc0 = S0, qc0 = Q0;
+                        else if (ci == 1) cm1 = cmv, sc1 = S0, qc1 = Q0;
+                        else if (ci == 2) cm2 = cmv, sc2 = S0, qc2 = Q0;
+                        else cm3 = cmv, sc3 = S0, qc3 = Q0;
                     } else {
                         // the other five methods: every position is scored with OpenCV's formula
 #pragma unroll
@@ -786,12 +940,75 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                     }
                 }
             }
+            clk_p1 += clock64() - c3;
+            uint32_t ncand = TC_MAXCAND + 1;       // the other methods: every position was scored in the first pass
+            if (method == 5) {
+                // Second pass: only positions within eps of the largest filter score of the whole tile can be its maximum.  The
+                // warps that hold such positions put them on the candidate list; usually there is one.
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) runmax = fmaxf(runmax, __shfl_xor_sync(0xffffffffu, runmax, o));
+                if (lane == 0 && runmax > -3.0e38f) atomicMax(&s_fmax, f32_key(runmax));
+                worker_bar();
+                const uint32_t kmax = *(volatile uint32_t *)&s_fmax;
+                const float thr = kmax ? key_f32(kmax) - eps_g : -3.0e38f;
+                const uint16_t *v1 = V1 + (size_t)vrow * P1;
+                const uint32_t *v2 = V2 + (size_t)vrow * P2;
+                const uint32_t rowidx = (uint32_t)y * (uint32_t)it.rw + (uint32_t)it.x0;
+                const int xend = min(TC_NB * nb1, it.rw_t);
+                if (epi_active) {
+                    int ci = 0;
+#pragma unroll 1
+                    for (int xb = TC_NB * nb0; xb < xend; xb += 16, ci++) {
+                        const float cmv = ci == 0 ? cm0 : (ci == 1 ? cm1 : (ci == 2 ? cm2 : cm3));
+                        if (!__any_sync(0xffffffffu, cmv >= thr)) continue;
+                        const uint32_t Sc = ci == 0 ? sc0 : (ci == 1 ? sc1 : (ci == 2 ? sc2 : sc3));
+                        const uint32_t Qc = ci == 0 ? qc0 : (ci == 1 ? qc1 : (ci == 2 ? qc2 : qc3));
+                        const int np = row_ok ? min(16, it.rw_t - xb) : 0;
+                        tc_collect(v1, v2, dcol_addr(tmem, acc, q4, xb), xb, np, tw, al, N, ntsum, Bflat, thr, rowidx + (uint32_t)xb, Sc, Qc,
+                                   &s_ncand, s_cand);
+                    }
+                }
+                worker_bar();
+                ncand = *(volatile uint32_t *)&s_ncand;
+                if (ncand > TC_MAXCAND && epi_active) {
+                    // too many for the list (flat or periodic windows): every lane scores its own candidates
+                    int ci = 0;
+#pragma unroll 1
+                    for (int xb = TC_NB * nb0; xb < xend; xb += 16, ci++) {
+                        const float cmv = ci == 0 ? cm0 : (ci == 1 ? cm1 : (ci == 2 ? cm2 : cm3));
+                        if (!__any_sync(0xffffffffu, cmv >= thr)) continue;
+                        const int np = row_ok ? min(16, it.rw_t - xb) : 0;
+                        const unsigned long long key = tc_second_pass(v1, v2, dcol_addr(tmem, acc, q4, xb), xb, np, tw, N, ntsum, Bflat, thr,
+                                                                      rowidx + (uint32_t)xb, tcp);
+                        mybest = key > mybest ? key : mybest;
+                    }
+                }
+            }
             const long long c3b = clock64();
-            for (int o = 16; o > 0; o >>= 1) {
-                unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);
-                mybest = other > mybest ? other : mybest;
+            // One candidate in a window that is this tile alone: it is the argmax whatever its exact score, and the
+            // neighbourhood warp computes that score anyway (the centre of the 3x3) -- the workers score nothing.
+            const bool deferred = do_nb && ncand == 1;
+            if (ncand <= TC_MAXCAND && !deferred) {
+                if (warp == 0) {          // the listed candidates, one per lane
+                    unsigned long long key = 0ull;
+                    if (lane < (int)ncand) {
+                        const uint4 cd = s_cand[lane];
+                        key = pack_key(tc_exact_score(cd.y, cd.z, cd.w, tcp), cd.x, false);
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                        key = other > key ? other : key;
+                    }
+                    mybest = key;
+                }
+            } else if (ncand > TC_MAXCAND) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);
+                    mybest = other > mybest ? other : mybest;
+                }
             }
             if (lane == 0) s_best[warp] = mybest;
+            if (do_nb && tid == 0 && k >= 2) mbar_wait(&nb_free[k & 1], ((k >> 1) - 1) & 1);    // the stash of item k-2 has been read
             worker_bar();
             const long long c3c = clock64();
             clk_e2 += c3b - c3;
@@ -799,76 +1016,63 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             unsigned long long b = s_best[0];
 #pragma unroll
             for (int w = 1; w < 8; w++) b = s_best[w] > b ? s_best[w] : b;
-            // The window is this tile alone (single_tile): b is its final argmax and the 3x3 neighbourhood the sub-pixel fit
-            // needs (LST4:2681-2717) is still in TMEM.  The warps that own rows by-1..by+1 collect the correlations and the
-            // window sums of the up to nine positions now, release the accumulator and the vertical sums, and score the
-            // positions afterwards (registers only) -- lst_epilogue does not have to recompute nine correlations.
-            uint32_t myS = 0, myQ = 0, myC = 0;
-            bool nb_mine = false;
+            if (deferred) b = (unsigned long long)(0xffffffffu - s_cand[0].x);      // index only; the score comes later
             if (tp.single_tile) {
-                if (tid == 0) best[it.task] = b;
-                if (hh == 0 && nbhd) {
+                // The window is this tile alone: b is its final argmax, and what the 3x3 neighbourhood of the sub-pixel fit
+                // (LST4:2681-2717) needs is still on chip.  The workers copy it into the stash -- the nine correlations from TMEM
+                // (the warps that own rows by-1 .. by+1), rows by-1 .. by+1 of the vertical sums at columns bx-1 .. bx+tw -- and
+                // go on; the neighbourhood warp scores the nine positions, so lst_epilogue does not recompute nine correlations.
+                if (tid == 0 && !deferred) best[it.task] = b;
+                if (do_nb) {
+                    TcStash *st = &s_stash[k & 1];
                     const uint32_t idx = 0xffffffffu - (uint32_t)(b & 0xffffffffull);
                     int by = __float2int_rz(__fmul_rn((float)idx, __frcp_rn((float)it.rw)));      // idx < 2^24: off by one at most
                     int bx = (int)idx - by * it.rw;
                     if (bx >= it.rw) by++, bx -= it.rw;
                     if (bx < 0) by--, bx += it.rw;
-                    const int ra = max(max(by - 1, 0), 32 * q4), rb = min(min(by + 1, it.rh_t - 1), 32 * q4 + 31);
-                    if (ra <= rb) {       // warp-uniform: this quarter holds some of the rows by-1 .. by+1
-                        // correlations of this lane's row at columns bx-1 .. bx+1
+                    if (tid == 0) {
+                        st->task = it.task, st->tpl = it.tpl, st->by = by, st->bx = bx;
+                        st->rw = it.rw, st->rh = it.rh_t, st->tw = tw, st->need_best = deferred ? 1 : 0;
+                    }
+                    if (!(tp.mode & 64) && hh == 0 && by + 1 >= 32 * q4 && by - 1 <= 32 * q4 + 31) {       // warp-uniform: this quarter holds some of the rows
                         uint32_t cv[3];
 #pragma unroll
                         for (int d = 0; d < 3; d++) cv[d] = tmem_ld1(dcol_addr(tmem, acc, q4, min(max(bx - 1 + d, 0), TC_NB * TC_MAXNB - 1)));
-                        // Window sums: for a row the lanes add the tw + 2 vertical sums of columns bx-1 .. bx+tw in parallel
-                        // (full sum F), then S(bx-1) = F - c[tw] - c[tw+1], S(bx) = F - c[0] - c[tw+1], S(bx+1) = F - c[0] - c[1].
-                        // Lane 3*(r-by+1) + d keeps the values of position (r, bx-1+d).
-                        for (int r = ra; r <= rb; r++) {
-                            const uint16_t *w1 = V1 + (size_t)r * P1;
-                            const uint32_t *w2 = V2 + (size_t)r * P2;
-                            uint32_t f1 = 0, f2 = 0;
-                            for (int c = lane; c < tw + 2; c += 32) {
-                                const int col = bx - 1 + c;
-                                if (col >= 0 && col < it.rw + tw - 1) f1 += w1[col], f2 += w2[col];
-                            }
+                        const int dr = row - by + 1;
+                        if (dr >= 0 && dr < 3) {
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                f1 += __shfl_xor_sync(0xffffffffu, f1, o);
-                                f2 += __shfl_xor_sync(0xffffffffu, f2, o);
-                            }
-                            const int cl[4] = {bx - 1, bx, bx - 1 + tw, bx + tw};
-                            uint32_t e1[4], e2[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const bool ok = cl[e] >= 0 && cl[e] < it.rw + tw - 1;
-                                e1[e] = ok ? w1[cl[e]] : 0u;
-                                e2[e] = ok ? w2[cl[e]] : 0u;
-                            }
-                            const uint32_t s3[3] = {f1 - e1[2] - e1[3], f1 - e1[0] - e1[3], f1 - e1[0] - e1[1]};
-                            const uint32_t q3[3] = {f2 - e2[2] - e2[3], f2 - e2[0] - e2[3], f2 - e2[0] - e2[1]};
-#pragma unroll
-                            for (int d = 0; d < 3; d++) {
-                                const uint32_t c_rd = __shfl_sync(0xffffffffu, cv[d], r & 31);
-                                if (lane == 3 * (r - by + 1) + d) myS = s3[d], myQ = q3[d], myC = c_rd;
-                            }
+                            for (int d = 0; d < 3; d++) st->corr[3 * dr + d] = cv[d];
                         }
-                        const int dy = lane / 3 - 1, dx = lane - 3 * (lane / 3) - 1;
-                        nb_mine = lane < 9 && by + dy >= ra && by + dy <= rb && bx + dx >= 0 && bx + dx < it.rw;
+                    }
+                    const int ncs = tw + 2, vmax = it.rw + tw - 1;
+                    for (int e = tid; e < 3 * ncs && !(tp.mode & 32); e += TC_WORKERS) {
+                        const int dr = e >= 2 * ncs ? 2 : (e >= ncs ? 1 : 0), c = e - dr * ncs;
+                        const int r = by - 1 + dr, col = bx - 1 + c;
+                        const bool ok = r >= 0 && r < it.rh_t && col >= 0 && col < vmax;
+                        st->v1[dr][c] = ok ? V1[(size_t)r * P1 + col] : (uint16_t)0;
+                        st->v2[dr][c] = ok ? V2[(size_t)r * P2 + col] : 0u;
                     }
                 }
             } else if (tid == 0) {
                 atomicMax(&best[it.task], b);
             }
+            const long long c3d = clock64();
             tc_fence_before();
             worker_bar();
-            if (tid == 0) mbar_arrive(&acc_free[acc]);
-            if (nb_mine) nbhd[(size_t)it.task * 12 + lane] = tc_exact_score(myC, myS, myQ, tcp);
-            if (tp.single_tile && nbhd && tid == 0) o_flag(nbhd, it.task);
+            const long long c3e = clock64();
+            clk_e4 += c3d - c3c;
+            clk_e5 += c3e - c3d;
+            if (tid == 0) {
+                mbar_arrive(&acc_free[acc]);
+                if (do_nb) mbar_arrive(&nb_full[k & 1]);
+            }
             const long long c4 = clock64();
             clk_wait += (c1 - c0) + (c3 - c2);
             clk_v += c2 - c1;
             clk_e += c4 - c3;
             k++;
         }
+        if (tp.dbg && lane == 0) tp.dbg[(size_t)(1536 + blockIdx.x) * 8 + warp] = (unsigned long long)clk_p1;
         if (tp.dbg && tid == 0) {
             unsigned long long *d = tp.dbg + (size_t)blockIdx.x * 8;
             d[0] = (unsigned long long)clk_wait;
@@ -879,6 +1083,8 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
             d2[0] = (unsigned long long)clk_e1;
             d2[1] = (unsigned long long)clk_e2;
             d2[2] = (unsigned long long)clk_e3;
+            d2[3] = (unsigned long long)clk_e4;
+            d2[4] = (unsigned long long)clk_e5;
         }
     }
     __syncwarp();
@@ -921,7 +1127,7 @@ static bool make_window_map(CUtensorMap *map, const uint8_t *win8, int pitch, lo
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static const size_t kTcSmemMax = 227 * 1024 - 2048;    // dynamic part; the static barriers and the 128-byte alignment take the rest
+static const size_t kTcSmemMax = 227 * 1024 - 9216;    // dynamic part; the static barriers, the two neighbourhood stashes and the 128-byte alignment take the rest
 
 // Picks the tile shape and the shared-memory split for a pass; returns the dynamic shared-memory size, 0 = does not fit.
 static size_t tc_plan(int max_rw, int max_rh, int tw, int th, TcParams *tp)
@@ -1040,18 +1246,25 @@ int launch_ncc_tc(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int
         cudaStreamSynchronize(stream);
         static unsigned long long h[2048 * 8];
         cudaMemcpy(h, tp.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        double a[8] = {0}, e[3] = {0};
+        double a[8] = {0}, e[5] = {0};
         for (int i = 0; i < grid; i++) {
             for (int j = 0; j < 8; j++) a[j] += (double)h[8 * i + j];
-            for (int j = 0; j < 3; j++) e[j] += (double)h[8 * (1024 + i) + j];
+            for (int j = 0; j < 5; j++) e[j] += (double)h[8 * (1024 + i) + j];
         }
         const double k = a[3];
+        {
+            double w8[8] = {0};
+            for (int i = 0; i < grid; i++)
+                for (int j = 0; j < 8; j++) w8[j] += (double)h[8 * (1536 + i) + j];
+            fprintf(stderr, "lst_ncc_tc first pass per worker warp (cycles per item): %.0f %.0f %.0f %.0f | %.0f %.0f %.0f %.0f\n", w8[0] / k, w8[1] / k,
+                    w8[2] / k, w8[3] / k, w8[4] / k, w8[5] / k, w8[6] / k, w8[7] / k);
+        }
         fprintf(stderr,
                 "lst_ncc_tc (cycles per item, mean over %d CTAs, %.0f items): workers wait %.0f vsums %.0f epilogue %.0f | mma wait-window %.0f "
                 "wait-acc %.0f wait-table %.0f total %.0f | nbc %d abuf %d stages %d x %d B smem %zu | epilogue warp 0: init %.0f, to end of chunks %.0f, "
-                "barrier %.0f\n",
+                "barrier %.0f, stash %.0f, barrier %.0f\n",
                 grid, k, a[0] / k, a[1] / k, a[2] / k, a[4] / k, a[5] / k, a[6] / k, a[7] / k, tp.nbc, tp.n_abuf, tp.stages, tp.stage_bytes,
-                smem, e[0] / k, e[1] / k, e[2] / k);
+                smem, e[0] / k, e[1] / k, e[2] / k, e[3] / k, e[4] / k);
     }
     return 1;
 }
