@@ -1,6 +1,7 @@
 // lst_device.h -- structures and launchers shared by the CUDA kernels (lst_kernels.cu) and the
 // runtime (lst_runtime.cu).  Internal; the public boundary is include/lst_b200.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -85,6 +86,13 @@ int launch_minmax(const DevTask *tasks, int n_tasks, int max_h, const Surface *s
                   uint32_t *mm_keys, cudaStream_t stream);
 int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces,
                       const PreprocParams &pp, const uint32_t *mm_keys, uint8_t *win8, cudaStream_t stream);
+// Second-generation blur kernel (lst_preprocess_win.cuh): one CTA keeps the whole raw crop of a window in shared memory.
+bool preprocess_win_eligible(int pixel_type, int max_w, int max_h);
+int launch_preprocess_win(const DevTask *tasks, int n_tasks, int max_w, int max_h, const Surface *surfaces, const PreprocParams &pp,
+                          uint8_t *win8, cudaStream_t stream);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda); rank <= 3, no swizzle, zero fill
+bool encode_tensor_map(CUtensorMap *map, CUtensorMapDataType type, int rank, const void *base, const uint64_t *dims,
+                       const uint64_t *strides_bytes, const uint32_t *box);
 // ROI ingest by kernel (irregularly placed slices): copy 5 rectangles of each of n_frames pinned host
 // slices (device-mapped pointers) into the ROI ring.
 int launch_gather_rois(const void *const *mapped_frames, int n_frames, const RoiDesc rois[5], int frame_w, int bpp,

@@ -10,7 +10,9 @@
 //
 // Compiled with -fmad=false: every float/double operation rounds once, like the Java and OpenCV
 // code it reproduces.  All heavy arithmetic is integer (IDP.4A.U8.U8), which is exact.
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -635,6 +637,10 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
     return launches;
 }
 
+}  // namespace lst
+#include "lst_preprocess_win.cuh"
+namespace lst {
+
 // ------------------------------------------------------------------------------------------------
 // exact NCC + window sums + argmax (one kernel)
 // ------------------------------------------------------------------------------------------------
@@ -1141,6 +1147,7 @@ static void prefer_max_shared_everywhere()
     cudaFuncSetAttribute(lst_epilogue, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_solve, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
     cudaFuncSetAttribute(lst_gather_rois, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    pt_set_attributes();
     cudaGetLastError();
 }
 

@@ -1114,6 +1114,19 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
+bool encode_tensor_map(CUtensorMap *map, CUtensorMapDataType type, int rank, const void *base, const uint64_t *dims,
+                       const uint64_t *strides_bytes, const uint32_t *box)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || rank < 1 || rank > 3) return false;
+    cuuint64_t d[3], st[2];
+    cuuint32_t b[3], es[3] = {1u, 1u, 1u};
+    for (int i = 0; i < rank; i++) d[i] = dims[i], b[i] = box[i];
+    for (int i = 0; i + 1 < rank; i++) st[i] = strides_bytes[i];
+    return enc(map, type, (cuuint32_t)rank, (void *)base, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // The pass's 8-bit windows as one 2-D byte image [total_rows][pitch]; box = {16 bytes, rows}.
 static bool make_window_map(CUtensorMap *map, const uint8_t *win8, int pitch, long long total_rows, int box_rows)
 {

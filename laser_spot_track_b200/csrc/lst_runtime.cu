@@ -123,6 +123,7 @@ struct lst_ctx : public Executor {
     int solve(const double *dis10, int n, double *out5) override;
     int run_group(const lst_task *tasks, int n, lst_task_result *results, bool preprocess_only, bool have_win8,
                   int tpl_override, float *map_out_host);
+    int preproc_engine = 0;      // 0 = auto (lst_preprocess_win when the window fits), 1 = always lst_preprocess (LST_PREPROC=old)
     int ensure_tasks(int n);
     int ensure_frames(int n);
     int ensure_scratch(size_t win_bytes, size_t map_elems);
@@ -397,8 +398,14 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     if (!have_win8) {
         PreprocParams pp;
         preproc_params(&pp, max_w, max_h);
-        if (pp.range_per_task && !pp.minmax_in_kernel) launches += launch_minmax(d_tasks, n, max_h, d_surf, pp, d_mm, s_compute);
-        launches += launch_preprocess(d_tasks, n, max_w, max_h, d_surf, pp, d_mm, d_win8, s_compute);
+        if (preproc_engine == 0 && preprocess_win_eligible(p.pixel_type, max_w, max_h)) {
+            int l2 = launch_preprocess_win(d_tasks, n, max_w, max_h, d_surf, pp, d_win8, s_compute);
+            if (l2 < 0) return fail(LST_ERR_CUDA, "lst_preprocess_win launch failed");
+            launches += l2;
+        } else {
+            if (pp.range_per_task && !pp.minmax_in_kernel) launches += launch_minmax(d_tasks, n, max_h, d_surf, pp, d_mm, s_compute);
+            launches += launch_preprocess(d_tasks, n, max_w, max_h, d_surf, pp, d_mm, d_win8, s_compute);
+        }
     }
     if (!preprocess_only) {
         MatchParams mp;
@@ -602,6 +609,7 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
             for (int k = 0; k < 5; k++) c->roi_margin[k] = c->roi_margin_fixed;
         }
         if (const char *a = getenv("LST_ROI_ALIGN")) c->roi_align_bytes = std::max(4, atoi(a));
+        if (const char *b = getenv("LST_PREPROC")) c->preproc_engine = !strcmp(b, "old") ? 1 : 0;   // A/B runs of the blur kernels
     }
     float kern[7], ksum[7];
     make_gaussian_kernel(kern, ksum);
@@ -1404,10 +1412,15 @@ struct lst_multi {
     int lead_in = 2;
 };
 
-static bool same_windows(const double a[10], const double b[10])
+// Do two displacement states give the same records from here on?  The windows depend on (int)dis only (LST4:1327-1328).
+// With search-area doubling the un-truncated displacement of mark1 also enters: when mark1 is lost and found again its
+// shift against the *previous* dis moves the other four windows (LST4:1757: int += double), so there the two mark1
+// components must agree exactly -- a fraction that differs could move a window by a pixel.
+static bool same_windows(const double a[10], const double b[10], bool doubling)
 {
     for (int i = 0; i < 10; i++)
         if (jint(a[i]) != jint(b[i])) return false;
+    if (doubling && (a[2] != b[2] || a[3] != b[3])) return false;
     return true;
 }
 
@@ -1531,7 +1544,7 @@ static int multi_track(lst_multi *m, const void *const *frame_ptrs, bool on_devi
         if (n == 0) continue;
         lst_ctx *c = m->ctx[r];
         bool any_ok = false;
-        if (!same_windows(verified, guess[r].data())) {
+        if (!same_windows(verified, guess[r].data(), c->p.doubling != 0)) {
             lst_set_state(c, verified);
             int rc = track(c, frame_ptrs + lo[r], first_frame_index + lo[r], n, out + lo[r]);
             if (rc != LST_OK) {

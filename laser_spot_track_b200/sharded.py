@@ -31,9 +31,13 @@ def _jint(v: float) -> int:
     return int(math.trunc(v))
 
 
-def same_windows(a: Sequence[float], b: Sequence[float]) -> bool:
-    """Two displacement states place all five search windows identically (LST4:1327-1328)."""
-    return all(_jint(x) == _jint(y) for x, y in zip(a, b))
+def same_windows(a: Sequence[float], b: Sequence[float], doubling: bool = False) -> bool:
+    """Two displacement states give the same records from here on: they place all five search windows identically
+    (LST4:1327-1328) and -- with search-area doubling, where mark1's un-truncated displacement shifts the other four
+    windows when mark1 is lost and found again (LST4:1757) -- agree exactly in the two mark1 components."""
+    if not all(_jint(x) == _jint(y) for x, y in zip(a, b)):
+        return False
+    return not doubling or (a[2] == b[2] and a[3] == b[3])
 
 
 def chunk_bounds(n_frames: int, world: int):
@@ -89,6 +93,8 @@ class ShardedTracker:
         self.comm = comm or LocalComm()
         self.rank, self.world = self.comm.rank, self.comm.world
         self.retracked = 0
+        params = getattr(tracker, "params", None)      # LaserSpotTrack4 keeps its lst_params; the CPU stand-ins of the tests may not
+        self.doubling = bool(getattr(params, "doubling", 0)) or bool(getattr(tracker, "doubling", False))
 
     def track_chunk(self, frames, first_frame_index: int, start_state: Sequence[float],
                     lead_in: Optional[Sequence] = None):
@@ -115,7 +121,7 @@ class ShardedTracker:
         first_bad = None
         for r in range(1, self.world):
             g_end, g_guess, g_any = gathered[r][:10], gathered[r][10:20], gathered[r][20] != 0.0
-            if not same_windows(verified, g_guess):
+            if not same_windows(verified, g_guess, self.doubling):
                 first_bad = r
                 break
             if r == self.rank:
@@ -126,7 +132,7 @@ class ShardedTracker:
                 # `verified` is the true state before chunk r on every rank that needs it (r's owner
                 # got it from the walk above or from the previous iteration's broadcast)
                 if self.rank == r:
-                    if not same_windows(verified, guess):
+                    if not same_windows(verified, guess, self.doubling):
                         tr.set_state(verified)
                         recs = tr.track(frames, first_frame_index)
                         end = list(tr.get_state())
