@@ -1429,6 +1429,7 @@ int lst_multi_create(const lst_params *params, const int32_t *devices, int32_t n
     if (!params || !devices || n_devices < 1 || !out) return LST_ERR_INVALID;
     *out = nullptr;
     lst_multi *m = new lst_multi();
+    if (const char *e = getenv("LST_MULTI_LEAD_IN")) m->lead_in = std::max(0, atoi(e));   // 0: chunks start from the state at call time (tests of the re-track path)
     for (int i = 0; i < n_devices; i++) {
         lst_ctx *c = nullptr;
         int rc = lst_create(params, devices[i], &c);

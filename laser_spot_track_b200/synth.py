@@ -37,6 +37,8 @@ class StackConfig:
     noise: float = 0.01          # read noise sigma, fraction of full scale
     spot_travel: float = 0.45    # spot travel as a fraction of s_area (survey motion)
     spot_amp: float = 3.0        # spot amplitude in px (periodic motion)
+    blob_variety: float = 0.0    # > 0: the five blobs get different, anisotropic widths -- needed when every template is
+                                 # searched over the whole slice (sArea = 0), where identical blobs are interchangeable
 
     @property
     def full_scale(self) -> float:
@@ -51,7 +53,7 @@ class StackConfig:
 CONFIGS = {
     "A": StackConfig(640, 480, "u8", 32, 32, 200),
     "B": StackConfig(1920, 1080, "u16", 48, 56, 10000),
-    "C": StackConfig(4096, 3072, "u16", 64, 0, 5000),
+    "C": StackConfig(4096, 3072, "u16", 64, 0, 5000, blob_variety=0.12),
     "D": StackConfig(2048, 2048, "u8", 128, 192, 2000),
     "E": StackConfig(1920, 1080, "u16", 48, 56, 100000),
 }
@@ -120,14 +122,15 @@ class SyntheticStack:
         img = self._bg + rng.standard_normal(self._bg.shape, dtype=np.float32) * np.float32(c.noise)
         sig = max(c.templ_size / 8.0, 1.5)
         rad = int(math.ceil(4 * sig))
-        for (x, y) in self.truth(j):
+        for k, (x, y) in enumerate(self.truth(j)):
+            sx, sy = sig * (1.0 + c.blob_variety * k), sig * (1.0 + c.blob_variety * (4 - k) * 0.7)
             x0, x1 = max(int(x) - rad, 0), min(int(x) + rad + 1, c.width)
             y0, y1 = max(int(y) - rad, 0), min(int(y) + rad + 1, c.height)
             if x1 <= x0 or y1 <= y0:
                 continue
             xs = np.arange(x0, x1, dtype=np.float64) - x
             ys = np.arange(y0, y1, dtype=np.float64) - y
-            blob = 0.70 * np.exp(-(ys[:, None] ** 2 + xs[None, :] ** 2) / (2 * sig * sig))
+            blob = 0.70 * np.exp(-(ys[:, None] ** 2 / (2 * sy * sy) + xs[None, :] ** 2 / (2 * sx * sx)))
             img[y0:y1, x0:x1] += blob.astype(np.float32)
         fs = c.full_scale
         if c.dtype == "f32":

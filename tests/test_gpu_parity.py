@@ -333,7 +333,8 @@ def test_large_template_regime(built_lib, oracle_clib):
 
 def test_batch_size_invariance_full_size(built_lib):
     """BASELINE config B at full slice size (1920x1080 16-bit, T=48, s=56): results do not depend on
-    how frames are batched (property test; the oracle would need minutes at this size)."""
+    how frames are batched (property test; the comparison with the oracle at this size is
+    tests/test_gpu_configs.py::test_config_b_full_size_vs_oracle)."""
     cfg = StackConfig(1920, 1080, "u16", 48, 56, 48, motion="periodic", period=48)
     st = SyntheticStack(cfg)
     frames = np.stack([st.frame(i) for i in range(0, 25)])
