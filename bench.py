@@ -40,6 +40,7 @@ UNIT = "frames/s"
 WORKLOADS = {
     "A": "synthetic 640x480 8-bit stack, 4 marks + spot, 32x32 templates, 96x96 search ROIs",
     "B": "1920x1080 16-bit timelapse, 48x48 templates, 160x160 search ROIs",
+    "C": "4096x3072 16-bit stack, whole-slice search (sArea = 0) of all five 64x64 templates",
     "D": "large-template stress: 2048x2048 8-bit, 128x128 marks and spot over 512x512 ROIs",
 }
 
@@ -69,7 +70,8 @@ def parse():
 
 def bench_config(name: str, ring: int) -> StackConfig:
     c = CONFIGS[name]
-    return StackConfig(c.width, c.height, c.dtype, c.templ_size, c.s_area, n_frames=ring, motion="periodic", period=ring)
+    return StackConfig(c.width, c.height, c.dtype, c.templ_size, c.s_area, n_frames=ring, motion="periodic", period=ring,
+                       blob_variety=c.blob_variety)
 
 
 # DRAM bytes per window of the match kernel from the committed ncu --set full captures (profiles/):
@@ -85,6 +87,7 @@ LANES_DEFAULT = 4
 DEFAULTS = {  # frames per step, ring length, max_batch, cpu sample
     "A": (8192, 256, 2048, 512),
     "B": (10240, 64, 1024, 128),
+    "C": (16, 8, 4, 2),
     "D": (64, 32, 64, 8),
 }
 

@@ -36,15 +36,16 @@
 extern "C" {
 #endif
 
-#define LST_ABI_VERSION 2
+#define LST_ABI_VERSION 3
 
 /* status codes */
 #define LST_OK               0
 #define LST_ERR_INVALID     -1   /* bad argument */
-#define LST_ERR_UNSUPPORTED -2   /* e.g. 16-bit or RGB stacks with matchIntensity=false (LST4:2510-2523), compressed slice files */
+#define LST_ERR_UNSUPPORTED -2   /* e.g. 16-bit or RGB stacks with matchIntensity=false (LST4:2510-2523), JPEG / tiled / RGB slice files */
 #define LST_ERR_CUDA        -3   /* no device / CUDA runtime error (see lst_last_error) */
 #define LST_ERR_NOMEM       -4
 #define LST_ERR_STATE       -5   /* call order (e.g. track before set_reference) */
+#define LST_WOULD_BLOCK      1   /* lst_submit: the queue is full; lst_fetch: nothing finished yet (not an error) */
 
 /* pixel types == ImageProcessor.getBitDepth() of the stack (LST4:172: DOES_8G, DOES_16, DOES_32) */
 #define LST_PIX_U8   8
@@ -56,6 +57,9 @@ extern "C" {
 #define LST_RANGE_DISPLAY 0      /* u8 and RGB: [0,255]; u16/f32: crop's own pre-blur min/max (default) */
 #define LST_RANGE_CROP    1      /* always the crop's own pre-blur min/max */
 #define LST_RANGE_FIXED   2      /* [range_lo, range_hi] */
+#define LST_RANGE_FRAME   3      /* the whole slice's pre-blur min/max (what the crop inherits if createProcessor hands the
+                                    parent's min/max down): given per slice with lst_set_frame_ranges
+                                    (slice_proc.getMin() / getMax(), LST4:1308-1312) or reduced on the device */
 #define LST_QUANT_ROUND255 0     /* (int)(v*255/(max-min) + 0.5f) */
 #define LST_QUANT_TRUNC256 1     /* (int)(v*256/(max-min)) */
 
@@ -142,6 +146,8 @@ typedef struct lst_stats {
     double  preprocess_ms;     /* CUDA-event time of lst_preprocess (+ lst_minmax), lst_box_sums and lst_epilogue over the */
     double  box_sums_ms;       /* same timed passes as ncc_kernel_ms (if timing on) */
     double  epilogue_ms;
+    double  preprocess_px;     /* pixels blurred in the timed passes (38 flops each: the roofline of lst_preprocess*) */
+    int64_t preprocess_launches;
 } lst_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------- */
@@ -165,10 +171,12 @@ int lst_set_reference(lst_ctx *ctx, const void *ref_frame, const float ref_xy[10
 /* frames: host memory, n_frames slices, consecutive slices frame_stride_bytes apart (0 = tightly
  * packed).  Slices are analysed in order with the reference's frame-to-frame recurrence
  * (LST4:1327-1328, 832-846); out receives n_frames records.  Synchronous.  Pageable or pinned
- * memory both work.  Pinned slices (lst_alloc_pinned / lst_host_register) stay where they are: only
- * the five search regions of each slice cross PCIe (gathered by a kernel on a copy stream while the
- * previous batch computes).  Pageable slices are copied whole with cudaMemcpyAsync into a
- * double-buffered device ring. */
+ * memory both work, and in both cases only the five search regions of each slice (plus a margin) cross
+ * PCIe: from pinned memory (lst_alloc_pinned / lst_host_register) as strided 3-D DMA copies on a copy
+ * stream while the previous batch computes; from pageable memory (e.g. Java arrays held through JNI) the
+ * rows of the regions are packed into pinned staging by reader threads first.  Whole slices are copied
+ * only on request (ingest_mode 1), for whole-slice search (sArea = 0) and when LST_RANGE_FRAME has to
+ * reduce the slices on the device. */
 int lst_track(lst_ctx *ctx, const void *frames, size_t frame_stride_bytes, int64_t first_frame_index,
               int32_t n_frames, lst_record *out);
 /* Same, scattered slices (one pointer per slice -- stack.getProcessor(i).getPixels()). */
@@ -181,10 +189,35 @@ int lst_track_device(lst_ctx *ctx, const void *dev_frames, size_t frame_stride_b
 int lst_track_device_ptrs(lst_ctx *ctx, const void *const *dev_frame_ptrs, int64_t first_frame_index,
                           int32_t n_frames, lst_record *out);
 
+/* LST_RANGE_FRAME: the [min, max] of the slices handed to the NEXT call that takes slices (lst_set_reference*: one pair for
+ * the reference slice; lst_track*: n_frames pairs), e.g. slice_proc.getMin() / getMax().  lo_hi = n x {lo, hi}; consumed by
+ * that call.  Without it the library reduces every slice on the device, which needs the whole slice there: host slices are
+ * then copied whole instead of by search region, and slice files are refused (LST_ERR_UNSUPPORTED). */
+int lst_set_frame_ranges(lst_ctx *ctx, const double *lo_hi, int32_t n);
+
 /* Displacement state (disX/disY x5, LST4:100-108): read it, or overwrite it -- the caller's
  * "keep the result" override (LST4:1281-1300) and the chunk hand-off of a sharded run. */
 int lst_get_state(const lst_ctx *ctx, double dis[10]);
 int lst_set_state(lst_ctx *ctx, const double dis[10]);
+
+/* ---- the same without blocking the caller (submit / fetch / override) ---------------
+ * The plugin's loop (LST4:793-902) and its folder monitor (LST4:958-1132, analyseSlice at LST4:1031) decode one slice after
+ * another; with these calls the decoder keeps running while earlier slices are on the device.  A worker thread owned by
+ * the context tracks the submitted batches in order with lst_track_ptrs.  The slices of a batch must stay valid until its
+ * records have been fetched.  While batches are queued or running the context must not be used through the synchronous
+ * entry points (LST_ERR_STATE).
+ *   lst_submit   queues n_frames slices (pointer list copied); LST_WOULD_BLOCK when `queue_depth` batches are already
+ *                waiting or running (default 2: one on the device, one whose ingest overlaps it).
+ *   lst_fetch    copies up to max_records finished records, in slice order, into out; *n_out = how many.  wait != 0 blocks
+ *                until at least one record is there (or nothing is in flight); LST_WOULD_BLOCK with *n_out = 0 otherwise.
+ *   lst_override the caller's verdict on a slice the library rejected (failureQuestionDlg "keep", LST4:1281-1300, or a
+ *                state typed in by the user): everything submitted after `frame_index` is dropped (finished or not), the
+ *                displacement state becomes `dis` and *resume_from receives the index the caller submits again from
+ *                (frame_index + 1).  Blocks until the worker is idle. */
+int lst_submit(lst_ctx *ctx, const void *const *frame_ptrs, int64_t first_frame_index, int32_t n_frames);
+int lst_fetch(lst_ctx *ctx, lst_record *out, int32_t max_records, int32_t *n_out, int32_t wait);
+int lst_override(lst_ctx *ctx, int64_t frame_index, const double dis[10], int64_t *resume_from);
+int lst_set_queue_depth(lst_ctx *ctx, int32_t queue_depth);
 
 /* ---- several GPUs in one process (north_star item 4) ----------------------------------- */
 /* One lst_ctx, one host worker thread and one stream set per device.  lst_multi_track cuts the slices it

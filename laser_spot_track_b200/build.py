@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblst_b200.so")
 SOURCES = ["lst_kernels.cu", "lst_ncc_tc.cu", "lst_runtime.cu", "lst_host.cpp", "lst_tiff.cpp"]
-HEADERS = ["lst_math.h", "lst_host.h", "lst_tiff.h", "lst_device.h", os.path.join("..", "..", "include", "lst_b200.h")]
+HEADERS = ["lst_math.h", "lst_host.h", "lst_tiff.h", "lst_device.h", "lst_preprocess_win.cuh", os.path.join("..", "..", "include", "lst_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-lz", "-o", LIB]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-lz", "-ldl", "-o", LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

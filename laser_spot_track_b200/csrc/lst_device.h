@@ -18,7 +18,8 @@ struct DevTask {
     int32_t pitch;        // row pitch of the 8-bit window in scratch (bytes, multiple of 16)
     int32_t rw, rh;       // result-map size: w - tw + 1, h - th + 1
     int32_t s_used;       // search area used by the accept test (searchWidth = 2*s_used)
-    int32_t pad0, pad1;
+    int32_t pad0;         // 1: the 8-bit window at win_off belongs to an earlier task of the pass (blur kernels skip this one)
+    int32_t pad1;         // slice index inside the batch (LST_RANGE_FRAME: row of PreprocParams.frame_mm)
     uint64_t win_off;     // byte offset of the 8-bit window in the win8 scratch
     uint64_t sum_off;     // element offset of this task's rw*rh score map (lst_match_single only)
 };
@@ -62,12 +63,13 @@ struct DevTemplates {
 struct PreprocParams {
     int pixel_type;        // LST_PIX_*
     int frame_w, frame_h;  // slice size in pixels
-    int range_per_task;    // 1: lo/hi from the per-task min/max keys, 0: fixed lo/hi below
+    int range_per_task;    // 0: fixed lo/hi below, 1: lo/hi = min/max of the task's crop, 2: lo/hi = frame_mm keys of slice DevTask.pad1
     float lo, hi;
     int quant_mode;        // LST_QUANT_*
     int tile_w;            // columns per CTA of the blur kernel (whole window when it fits)
     int minmax_in_kernel;  // the blur kernel finds the crop min/max itself (single column block)
     int swap_bytes;        // the slices hold big-endian samples (files read by lst_track_files)
+    const uint32_t *frame_mm;   // LST_RANGE_FRAME: {min key, max key} per slice of the batch (px_key order)
 };
 
 struct MatchParams {

@@ -51,7 +51,7 @@ int validate_params(const lst_params &p, std::string *err)
         return fail(LST_ERR_UNSUPPORTED, "templSize must be in [14, 256]");
     if (p.s_area < 0 || p.s_area > 8192) return fail(LST_ERR_INVALID, "bad sArea");
     if (p.templ_size > p.width || p.templ_size > p.height) return fail(LST_ERR_INVALID, "template larger than the slice");
-    if (p.range_mode < 0 || p.range_mode > 2 || p.quant_mode < 0 || p.quant_mode > 1)
+    if (p.range_mode < 0 || p.range_mode > LST_RANGE_FRAME || p.quant_mode < 0 || p.quant_mode > 1)
         return fail(LST_ERR_INVALID, "bad range/quant mode");
     if (p.max_batch < 0) return fail(LST_ERR_INVALID, "bad max_batch");
     if (p.ingest_mode < 0 || p.ingest_mode > 3) return fail(LST_ERR_INVALID, "bad ingest_mode");

@@ -139,6 +139,7 @@ __global__ void lst_minmax(const DevTask *__restrict__ tasks, const Surface *__r
                            uint32_t *__restrict__ mm_keys, int swap_bytes)
 {
     const DevTask t = tasks[blockIdx.y];
+    if (t.pad0) return;
     const Surface sf = surfaces[t.frame];
     const void *fr = sf.ptr;
     uint32_t lo = 0xffffffffu, hi = 0u;
@@ -446,6 +447,7 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
     extern __shared__ __align__(16) float smem_f[];
     __shared__ uint32_t s_mm[2];
     const DevTask t = tasks[blockIdx.y];
+    if (t.pad0) return;                        // shares the 8-bit window of an earlier task (whole-slice search)
     const int TW = pp.tile_w;                  // multiple of 16
     const int tiles_x = (t.w + TW - 1) / TW;
     if ((int)blockIdx.x >= tiles_x) return;
@@ -467,7 +469,10 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = NT >> 5;
 
     float lo = pp.lo, hi = pp.hi;
-    if (pp.range_per_task) {
+    if (pp.range_per_task == 2) {              // the whole slice's min/max (LST_RANGE_FRAME)
+        lo = key_to_float<PIX>(pp.frame_mm[2 * t.pad1]);
+        hi = key_to_float<PIX>(pp.frame_mm[2 * t.pad1 + 1]);
+    } else if (pp.range_per_task) {
         if (pp.minmax_in_kernel) {
             if (threadIdx.x == 0) {
                 s_mm[0] = 0xffffffffu;
@@ -1124,31 +1129,43 @@ int launch_solve(const double *dis10, int n, const float *ref_xy, double mark_di
 // compute stream, so all kernels ask for the maximum-shared split and can co-reside.
 static void prefer_max_shared_everywhere()
 {
-    // function attributes belong to the current device: this runs once per lst_create
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    // function attributes belong to the current device: this runs once per lst_create.  A failure is reported (a kernel that
+    // was refused its shared memory would fail at launch with a less telling message) and does not stop the others.
+    auto set = [](const void *fn, cudaFuncAttribute attr, int value, const char *what) {
+        const cudaError_t e = cudaFuncSetAttribute(fn, attr, value);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "lst_b200: cudaFuncSetAttribute(%s, %s) failed: %s\n", what,
+                    attr == cudaFuncAttributeMaxDynamicSharedMemorySize ? "MaxDynamicSharedMemorySize" : "PreferredSharedMemoryCarveout",
+                    cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    };
+    const cudaFuncAttribute dyn = cudaFuncAttributeMaxDynamicSharedMemorySize, carve = cudaFuncAttributePreferredSharedMemoryCarveout;
     const int mx = (int)cudaSharedmemCarveoutMaxShared;
-    cudaFuncSetAttribute(lst_init_pass, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_upload, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_minmax<LST_PIX_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_minmax<LST_PIX_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_minmax<LST_PIX_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_minmax<LST_PIX_RGB>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_preprocess<LST_PIX_RGB>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_ncc_match<false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_ncc_match<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_epilogue, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_solve, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_gather_rois, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    pt_set_attributes();
-    cudaGetLastError();
+#define LST_SET_BOTH(fn, bytes)                     \
+    set((const void *)(fn), dyn, (bytes), #fn);     \
+    set((const void *)(fn), carve, mx, #fn)
+#define LST_SET_CARVE(fn) set((const void *)(fn), carve, mx, #fn)
+    LST_SET_BOTH(lst_preprocess<LST_PIX_U8>, 200 * 1024);
+    LST_SET_BOTH(lst_preprocess<LST_PIX_U16>, 200 * 1024);
+    LST_SET_BOTH(lst_preprocess<LST_PIX_F32>, 200 * 1024);
+    LST_SET_BOTH(lst_preprocess<LST_PIX_RGB>, 200 * 1024);
+    LST_SET_BOTH(lst_preprocess_win<LST_PIX_U8>, 200 * 1024);
+    LST_SET_BOTH(lst_preprocess_win<LST_PIX_U16>, 200 * 1024);
+    LST_SET_BOTH(lst_preprocess_win<LST_PIX_F32>, 200 * 1024);
+    LST_SET_BOTH(lst_ncc_match<false>, 220 * 1024);
+    LST_SET_BOTH(lst_ncc_match<true>, 220 * 1024);
+    LST_SET_CARVE(lst_init_pass);
+    LST_SET_CARVE(lst_upload);
+    LST_SET_CARVE(lst_minmax<LST_PIX_U8>);
+    LST_SET_CARVE(lst_minmax<LST_PIX_U16>);
+    LST_SET_CARVE(lst_minmax<LST_PIX_F32>);
+    LST_SET_CARVE(lst_minmax<LST_PIX_RGB>);
+    LST_SET_CARVE(lst_epilogue);
+    LST_SET_CARVE(lst_solve);
+    LST_SET_CARVE(lst_gather_rois);
+#undef LST_SET_BOTH
+#undef LST_SET_CARVE
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -128,6 +128,7 @@ lst_preprocess_win(const DevTask *__restrict__ tasks, const Surface *__restrict_
     extern __shared__ __align__(128) uint8_t pt_smem[];
     __shared__ uint32_t s_mm[2];
     const DevTask t = tasks[blockIdx.x];
+    if (t.pad0) return;                        // shares the 8-bit window of an earlier task (whole-slice search)
     const int w = t.w, h = t.h;
     const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     const int rp = bw * ES;                                   // raw row pitch in bytes
@@ -153,7 +154,7 @@ lst_preprocess_win(const DevTask *__restrict__ tasks, const Surface *__restrict_
         const int nv = rp >> 4;
         int r = tid / nv, q = tid - r * nv;
         const int dr = NT / nv, dq = NT - dr * nv;
-        const bool want_mm = pp.range_per_task != 0;
+        const bool want_mm = pp.range_per_task == 1;
         while (r < h) {
             const uint8_t *g = crop00 + (size_t)r * pitch_b;
             const int lo = 16 * q - 8 * ES;                               // crop byte of this vector's first byte
@@ -202,7 +203,10 @@ lst_preprocess_win(const DevTask *__restrict__ tasks, const Surface *__restrict_
 
     // ---- range of the float -> 8-bit conversion ----
     float lo = pp.lo, hi = pp.hi;
-    if (pp.range_per_task) {
+    if (pp.range_per_task == 2) {              // the whole slice's min/max (LST_RANGE_FRAME)
+        lo = key_to_float<PIX>(pp.frame_mm[2 * t.pad1]);
+        hi = key_to_float<PIX>(pp.frame_mm[2 * t.pad1 + 1]);
+    } else if (pp.range_per_task) {
         mm_finish<PIX>(klo, khi);
         for (int o = 16; o > 0; o >>= 1) {
             klo = min(klo, __shfl_xor_sync(0xffffffffu, klo, o));
@@ -400,17 +404,6 @@ bool preprocess_win_eligible(int pixel_type, int max_w, int max_h)
     if (pixel_type != LST_PIX_U8 && pixel_type != LST_PIX_U16 && pixel_type != LST_PIX_F32) return false;
     if (max_w > 240 || max_h > 256 || max_w < 2 * KR || max_h < 2 * KR) return false;
     return pt_smem_bytes(pixel_type, max_w, max_h, 32) <= 200 * 1024;
-}
-
-static void pt_set_attributes()
-{
-    cudaFuncSetAttribute(lst_preprocess_win<LST_PIX_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lst_preprocess_win<LST_PIX_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(lst_preprocess_win<LST_PIX_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const int mx = (int)cudaSharedmemCarveoutMaxShared;
-    cudaFuncSetAttribute(lst_preprocess_win<LST_PIX_U8>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_preprocess_win<LST_PIX_U16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaFuncSetAttribute(lst_preprocess_win<LST_PIX_F32>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
 }
 
 }  // namespace lst

@@ -1,14 +1,21 @@
-// lst_runtime.cu -- device context, the CUDA executor behind the recurrence resolver, frame
-// ingest (double-buffered cudaMemcpyAsync ring) and the C ABI of include/lst_b200.h.
+// lst_runtime.cu -- device context, the CUDA executor behind the recurrence resolver, slice ingest (two-half rings on a copy
+// stream: search regions as strided 3-D DMA copies from pinned memory, packed by reader threads from pageable memory and
+// from slice files, whole slices on request), the asynchronous front end and the C ABI of include/lst_b200.h.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <future>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -20,6 +27,15 @@
 #include "lst_tiff.h"
 
 using namespace lst;
+
+// NVTX ranges (tracing): one per tracking call, batch and device pass; they cost nothing without a tool attached
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+// bumped whenever pinned memory is released: the contexts drop their host-pointer -> device-alias caches
+static std::atomic<uint64_t> g_pin_generation{0};
 
 static thread_local std::string g_create_error;
 static const int kRoiMarginMax = 32;   // ROI ingest: the region ring is sized for this margin
@@ -84,6 +100,7 @@ struct lst_ctx : public Executor {
     int roi_margin_fixed = -1;   // LST_ROI_MARGIN pins it
     int roi_align_bytes = 16;
     std::unordered_map<const void *, const void *> mapped_cache;   // pinned host ptr -> device-visible ptr
+    uint64_t mapped_generation = 0;    // g_pin_generation the cache was filled under
     // slices read from files (lst_track_files): pinned staging with the layout of the ROI ring
     uint8_t *h_fstage[2] = {nullptr, nullptr};
     size_t fstage_cap = 0;
@@ -102,6 +119,7 @@ struct lst_ctx : public Executor {
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
     std::vector<int> order;   // device slot -> caller's task index (tasks are grouped by template)
+    std::vector<int> first_task_of_frame;   // whole-slice search: the task whose 8-bit window the later tasks of a surface share
     size_t scratch_limit = (size_t)6 << 30;
 
     size_t bpp() const { return p.pixel_type == LST_PIX_U8 ? 1 : (p.pixel_type == LST_PIX_U16 ? 2 : 4); }
@@ -123,6 +141,40 @@ struct lst_ctx : public Executor {
     int solve(const double *dis10, int n, double *out5) override;
     int run_group(const lst_task *tasks, int n, lst_task_result *results, bool preprocess_only, bool have_win8,
                   int tpl_override, float *map_out_host);
+    // LST_RANGE_FRAME: per-slice {min, max} keys of the batch being resolved, and what the caller announced for the next call
+    uint32_t *d_frame_mm = nullptr, *h_frame_mm = nullptr;
+    DevTask *d_ftasks = nullptr, *h_ftasks = nullptr;
+    int frame_mm_cap = 0;
+    std::vector<double> user_ranges;     // announced with lst_set_frame_ranges for the next call
+    std::vector<double> cur_ranges;      // the ranges of the tracking call in progress, slice `range_first` first
+    int64_t range_first = 0;
+    int track_depth = 0;
+    bool frame_range_mode() const { return p.range_mode == LST_RANGE_FRAME && !(p.pixel_type == LST_PIX_U8 && !p.match_intensity); }
+    int prepare_frame_ranges(int nb, const double *lo_hi);
+    // asynchronous front end (lst_submit / lst_fetch / lst_override): batches tracked in order by a worker thread
+    struct AsyncJob {
+        std::vector<const void *> ptrs;
+        int64_t first = 0;
+        std::vector<lst_record> out;
+        size_t fetched = 0;
+        int rc = LST_OK;
+        std::string err;
+        int state = 0;       // 0 queued, 1 running, 2 done
+    };
+    std::deque<std::unique_ptr<AsyncJob>> aq;
+    std::mutex amx;
+    std::condition_variable acv_work, acv_done;
+    std::thread aworker;
+    bool astop = false;
+    int queue_depth = 2;
+    bool async_busy()
+    {
+        std::lock_guard<std::mutex> lk(amx);
+        for (auto &j : aq)
+            if (j->state != 2) return true;
+        return false;
+    }
+    void async_loop();
     int preproc_engine = 0;      // 0 = auto (lst_preprocess_win when the window fits), 1 = always lst_preprocess (LST_PREPROC=old)
     int ensure_tasks(int n);
     int ensure_frames(int n);
@@ -229,6 +281,9 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
         pp->range_per_task = 0;
         pp->lo = (float)p.range_lo;
         pp->hi = (float)p.range_hi;
+    } else if (p.range_mode == LST_RANGE_FRAME) {
+        pp->range_per_task = 2;
+        pp->frame_mm = d_frame_mm;
     } else if (p.range_mode == LST_RANGE_DISPLAY && (p.pixel_type == LST_PIX_U8 || p.pixel_type == LST_PIX_RGB)) {
         // 8-bit and RGB images keep their 0..255 display range through convertToGray32
         pp->range_per_task = 0;
@@ -239,7 +294,7 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
     }
     int tw = (max_w + 7) & ~7;
     pp->tile_w = tw < 192 ? ((tw + 15) & ~15) : 192;   // whole window rows for the named configurations (S <= 192); multiple of 16
-    pp->minmax_in_kernel = (pp->range_per_task && max_w <= pp->tile_w && (long)max_w * max_h <= 256L * 256) ? 1 : 0;
+    pp->minmax_in_kernel = (pp->range_per_task == 1 && max_w <= pp->tile_w && (long)max_w * max_h <= 256L * 256) ? 1 : 0;
     pp->swap_bytes = swap_bytes ? 1 : 0;
 }
 
@@ -296,12 +351,61 @@ void lst_ctx::drain_timers()
     timed.clear();
 }
 
+// order-preserving key of a slice's min or max as the blur kernels read it back (px_key / key_to_float of lst_kernels.cu)
+static uint32_t host_range_key(int pixel_type, double v)
+{
+    if (pixel_type == LST_PIX_F32) {
+        const float f = (float)v;
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    }
+    const double hi = pixel_type == LST_PIX_U16 ? 65535.0 : 255.0;
+    return (uint32_t)std::min(std::max(v, 0.0), hi);
+}
+
+// LST_RANGE_FRAME: fills d_frame_mm for the nb slices of the batch whose whole-slice surfaces are d_surf[0 .. nb) -- from
+// the caller's ranges, or by reducing every slice on the device (lst_minmax over the whole slice).
+int lst_ctx::prepare_frame_ranges(int nb, const double *lo_hi)
+{
+    if (nb > frame_mm_cap) {
+        CU(cudaStreamSynchronize(s_compute));
+        const int cap = std::max(nb, frame_mm_cap * 2);
+        CU(regrow(&d_frame_mm, (size_t)cap * 2));
+        CU(regrow_host(&h_frame_mm, (size_t)cap * 2));
+        CU(regrow(&d_ftasks, cap));
+        CU(regrow_host(&h_ftasks, cap));
+        frame_mm_cap = cap;
+    }
+    for (int i = 0; i < nb; i++) {
+        h_frame_mm[2 * i] = lo_hi ? host_range_key(p.pixel_type, lo_hi[2 * i]) : 0xffffffffu;
+        h_frame_mm[2 * i + 1] = lo_hi ? host_range_key(p.pixel_type, lo_hi[2 * i + 1]) : 0u;
+    }
+    if (launch_upload(d_frame_mm, h_frame_mm, sizeof(uint32_t) * 2 * nb, s_compute) < 0) return fail(LST_ERR_CUDA, "range upload failed");
+    stats.kernel_launches += 1;
+    if (!lo_hi) {
+        for (int i = 0; i < nb; i++) {
+            DevTask &d = h_ftasks[i];
+            memset(&d, 0, sizeof(d));
+            d.frame = i;
+            d.w = p.width;
+            d.h = p.height;
+        }
+        if (launch_upload(d_ftasks, h_ftasks, sizeof(DevTask) * nb, s_compute) < 0) return fail(LST_ERR_CUDA, "task upload failed");
+        PreprocParams pp;
+        preproc_params(&pp, p.width, p.height);
+        stats.kernel_launches += 1 + launch_minmax(d_ftasks, nb, p.height, d_surf, pp, d_frame_mm, s_compute);
+    }
+    return LST_OK;
+}
+
 // One device pass over a group of windows that fits the scratch.
 //   preprocess_only: stop after the 8-bit windows (template extraction, lst_preprocess)
 //   have_win8:       the 8-bit windows are already in scratch (lst_match_single)
 int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, bool preprocess_only, bool have_win8,
                        int tpl_override, float *map_out_host)
 {
+    NvtxRange nvtx_pass(preprocess_only ? "lst pass (blur only)" : "lst pass");
     int rc = ensure_tasks(n);
     if (rc != LST_OK) return rc;
     size_t win_off = 0, sum_off = 0;
@@ -326,6 +430,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             Rect c = have_win8 ? Rect{0, 0, t.ww, t.wh} : clip_rect(t.wx, t.wy, t.ww, t.wh, p.width, p.height);
             pass_pitch = std::max(pass_pitch, (c.w + 15) & ~15);
         }
+    first_task_of_frame.assign(first_task_of_frame.size(), -1);
     for (int i = 0; i < n; i++) {
         const lst_task &t = tasks[order[i]];
         DevTask &d = h_tasks[i];
@@ -346,6 +451,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             }
         }
         d.tpl = tpl_override >= 0 ? tpl_override : t.tpl;
+        d.pad1 = t.frame;
         d.x0 = c.x;
         d.y0 = c.y;
         d.w = c.w;
@@ -365,9 +471,27 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             max_th = std::max(max_th, tc.th);
             macs += (double)d.rw * d.rh * tc.tw * tc.th;
         }
-        d.win_off = win_off;
         d.sum_off = sum_off;
-        win_off += tc_layout ? (size_t)d.pitch * d.h : (((size_t)d.pitch * d.h + 255) & ~(size_t)255);
+        // Whole-slice search (sArea = 0, LST4:1316-1320): the five templates of a slice are matched against the same image --
+        // it is blurred once, the other four tasks point at that 8-bit window (pad0 = 1: the blur kernels skip the task).
+        int twin = -1;
+        if (p.s_area == 0 && !have_win8 && !preprocess_only && d.frame >= 0) {
+            if ((size_t)d.frame >= first_task_of_frame.size()) first_task_of_frame.resize((size_t)d.frame + 1, -1);
+            const int j = first_task_of_frame[d.frame];
+            if (j < 0) {
+                first_task_of_frame[d.frame] = i;
+            } else {
+                const DevTask &e = h_tasks[j];
+                if (e.x0 == d.x0 && e.y0 == d.y0 && e.w == d.w && e.h == d.h && e.pitch == d.pitch) twin = j;
+            }
+        }
+        if (twin >= 0) {
+            d.win_off = h_tasks[twin].win_off;
+            d.pad0 = 1;
+        } else {
+            d.win_off = win_off;
+            win_off += tc_layout ? (size_t)d.pitch * d.h : (((size_t)d.pitch * d.h + 255) & ~(size_t)255);
+        }
         sum_off += (size_t)d.rw * d.rh;
         max_w = std::max(max_w, d.w);
         max_h = std::max(max_h, d.h);
@@ -396,6 +520,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         CU(cudaEventRecord(tl.ea, s_compute));
     }
     if (!have_win8) {
+        NvtxRange nvtx_blur("lst_preprocess");
         PreprocParams pp;
         preproc_params(&pp, max_w, max_h);
         if (preproc_engine == 0 && preprocess_win_eligible(p.pixel_type, max_w, max_h)) {
@@ -403,7 +528,7 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             if (l2 < 0) return fail(LST_ERR_CUDA, "lst_preprocess_win launch failed");
             launches += l2;
         } else {
-            if (pp.range_per_task && !pp.minmax_in_kernel) launches += launch_minmax(d_tasks, n, max_h, d_surf, pp, d_mm, s_compute);
+            if (pp.range_per_task == 1 && !pp.minmax_in_kernel) launches += launch_minmax(d_tasks, n, max_h, d_surf, pp, d_mm, s_compute);
             launches += launch_preprocess(d_tasks, n, max_w, max_h, d_surf, pp, d_mm, d_win8, s_compute);
         }
     }
@@ -626,6 +751,14 @@ int lst_create(const lst_params *params, int device, lst_ctx **out)
 void lst_destroy(lst_ctx *c)
 {
     if (!c) return;
+    if (c->aworker.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(c->amx);
+            c->astop = true;
+        }
+        c->acv_work.notify_all();
+        c->aworker.join();
+    }
     cudaSetDevice(c->device);
     if (c->s_compute) cudaStreamSynchronize(c->s_compute);
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
@@ -643,6 +776,8 @@ void lst_destroy(lst_ctx *c)
     cudaFree(c->d_win8);
     cudaFree(c->d_map);
     cudaFree(c->d_surf);
+    cudaFree(c->d_frame_mm);
+    cudaFree(c->d_ftasks);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_roi[i]);
         cudaFree(c->d_gptr[i]);
@@ -655,6 +790,8 @@ void lst_destroy(lst_ctx *c)
     cudaFreeHost(c->h_tasks);
     cudaFreeHost(c->h_results);
     cudaFreeHost(c->h_surf);
+    cudaFreeHost(c->h_frame_mm);
+    cudaFreeHost(c->h_ftasks);
     cudaFreeHost(c->h_dis10);
     cudaFreeHost(c->h_out5);
     for (TimedLaunch &t : c->timed) {
@@ -682,6 +819,7 @@ static int ensure_ring(lst_ctx *c, size_t bytes_per_half)
 int lst_set_reference(lst_ctx *c, const void *ref_frame, const float ref_xy[10], lst_reference_info *out)
 {
     if (!c || !ref_frame || !ref_xy) return LST_ERR_INVALID;
+    if (c->async_busy()) return c->fail(LST_ERR_STATE, "batches submitted with lst_submit are still in flight");
     CUC(c, cudaSetDevice(c->device));
     int rc = ensure_ring(c, c->frame_bytes());
     if (rc != LST_OK) return rc;
@@ -691,6 +829,12 @@ int lst_set_reference(lst_ctx *c, const void *ref_frame, const float ref_xy[10],
     c->stats.h2d_bytes += (int64_t)c->frame_bytes();
     c->h_surf[0] = whole_slice(c->d_ring[0], c->p.width, c->p.height);
     CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface), cudaMemcpyHostToDevice, c->s_compute));
+    if (c->frame_range_mode()) {
+        std::vector<double> ur;
+        ur.swap(c->user_ranges);            // consumed by this call
+        rc = c->prepare_frame_ranges(1, ur.size() >= 2 ? ur.data() : nullptr);
+        if (rc != LST_OK) return rc;
+    }
     lst_task tasks[5];
     Rect crop[5];
     for (int k = 0; k < 5; k++) {
@@ -790,6 +934,11 @@ static const void *mapped_host_ptr_uncached(const void *p)
 
 static const void *mapped_host_ptr(lst_ctx *c, const void *p)
 {
+    const uint64_t gen = g_pin_generation.load(std::memory_order_acquire);
+    if (gen != c->mapped_generation) {       // some pinned block was freed or unregistered: an alias may be stale
+        c->mapped_cache.clear();
+        c->mapped_generation = gen;
+    }
     auto it = c->mapped_cache.find(p);
     if (it != c->mapped_cache.end()) return it->second;
     const void *d = mapped_host_ptr_uncached(p);
@@ -957,6 +1106,7 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     if (!c->have_ref) return c->fail(LST_ERR_STATE, "lst_set_reference must be called before tracking");
     CUC(c, cudaSetDevice(c->device));
     if (n_frames == 0) return LST_OK;
+    NvtxRange nvtx_call("lst_track");
     struct HostTimer {
         lst_ctx *c;
         double t0;
@@ -965,8 +1115,28 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     const size_t fb = c->frame_bytes();
     if (stride == 0) stride = fb;
     const int B = c->p.max_batch;
+    // LST_RANGE_FRAME: the outermost call takes over the ranges the caller announced (nested calls -- fallbacks that hand
+    // a sub-range of the slices down -- find them by frame index)
+    struct DepthGuard {
+        lst_ctx *c;
+        ~DepthGuard()
+        {
+            if (--c->track_depth == 0) c->cur_ranges.clear();
+        }
+    } depth_guard{c};
+    if (c->track_depth++ == 0) {
+        c->cur_ranges.clear();
+        c->cur_ranges.swap(c->user_ranges);
+        if (c->cur_ranges.size() < 2 * (size_t)n_frames) c->cur_ranges.clear();
+        c->range_first = first_index;
+    }
+    const bool frame_mode = c->frame_range_mode();
+    const bool have_ranges = frame_mode && !c->cur_ranges.empty();
+    const bool need_whole = frame_mode && !have_ranges;      // the slices must be reduced on the device: whole slices only
+    if (need_whole && fs && !fs->is_mem())
+        return c->fail(LST_ERR_UNSUPPORTED, "LST_RANGE_FRAME with slice files: give the slice ranges with lst_set_frame_ranges");
     if (fs && c->p.s_area == 0) return track_files_whole(c, *fs, 0, n_frames, first_index, out);   // whole-slice search
-    if (!fs && !on_device && c->p.s_area > 0 && c->p.ingest_mode != 1 && c->p.ingest_mode != 2) {
+    if (!fs && !on_device && !need_whole && c->p.s_area > 0 && c->p.ingest_mode != 1 && c->p.ingest_mode != 2) {
         // Host-packed ROI ingest: reader threads copy the rows of the search regions into pinned staging and
         // one contiguous DMA per region follows.  Taken for pageable memory (the copy engine cannot gather
         // from it; whole-slice copies would move 14x the bytes) and on request (ingest_mode 3, LST_HOST_PACK).
@@ -1004,10 +1174,10 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     }
     const int nbatches = (int)bstart.size() - 1;
 
-    bool use_roi = !on_device && c->p.s_area > 0 && (fs || c->p.ingest_mode != 1);
+    bool use_roi = !on_device && !need_whole && c->p.s_area > 0 && (fs || c->p.ingest_mode != 1);
     std::vector<const void *> mapped;
+    std::string file_err[2];          // declared first: the reader threads of file_job write them and are joined first
     std::future<int> file_job[2];
-    std::string file_err[2];
     if (use_roi && !fs) {
         mapped.resize(n_frames);
         for (int64_t i = 0; i < n_frames && use_roi; i++) {
@@ -1190,11 +1360,21 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
             return c->fail(LST_ERR_CUDA, "surface upload failed");
         c->stats.kernel_launches += 1;
         c->stats.h2d_bytes += (int64_t)sizeof(Surface) * nsurf;
+        if (frame_mode) {
+            const int64_t r0 = first_index + f0 - c->range_first;
+            const bool ok = have_ranges && r0 >= 0 && (size_t)(2 * (r0 + nb)) <= c->cur_ranges.size();
+            if (!ok && use_roi) return c->fail(LST_ERR_STATE, "internal: slice ranges missing for a region-ingest batch");
+            rc = c->prepare_frame_ranges(nb, ok ? &c->cur_ranges[2 * r0] : nullptr);
+            if (rc != LST_OK) return rc;
+        }
         c->roi_active = use_roi;
         c->roi_half = half;
         c->roi_nb = nb;
         c->file_mode = fs != nullptr;
-        rc = resolve_batch(in, c->dis, first_index + f0, nb, *c, out + f0, &c->stats);
+        {
+            NvtxRange nvtx_batch("lst batch");
+            rc = resolve_batch(in, c->dis, first_index + f0, nb, *c, out + f0, &c->stats);
+        }
         c->roi_active = false;
         c->file_mode = false;
         if (rc == kRetryWholeSlices && fs) {
@@ -1607,6 +1787,133 @@ int lst_multi_reset_stats(lst_multi *m)
     return LST_OK;
 }
 
+int lst_set_frame_ranges(lst_ctx *c, const double *lo_hi, int32_t n)
+{
+    if (!c || n < 0 || (n > 0 && !lo_hi)) return LST_ERR_INVALID;
+    c->user_ranges.assign(lo_hi, lo_hi + 2 * (size_t)n);
+    return LST_OK;
+}
+
+// ---- asynchronous front end -------------------------------------------------------------------------
+void lst_ctx::async_loop()
+{
+    for (;;) {
+        AsyncJob *job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(amx);
+            acv_work.wait(lk, [&] {
+                if (astop) return true;
+                for (auto &j : aq)
+                    if (j->state == 0) return true;
+                return false;
+            });
+            if (astop) return;
+            for (auto &j : aq)
+                if (j->state == 0) {
+                    job = j.get();
+                    break;
+                }
+            job->state = 1;
+        }
+        // batches run strictly one after the other: the recurrence (LST4:1327-1328) carries the state across them
+        const int rc = lst_track_ptrs(this, job->ptrs.data(), job->first, (int32_t)job->ptrs.size(), job->out.data());
+        {
+            std::lock_guard<std::mutex> lk(amx);
+            job->rc = rc;
+            if (rc != LST_OK) job->err = err;
+            job->state = 2;
+        }
+        acv_done.notify_all();
+    }
+}
+
+int lst_set_queue_depth(lst_ctx *c, int32_t queue_depth)
+{
+    if (!c || queue_depth < 1 || queue_depth > 64) return LST_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->amx);
+    c->queue_depth = queue_depth;
+    return LST_OK;
+}
+
+int lst_submit(lst_ctx *c, const void *const *frame_ptrs, int64_t first_frame_index, int32_t n_frames)
+{
+    if (!c || !frame_ptrs || n_frames <= 0) return LST_ERR_INVALID;
+    if (!c->have_ref) return c->fail(LST_ERR_STATE, "lst_submit before lst_set_reference");
+    std::unique_lock<std::mutex> lk(c->amx);
+    int pending = 0;
+    for (auto &j : c->aq)
+        if (j->state != 2) pending++;
+    // finished batches nobody fetched count as well: they hold their records until lst_fetch takes them
+    if (pending >= c->queue_depth || (int)c->aq.size() >= c->queue_depth + 2) return LST_WOULD_BLOCK;
+    std::unique_ptr<lst_ctx::AsyncJob> job(new lst_ctx::AsyncJob());
+    job->ptrs.assign(frame_ptrs, frame_ptrs + n_frames);
+    job->first = first_frame_index;
+    job->out.resize((size_t)n_frames);
+    c->aq.push_back(std::move(job));
+    if (!c->aworker.joinable()) c->aworker = std::thread([c] { c->async_loop(); });
+    lk.unlock();
+    c->acv_work.notify_one();
+    return LST_OK;
+}
+
+int lst_fetch(lst_ctx *c, lst_record *out, int32_t max_records, int32_t *n_out, int32_t wait)
+{
+    if (!c || !out || !n_out || max_records < 0) return LST_ERR_INVALID;
+    *n_out = 0;
+    std::unique_lock<std::mutex> lk(c->amx);
+    for (;;) {
+        while (!c->aq.empty() && c->aq.front()->state == 2 && *n_out < max_records) {
+            lst_ctx::AsyncJob &j = *c->aq.front();
+            if (j.rc != LST_OK) {      // the batch failed: what came before it has been delivered; report it once
+                if (*n_out > 0) return LST_OK;
+                const int rc = j.rc;
+                c->err = j.err;
+                c->aq.pop_front();
+                return rc;
+            }
+            const size_t take = std::min(j.out.size() - j.fetched, (size_t)(max_records - *n_out));
+            memcpy(out + *n_out, j.out.data() + j.fetched, take * sizeof(lst_record));
+            j.fetched += take;
+            *n_out += (int32_t)take;
+            if (j.fetched == j.out.size()) c->aq.pop_front();
+        }
+        if (*n_out > 0 || max_records == 0) return LST_OK;
+        if (c->aq.empty()) return LST_OK;                  // nothing in flight: zero records is the answer
+        if (!wait) return LST_WOULD_BLOCK;
+        c->acv_done.wait(lk);
+    }
+}
+
+int lst_override(lst_ctx *c, int64_t frame_index, const double dis[10], int64_t *resume_from)
+{
+    if (!c || !dis) return LST_ERR_INVALID;
+    {
+        std::unique_lock<std::mutex> lk(c->amx);
+        // batches that have not started never will; the one that runs is waited for
+        for (auto it = c->aq.begin(); it != c->aq.end();) it = (*it)->state == 0 ? c->aq.erase(it) : it + 1;
+        c->acv_done.wait(lk, [&] {
+            for (auto &j : c->aq)
+                if (j->state == 1) return false;
+            return true;
+        });
+        // records after frame_index are void: the recurrence restarts from the caller's state
+        for (auto it = c->aq.begin(); it != c->aq.end();) {
+            lst_ctx::AsyncJob &j = **it;
+            if (j.first > frame_index) {
+                it = c->aq.erase(it);
+                continue;
+            }
+            const size_t keep = (size_t)std::min<int64_t>((int64_t)j.out.size(), frame_index - j.first + 1);
+            j.out.resize(keep);
+            j.ptrs.resize(keep);
+            if (j.fetched >= j.out.size()) it = c->aq.erase(it);
+            else ++it;
+        }
+    }
+    if (resume_from) *resume_from = frame_index + 1;
+    return lst_set_state(c, dis);
+}
+
 int lst_get_state(const lst_ctx *c, double dis[10])
 {
     if (!c || !dis) return LST_ERR_INVALID;
@@ -1672,6 +1979,12 @@ int lst_preprocess(lst_ctx *c, const void *frame, int32_t x0, int32_t y0, int32_
     CUC(c, cudaMemcpyAsync(c->d_ring[1], frame, c->frame_bytes(), cudaMemcpyHostToDevice, c->s_compute));
     c->h_surf[0] = whole_slice(c->d_ring[1], c->p.width, c->p.height);
     CUC(c, cudaMemcpyAsync(c->d_surf, c->h_surf, sizeof(Surface), cudaMemcpyHostToDevice, c->s_compute));
+    if (c->frame_range_mode()) {
+        std::vector<double> ur;
+        ur.swap(c->user_ranges);
+        rc = c->prepare_frame_ranges(1, ur.size() >= 2 ? ur.data() : nullptr);
+        if (rc != LST_OK) return rc;
+    }
     lst_task t;
     memset(&t, 0, sizeof(t));
     t.wx = x0;
@@ -1698,12 +2011,20 @@ int lst_alloc_pinned(size_t bytes, void **out)
     if (!out) return LST_ERR_INVALID;
     return cudaMallocHost(out, bytes) == cudaSuccess ? LST_OK : LST_ERR_NOMEM;
 }
-int lst_free_pinned(void *p) { return cudaFreeHost(p) == cudaSuccess ? LST_OK : LST_ERR_CUDA; }
+int lst_free_pinned(void *p)
+{
+    g_pin_generation.fetch_add(1, std::memory_order_acq_rel);
+    return cudaFreeHost(p) == cudaSuccess ? LST_OK : LST_ERR_CUDA;
+}
 int lst_host_register(void *p, size_t bytes)
 {
     return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? LST_OK : LST_ERR_CUDA;
 }
-int lst_host_unregister(void *p) { return cudaHostUnregister(p) == cudaSuccess ? LST_OK : LST_ERR_CUDA; }
+int lst_host_unregister(void *p)
+{
+    g_pin_generation.fetch_add(1, std::memory_order_acq_rel);
+    return cudaHostUnregister(p) == cudaSuccess ? LST_OK : LST_ERR_CUDA;
+}
 
 int lst_device_alloc(lst_ctx *c, size_t bytes, void **out)
 {

@@ -12,9 +12,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liblst_b200.so")
 
 LST_OK, LST_ERR_INVALID, LST_ERR_UNSUPPORTED, LST_ERR_CUDA, LST_ERR_NOMEM, LST_ERR_STATE = 0, -1, -2, -3, -4, -5
-ABI_VERSION = 2          # LST_ABI_VERSION of include/lst_b200.h
+ABI_VERSION = 3          # LST_ABI_VERSION of include/lst_b200.h
 PIX_U8, PIX_U16, PIX_F32, PIX_RGB = 8, 16, 32, 24
-RANGE_DISPLAY, RANGE_CROP, RANGE_FIXED = 0, 1, 2
+RANGE_DISPLAY, RANGE_CROP, RANGE_FIXED, RANGE_FRAME = 0, 1, 2, 3
+LST_WOULD_BLOCK = 1
 QUANT_ROUND255, QUANT_TRUNC256 = 0, 1
 STATUS_OK, STATUS_SKIP, STATUS_STOP = 0, 1, 2
 
@@ -31,6 +32,7 @@ EXPORTS = [
     "lst_multi_get_state", "lst_multi_set_state", "lst_multi_retracked", "lst_multi_track_device",
     "lst_multi_get_stats", "lst_multi_reset_stats",
     "lst_tiff_probe", "lst_tiff_read_rect", "lst_set_reference_file", "lst_track_files", "lst_results_rows",
+    "lst_set_frame_ranges", "lst_submit", "lst_fetch", "lst_override", "lst_set_queue_depth",
 ]
 
 
@@ -77,6 +79,7 @@ class Stats(C.Structure):
         ("ncc_kernel_ms", C.c_double), ("ncc_kernel_launches", C.c_int64), ("ncc_algorithmic_macs", C.c_double),
         ("roi_fallback_tasks", C.c_int64), ("device_wait_ms", C.c_double), ("host_ms", C.c_double),
         ("preprocess_ms", C.c_double), ("box_sums_ms", C.c_double), ("epilogue_ms", C.c_double),
+        ("preprocess_px", C.c_double), ("preprocess_launches", C.c_int64),
     ]
 
 
@@ -159,6 +162,11 @@ def load() -> C.CDLL:
         "lst_multi_get_state": ([vp, P(dbl)], C.c_int),
         "lst_multi_set_state": ([vp, P(dbl)], C.c_int),
         "lst_multi_retracked": ([vp], C.c_int64),
+        "lst_set_frame_ranges": ([vp, P(dbl), i32], C.c_int),
+        "lst_submit": ([vp, P(vp), i64, i32], C.c_int),
+        "lst_fetch": ([vp, P(Record), i32, P(i32), i32], C.c_int),
+        "lst_override": ([vp, i64, P(dbl), P(i64)], C.c_int),
+        "lst_set_queue_depth": ([vp, i32], C.c_int),
         "lst_host_resolve": ([P(Params), P((i32 * 4) * 5), P(C.c_float), P(dbl), P(dbl), i64, i32, COMPUTE_FN, vp,
                               P(Record), P(Stats)], C.c_int),
     }

@@ -102,6 +102,12 @@ class LaserSpotTrack4:
         return a
 
     # -- template selection: LST4:486-702 -----------------------------------------------------
+    def set_frame_ranges(self, lo_hi) -> None:
+        """LST_RANGE_FRAME: [min, max] of the slices of the NEXT call that takes slices (slice_proc.getMin() / getMax(),
+        LST4:1308-1312); lo_hi = n pairs.  Without it the library reduces every slice on the device."""
+        a = np.ascontiguousarray(lo_hi, dtype=np.float64).reshape(-1, 2)
+        self._check(self._lib.lst_set_frame_ranges(self._ctx, a.ctypes.data_as(C.POINTER(C.c_double)), len(a)))
+
     def set_reference(self, ref_slice: np.ndarray, points: Sequence[Tuple[float, float]]) -> N.ReferenceInfo:
         """points: click points of spot, mark1, mark2, mark3, mark4 (x, y)."""
         fr = self._frame(ref_slice)
@@ -144,6 +150,35 @@ class LaserSpotTrack4:
         out = (N.Record * n)() if out is None else out
         self._check(self._lib.lst_track_device_ptrs(self._ctx, ptrs, first_frame_index, n, out))
         return out
+
+    # ---- without blocking the caller (submit / fetch / override; the loop of LST4:793-902 keeps decoding) ----
+    def submit(self, host_ptrs, first_frame_index: int) -> bool:
+        """Queue a batch of slices (raw host addresses, valid until their records are fetched).  False = the queue is
+        full (LST_WOULD_BLOCK): fetch first."""
+        n = len(host_ptrs)
+        ptrs = host_ptrs if isinstance(host_ptrs, C.Array) else (C.c_void_p * n)(*host_ptrs)
+        rc = self._lib.lst_submit(self._ctx, ptrs, first_frame_index, n)
+        if rc == N.LST_WOULD_BLOCK:
+            return False
+        self._check(rc)
+        return True
+
+    def fetch(self, max_records: int, wait: bool = False):
+        """Finished records in slice order (possibly none)."""
+        out = (N.Record * max_records)()
+        n = C.c_int32(0)
+        rc = self._lib.lst_fetch(self._ctx, out, max_records, C.byref(n), int(wait))
+        if rc != N.LST_WOULD_BLOCK:
+            self._check(rc)
+        return [out[i] for i in range(n.value)]
+
+    def override(self, frame_index: int, dis) -> int:
+        """The caller's verdict on slice ``frame_index`` (failureQuestionDlg "keep", LST4:1281-1300): later slices are
+        dropped, the state becomes ``dis``; returns the index to submit again from."""
+        d = (C.c_double * 10)(*[float(v) for v in dis])
+        resume = C.c_int64(0)
+        self._check(self._lib.lst_override(self._ctx, frame_index, d, C.byref(resume)))
+        return int(resume.value)
 
     def track_host_ptrs(self, host_ptrs, first_frame_index: int = 1, out=None):
         """Slices given as raw host addresses (e.g. a pinned ring): no numpy conversion on the way."""

@@ -45,6 +45,8 @@ RANGE_DISPLAY = 0   # float->8-bit range = display range carried through convert
                     #   u8 crop -> [0,255]; u16 / f32 crop -> the crop's own pre-blur min/max
 RANGE_CROP = 1      # always the crop's own pre-blur min/max (FloatProcessor.findMinAndMax)
 RANGE_FIXED = 2     # caller-supplied [lo, hi]
+RANGE_FRAME = 3     # the whole slice's pre-blur min/max: what a crop inherits if createProcessor hands the parent's
+                    # min/max down (SURVEY 8c, H1 alternative; slice_proc.getMin()/getMax(), LST4:1308-1312)
 QUANT_ROUND255 = 0  # scale = 255/(max-min), ivalue = (int)(v*scale + 0.5f)  (recent ImageJ)
 QUANT_TRUNC256 = 1  # scale = 256/(max-min), ivalue = (int)(v*scale)          (old ImageJ)
 
@@ -259,12 +261,15 @@ def preprocess_crop(frame: np.ndarray, x0: int, y0: int, w: int, h: int, p: Para
     unsupported here as there."""
     x0, y0, w, h = clip_rect(x0, y0, w, h, frame.shape[1], frame.shape[0])
     crop = frame[y0:y0 + h, x0:x0 + w]
+    whole = frame
     if frame.dtype == np.uint32:
         # RGB slice (DOES_RGB, LST4:172): matched on intensity; an 8-bit grey image from here on, whose
         # 0..255 display range survives convertToGray32 like an 8-bit slice's
         if not p.match_intensity:
             raise ValueError("RGB stacks: only matchIntensity=true is on this path")
         crop = rgb_to_gray8(crop, p.rgb_weights)
+        if p.range_mode == RANGE_FRAME:
+            whole = rgb_to_gray8(frame, p.rgb_weights)
         frame = crop
     if frame.dtype == np.uint8 and not p.match_intensity:
         lo, hi, qm = 0.0, 255.0, QUANT_ROUND255
@@ -274,6 +279,8 @@ def preprocess_crop(frame: np.ndarray, x0: int, y0: int, w: int, h: int, p: Para
         qm = p.quant_mode
         if p.range_mode == RANGE_FIXED:
             lo, hi = p.range_lo, p.range_hi
+        elif p.range_mode == RANGE_FRAME:
+            lo, hi = float(whole.min()), float(whole.max())
         elif p.range_mode == RANGE_DISPLAY and frame.dtype == np.uint8:
             lo, hi = 0.0, 255.0
         else:

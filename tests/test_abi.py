@@ -45,7 +45,7 @@ def test_struct_sizes_match_header(built_lib):
 
 def test_version_and_no_gpu_is_loud(built_lib):
     lib = N.load()
-    assert lib.lst_abi_version() == N.ABI_VERSION == 2
+    assert lib.lst_abi_version() == N.ABI_VERSION == 3
     if lib.lst_device_count() == 0:
         p = N.default_params(640, 480, N.PIX_U8)
         ctx = C.c_void_p()

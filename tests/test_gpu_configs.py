@@ -240,3 +240,64 @@ def test_sharded_tracker_retrack_on_gpu(built_lib, oracle_clib):
     util.compare_records(got, want, label="sharded, 2 ranks")
     assert out[1][2] == 1, "rank 1 speculated the reference state and must have re-tracked"
     assert out[1][1] == [v for d in otr.dis for v in d]
+
+
+def _rec_key(r):
+    return (int(r.frame), r.status, [(m.ix, m.iy, m.wx, m.wy, m.score, m.x, m.y, m.accepted) for m in r.tm], list(r.dis),
+            (r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL))
+
+
+def test_submit_fetch_override(built_lib, oracle_clib):
+    """lst_submit / lst_fetch / lst_override.  Batches are queued while earlier ones run (LST_WOULD_BLOCK when
+    the queue is full), the records come back in slice order and equal lst_track's; an override drops everything after
+    the overridden slice and restarts the recurrence from the caller's state."""
+    import ctypes as C
+    cfg, st, frames = _drift_stack()
+    op = util.oracle_params(cfg, match_intensity=False)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    lib = N.load()
+    stack = np.ascontiguousarray(np.stack(frames[1:]))
+    ptr = C.c_void_p()
+    assert lib.lst_alloc_pinned(stack.nbytes, C.byref(ptr)) == 0
+    try:
+        view = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(stack.nbytes,)).view(stack.dtype).reshape(stack.shape)
+        view[...] = stack
+        addr = [view[i].ctypes.data for i in range(len(view))]
+        with _tracker(cfg, op, max_batch=8) as t:
+            t.set_reference(frames[0], st.ref_xy)
+            got, nxt, blocked = [], 0, 0
+            while len(got) < len(addr):
+                if nxt < len(addr):
+                    n = min(7, len(addr) - nxt)
+                    if t.submit(addr[nxt:nxt + n], 1 + nxt):
+                        nxt += n
+                        continue
+                    blocked += 1
+                got += t.fetch(5, wait=True)
+            assert blocked >= 1, "the queue never filled up: nothing was in flight while the caller went on"
+            assert t.fetch(5) == []
+            util.compare_records(got, want, label="submit/fetch")
+            assert [int(r.frame) for r in got] == list(range(1, len(addr) + 1))
+            # override: keep slice 20's state, drop what follows (some of it finished, some queued), resume from 21
+            t.set_state([0.0] * 10)
+            assert t.submit(addr[:30], 1) and t.submit(addr[30:45], 31)
+            first = t.fetch(12, wait=True)
+            resume = t.override(20, list(want[19].dis[k][j] for k in range(5) for j in range(2)))
+            assert resume == 21
+            rest = []
+            while True:
+                part = t.fetch(64)
+                if not part:
+                    break
+                rest += part
+            kept = first + rest
+            assert [int(r.frame) for r in kept] == list(range(1, 21)), "records after the overridden slice must be dropped"
+            assert t.submit(addr[20:], 21)
+            tail = []
+            while len(tail) < len(addr) - 20:
+                tail += t.fetch(64, wait=True)
+            util.compare_records(kept + tail, want, label="after override")
+    finally:
+        lib.lst_free_pinned(ptr)

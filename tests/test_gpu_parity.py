@@ -44,6 +44,9 @@ def test_device_present(built_lib):
     ("u16", True, O.RANGE_DISPLAY, O.QUANT_ROUND255),
     ("u16", True, O.RANGE_FIXED, O.QUANT_ROUND255),
     ("f32", True, O.RANGE_DISPLAY, O.QUANT_ROUND255),
+    ("u16", True, O.RANGE_FRAME, O.QUANT_ROUND255),
+    ("f32", True, O.RANGE_FRAME, O.QUANT_TRUNC256),
+    ("u8", True, O.RANGE_FRAME, O.QUANT_ROUND255),
 ])
 def test_preprocess_bit_exact(built_lib, dtype, mi, range_mode, quant):
     """crop -> float -> blur -> 8-bit: every byte equal to the oracle's, incl. windows touching the borders."""
@@ -168,6 +171,36 @@ def test_track_u16_small(built_lib, oracle_clib):
         t.set_reference(frames[0], st.ref_xy)
         got = t.track_slices(frames[1:])
         util.compare_records(got, want, label="u16")
+
+
+@pytest.mark.parametrize("dtype", ["u16", "f32"])
+@pytest.mark.parametrize("supplied", [False, True])
+def test_track_range_frame(built_lib, oracle_clib, dtype, supplied):
+    """LST_RANGE_FRAME (the crop inherits the whole slice's min/max): records bit-exact against the oracle,
+    with the ranges reduced on the device and with the ranges the caller announces (slice_proc.getMin()/getMax()) --
+    the second with pinned slices, so that only the search regions cross PCIe."""
+    cfg = StackConfig(480, 400, dtype, 48, 56, 24)
+    st = SyntheticStack(cfg)
+    frames = [st.frame(i) for i in range(0, 13)]
+    op = util.oracle_params(cfg, range_mode=O.RANGE_FRAME)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    with _tracker(cfg, op, max_batch=5) as t:
+        if supplied:
+            t.set_frame_ranges([(float(frames[0].min()), float(frames[0].max()))])
+        t.set_reference(frames[0], st.ref_xy)
+        if supplied:
+            view, ptr = _pinned_stack(frames[1:])
+            try:
+                t.set_frame_ranges([(float(f.min()), float(f.max())) for f in frames[1:]])
+                got = t.track(view)
+                util.compare_records(got, want, label=f"range FRAME supplied {dtype}")
+            finally:
+                N.load().lst_free_pinned(ptr)
+        else:
+            got = t.track_slices(frames[1:])
+            util.compare_records(got, want, label=f"range FRAME reduced {dtype}")
 
 
 def test_rejects_and_skips(stack_a):
