@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="frames of the CPU baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short device-resident runs of configs A, C and D")
     ap.add_argument("--lanes", type=int, default=0,
                     help="tracking lanes per GPU (lst_multi_create with the device listed this many times): the host-side "
                          "chain walk of one lane overlaps the kernels of the others; 0 = up to %d, fewer when the host has "
@@ -66,6 +67,12 @@ def parse():
     ap.add_argument("--ingest", type=int, default=0, choices=[0, 1, 2], help="0 ROI DMA (default), 1 whole slices, 2 ROI gather kernel")
     ap.add_argument("--engine", default="auto", choices=["auto", "dp4a", "tc"], help="match kernel: tensor cores (default when the template fits) or IDP.4A")
     return ap.parse_args()
+
+
+def config_dict(name: str, cfg) -> dict:
+    """The workload as BOTH arms name it (identical keys and values: the driver compares them)."""
+    return {"workload": WORKLOADS[name], "frame": [cfg.width, cfg.height], "depth": cfg.dtype,
+            "templ_size": cfg.templ_size, "s_area": cfg.s_area}
 
 
 def bench_config(name: str, ring: int) -> StackConfig:
@@ -198,8 +205,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nfr / rate, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "frame": [cfg.width, cfg.height], "depth": cfg.dtype,
-                   "templ_size": cfg.templ_size, "s_area": cfg.s_area, "frames_per_step": nfr},
+        "config": config_dict(args.config, cfg), "details": {"frames_per_step": nfr},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": f"{nfr} frames per step on {procs} processes: oracle loop (numpy ImageJ blur + "
                                    f"cv2.matchTemplate TM_CCOEFF_NORMED, IPP off, 1 thread each); the Java plugin "
@@ -228,6 +234,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the tracking path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # Host placement: every rank gets its own slice of the cores this process may use, so that the lane threads of one
+    # rank (they poll their streams) never preempt another rank's.  LST_BENCH_NO_PIN=1 leaves the scheduler alone.
+    host_cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    my_cores = host_cores
+    if world > 1 and not os.environ.get("LST_BENCH_NO_PIN") and len(host_cores) >= 2 * world:
+        per = len(host_cores) // world
+        my_cores = host_cores[local_rank * per:(local_rank + 1) * per]
+        try:
+            os.sched_setaffinity(0, my_cores)
+        except OSError:
+            my_cores = host_cores
     host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -263,7 +280,8 @@ def main():
     trk._check(lib.lst_device_upload(trk._ctx, C.c_void_p(dev_ring), host_ring, ring * fb))
     info = trk.set_reference(st.frame(0), st.ref_xy)
     # every lane is a host thread that waits on its stream: keep one host core per lane across the ranks of this node
-    lanes = args.lanes if args.lanes > 0 else max(1, min(LANES_DEFAULT, (os.cpu_count() or 8) // world))
+    # one core per lane thread plus one for this rank's main / communication threads
+    lanes = args.lanes if args.lanes > 0 else max(1, min(LANES_DEFAULT, len(my_cores) - 1))
     if args.lanes <= 0 and F // (args.max_batch or mb_d) < 4:
         lanes = 1       # a lane should get several full batches; short steps (config D: 64 slices) stay on one
     runner = trk
@@ -457,8 +475,12 @@ def main():
         del page_ptrs, page_ring
 
     value = world * F * K / (ms_dev * 1e-3)
+    win_bytes_per_frame = (5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 if cfg.s_area > 0 else cfg.width * cfg.height) * (bits // 8)
     # roofline of the dominant kernel (the template match): exact u8 x u8 -> s32 multiply-accumulates
-    win_macs = float((2 * cfg.s_area + 1) ** 2 * cfg.templ_size ** 2)
+    if cfg.s_area > 0:
+        win_macs = float((2 * cfg.s_area + 1) ** 2 * cfg.templ_size ** 2)
+    else:
+        win_macs = float((cfg.width - cfg.templ_size + 1) * (cfg.height - cfg.templ_size + 1) * cfg.templ_size ** 2)
     macs_per_launch = s_roof.ncc_algorithmic_macs / max(s_roof.ncc_kernel_launches, 1)
     kern_ms = s_roof.ncc_kernel_ms / max(s_roof.ncc_kernel_launches, 1)
     achieved = 2.0 * macs_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else None
@@ -483,17 +505,26 @@ def main():
                     "roofline is given as dp4a_engine_peak",
             "dp4a_engine_peak": dp4a_peak, "achieved_over_dp4a_peak": (achieved / dp4a_peak) if (achieved and dp4a_peak) else None,
         }
-        # The bound that applies to this embedding: an M128 K32 tcgen05.mma.kind::i8 with operands in shared
-        # memory takes >= 42 cycles for any N <= 64 (tools/tc_rate.cu on this GPU), and a window needs
-        # th * ceil(R/32) * ceil((31 + tw)/32) of them.
-        R = 2 * cfg.s_area + 1
-        mmas_per_window = cfg.templ_size * ((R + 31) // 32) * ((31 + cfg.templ_size + 31) // 32)
-        windows_per_launch = macs_per_launch / max(win_macs, 1)
-        sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-        floor_ms = windows_per_launch * mmas_per_window * 42.0 / (148 * sm_hz * 1e6) * 1e3
-        roofline["mma_issue_floor"] = {"cycles_per_mma": 42, "mmas_per_window": mmas_per_window, "floor_ms_per_launch": floor_ms,
-                                       "frac_of_floor": floor_ms / kern_ms if kern_ms > 0 else None,
-                                       "source": "tools/tc_rate.cu, profiles/README.md"}
+        # The bound that applies to this embedding: tcgen05.mma.kind::i8 reads both operands from shared memory at
+        # 128 B/clk/SM (tools/tc_rate.cu: an M128 K32 MMA takes 40 cycles at N = 32 and 64 at N = 128 -- exactly
+        # (4 KB + N * 32 B) / 128).  Per template row the window tile's K steps are read once (4 KB each) and the
+        # Toeplitz band blocks they feed (1 KB each).
+        if cfg.s_area > 0:
+            R = 2 * cfg.s_area + 1
+            nd = (cfg.templ_size + 62) // 32
+            nbe = min(4, (R + 31) // 32)
+            nk = nbe + nd - 1
+            bblocks = sum(min(nbe - 1, j) - max(0, j - nd + 1) + 1 for j in range(nk))
+            tiles = ((R + 127) // 128) * ((R + 32 * nbe - 1) // (32 * nbe))
+            smem_bytes_per_window = tiles * cfg.templ_size * (nk * 4096 + bblocks * 1024)
+            windows_per_launch = macs_per_launch / max(win_macs, 1)
+            sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+            floor_ms = windows_per_launch * smem_bytes_per_window / 128.0 / (148 * sm_hz) * 1e3
+            roofline["smem_operand_floor"] = {
+                "bytes_per_window": smem_bytes_per_window, "floor_ms_per_launch": floor_ms,
+                "frac_of_floor": floor_ms / kern_ms if kern_ms > 0 else None,
+                "what": "time the tensor core needs just to read its operands from shared memory (128 B/clk/SM) for the "
+                        "launch's windows; the vertical sums and the epilogue of the worker warps share that pipe"}
     else:
         peak = dp4a_peak
         roofline = {
@@ -511,15 +542,31 @@ def main():
         "algorithmic_ops_per_launch": 2.0 * macs_per_launch, "avg_launch_ms": kern_ms,
         "kernel_share_of_step": s_roof.ncc_kernel_ms / ms_roof if ms_roof > 0 else None,
         "launches_timed": int(s_roof.ncc_kernel_launches),
-        "kernel_ms_per_step": {"lst_preprocess": s_roof.preprocess_ms / K, "lst_box_sums": s_roof.box_sums_ms / K,
-                               "match": s_roof.ncc_kernel_ms / K, "lst_epilogue": s_roof.epilogue_ms / K,
+        "kernel_ms_per_step": {"lst_preprocess": s_roof.preprocess_ms / K, "match": s_roof.ncc_kernel_ms / K,
+                               "lst_epilogue": s_roof.epilogue_ms / K, "sum": (s_roof.preprocess_ms + s_roof.ncc_kernel_ms + s_roof.epilogue_ms + s_roof.box_sums_ms) / K,
                                "step": ms_roof / K},
+        # every kernel of the step against the unit that bounds it, recomputable from the numbers beside it
+        "per_kernel": {
+            "lst_preprocess": {
+                "bound": "fp32-issue", "unit": "TFLOP/s",
+                "flop_per_px": 38, "px_per_step": s_roof.preprocess_px / K, "ms_per_step": s_roof.preprocess_ms / K,
+                "achieved": (38.0 * s_roof.preprocess_px / (s_roof.preprocess_ms * 1e-3) / 1e12) if s_roof.preprocess_ms > 0 else None,
+                "peak": (peaks[1] / 1e12) if have_peaks else None,
+                "frac": (38.0 * s_roof.preprocess_px / (s_roof.preprocess_ms * 1e-3) / peaks[1]) if (have_peaks and s_roof.preprocess_ms > 0 and peaks[1] > 0) else None,
+                "peak_source": "measured live FFMA instruction rate (lst_measure_alu_peaks): ImageJ's blur multiplies and adds "
+                               "separately in Java's float order, so a flop is an instruction -- half the FMA flop peak"},
+            "match": {"bound": roofline["bound"], "unit": "TOP/s", "achieved": achieved, "peak": peak,
+                      "frac": roofline["frac"], "ms_per_step": s_roof.ncc_kernel_ms / K},
+            "lst_epilogue": {"bound": "latency", "ms_per_step": s_roof.epilogue_ms / K,
+                             "what": "one small block per window: sub-pixel fit and accept test from the nine scores the match kernel left"},
+        },
         "measured_with": "the timed region of `value`" if lanes == 1 else
                          "a second timed region of the same %d steps on ONE lane (per-launch CUDA-event times need kernels that "
                          "do not overlap; `value` runs %d lanes): %.0f frames/s" % (K, lanes, world * F * K / (ms_roof * 1e-3)),
-        "window_bytes_per_frame": 5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 * (bits // 8),
-        "hbm_view": {"peak_gbs": measured.get("hbm_gbs"),
-                     "window_bytes_per_s": value * 5 * (cfg.templ_size + 2 * cfg.s_area) ** 2 * (bits // 8) / 1e9},
+        "window_bytes_per_frame": win_bytes_per_frame,
+        "hbm_view": {"peak_gbs": measured.get("hbm_gbs"), "window_bytes_per_s": value * win_bytes_per_frame / 1e9,
+                     "frac": (value * win_bytes_per_frame / 1e9 / measured["hbm_gbs"]) if measured.get("hbm_gbs") else None,
+                     "what": "raw window bytes the blur kernel reads per second against the HBM copy peak: the path is not HBM bound"},
     })
 
     # the other match engine on the same device-resident workload, for its roofline (not the headline)
@@ -545,6 +592,49 @@ def main():
                             (a.status, a.x_abs, a.y_abs, a.dL) == (b.status, b.x_abs, b.y_abs, b.dL) for a, b in zip(out, out2))}
         alt.close()
 
+    # The other named configurations, device resident, a few steps each (one context, one lane): so that every BASELINE
+    # config has a number from the same run.  Their full-geometry parity tests are tests/test_gpu_configs.py.
+    extra = None
+    if world == 1 and args.config == "B" and not args.no_extra:
+        extra = {}
+        for name in ("A", "C", "D"):
+            try:
+                xf, xring, xmb, _ = DEFAULTS[name]
+                xcfg = bench_config(name, xring)
+                xst = SyntheticStack(xcfg)
+                xbits = {"u8": 8, "u16": 16, "f32": 32}[xcfg.dtype]
+                xfb = xcfg.width * xcfg.height * (xbits // 8)
+                xt = LaserSpotTrack4(xcfg.width, xcfg.height, xbits, device=local_rank, templSize=xcfg.templ_size, sArea=xcfg.s_area,
+                                     max_batch=xmb)
+                xdev = xt.device_alloc(xring * xfb)
+                for i in range(xring):
+                    fr = np.ascontiguousarray(xst.frame(i))
+                    xt._check(lib.lst_device_upload(xt._ctx, C.c_void_p(xdev + i * xfb), fr.ctypes.data, xfb))
+                xt.set_reference(xst.frame(0), xst.ref_xy)
+                xptrs = (C.c_void_p * xf)(*[xdev + ((1 + j) % xring) * xfb for j in range(xf)])
+                xout = (N.Record * xf)()
+
+                def xstep():
+                    xt.track_device_ptrs(xptrs, 1, xout)
+
+                xt.set_kernel_timing(True)
+                xms, _, xs = timed(xstep, 3, 2, xt)
+                xmacs = xs.ncc_algorithmic_macs / max(xs.ncc_kernel_launches, 1)
+                xk = xs.ncc_kernel_ms / max(xs.ncc_kernel_launches, 1)
+                extra["config_" + name] = {
+                    "config": config_dict(name, xcfg), "value": xf * 3 / (xms * 1e-3), "unit": UNIT, "ms_per_step": xms / 3,
+                    "frames_per_step": xf, "lanes": 1, "accepted_frames_last_step": sum(1 for r in xout if r.status == 0),
+                    "match_top_s": (2.0 * xmacs / (xk * 1e-3) / 1e12) if xk > 0 else None,
+                    "match_frac_of_int8_tensor_peak": (2.0 * xmacs / (xk * 1e-3) / 1e12 / imma_peak) if (xk > 0 and imma_peak) else None,
+                    "kernel_ms_per_step": {"lst_preprocess": xs.preprocess_ms / 3, "match": xs.ncc_kernel_ms / 3, "lst_epilogue": xs.epilogue_ms / 3},
+                    "preprocess_tflops": (38.0 * xs.preprocess_px / (xs.preprocess_ms * 1e-3) / 1e12) if xs.preprocess_ms > 0 else None,
+                    "preprocess_hbm_gbs": (xs.preprocess_px * ((xbits // 8) + 1) / (xs.preprocess_ms * 1e-3) / 1e9) if xs.preprocess_ms > 0 else None,
+                }
+                xt.device_free(xdev)
+                xt.close()
+            except Exception as e:      # the extras never fail the run
+                extra["config_" + name] = {"error": str(e)[:200]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_sample or sample_d
@@ -558,16 +648,16 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.config], "frame": [cfg.width, cfg.height], "depth": cfg.dtype,
-                       "templ_size": cfg.templ_size, "s_area": cfg.s_area, "frames_per_step_per_gpu": F,
-                       "ring_frames": ring, "ring_bytes": ring * fb,
-                       "l2": "inputs larger than L2 (ring of distinct slices cycled)" if ring * fb > 126e6 else
-                             "ring smaller than L2; windows are re-read from HBM/L2 each pass",
-                       "max_batch": args.max_batch or mb_d, "parallelism": f"frames sharded over {world} GPU(s), no collective" + (f"; {lanes} lanes per GPU" if lanes > 1 else ""),
-                       "lanes_per_gpu": lanes,
-                       "accepted_frames_last_step": ok_frames},
+            "config": config_dict(args.config, cfg),
+            "details": {"frames_per_step_per_gpu": F, "ring_frames": ring, "ring_bytes": ring * fb,
+                        "l2": "inputs larger than L2 (ring of distinct slices cycled)" if ring * fb > 126e6 else
+                              "ring smaller than L2; windows are re-read from HBM/L2 each pass",
+                        "max_batch": args.max_batch or mb_d,
+                        "parallelism": f"frames sharded over {world} GPU(s), no collective" + (f"; {lanes} lanes per GPU" if lanes > 1 else ""),
+                        "lanes_per_gpu": lanes, "host_cores_of_this_rank": len(my_cores),
+                        "accepted_frames_last_step": ok_frames},
             "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "e2e_pageable": e2e_pageable, "gpu_launches": int(s_dev.kernel_launches),
-            "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline, "extra": extra,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
                          "chunks_retracked": sh_dev.retracked, "host_ms_per_step": s_dev.host_ms / K,
                          "device_wait_ms_per_step": s_dev.device_wait_ms / K},

@@ -567,6 +567,9 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         if (timed_pass) {
             CU(cudaEventRecord(tl.ec, s_compute));
             timed.push_back(tl);
+            for (int i = 0; i < n; i++)
+                if (!h_tasks[i].pad0) stats.preprocess_px += (double)h_tasks[i].w * h_tasks[i].h;
+            stats.preprocess_launches += 1;
         }
         CU(cudaMemcpyAsync(h_results, d_results, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, s_compute));
         stats.d2h_bytes += (int64_t)sizeof(DevResult) * n;
@@ -1776,6 +1779,8 @@ int lst_multi_get_stats(const lst_multi *m, lst_stats *out)
         out->preprocess_ms += s.preprocess_ms;
         out->box_sums_ms += s.box_sums_ms;
         out->epilogue_ms += s.epilogue_ms;
+        out->preprocess_px += s.preprocess_px;
+        out->preprocess_launches += s.preprocess_launches;
     }
     return LST_OK;
 }
