@@ -249,7 +249,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        host_group = dist.new_group(backend="gloo")     # chunk-boundary hand-off: 21 doubles, host side
+        host_group = dist.new_group(backend="gloo")     # alternative carrier of the chunk-boundary hand-off (LST_BENCH_EXCHANGE=gloo)
 
     def barrier():
         if world > 1:
@@ -280,8 +280,8 @@ def main():
     trk._check(lib.lst_device_upload(trk._ctx, C.c_void_p(dev_ring), host_ring, ring * fb))
     info = trk.set_reference(st.frame(0), st.ref_xy)
     # every lane is a host thread that waits on its stream: keep one host core per lane across the ranks of this node
-    # one core per lane thread plus one for this rank's main / communication threads
-    lanes = args.lanes if args.lanes > 0 else max(1, min(LANES_DEFAULT, len(my_cores) - 1))
+    # one core per lane thread (this rank's main thread sleeps while the lanes run)
+    lanes = args.lanes if args.lanes > 0 else max(1, min(LANES_DEFAULT, len(my_cores)))
     if args.lanes <= 0 and F // (args.max_batch or mb_d) < 4:
         lanes = 1       # a lane should get several full batches; short steps (config D: 64 slices) stay on one
     runner = trk
@@ -315,20 +315,61 @@ def main():
         def track(self, frames, first):
             return self.fn(frames, first, out)
 
-    comm = TorchComm(host_group, "cpu") if world > 1 else None
+    # Boundary hand-off between the ranks: 21 doubles per rank and step -- control information, not slice data; nothing
+    # on the data path is reduced between GPUs.  They travel as a tiny device tensor through the NCCL group the timing
+    # barrier uses anyway: measured on 8 GPUs 6.46 M frames/s against 6.21 M with a gloo (TCP loopback) group, whose
+    # helper threads compete with the lane threads for this rank's host cores.  LST_BENCH_EXCHANGE=gloo switches back.
+    if world > 1 and os.environ.get("LST_BENCH_EXCHANGE", "nccl") == "nccl":
+        comm = TorchComm(None, torch.device("cuda", local_rank))
+    else:
+        comm = TorchComm(host_group, "cpu") if world > 1 else None
+    if os.environ.get("LST_BENCH_NO_COMM"):      # diagnosis only: no boundary exchange (each rank trusts its own guess)
+        comm = None
     sh_dev = ShardedTracker(_Adapter(runner.track_device_ptrs), comm)
     sh_e2e = ShardedTracker(_Adapter(runner.track_host_ptrs), comm)
 
+    # N > 1: the exchange of a step's boundary states (21 doubles, gloo) travels while the next step -- an independent
+    # stack -- is already being tracked (ShardedTracker.track_chunk_pipelined); the records of a step are final when its
+    # exchange has completed, which for the last step happens inside the timed region (finish()).  The two record
+    # buffers alternate so that a late re-track would find its records intact.
+    out_alt = (N.Record * F)() if world > 1 else out
+    flip = [0]
+
+    def _next_out():
+        flip[0] ^= 1
+        return out if flip[0] else out_alt
+
+    class _AdapterAlt(_Adapter):
+        def track(self, frames, first):
+            return self.fn(frames, first, _next_out())
+
+    pipelined = world > 1 and comm is not None and bool(os.environ.get("LST_BENCH_PIPELINED_EXCHANGE"))
+    if pipelined:
+        sh_dev = ShardedTracker(_AdapterAlt(runner.track_device_ptrs), comm)
+        sh_e2e = ShardedTracker(_AdapterAlt(runner.track_host_ptrs), comm)
+
     def step_device():
-        sh_dev.track_chunk(dev_ptrs, 1 + rank * F, runner.get_state())
+        if pipelined:
+            sh_dev.track_chunk_pipelined(dev_ptrs, 1 + rank * F, runner.get_state())
+        else:
+            sh_dev.track_chunk(dev_ptrs, 1 + rank * F, runner.get_state())
 
     def step_e2e():
-        sh_e2e.track_chunk(host_ptrs, 1 + rank * F, runner.get_state())
+        if pipelined:
+            sh_e2e.track_chunk_pipelined(host_ptrs, 1 + rank * F, runner.get_state())
+        else:
+            sh_e2e.track_chunk(host_ptrs, 1 + rank * F, runner.get_state())
+
+    def _finish_exchanges():
+        for sh in (sh_dev, sh_e2e):
+            if getattr(sh, "_pending", None) is not None:
+                sh.finish()
 
     def timed(step_fn, K, W, who=None):
         who = who or runner
         for _ in range(W):
             step_fn()
+        _finish_exchanges()
         who.reset_stats()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -336,6 +377,7 @@ def main():
         e0.record()
         for _ in range(K):
             step_fn()
+        _finish_exchanges()       # the last step's boundary exchange completes inside the timed region
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -659,7 +701,9 @@ def main():
             "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "e2e_pageable": e2e_pageable, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline, "extra": extra,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
-                         "chunks_retracked": sh_dev.retracked, "host_ms_per_step": s_dev.host_ms / K,
+                         "chunks_retracked": sh_dev.retracked, "chunks_retracked_late": getattr(sh_dev, "retracked_late", 0),
+                         "boundary_exchange": ("pipelined: overlaps the next step" if pipelined else "synchronous") +
+                                              (", " + os.environ.get("LST_BENCH_EXCHANGE", "nccl") if world > 1 else ""), "host_ms_per_step": s_dev.host_ms / K,
                          "device_wait_ms_per_step": s_dev.device_wait_ms / K},
             "wall_ms_per_step": wall_dev / K,
         }

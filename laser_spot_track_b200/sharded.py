@@ -96,12 +96,7 @@ class ShardedTracker:
         params = getattr(tracker, "params", None)      # LaserSpotTrack4 keeps its lst_params; the CPU stand-ins of the tests may not
         self.doubling = bool(getattr(params, "doubling", 0)) or bool(getattr(tracker, "doubling", False))
 
-    def track_chunk(self, frames, first_frame_index: int, start_state: Sequence[float],
-                    lead_in: Optional[Sequence] = None):
-        """Track this rank's chunk.  ``start_state``: speculated displacement state before the chunk
-        (rank 0: the true one).  ``lead_in``: optionally the last few frames of the previous chunk,
-        tracked first from ``start_state`` to refine the speculation.  Returns (records, end_state);
-        both are final after the boundary verification."""
+    def _track(self, frames, first_frame_index, start_state, lead_in):
         tr = self.tracker
         guess = list(start_state)
         if self.rank > 0 and lead_in is not None and len(lead_in) > 0:
@@ -111,12 +106,15 @@ class ShardedTracker:
         tr.set_state(guess)
         recs = tr.track(frames, first_frame_index)
         end = list(tr.get_state())
-        # Boundary verification.  One all_gather of (end state, speculated start, any-accepted flag)
-        # lets every rank walk the chain of boundaries identically; in the common case (every
-        # speculation placed the windows right) that is all.  From the first wrong speculation on,
-        # the ranks fall back to handing the verified state down one boundary at a time.
         accepted_any = any(r.status == 0 for r in recs)
-        gathered = self.comm.all_gather(end + guess + [1.0 if accepted_any else 0.0])
+        return recs, end, guess, end + guess + [1.0 if accepted_any else 0.0]
+
+    def _verify(self, gathered, frames, first_frame_index, recs, end, guess):
+        """Boundary verification.  One all_gather of (end state, speculated start, any-accepted flag)
+        lets every rank walk the chain of boundaries identically; in the common case (every
+        speculation placed the windows right) that is all.  From the first wrong speculation on,
+        the ranks fall back to handing the verified state down one boundary at a time."""
+        tr = self.tracker
         verified = list(gathered[0][:10])          # rank 0 started from the true state
         first_bad = None
         for r in range(1, self.world):
@@ -143,8 +141,54 @@ class ShardedTracker:
                     if not accepted_any:
                         end = list(verified)
                 verified = self.comm.broadcast(end if self.rank == r else None, src=r, n=10)
-        tr.set_state(end)
         return recs, end
+
+    def track_chunk(self, frames, first_frame_index: int, start_state: Sequence[float],
+                    lead_in: Optional[Sequence] = None):
+        """Track this rank's chunk.  ``start_state``: speculated displacement state before the chunk
+        (rank 0: the true one).  ``lead_in``: optionally the last few frames of the previous chunk,
+        tracked first from ``start_state`` to refine the speculation.  Returns (records, end_state);
+        both are final after the boundary verification."""
+        recs, end, guess, vals = self._track(frames, first_frame_index, start_state, lead_in)
+        gathered = self.comm.all_gather(vals)
+        recs, end = self._verify(gathered, frames, first_frame_index, recs, end, guess)
+        self.tracker.set_state(end)
+        return recs, end
+
+    # ---- the same with the boundary exchange off the critical path --------------------------------
+    def track_chunk_pipelined(self, frames, first_frame_index: int, start_state: Sequence[float],
+                              lead_in: Optional[Sequence] = None):
+        """Like track_chunk, but the exchange of THIS chunk's boundary states travels (on a helper thread) while the
+        caller goes on -- typically into the next independent stack -- and the PREVIOUS call's exchange is completed
+        after this chunk has been tracked.  Returns (records, end_state, previous) where ``previous`` is the verified
+        (records, end_state) of the previous call, or None.  ``finish()`` completes the last one.  A boundary that
+        fails verification re-tracks that chunk as track_chunk does; its records must not have been overwritten, so
+        callers alternate their record buffers.  ``retracked_late`` counts such late re-tracks: whatever was tracked
+        in between started from that chunk's unverified end state and has to be looked at by the caller."""
+        recs, end, guess, vals = self._track(frames, first_frame_index, start_state, lead_in)
+        prev, self._pending = getattr(self, "_pending", None), None
+        if not hasattr(self, "_pool"):
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=1)
+            self.retracked_late = 0
+        done = self._complete(prev) if prev else None
+        self._pending = (self._pool.submit(self.comm.all_gather, vals), frames, first_frame_index, recs, end, guess)
+        return recs, end, done
+
+    def _complete(self, pending):
+        fut, frames, first, recs, end, guess = pending
+        before = self.retracked
+        keep = list(self.tracker.get_state())
+        out = self._verify(fut.result(), frames, first, recs, end, guess)
+        if self.retracked != before:
+            self.retracked_late += 1
+        self.tracker.set_state(keep)       # the tracker has moved on; a late re-track must not pull it back
+        return out
+
+    def finish(self):
+        """Completes the exchange left in flight by the last track_chunk_pipelined call."""
+        pending, self._pending = getattr(self, "_pending", None), None
+        return self._complete(pending) if pending else None
 
     @staticmethod
     def _patch_carried_state(recs, end, guess, true_start):

@@ -45,7 +45,18 @@ def _worker(rank, world, port, mode, q):
         lo, hi = chunk_bounds(len(frames) - 1, world)[rank]
         chunk = frames[1 + lo:1 + hi]
         lead = frames[1 + lo - 2:1 + lo] if (mode == "lead_in" and rank > 0) else None
-        recs, end = sh.track_chunk(chunk, 1 + lo, [0.0] * 10, lead_in=lead)
+        if mode == "pipelined":
+            # two independent passes over the same stack: the exchange of the first travels while the second is tracked
+            _, _, none = sh.track_chunk_pipelined(chunk, 1 + lo, [0.0] * 10)
+            assert none is None
+            _, _, first = sh.track_chunk_pipelined(chunk, 1 + lo, [0.0] * 10)
+            second = sh.finish()
+            assert first is not None and second is not None
+            key = lambda rr: [(int(r.frame), r.status, [(t.ix, t.iy, t.score) for t in r.tm]) for r in rr]
+            assert key(first[0]) == key(second[0]) and first[1] == second[1]
+            recs, end = second
+        else:
+            recs, end = sh.track_chunk(chunk, 1 + lo, [0.0] * 10, lead_in=lead)
         rows = [(int(r.frame), r.status, [(t.ix, t.iy, t.wx, t.wy, t.score, t.x, t.y) for t in r.tm],
                  list(r.dis), (r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL)) for r in recs]
         q.put((rank, rows, end, sh.retracked))
@@ -53,7 +64,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["zero_guess", "lead_in"])
+@pytest.mark.parametrize("mode", ["zero_guess", "lead_in", "pipelined"])
 def test_two_ranks_reproduce_sequential_loop(built_lib, oracle_clib, mode):
     import torch.multiprocessing as mp
     import util
@@ -88,6 +99,8 @@ def test_two_ranks_reproduce_sequential_loop(built_lib, oracle_clib, mode):
     assert got[1][2] == [v for d in seq.dis for v in d]
     if mode == "zero_guess":
         assert got[1][3] == 1, "rank 1 speculated the reference state and must have re-tracked"
+    elif mode == "pipelined":
+        assert got[1][3] == 2, "both passes of rank 1 started from the reference state and must have been re-tracked"
     else:
         assert got[1][3] == 0, "the lead-in should have found the right windows"
 
