@@ -83,11 +83,11 @@ def bench_config(name: str, ring: int) -> StackConfig:
 
 # DRAM bytes per window of the match kernel from the committed ncu --set full captures (profiles/):
 # lst_ncc_match (IDP.4A), config B: 66.9 MB for 2560 windows of 160x160 8-bit pixels (the window is
-#   read once; 25.6 KB algorithmic);
-# lst_ncc_tc (tensor core), config B: 717.9 MB read + 29.6 MB written for 4704 windows = 159 KB per
-#   window: the 8-bit window (25.6 KB), the window sums lst_box_sums left in HBM (2 x 4 B x 113^2 =
-#   102 KB, read once plus an L2 prefetch that is partly evicted again) and the Toeplitz table.
-NCU_DRAM_BYTES_PER_WINDOW = {("B", False): 66.9e6 / 2560, ("B", True): 747.44e6 / 4704}
+#   read once; 25.6 KB algorithmic) -- profiles/r1_ncu_full_lst_ncc_match_configB.txt;
+# lst_ncc_tc (tensor core), config B: 121.6 MB read + 4.3 MB written for 4704 windows = 26.8 KB per window
+#   (1.05 x the 25.6 KB of the 8-bit window: the window sums never leave the SM any more) --
+#   profiles/r2_ncu_full_three_kernels_configB.txt.
+NCU_DRAM_BYTES_PER_WINDOW = {("B", False): 66.9e6 / 2560, ("B", True): (121.614848e6 + 4.339712e6) / 4704}
 
 LANES_DEFAULT = 4
 
