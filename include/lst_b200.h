@@ -41,7 +41,7 @@ extern "C" {
 /* status codes */
 #define LST_OK               0
 #define LST_ERR_INVALID     -1   /* bad argument */
-#define LST_ERR_UNSUPPORTED -2   /* e.g. 16-bit or RGB stacks with matchIntensity=false (LST4:2510-2523), JPEG / tiled / RGB slice files */
+#define LST_ERR_UNSUPPORTED -2   /* e.g. 16-bit stacks with matchIntensity=false (LST4:2510-2523), tiled / RGB slice files */
 #define LST_ERR_CUDA        -3   /* no device / CUDA runtime error (see lst_last_error) */
 #define LST_ERR_NOMEM       -4
 #define LST_ERR_STATE       -5   /* call order (e.g. track before set_reference) */
@@ -79,7 +79,7 @@ typedef struct lst_params {
     int32_t templ_size;        /* templSize LST4:84 */
     int32_t s_area;            /* sArea LST4:83; 0 => whole-slice search (LST4:1316-1320) */
     int32_t sub_pixel;         /* LST4:89 */
-    int32_t match_intensity;   /* LST4:88 */
+    int32_t match_intensity;   /* LST4:88; 0 on an RGB stack = 3-channel match (channels blurred separately, CV_8UC3 matchTemplate) */
     int32_t range_mode;        /* LST_RANGE_* */
     int32_t quant_mode;        /* LST_QUANT_* */
     int32_t doubling;          /* search-area doubling recovery (LST4:1666-1735, 2058-2128) */
@@ -295,7 +295,8 @@ int lst_match_single(lst_ctx *ctx, const uint8_t *src8, int32_t sw, int32_t sh,
 /* doMatch_test(src, method): matchTemplate(src, src) 1x1 (LST4:2724-2767). */
 int lst_match_test(lst_ctx *ctx, const uint8_t *src8, int32_t sw, int32_t sh, int32_t method, double *out);
 /* crop -> [convertToGray32] -> blurGaussian(2,2,0.02) -> 8-bit of one rectangle of a host frame:
- * the image handed to matchTemplate (LST4:1346-1347, 1456-1473, 2529).  out8: w*h bytes. */
+ * the image handed to matchTemplate (LST4:1346-1347, 1456-1473, 2529).  out8: w*h bytes; for LST_PIX_RGB with
+ * match_intensity = 0 (the 3-channel match, LST4:2525-2535 case 24) 3*w*h bytes: the blurred planes R, G, B in turn. */
 int lst_preprocess(lst_ctx *ctx, const void *frame, int32_t x0, int32_t y0, int32_t w, int32_t h, uint8_t *out8);
 /* calcDisplacement() as a pure function (LST4:2318-2365); spot0 NULL => first call (latches). */
 int lst_calc_displacement(const float ref_xy[10], const double dis[10], double mark_dist,

@@ -70,6 +70,7 @@ struct PreprocParams {
     int minmax_in_kernel;  // the blur kernel finds the crop min/max itself (single column block)
     int swap_bytes;        // the slices hold big-endian samples (files read by lst_track_files)
     const uint32_t *frame_mm;   // LST_RANGE_FRAME: {min key, max key} per slice of the batch (px_key order)
+    int rgb_shift;         // RGB slices: -1 = grey value of the pixel (matchIntensity), 16 / 8 / 0 = that channel alone (3-channel match)
 };
 
 struct MatchParams {
@@ -80,6 +81,7 @@ struct MatchParams {
     int sub_pixel;
     int templ_size;
     double thresh;
+    unsigned long long plane_bytes;   // 3-channel match: distance between the channel planes of the 8-bit windows (0 = one channel)
 };
 
 // launchers (all asynchronous on `stream`); each returns the number of kernels it launched or <0
@@ -102,6 +104,10 @@ int launch_gather_rois(const void *const *mapped_frames, int n_frames, const Roi
 int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, int tw, int th,
                      const DevTemplates *tpls, const uint8_t *win8, unsigned long long *best, float *score_map,
                      const MatchParams &mp, cudaStream_t stream);
+// 3-channel match (RGB stacks with matchIntensity = false): exact correlation summed over the channel planes, per-channel
+// window sums, common_matchTemplate's cn = 3 normalisation, first-maximum argmax.  The planes of a window lie plane_bytes apart.
+int launch_ncc_rgb(const DevTask *tasks, int n_tasks, int max_rh, int max_w, int max_tw, int max_th, const DevTemplates *tpls,
+                   const uint8_t *win8, size_t plane_bytes, unsigned long long *best, cudaStream_t stream);
 int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls, const uint8_t *win8,
                     const unsigned long long *best, const float *nbhd, DevResult *results, const MatchParams &mp,
                     cudaStream_t stream);

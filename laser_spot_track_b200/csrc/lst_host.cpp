@@ -41,8 +41,6 @@ int validate_params(const lst_params &p, std::string *err)
     if (p.pixel_type != LST_PIX_U8 && p.pixel_type != LST_PIX_U16 && p.pixel_type != LST_PIX_F32 && p.pixel_type != LST_PIX_RGB)
         return fail(LST_ERR_UNSUPPORTED, "Unsupported image type");   // IJ.error text of LST4:2537
     if (p.method < 0 || p.method > 5) return fail(LST_ERR_INVALID, "matching method must be 0..5 (LST4:2381)");
-    if (p.pixel_type == LST_PIX_RGB && !p.match_intensity)
-        return fail(LST_ERR_UNSUPPORTED, "RGB stacks are matched on intensity only (matchIntensity=true): the 3-channel match is not on this path");
     if (p.pixel_type == LST_PIX_U16 && !p.match_intensity)
         return fail(LST_ERR_UNSUPPORTED,
                     "16-bit stacks need matchIntensity=true (the reference dereferences a null Mat, LST4:2510-2523)");
@@ -166,6 +164,7 @@ TplConst template_consts(const uint8_t *tpl8, int tw, int th, int method)
     double n = (double)(tw * th);
     c.tw = tw;
     c.th = th;
+    c.channels = 1;
     c.kw = packed_words(tw);
     c.tsum = (uint32_t)s;
     c.tsq_lo = (uint32_t)q;
@@ -191,6 +190,54 @@ TplConst template_consts(const uint8_t *tpl8, int tw, int th, int method)
     // *_mideal = doMatch_test(tpl, method == 0 ? 2 : method): the template matched against itself (LST4:566)
     c.method = method == 0 ? 2 : method;
     c.mideal = (double)match_score(c, (double)q, (double)s, (double)q);
+    c.method = method;
+    return c;
+}
+
+// planes: three tw x th planes one after the other (the channels of a ColorProcessor template after its per-channel blur)
+TplConst template_consts3(const uint8_t *planes, int tw, int th, int method)
+{
+    TplConst c;
+    memset(&c, 0, sizeof(c));
+    const int n_px = tw * th;
+    const double n = (double)n_px;
+    c.tw = tw;
+    c.th = th;
+    c.kw = packed_words(tw);
+    c.channels = 3;
+    c.inv_area = 1.0 / n;
+    uint64_t s[3], q[3], qsum = 0;
+    double sdv2 = 0.0, mean2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+        s[k] = q[k] = 0;
+        for (int i = 0; i < n_px; i++) {
+            const uint64_t v = planes[(size_t)k * n_px + i];
+            s[k] += v;
+            q[k] += v * v;
+        }
+        qsum += q[k];
+        c.mean3[k] = (double)s[k] / n;                       // meanStdDev per channel
+        double var = (double)q[k] / n - c.mean3[k] * c.mean3[k];
+        if (var < 0.0) var = 0.0;
+        const double sdv = sqrt(var);
+        sdv2 += sdv * sdv;                                   // templSdv[0]^2 + templSdv[1]^2 + templSdv[2]^2 (+ 0)
+        mean2 += c.mean3[k] * c.mean3[k];
+    }
+    c.tsum = (uint32_t)(s[0] + s[1] + s[2]);
+    c.tsq_lo = (uint32_t)qsum;
+    c.mean = 0.0;
+    c.flat = sdv2 < 2.220446049250313e-16;
+    c.norm = sqrt(sdv2) / sqrt(c.inv_area);
+    {   // templSum2 = templNorm + sum of the squared means, then / invArea; the non-CCOEFF templNorm = sqrt(templSum2 before the division)
+        double sum2 = sdv2;
+        for (int k = 0; k < 3; k++) sum2 += c.mean3[k] * c.mean3[k];
+        c.norm_raw = sqrt(sum2) / sqrt(c.inv_area);
+        c.sum2 = sum2 / c.inv_area;
+    }
+    (void)mean2;
+    const double ws[3] = {(double)s[0], (double)s[1], (double)s[2]};
+    c.method = method == 0 ? 2 : method;                     // *_mideal = doMatch_test(tpl, method == 0 ? 2 : method), LST4:566
+    c.mideal = (double)match_score3(c, (double)qsum, ws, (double)qsum);
     c.method = method;
     return c;
 }

@@ -34,6 +34,7 @@ void make_gaussian_kernel(float kern[kBlurRadius], float ksum[kBlurRadius]);
 
 // cv::meanStdDev + the template constants of common_matchTemplate; tpl8 has row pitch tw.
 TplConst template_consts(const uint8_t *tpl8, int tw, int th, int method = 5);
+TplConst template_consts3(const uint8_t *planes, int tw, int th, int method = 5);   // three planes, one after the other
 // The template packed for IDP.4A: word[v*kw + k] holds template bytes T[v][4k .. 4k+3] (0 beyond tw);
 // kw = words per row, rounded up to a multiple of 4 so that rows load as 128-bit words.
 int packed_words(int tw);

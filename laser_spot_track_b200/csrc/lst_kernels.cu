@@ -330,7 +330,7 @@ __device__ __forceinline__ uint32_t byte_range_mask(int s, int e)
 template <int PIX, bool STORE, bool MINMAX>
 __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, size_t row_pitch_bytes, int row0, int nrows,
                                            int lo0, int vpr, int row_bytes, const uint8_t *surf_lo, const uint8_t *surf_hi,
-                                           float *sraw, int rwp, uint32_t &mlo, uint32_t &mhi, bool swap)
+                                           float *sraw, int rwp, uint32_t &mlo, uint32_t &mhi, bool swap, int rgb_shift = -1)
 {
     constexpr int ES = PIX == LST_PIX_U8 ? 1 : (PIX == LST_PIX_U16 ? 2 : 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -408,7 +408,11 @@ __device__ __forceinline__ void stage_rows(const uint8_t *__restrict__ crop00, s
                         ((float4 *)d)[j] = make_float4((float)(o[2 * j] & 0xffffu), (float)(o[2 * j] >> 16),
                                                        (float)(o[2 * j + 1] & 0xffffu), (float)(o[2 * j + 1] >> 16));
                 } else if (PIX == LST_PIX_RGB) {
-                    *(float4 *)d = make_float4((float)rgb_gray(o[0]), (float)rgb_gray(o[1]), (float)rgb_gray(o[2]), (float)rgb_gray(o[3]));
+                    if (rgb_shift >= 0)      // one channel of the ColorProcessor (GaussianBlur blurs the channels separately)
+                        *(float4 *)d = make_float4((float)((o[0] >> rgb_shift) & 0xffu), (float)((o[1] >> rgb_shift) & 0xffu),
+                                                   (float)((o[2] >> rgb_shift) & 0xffu), (float)((o[3] >> rgb_shift) & 0xffu));
+                    else
+                        *(float4 *)d = make_float4((float)rgb_gray(o[0]), (float)rgb_gray(o[1]), (float)rgb_gray(o[2]), (float)rgb_gray(o[3]));
                 } else {
                     *(float4 *)d = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
                 }
@@ -517,7 +521,7 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
         {
             uint32_t d0 = 0, d1 = 0;
             stage_rows<PIX, true, false>(crop00, row_pitch_bytes, xdone, newr, RB * ES, VPR, row_bytes, surf_lo, surf_hi, sraw,
-                                         RWP, d0, d1, pp.swap_bytes != 0);
+                                         RWP, d0, d1, pp.swap_bytes != 0, PIX == LST_PIX_RGB ? pp.rgb_shift : -1);
         }
         // the X-pass rows this strip shares with the previous one move to the front
         if (cy0 > 0) {
@@ -1019,6 +1023,103 @@ int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, 
 
 
 // ------------------------------------------------------------------------------------------------
+// 3-channel match (RGB stacks, matchIntensity = false: LST4:2525-2535 case 24 hands OpenCV a CV_8UC3 image)
+// ------------------------------------------------------------------------------------------------
+// matchTemplate sums the correlation over the channels and normalises with per-channel window sums.  A rarely used mode:
+// a plain direct kernel -- a CTA owns a band of RGB_BAND result rows of one window, keeps the window rows of the three
+// planes it needs and the three template planes in shared memory, every thread walks the template for its positions
+// (integer arithmetic, exact), scores them with match_score3 and the CTA reduces the first maximum.
+#define RGB_BAND 4
+#define RGB_THREADS 256
+
+__global__ void __launch_bounds__(RGB_THREADS)
+lst_ncc_rgb(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
+            unsigned long long plane_bytes, unsigned long long *__restrict__ best, int smem_pitch, int max_th)
+{
+    extern __shared__ __align__(16) uint8_t smem_rgb[];
+    __shared__ unsigned long long s_best[RGB_THREADS / 32];
+    const DevTask t = tasks[blockIdx.y];
+    const TplConst tc = tpls->c[t.tpl];
+    const int tw = tc.tw, th = tc.th;
+    const int y0 = blockIdx.x * RGB_BAND;
+    if (y0 >= t.rh) return;
+    const int nrows = min(RGB_BAND, t.rh - y0);
+    const int wrows = nrows + th - 1;
+    uint8_t *s_win = smem_rgb;                                        // [3][RGB_BAND + max_th - 1][smem_pitch]
+    const size_t plane_smem = (size_t)(RGB_BAND + max_th - 1) * smem_pitch;
+    uint8_t *s_tpl = smem_rgb + 3 * plane_smem;                       // [3][th][tw]
+    for (int c = 0; c < 3; c++) {
+        const uint8_t *src = win8 + (size_t)c * plane_bytes + t.win_off;
+        const int vec = smem_pitch / 16;
+        for (int i = threadIdx.x; i < wrows * vec; i += blockDim.x) {
+            const int r = i / vec, cc = (i - r * vec) * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (cc < t.pitch) v = *(const uint4 *)(src + (size_t)(y0 + r) * t.pitch + cc);
+            *(uint4 *)(s_win + c * plane_smem + (size_t)r * smem_pitch + cc) = v;
+        }
+        const uint8_t *tp = tpls->raw[t.tpl] + (size_t)c * tw * th;
+        for (int i = threadIdx.x; i < tw * th; i += blockDim.x) s_tpl[(size_t)c * tw * th + i] = tp[i];
+    }
+    __syncthreads();
+    unsigned long long mybest = 0ull;
+    const bool want_min = method_wants_min(tc.method);
+    for (int pos = threadIdx.x; pos < nrows * t.rw; pos += blockDim.x) {
+        const int r = pos / t.rw, x = pos - r * t.rw;
+        unsigned long long corr = 0, q = 0;      // a channel's sums fit 32 bits (tw * th <= 66000), the three together may not
+        uint32_t s3[3];
+        for (int c = 0; c < 3; c++) {
+            const uint8_t *w = s_win + c * plane_smem + (size_t)r * smem_pitch + x;
+            const uint8_t *tp = s_tpl + (size_t)c * tw * th;
+            uint32_t sc = 0, cc = 0, qc = 0;
+            for (int v = 0; v < th; v++) {
+                const uint8_t *wr = w + (size_t)v * smem_pitch, *tr = tp + v * tw;
+#pragma unroll 4
+                for (int u = 0; u < tw; u++) {
+                    const uint32_t px = wr[u];
+                    cc += px * tr[u];
+                    sc += px;
+                    qc += px * px;
+                }
+            }
+            s3[c] = sc;
+            corr += cc;
+            q += qc;
+        }
+        const double ws[3] = {(double)s3[0], (double)s3[1], (double)s3[2]};
+        const float score = match_score3(tc, (double)corr, ws, (double)q);
+        const unsigned long long key = pack_key(score, (uint32_t)((y0 + r) * t.rw + x), want_min);
+        mybest = key > mybest ? key : mybest;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, mybest, o);
+        mybest = other > mybest ? other : mybest;
+    }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = mybest;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < RGB_THREADS / 32; w++) mybest = s_best[w] > mybest ? s_best[w] : mybest;
+        atomicMax(&best[blockIdx.y], mybest);
+    }
+}
+
+int launch_ncc_rgb(const DevTask *tasks, int n_tasks, int max_rh, int max_w, int max_tw, int max_th, const DevTemplates *tpls,
+                   const uint8_t *win8, size_t plane_bytes, unsigned long long *best, cudaStream_t stream)
+{
+    const int pitch = (max_w + 15) & ~15;
+    const size_t smem = 3 * (size_t)(RGB_BAND + max_th - 1) * pitch + 3 * (size_t)max_tw * max_th + 16;
+    if (smem > 200 * 1024 || (long)max_tw * max_th > 66000) return -1;
+    if (cudaFuncSetAttribute(lst_ncc_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+    const int bands = (max_rh + RGB_BAND - 1) / RGB_BAND;
+    int launches = 0;
+    for (int base = 0; base < n_tasks; base += 65535) {
+        const int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
+        lst_ncc_rgb<<<dim3(bands, n), RGB_THREADS, smem, stream>>>(tasks + base, tpls, win8, plane_bytes, best + base, pitch, max_th);
+        launches++;
+    }
+    return cudaPeekAtLastError() == cudaSuccess ? launches : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-window epilogue: 3x3 neighbourhood, sub-pixel fit, accept test
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(288)
@@ -1043,6 +1144,31 @@ lst_epilogue(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__
     const bool have = nbhd[12 * (size_t)blockIdx.x + 9] != 0.0f;
     if (have) {
         if (inside) sc = nbhd[12 * (size_t)blockIdx.x + warp];
+    } else if (inside && tc.channels == 3) {
+        unsigned long long acc = 0, q = 0;
+        uint32_t s3[3] = {0, 0, 0};
+        for (int c = 0; c < 3; c++) {
+            const uint8_t *w = win8 + (size_t)c * mp.plane_bytes + t.win_off + (size_t)ny * t.pitch + nx;
+            const uint8_t *tp = tpls->raw[t.tpl] + (size_t)c * tc.tw * tc.th;
+            uint32_t s = 0, a = 0, qq = 0;
+            for (int e = lane; e < tc.tw * tc.th; e += 32) {
+                int v = e / tc.tw, u = e - v * tc.tw;
+                uint32_t px = w[(size_t)v * t.pitch + u];
+                a += px * (uint32_t)tp[e];
+                s += px;
+                qq += px * px;
+            }
+            s3[c] = s;
+            acc += a;
+            q += qq;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+            for (int c = 0; c < 3; c++) s3[c] += __shfl_xor_sync(0xffffffffu, s3[c], o);
+        }
+        const double ws[3] = {(double)s3[0], (double)s3[1], (double)s3[2]};
+        sc = match_score3(tc, (double)acc, ws, (double)q);
     } else if (inside) {
         const uint8_t *w = win8 + t.win_off + (size_t)ny * t.pitch + nx;
         const uint8_t *tp = tpls->raw[t.tpl];

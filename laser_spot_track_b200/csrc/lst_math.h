@@ -30,6 +30,11 @@ struct TplConst {
     int32_t method;     // OpenCV match method 0..5 (LST4:2547-2552); 5 = TM_CCOEFF_NORMED
     double sum2;        // templSum2 = sum of t^2 as common_matchTemplate derives it
     double norm_raw;    // sqrt(E[t^2])/sqrt(invArea): templNorm of the non-CCOEFF methods
+    // 3-channel templates (RGB stacks matched with matchIntensity = false, LST4:2525-2535 case 24): channels = 3, mean3 = the
+    // per-channel templMean; norm / norm_raw / sum2 / flat then hold the sums over the channels as common_matchTemplate forms them
+    int32_t channels;   // 1 or 3
+    int32_t pad_;
+    double mean3[3];
 };
 
 // One position of common_matchTemplate for TM_CCOEFF_NORMED with an exact integer numerator:
@@ -82,6 +87,46 @@ LST_HD float match_score(const TplConst &c, double corr, double wsum, double wsq
         double thr = 10.0 * 1.1920928955078125e-07 * wnd_sum2;
         if (thr > 0.5) thr = 0.5;
         double tt = (diff2 <= thr) ? 0.0 : sqrt(diff2) * c.norm_raw;
+        double a = fabs(num);
+        if (a < tt) num = num / tt;
+        else if (a < tt * 1.125) num = num > 0.0 ? 1.0 : -1.0;
+        else num = method != 1 ? 0.0 : 1.0;
+    }
+    return (float)num;
+}
+
+// The same for a 3-channel image (cn = 3 in common_matchTemplate): corr = sum over the channels of sum I_c*T_c, wsum[k] = the
+// window sum of channel k, wsq = sum over the channels of the window sums of I_c^2.  Operation order as in templmatch.cpp:
+// wndMean2 and num accumulate channel by channel, wndMean2 is scaled by invArea afterwards.
+LST_HD float match_score3(const TplConst &c, double corr, const double wsum[3], double wsq)
+{
+    const int method = c.method;
+    if (method == 5 && c.flat) return 1.0f;
+    const int num_type = (method == 2 || method == 3) ? 0 : ((method == 4 || method == 5) ? 1 : 2);
+    const bool normed = method == 1 || method == 3 || method == 5;
+    double num = corr, wnd_mean2 = 0.0, wnd_sum2 = 0.0;
+    if (num_type == 1) {
+        for (int k = 0; k < 3; k++) {
+            const double t = wsum[k];
+            wnd_mean2 += t * t;
+            num -= t * c.mean3[k];
+        }
+        wnd_mean2 *= c.inv_area;
+    }
+    if (normed || num_type == 2) {
+        wnd_sum2 = wsq;
+        if (num_type == 2) {
+            num = wnd_sum2 - 2.0 * num + c.sum2;
+            if (num < 0.0) num = 0.0;
+        }
+    }
+    if (normed) {
+        double diff2 = wnd_sum2 - wnd_mean2;
+        if (diff2 < 0.0) diff2 = 0.0;
+        double thr = 10.0 * 1.1920928955078125e-07 * wnd_sum2;
+        if (thr > 0.5) thr = 0.5;
+        const double tn = method == 5 ? c.norm : c.norm_raw;
+        double tt = (diff2 <= thr) ? 0.0 : sqrt(diff2) * tn;
         double a = fabs(num);
         if (a < tt) num = num / tt;
         else if (a < tt * 1.125) num = num > 0.0 ? 1.0 : -1.0;

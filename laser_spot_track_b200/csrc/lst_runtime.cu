@@ -149,7 +149,14 @@ struct lst_ctx : public Executor {
     std::vector<double> cur_ranges;      // the ranges of the tracking call in progress, slice `range_first` first
     int64_t range_first = 0;
     int track_depth = 0;
-    bool frame_range_mode() const { return p.range_mode == LST_RANGE_FRAME && !(p.pixel_type == LST_PIX_U8 && !p.match_intensity); }
+    // RGB stack with matchIntensity = false: the channels are blurred separately (ColorProcessor) and OpenCV gets a CV_8UC3 image
+    bool rgb3() const { return p.pixel_type == LST_PIX_RGB && !p.match_intensity; }
+    bool frame_range_mode() const
+    {
+        return p.range_mode == LST_RANGE_FRAME && !((p.pixel_type == LST_PIX_U8 || p.pixel_type == LST_PIX_RGB) && !p.match_intensity);
+    }
+    int upload_template3(int slot, const uint8_t *planes, int tw, int th);
+    size_t last_plane_bytes = 0;   // distance between the channel planes in d_win8 after the last pass (rgb3)
     int prepare_frame_ranges(int nb, const double *lo_hi);
     // asynchronous front end (lst_submit / lst_fetch / lst_override): batches tracked in order by a worker thread
     struct AsyncJob {
@@ -271,8 +278,9 @@ void lst_ctx::preproc_params(PreprocParams *pp, int max_w, int max_h) const
     pp->frame_w = p.width;
     pp->frame_h = p.height;
     pp->quant_mode = p.quant_mode;
-    if (p.pixel_type == LST_PIX_U8 && !p.match_intensity) {
-        // ByteProcessor blur rounds back with (int)(v+0.5f), clamped: == ROUND255 on [0,255]
+    pp->rgb_shift = -1;
+    if ((p.pixel_type == LST_PIX_U8 || p.pixel_type == LST_PIX_RGB) && !p.match_intensity) {
+        // ByteProcessor blur (and ColorProcessor blur, channel by channel) rounds back with (int)(v+0.5f), clamped: == ROUND255 on [0,255]
         pp->range_per_task = 0;
         pp->lo = 0.0f;
         pp->hi = 255.0f;
@@ -331,6 +339,25 @@ int lst_ctx::upload_template(int slot, const uint8_t *tpl8, int tw, int th, int 
     CU(cudaMemcpyAsync(d_tpls, &h_tpls, sizeof(DevTemplates), cudaMemcpyHostToDevice, s_compute));
     CU(cudaStreamSynchronize(s_compute));   // sh / h_tpls are pageable: finish before they go away
     stats.h2d_bytes += (int64_t)(sh.size() * 4 + (size_t)tw * th + sizeof(DevTemplates));
+    return LST_OK;
+}
+
+// 3-channel template (rgb3): the three blurred channel planes one after the other; matched by lst_ncc_rgb only
+int lst_ctx::upload_template3(int slot, const uint8_t *planes, int tw, int th)
+{
+    const size_t bytes = 3 * (size_t)tw * th;
+    if (bytes > raw_cap[slot]) {
+        CU(regrow(&d_raw[slot], bytes));
+        raw_cap[slot] = bytes;
+    }
+    CU(cudaMemcpyAsync(d_raw[slot], planes, bytes, cudaMemcpyHostToDevice, s_compute));
+    h_tpls.c[slot] = template_consts3(planes, tw, th, p.method);
+    h_tpls.raw[slot] = d_raw[slot];
+    h_tpls.packed[slot] = nullptr;
+    h_tpls.toeplitz[slot] = nullptr;
+    CU(cudaMemcpyAsync(d_tpls, &h_tpls, sizeof(DevTemplates), cudaMemcpyHostToDevice, s_compute));
+    CU(cudaStreamSynchronize(s_compute));
+    stats.h2d_bytes += (int64_t)(bytes + sizeof(DevTemplates));
     return LST_OK;
 }
 
@@ -422,7 +449,9 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
     }
     // The tensor-core engine reads the 8-bit windows by TMA as one 2-D byte image: every window of the pass gets
     // the same row pitch (the widest window's) and starts at a multiple of it.
-    const bool tc_layout = ncc_engine == 1 && !preprocess_only && !map_out_host;
+    const bool rgb = rgb3() && !have_win8;   // three channel planes per window, matched by lst_ncc_rgb
+    if (rgb && map_out_host) return fail(LST_ERR_UNSUPPORTED, "no score map output for the 3-channel match");
+    const bool tc_layout = ncc_engine == 1 && !preprocess_only && !map_out_host && !rgb;
     int pass_pitch = 0;
     if (tc_layout)
         for (int i = 0; i < n; i++) {
@@ -496,7 +525,9 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         max_w = std::max(max_w, d.w);
         max_h = std::max(max_h, d.h);
     }
-    rc = ensure_scratch(win_off + 64, map_out_host ? sum_off + 32 : 0);
+    const size_t plane_bytes = rgb ? ((win_off + 255) & ~(size_t)255) : 0;
+    last_plane_bytes = plane_bytes;
+    rc = ensure_scratch(rgb ? 3 * plane_bytes + 64 : win_off + 64, map_out_host ? sum_off + 32 : 0);
     if (rc != LST_OK) return rc;
     int launches = 0;
     {
@@ -523,7 +554,14 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         NvtxRange nvtx_blur("lst_preprocess");
         PreprocParams pp;
         preproc_params(&pp, max_w, max_h);
-        if (preproc_engine == 0 && preprocess_win_eligible(p.pixel_type, max_w, max_h)) {
+        if (rgb) {
+            for (int k = 0; k < 3; k++) {   // planes in the order R, G, B (matchTemplate sums over the channels: the order is immaterial)
+                pp.rgb_shift = 16 - 8 * k;
+                const int l3 = launch_preprocess(d_tasks, n, max_w, max_h, d_surf, pp, d_mm, d_win8 + k * plane_bytes, s_compute);
+                if (l3 < 0) return fail(LST_ERR_CUDA, "lst_preprocess launch failed");
+                launches += l3;
+            }
+        } else if (preproc_engine == 0 && preprocess_win_eligible(p.pixel_type, max_w, max_h)) {
             int l2 = launch_preprocess_win(d_tasks, n, max_w, max_h, d_surf, pp, d_win8, s_compute);
             if (l2 < 0) return fail(LST_ERR_CUDA, "lst_preprocess_win launch failed");
             launches += l2;
@@ -539,11 +577,19 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
         mp.sub_pixel = p.sub_pixel;
         mp.templ_size = p.templ_size;
         mp.thresh = p.match_threshold;
-        if (smem > 200 * 1024) return fail(LST_ERR_UNSUPPORTED, "match tile needs %zu bytes of shared memory", smem);
+        mp.plane_bytes = plane_bytes;
+        if (smem > 200 * 1024 && !rgb) return fail(LST_ERR_UNSUPPORTED, "match tile needs %zu bytes of shared memory", smem);
         if (timed_pass) {
             tl.macs = macs;
             CU(cudaEventRecord(tl.eb, s_compute));
             CU(cudaEventRecord(tl.e0, s_compute));
+        }
+        if (rgb) {
+            for (int i = 0; i < n; i++)
+                if (h_tpls.c[h_tasks[i].tpl].channels != 3) return fail(LST_ERR_STATE, "3-channel match without a 3-channel template");
+            const int l3 = launch_ncc_rgb(d_tasks, n, max_rh, max_w, max_tw, max_th, d_tpls, d_win8, plane_bytes, d_best, s_compute);
+            if (l3 < 0) return fail(LST_ERR_UNSUPPORTED, "3-channel match: window %dx%d / template %dx%d too large", max_w, max_h, max_tw, max_th);
+            launches += l3;
         }
         bool use_tc = tc_layout && tc_supported(max_tw, max_th);
         if (use_tc)
@@ -557,7 +603,9 @@ int lst_ctx::run_group(const lst_task *tasks, int n, lst_task_result *results, b
             if (!warned) fprintf(stderr, "lst_b200: tensor-core match engine not applicable to this window/template size; using IDP.4A\n");
             warned = true;
         }
-        if (tcl >= 0)
+        if (rgb)
+            ;
+        else if (tcl >= 0)
             launches += tcl;
         else
             launches += launch_ncc_match(d_tasks, n, max_rw, max_rh, max_tw, max_th, d_tpls, d_win8, d_best,
@@ -614,7 +662,7 @@ int lst_ctx::compute(const lst_task *tasks, int n, lst_task_result *results)
         while (j < n) {
             const lst_task &t = tasks[j];
             size_t pitch = (t.ww + 15) & ~15;
-            size_t need = pitch * t.wh + 256;
+            size_t need = (pitch * t.wh + 256) * (rgb3() ? 3 : 1);
             if (j > i && bytes + need > scratch_limit) break;
             bytes += need;
             j++;
@@ -858,13 +906,17 @@ int lst_set_reference(lst_ctx *c, const void *ref_frame, const float ref_xy[10],
     rc = c->run_group(tasks, 5, nullptr, true, false, -1, nullptr);
     if (rc != LST_OK) return rc;
     for (int k = 0; k < 5; k++) {
-        std::vector<uint8_t> t8((size_t)crop[k].w * crop[k].h);
+        const int planes = c->rgb3() ? 3 : 1;
+        const size_t plane_px = (size_t)crop[k].w * crop[k].h;
+        std::vector<uint8_t> t8(planes * plane_px);
         int slot = 0;
         while (c->order[slot] != k) slot++;
         const DevTask &d = c->h_tasks[slot];
-        CUC(c, cudaMemcpy2D(t8.data(), crop[k].w, c->d_win8 + d.win_off, d.pitch, crop[k].w, crop[k].h, cudaMemcpyDeviceToHost));
+        for (int pl = 0; pl < planes; pl++)
+            CUC(c, cudaMemcpy2D(t8.data() + pl * plane_px, crop[k].w, c->d_win8 + pl * c->last_plane_bytes + d.win_off, d.pitch, crop[k].w,
+                                crop[k].h, cudaMemcpyDeviceToHost));
         c->stats.d2h_bytes += (int64_t)t8.size();
-        rc = c->upload_template(k, t8.data(), crop[k].w, crop[k].h);
+        rc = planes == 3 ? c->upload_template3(k, t8.data(), crop[k].w, crop[k].h) : c->upload_template(k, t8.data(), crop[k].w, crop[k].h);
         if (rc != LST_OK) return rc;
     }
     for (int i = 0; i < 10; i++) c->dis[i] = 0.0;
@@ -1998,7 +2050,9 @@ int lst_preprocess(lst_ctx *c, const void *frame, int32_t x0, int32_t y0, int32_
     t.wh = h;
     rc = c->run_group(&t, 1, nullptr, true, false, -1, nullptr);
     if (rc != LST_OK) return rc;
-    CUC(c, cudaMemcpy2D(out8, w, c->d_win8 + c->h_tasks[0].win_off, c->h_tasks[0].pitch, w, h, cudaMemcpyDeviceToHost));
+    for (int pl = 0; pl < (c->rgb3() ? 3 : 1); pl++)   // 3-channel match: the planes R, G, B one after the other
+        CUC(c, cudaMemcpy2D(out8 + (size_t)pl * w * h, w, c->d_win8 + pl * c->last_plane_bytes + c->h_tasks[0].win_off, c->h_tasks[0].pitch, w, h,
+                            cudaMemcpyDeviceToHost));
     return LST_OK;
 }
 

@@ -247,9 +247,10 @@ class LaserSpotTrack4:
     def preprocess(self, frame: np.ndarray, x0: int, y0: int, w: int, h: int) -> np.ndarray:
         """The 8-bit image handed to matchTemplate for one rectangle of ``frame``."""
         fr = self._frame(frame)
-        out = np.zeros((h, w), dtype=np.uint8)
+        rgb3 = self.params.pixel_type == N.PIX_RGB and not self.params.match_intensity
+        out = np.zeros((3, h, w) if rgb3 else (h, w), dtype=np.uint8)
         self._check(self._lib.lst_preprocess(self._ctx, fr.ctypes.data, x0, y0, w, h, out.ctypes.data))
-        return out
+        return np.ascontiguousarray(out.transpose(1, 2, 0)) if rgb3 else out   # 3-channel match: (h, w, 3), channels R, G, B
 
     @staticmethod
     def calcDisplacement(ref_xy, dis, markDist: float, spot0=None):

@@ -266,7 +266,14 @@ def preprocess_crop(frame: np.ndarray, x0: int, y0: int, w: int, h: int, p: Para
         # RGB slice (DOES_RGB, LST4:172): matched on intensity; an 8-bit grey image from here on, whose
         # 0..255 display range survives convertToGray32 like an 8-bit slice's
         if not p.match_intensity:
-            raise ValueError("RGB stacks: only matchIntensity=true is on this path")
+            # matchIntensity=false: no convertToGray32 (LST4:1456-1468); GaussianBlur.blurGaussian on a ColorProcessor blurs
+            # the channels one by one as float images and writes each back with (int)(v+0.5f) clamped to 0..255
+            # (ColorProcessor.setPixels(channel, fp)) [ImageJ, 3P-recall]; getBufferedImage -> Java2DFrameUtils.toMat gives
+            # OpenCV a CV_8UC3 image (LST4:2525-2535 case 24).  Returned as (h, w, 3), channel order R, G, B (matchTemplate
+            # sums over the channels, so the order of the planes does not matter).
+            planes = [quantize_u8(blur_gaussian_float(((crop >> np.uint32(sh)) & np.uint32(0xff)).astype(f32)), 0.0, 255.0,
+                                  QUANT_ROUND255) for sh in (16, 8, 0)]
+            return np.stack(planes, axis=-1)
         crop = rgb_to_gray8(crop, p.rgb_weights)
         if p.range_mode == RANGE_FRAME:
             whole = rgb_to_gray8(frame, p.rgb_weights)
@@ -433,8 +440,74 @@ def match_from_sums(method: int, corr, wsum, wsq, tpl8: np.ndarray):
     return np.asarray(num).astype(f32)
 
 
+def match_from_sums3(method: int, corr, wsum3, wsq, tpl8: np.ndarray):
+    """common_matchTemplate (templmatch.cpp) with cn = 3 (RGB stacks with matchIntensity=false, LST4:2525-2535 case 24):
+    corr = sum over the channels of the exact correlations, wsum3[k] = window sums of channel k, wsq = sum over the channels
+    of the window sums of squares; tpl8 is (th, tw, 3).  templNorm = sdv0^2 + sdv1^2 + sdv2^2, templSum2 = templNorm +
+    mean0^2 + mean1^2 + mean2^2, wndMean2 and num accumulate channel by channel -- OpenCV's operation order, in double."""
+    corr = np.asarray(corr, dtype=np.float64)
+    if method == 2:
+        return corr.astype(f32)
+    n = tpl8.shape[0] * tpl8.shape[1]
+    inv_area = 1.0 / float(n)
+    means, norm = [], 0.0
+    for k in range(3):
+        t = tpl8[:, :, k].astype(np.int64)
+        mean = float(int(t.sum())) / float(n)
+        var = float(int((t * t).sum())) / float(n) - mean * mean
+        sdv = math.sqrt(max(var, 0.0))
+        norm += sdv * sdv
+        means.append(mean)
+    if method == 5 and norm < DBL_EPSILON:
+        return np.ones(corr.shape, dtype=f32)
+    sum2 = norm
+    for k in range(3):
+        sum2 += means[k] * means[k]
+    num_type = 0 if method in (2, 3) else (1 if method in (4, 5) else 2)
+    normed = method in (1, 3, 5)
+    if num_type != 1:
+        means = [0.0, 0.0, 0.0]
+        norm = sum2
+    sum2 = sum2 / inv_area
+    norm = math.sqrt(norm) / math.sqrt(inv_area)
+    num = corr
+    wnd_mean2 = 0.0
+    wnd_sum2 = 0.0
+    if num_type == 1:
+        wnd_mean2 = np.zeros(corr.shape, dtype=np.float64)
+        for k in range(3):
+            t = np.asarray(wsum3[k], dtype=np.float64)
+            wnd_mean2 = wnd_mean2 + t * t
+            num = num - t * means[k]
+        wnd_mean2 = wnd_mean2 * inv_area
+    if normed or num_type == 2:
+        wnd_sum2 = np.asarray(wsq, dtype=np.float64)
+        if num_type == 2:
+            num = np.maximum(wnd_sum2 - 2.0 * num + sum2, 0.0)
+    if normed:
+        diff2 = np.maximum(wnd_sum2 - wnd_mean2, 0.0)
+        thr = np.minimum(0.5, 10.0 * FLT_EPSILON * wnd_sum2)
+        tt = np.where(diff2 <= thr, 0.0, np.sqrt(diff2) * norm)
+        anum = np.abs(num)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            q = num / tt
+        other = 1.0 if method == 1 else 0.0
+        num = np.where(anum < tt, q, np.where(anum < tt * 1.125, np.where(num > 0, 1.0, -1.0), other))
+    return np.asarray(num).astype(f32)
+
+
 def ncc_map_exact(win8: np.ndarray, tpl8: np.ndarray, method: int = TM_CCOEFF_NORMED) -> np.ndarray:
     """matchTemplate(win, tpl, method) with an exact numerator (LST4:2560)."""
+    if tpl8.ndim == 3:
+        th, tw = tpl8.shape[:2]
+        corr, wsq, wsum3 = 0, 0, []
+        for k in range(3):
+            wk = np.ascontiguousarray(win8[:, :, k])
+            corr = corr + xcorr_exact(wk, np.ascontiguousarray(tpl8[:, :, k]))
+            s1, s2 = box_sums(wk, th, tw)
+            wsum3.append(s1)
+            wsq = wsq + s2
+        return match_from_sums3(method, corr, wsum3, wsq, tpl8)
     th, tw = tpl8.shape
     corr = xcorr_exact(win8, tpl8)
     wsum, wsq = box_sums(win8, th, tw)

@@ -63,7 +63,6 @@ def test_param_validation_mirrors_reference(built_lib):
     for kw, code in [(dict(method=6), N.LST_ERR_INVALID),
                      (dict(method=-1), N.LST_ERR_INVALID),
                      (dict(pixel_type=12), N.LST_ERR_UNSUPPORTED),
-                     (dict(pixel_type=N.PIX_RGB, match_intensity=0), N.LST_ERR_UNSUPPORTED),
                      (dict(pixel_type=N.PIX_U16, match_intensity=0), N.LST_ERR_UNSUPPORTED),
                      (dict(templ_size=4), N.LST_ERR_UNSUPPORTED),
                      (dict(width=0), N.LST_ERR_INVALID),

@@ -538,6 +538,56 @@ def test_rgb_stack_matched_on_intensity(built_lib, oracle_clib, weights):
         assert np.array_equal(t.preprocess(rgb3, 10, 10, 80, 80), O.preprocess_crop(frames[5], 10, 10, 80, 80, op))
 
 
+def _rgb3_stack(cfg, n):
+    """An RGB stack whose channels carry different pictures: the scene, its negative and a shifted copy -- the sums over the
+    channels then differ from any single-channel match."""
+    st = SyntheticStack(cfg)
+    frames = []
+    for i in range(n):
+        g = st.frame(i).astype(np.uint32)
+        r = (255 - g) & 0xff
+        b = np.roll(g, (3, -2), axis=(0, 1)) // 2 + (np.arange(cfg.width, dtype=np.uint32)[None, :] * 5) % 64
+        frames.append((r << 16) | (g << 8) | (b & 0xff))
+    return st, frames
+
+
+@pytest.mark.parametrize("method", [5, 0, 1, 3, 4])
+def test_rgb_stack_three_channel_match(built_lib, oracle_clib, method):
+    """SURVEY 8f-N4, LST4:2525-2535 case 24 with matchIntensity=false on an RGB stack: the ColorProcessor is blurred channel by
+    channel and OpenCV matches a CV_8UC3 image (correlation and norms summed over the channels).  Blurred planes byte-exact,
+    records bit-exact against the exact oracle and within the north_star tolerances against cv2's 3-channel matchTemplate."""
+    cfg = StackConfig(320, 240, "u8", 32, 20, 14)
+    st, frames = _rgb3_stack(cfg, 12)
+    op = util.oracle_params(cfg, match_intensity=False, method=method)
+    otr = O.OracleTracker(op)
+    otr.set_reference(frames[0], st.ref_xy)
+    want = otr.run(frames[1:])
+    assert sum(w.status == 0 for w in want) >= 8
+    ocv = O.OracleTracker(op, backend="cv2")
+    ocv.set_reference(frames[0], st.ref_xy)
+    want_cv = ocv.run(frames[1:])
+    with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area, matchIntensity=False,
+                         method=method, max_batch=5) as t:
+        for (x0, y0, w, h) in [(0, 0, 72, 72), (101, 57, 75, 91), (248, 168, 72, 72)]:
+            got8 = t.preprocess(frames[3], x0, y0, w, h)
+            assert got8.shape == (h, w, 3)
+            assert np.array_equal(got8, O.preprocess_crop(frames[3], x0, y0, w, h, op))
+        info = t.set_reference(frames[0], st.ref_xy)
+        assert list(info.mideal) == otr.mideal
+        got = t.track(np.stack(frames[1:]))
+        util.compare_records(got, want, label=f"RGB 3-channel method {method}")
+        if method in (1, 3, 5):   # the normalised maps: scores on cv2's own scale
+            for i, (g, w) in enumerate(zip(got, want_cv)):
+                assert g.status == w.status
+                for k in range(5):
+                    a, e = g.tm[k], w.tm[k]
+                    if not e.evaluated:
+                        continue
+                    assert abs(a.score - e.score) <= SCORE_TOL_CV2, f"frame {i} tpl {k}"
+                    if (a.ix, a.iy) == (e.ix, e.iy):
+                        assert abs(a.x - e.x) <= SUBPIX_TOL_CV2 and abs(a.y - e.y) <= SUBPIX_TOL_CV2, f"frame {i} tpl {k}"
+
+
 def test_lanes_on_one_device_with_device_resident_slices(stack_a):
     """Several lanes on one GPU (the device listed more than once in lst_multi_create) over slices that
     already lie in device memory: records identical to the sequential oracle, stats summed over lanes."""

@@ -239,3 +239,38 @@ def test_methods_golden(oracle_clib, method):
     assert (x, y) == (int(g[f"cv2best{method}"][0]), int(g[f"cv2best{method}"][1]))
     assert abs(v - g[f"cv2best{method}"][2]) / scale < 1e-4
     assert O.do_match_test(tpl, "exact", method) == g[f"self{method}"][0]
+
+
+def test_three_channel_match_restatement_vs_cv2():
+    """common_matchTemplate with cn = 3 (RGB stacks, matchIntensity=false, LST4:2525-2535 case 24) restated with an exact
+    numerator, pinned against the real cv2.matchTemplate on CV_8UC3 images: maps within OpenCV's float32-DFT noise
+    (relative to the map's scale for the unnormalised methods), same extremum."""
+    import cv2
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        win = cv2.GaussianBlur(rng.integers(0, 256, (70, 90, 3), dtype=np.uint8), (0, 0), 2)
+        tpl = win[20:52, 30:62].copy()
+        for method in range(6):
+            a = O.ncc_map_exact(win, tpl, method)
+            b = O.ncc_map_cv2(win, tpl, method)
+            scale = max(1.0, float(np.abs(b).max())) if method in (0, 2, 4) else 1.0
+            assert float(np.abs(a - b).max()) / scale <= 1e-4, (trial, method)
+            assert O.best_loc_first(a, method)[:2] == O.best_loc_first(b, method)[:2]
+            if method in (0, 1, 3, 5):   # the template was cut from the window at (30, 20)
+                assert O.best_loc_first(a, method)[:2] == (30, 20)
+    flat = np.full((16, 16, 3), 9, np.uint8)
+    assert np.all(O.ncc_map_exact(win, flat, 5) == 1.0) and np.all(O.ncc_map_cv2(win, flat, 5) == 1.0)
+
+
+def test_rgb_three_channel_preprocess_planes():
+    """matchIntensity=false on a ColorProcessor: every channel is blurred like an 8-bit image of its own (ByteProcessor rule:
+    (int)(v+0.5f) clamped), so the planes equal the 8-bit path applied to each channel."""
+    rng = np.random.default_rng(2)
+    rgb = rng.integers(0, 1 << 24, (60, 80), dtype=np.uint32)
+    p = O.Params(80, 60, 16, 8)
+    p.match_intensity = False
+    got = O.preprocess_crop(rgb, 5, 7, 50, 40, p)
+    assert got.shape == (40, 50, 3)
+    for k, sh in enumerate((16, 8, 0)):
+        ch = ((rgb >> sh) & 0xff).astype(np.uint8)
+        assert np.array_equal(got[:, :, k], O.preprocess_crop(ch, 5, 7, 50, 40, p))
