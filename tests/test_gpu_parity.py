@@ -229,8 +229,6 @@ def test_unsupported_like_reference(built_lib):
         LaserSpotTrack4(640, 480, 8, method=6)
     with pytest.raises(LstError):
         LaserSpotTrack4(640, 480, 12)
-    with pytest.raises(LstError):
-        LaserSpotTrack4(640, 480, 24, matchIntensity=False)     # the 3-channel match is not on this path
     with LaserSpotTrack4(640, 480, 8) as t:
         with pytest.raises(LstError):
             t.track(np.zeros((1, 480, 640), np.uint8))            # no reference yet
