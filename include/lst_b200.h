@@ -254,13 +254,18 @@ int64_t lst_multi_retracked(const lst_multi *m);
  * unsigned or 32-bit float, strips that are uncompressed or PackBits / LZW / Deflate compressed (with
  * or without the horizontal predictor; only the strips covering the search regions are decoded);
  * `pages` (nullable) selects a page of a multi-page file or a slice of an ImageJ stack file.  Grey 8/16-bit
- * PNG files (not interlaced) are read as well.  Other files (JPEG, tiled or RGB TIFF / PNG ...):
- * LST_ERR_UNSUPPORTED -- decode them and use lst_track_ptrs. */
+ * PNG files (not interlaced) are read as well, and JPEG files -- the camera time-lapse of the EXIF path,
+ * LST4:1199-1223: baseline / extended-sequential Huffman, 8-bit, grey (an 8-bit slice) or YCbCr 4:4:4 /
+ * 4:2:2 / 4:2:0 (a ColorProcessor slice, LST_PIX_RGB), restart intervals; reconstructed with the IJG
+ * library's default integer IDCT, triangle-filter upsampling and colour tables -- what the JDK decoder
+ * behind ImageJ's opener computes -- for the MCUs under the search regions only.  Other files (progressive
+ * or arithmetic-coded JPEG, tiled or RGB TIFF / PNG ...): LST_ERR_UNSUPPORTED -- decode them and use
+ * lst_track_ptrs. */
 typedef struct lst_tiff_info {
-    int32_t width, height, bits, sample_format; /* sample_format: 1 unsigned integer, 3 IEEE float */
+    int32_t width, height, bits, sample_format; /* sample_format: 1 unsigned integer, 3 IEEE float; bits 24 = 0x00RRGGBB pixels (int32) */
     int32_t big_endian, rows_per_strip, n_strips;
     int32_t imagej_images;                      /* "images=N" of an ImageJ description, else 0 */
-    int32_t compression, predictor;             /* TIFF tags 259 and 317 */
+    int32_t compression, predictor;             /* TIFF tags 259 and 317; a JPEG file reports compression 7 */
     int64_t first_strip_offset;
 } lst_tiff_info;
 /* host only, no GPU needed; err (nullable) receives a message */

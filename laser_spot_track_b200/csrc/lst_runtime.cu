@@ -1083,7 +1083,7 @@ static int read_slices(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, con
             int rc = fm.open(fs.paths[f0 + i], &errs[ti]);
             if (rc == LST_OK) rc = tiff_parse(fm.data, fm.size, fs.pages ? fs.pages[f0 + i] : 0, &L, &errs[ti]);
             if (rc == LST_OK && (L.width != c->p.width || L.height != c->p.height || L.bits != want_bits ||
-                                 (L.bits > 8 && L.big_endian != fs.big_endian))) {
+                                 L.rgb != (c->p.pixel_type == LST_PIX_RGB) || (L.bits > 8 && L.big_endian != fs.big_endian))) {
                 errs[ti] = std::string("slice file differs from the stack's geometry or byte order: ") + fs.paths[f0 + i];
                 rc = LST_ERR_INVALID;   // all stack images must have the same size and type (LST4:393)
             }
@@ -1539,7 +1539,7 @@ int lst_tiff_probe(const char *path, int32_t page, lst_tiff_info *out, char *err
     if (rc != LST_OK) return rc;
     out->width = L.width;
     out->height = L.height;
-    out->bits = L.bits;
+    out->bits = L.rgb ? 24 : L.bits;        // 24 = ColorProcessor pixels (one int32 0x00RRGGBB each), ImageJ's bit depth for RGB
     out->sample_format = L.sample_format;
     out->big_endian = L.big_endian ? 1 : 0;
     out->rows_per_strip = L.rows_per_strip;
@@ -1577,15 +1577,14 @@ int lst_tiff_read_rect(const char *path, int32_t page, int32_t x, int32_t y, int
 
 static int check_slice_file(lst_ctx *c, const char *path, int page, FileMap *fm, TiffLayout *L)
 {
-    if (c->p.pixel_type == LST_PIX_RGB) return c->fail(LST_ERR_UNSUPPORTED, "RGB slice files are not read here: decode them and use lst_track_ptrs");
     std::string e;
     int rc = fm->open(path, &e);
     if (rc == LST_OK) rc = tiff_parse(fm->data, fm->size, page, L, &e);
     if (rc != LST_OK) return c->fail(rc, "%s: %s", path, e.c_str());
     const int want_bits = c->p.pixel_type == LST_PIX_U8 ? 8 : (c->p.pixel_type == LST_PIX_U16 ? 16 : 32);
-    if (L->width != c->p.width || L->height != c->p.height || L->bits != want_bits)
-        return c->fail(LST_ERR_INVALID, "%s is %dx%d %d-bit, the context was created for %dx%d %d-bit", path, L->width, L->height,
-                       L->bits, c->p.width, c->p.height, want_bits);
+    if (L->width != c->p.width || L->height != c->p.height || L->bits != want_bits || L->rgb != (c->p.pixel_type == LST_PIX_RGB))
+        return c->fail(LST_ERR_INVALID, "%s is %dx%d %s%d-bit, the context was created for %dx%d %s%d-bit", path, L->width, L->height,
+                       L->rgb ? "RGB " : "", L->bits, c->p.width, c->p.height, c->p.pixel_type == LST_PIX_RGB ? "RGB " : "", want_bits);
     return LST_OK;
 }
 

@@ -11,8 +11,10 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "../../include/lst_b200.h"
+#include "lst_jpeg.h"
 
 namespace lst {
 
@@ -105,6 +107,7 @@ int tiff_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, st
 {
     static const uint8_t kPngSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (data && size >= 8 && !memcmp(data, kPngSig, 8)) return png_parse(data, size, page, out, err);
+    if (jpeg_signature(data, size)) return jpeg_parse(data, size, page, out, err);
     if (!data || size < 8 || page < 0) return fail(err, LST_ERR_INVALID, "not a TIFF file (too short)");
     Reader r{data, size, false};
     if (data[0] == 'I' && data[1] == 'I') r.be = false;
@@ -392,6 +395,19 @@ int tiff_copy_rects(const FileMap &fm, const TiffLayout &L, const TiffRect *rect
         const TiffRect &q = rects[k];
         if (q.x < 0 || q.y < 0 || q.w < 0 || q.h < 0 || q.x + q.w > L.width || q.y + q.h > L.height)
             return fail(err, LST_ERR_INVALID, "rectangle outside the TIFF image");
+    }
+    if (L.jpeg) {
+        // the whole file is read (pread, not the mapping: page faults would serialise the reader threads) and the scan parsed
+        // from its start down to the last MCU row a rectangle needs
+        static thread_local std::vector<uint8_t> file;
+        if (file.size() < fm.size) file.resize(fm.size);
+        uint64_t got = 0;
+        while (got < fm.size) {
+            const ssize_t k = pread(fm.fd, file.data() + got, fm.size - got, (off_t)got);
+            if (k <= 0) return fail(err, LST_ERR_INVALID, "short read of a JPEG file");
+            got += (uint64_t)k;
+        }
+        return jpeg_copy_rects(file.data(), fm.size, rects, n, err);
     }
     if (L.png) {
         // one zlib stream over all IDAT chunks; rows are filtered against the row above, so the image is

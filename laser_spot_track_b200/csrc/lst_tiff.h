@@ -8,7 +8,7 @@
 // are decoded; page p of a multi-page file by walking the IFD chain, or -- for stacks written by
 // ImageJ (one IFD, "images=N" in the ImageDescription, slices back to back) -- by offset.  Anything
 // else (JPEG-in-TIFF, tiles, RGB, BigTIFF, WhiteIsZero) is LST_ERR_UNSUPPORTED: the caller decodes such
-// files itself and uses lst_track_ptrs.
+// files itself and uses lst_track_ptrs.  JPEG files (baseline, grey or YCbCr) are decoded by lst_jpeg.cpp.
 #pragma once
 #include <stdint.h>
 #include <string>
@@ -30,6 +30,8 @@ struct TiffLayout {
     uint64_t file_size = 0;
     int imagej_images = 0;   // "images=N" of an ImageJ ImageDescription (0 = none)
     bool png = false;        // a PNG file (grey 8/16-bit, not interlaced): strip_off/strip_len list its IDAT chunks
+    bool jpeg = false;       // a JPEG file (lst_jpeg.h): strip 0 is the entropy-coded scan
+    bool rgb = false;        // the pixels are ColorProcessor pixels (int32 0x00RRGGBB, bits = 32): 3-component JPEG
     uint64_t offset_of_row(int y) const { return strip_off[(size_t)(y / rows_per_strip)] + (uint64_t)(y % rows_per_strip) * row_bytes; }
 };
 

@@ -405,7 +405,7 @@ def tiff_read(path: str, page: int = 0, rect=None) -> np.ndarray:
     ``lst_track_files`` decode them: host only."""
     info = tiff_probe(path, page)
     x, y, w, h = rect if rect is not None else (0, 0, info.width, info.height)
-    dt = {8: np.uint8, 16: np.uint16, 32: np.float32}[info.bits]
+    dt = {8: np.uint8, 16: np.uint16, 32: np.float32, 24: np.uint32}[info.bits]   # 24: ColorProcessor pixels 0x00RRGGBB (3-component JPEG)
     out = np.zeros((h, w), dtype=dt)
     err = C.create_string_buffer(256)
     rc = N.load().lst_tiff_read_rect(os.fsencode(path), int(page), int(x), int(y), int(w), int(h), out.ctypes.data, err, 256)

@@ -145,3 +145,55 @@ def test_track_png_slice_files(built_lib, oracle_clib, tmp_path):
     with _tracker(cfg, op, max_batch=5) as t:
         t.set_reference_file(paths[0], st.ref_xy)
         util.compare_records(t.track_files(paths[1:]), want, label="png files")
+
+
+@pytest.mark.parametrize("sampling,intensity", [("420", True), ("444", True), ("422", False)])
+def test_track_jpeg_slices(built_lib, oracle_clib, tmp_path, sampling, intensity):
+    """a time-lapse of JPEG files (the virtual stack of LST4:808-831).  A 3-component JPEG is a ColorProcessor
+    slice; the oracle runs on the frames cv2.imread decodes (libjpeg-turbo, bit-compatible with the JDK's IJG decoder), the
+    library reads the files itself -- only the MCUs under the search regions are reconstructed.  matchIntensity true
+    (convertToGray32) and false (3-channel match)."""
+    import cv2
+    samp = {"420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444,
+            "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422}[sampling]
+    cfg = StackConfig(400, 300, "u8", 32, 24, 16)
+    st = SyntheticStack(cfg)
+    paths, frames = [], []
+    for i in range(16):
+        g = st.frame(i).astype(np.uint8)
+        bgr = np.stack([255 - g // 2, g, (g.astype(np.uint16) * 3 // 4 + 17).astype(np.uint8)], axis=-1)
+        p = str(tmp_path / f"t{i:04d}.jpg")
+        assert cv2.imwrite(p, bgr, [cv2.IMWRITE_JPEG_QUALITY, 93, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, samp,
+                                    cv2.IMWRITE_JPEG_RST_INTERVAL, 4 if i % 2 else 0])
+        dec = cv2.imread(p, cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        frames.append((dec[:, :, 2].astype(np.uint32) << 16) | (dec[:, :, 1].astype(np.uint32) << 8) | dec[:, :, 0])
+        paths.append(p)
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=intensity)
+    assert sum(w.status == 0 for w in want) >= 12
+    with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area, matchIntensity=intensity,
+                         max_batch=6) as t:
+        info = t.set_reference_file(paths[0], st.ref_xy)
+        assert list(info.mideal) == otr.mideal
+        got = t.track_files(paths[1:])
+        util.compare_records(got, want, label=f"JPEG {sampling} intensity={intensity}")
+        assert t.stats().roi_fallback_tasks == 0
+
+
+def test_track_grey_jpeg_slices(built_lib, oracle_clib, tmp_path):
+    """1-component JPEG files are 8-bit slices (ImageJ converts grey JPEGs to 8 bits)."""
+    import cv2
+    cfg = StackConfig(400, 300, "u8", 32, 24, 12)
+    st = SyntheticStack(cfg)
+    paths, frames = [], []
+    for i in range(12):
+        p = str(tmp_path / f"g{i:04d}.jpg")
+        assert cv2.imwrite(p, st.frame(i).astype(np.uint8), [cv2.IMWRITE_JPEG_QUALITY, 95])
+        frames.append(cv2.imread(p, cv2.IMREAD_UNCHANGED))
+        paths.append(p)
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    with _tracker(cfg, op, max_batch=5) as t:
+        t.set_reference_file(paths[0], st.ref_xy)
+        util.compare_records(t.track_files(paths[1:]), want, label="grey JPEG")
+    with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area) as t:
+        with pytest.raises(LstError):
+            t.set_reference_file(paths[0], st.ref_xy)       # an 8-bit file in an RGB context
