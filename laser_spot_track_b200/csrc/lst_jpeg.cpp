@@ -32,6 +32,7 @@ struct Huff {
     int32_t maxcode[18];
     int32_t valoff[17];
     uint16_t look[512];   // 9-bit lookahead: (code length << 8) | symbol, 0 = longer code
+    int16_t fast[512];    // AC tables: code and magnitude bits together within 9 bits: (value << 8) | (run << 4) | total bits
 
     bool build()
     {
@@ -51,6 +52,16 @@ struct Huff {
             code <<= 1;
         }
         maxcode[17] = 0x7fffffff;
+        for (int i = 0; i < 512; i++) {
+            fast[i] = 0;
+            const int e = look[i];
+            if (!e) continue;
+            const int len = e >> 8, rs = e & 255, run = rs >> 4, ss = rs & 15;
+            if (ss == 0 || len + ss > 9) continue;
+            int v = (i >> (9 - len - ss)) & ((1 << ss) - 1);       // the magnitude bits that follow the code
+            if (v < (1 << (ss - 1))) v += -(1 << ss) + 1;
+            if (v >= -128 && v <= 127) fast[i] = (int16_t)(v * 256 + run * 16 + len + ss);
+        }
         ok = true;
         return true;
     }
@@ -203,6 +214,19 @@ struct BitReader {
 
     inline void fill()
     {
+        if (!marker && pos + 8 <= n && nbits <= 56) {
+            uint64_t w;
+            memcpy(&w, d + pos, 8);
+            const uint64_t inv = ~w;
+            if (!((inv - 0x0101010101010101ull) & ~inv & 0x8080808080808080ull)) {     // no 0xff among the next eight bytes
+                w = __builtin_bswap64(w);
+                const int k = (64 - nbits) >> 3;
+                acc |= (w >> (64 - 8 * k)) << (64 - nbits - 8 * k);
+                pos += (uint64_t)k;
+                nbits += 8 * k;
+                return;
+            }
+        }
         while (nbits <= 56) {
             uint32_t b = 0;
             if (!marker) {
@@ -224,9 +248,13 @@ struct BitReader {
     }
     inline uint32_t peek(int k) { return (uint32_t)(acc >> (64 - k)); }
     inline void skip(int k) { acc <<= k, nbits -= k; }
+    // a Huffman code (<= 16 bits) and its magnitude bits (<= 15) never need more than 31 bits
+    inline void need32()
+    {
+        if (nbits < 32) fill();
+    }
     inline int decode(const Huff &T)
     {
-        if (nbits < 16) fill();
         const uint32_t e = T.look[peek(9)];
         if (e) {
             skip((int)(e >> 8));
@@ -247,7 +275,6 @@ struct BitReader {
     }
     inline int receive_extend(int s)
     {
-        if (nbits < s) fill();
         const int v = (int)peek(s);
         skip(s);
         return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
@@ -458,6 +485,7 @@ int jpeg_copy_rects(const uint8_t *data, uint64_t size, const TiffRect *rects, i
                 for (int by = 0; by < C.v; by++)
                     for (int bx = 0; bx < C.h; bx++) {
                         if (need) memset(coef, 0, sizeof(coef));
+                        br.need32();
                         int s = br.decode(DC);
                         if (s) {
                             if (s > 15) s = 15;
@@ -465,6 +493,14 @@ int jpeg_copy_rects(const uint8_t *data, uint64_t size, const TiffRect *rects, i
                         }
                         coef[0] = (int16_t)C.pred;
                         for (int k = 1; k < 64; k++) {
+                            br.need32();
+                            const int f = AC.fast[br.peek(9)];
+                            if (f) {                     // code and value in one look-up
+                                k += (f >> 4) & 15;
+                                br.skip(f & 15);
+                                if (need && k < 64) coef[kNatural[k]] = (int16_t)(f >> 8);
+                                continue;
+                            }
                             const int rs = br.decode(AC);
                             const int rr = rs >> 4, ss = rs & 15;
                             if (ss) {
