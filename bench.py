@@ -495,6 +495,46 @@ def main():
         finally:
             shutil.rmtree(tdir, ignore_errors=True)
 
+    # The same scene as a camera time-lapse of JPEG files (the EXIF path LST4:1199-1223): 4:2:0 baseline JPEGs
+    # of the 8-bit scene (RGB slices, matched on intensity).  Entropy decoding is sequential per file and spreads over the
+    # reader threads; only the MCUs under the search regions are reconstructed.  Bounded: 1024 slices, one step.
+    e2e_jpeg = None
+    if not args.no_e2e and not args.no_files and world == 1 and args.config == "B":
+        import shutil
+        import tempfile
+        try:
+            import cv2
+            jdir = tempfile.mkdtemp(prefix="lst_bench_jpg_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            try:
+                jfiles = []
+                nj = min(ring, 32)
+                for i in range(nj):
+                    g = (st.frame(i) >> 8).astype(np.uint8) if st.frame(i).dtype == np.uint16 else st.frame(i).astype(np.uint8)
+                    fp = os.path.join(jdir, f"shot{i:05d}.jpg")
+                    cv2.imwrite(fp, np.stack([g, g, g], axis=-1), [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                                                   cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420])
+                    jfiles.append(fp)
+                FJ = min(F, 1024)
+                jpaths = [jfiles[i % nj] for i in range(1, FJ + 1)]
+                with LaserSpotTrack4(cfg.width, cfg.height, 24, device=local_rank, templSize=cfg.templ_size, sArea=cfg.s_area,
+                                     max_batch=args.max_batch) as jt:
+                    jt.set_reference_file(jfiles[0], st.ref_xy)
+                    jt.track_files(jpaths)          # warm-up at full size: the pinned staging is allocated here, not in the timed run
+                    jt.set_state([0.0] * 10)
+                    t0 = time.perf_counter()
+                    recs = jt.track_files(jpaths)
+                    wall_j = (time.perf_counter() - t0) * 1e3
+                    e2e_jpeg = {"value": FJ / (wall_j * 1e-3), "unit": UNIT, "ms_per_step": wall_j, "frames": FJ,
+                                "accepted": int(sum(1 for r in recs if r.status == 0)),
+                                "file_bytes": int(os.path.getsize(jfiles[1])),
+                                "reader_threads": int(os.environ.get("LST_FILE_THREADS", min(16, os.cpu_count() or 1))),
+                                "what": "lst_track_files over %d paths cycling %d 4:2:0 JPEG files of the same scene (RGB slices, matchIntensity); "
+                                        "wall clock; Huffman decoding of every file on the reader threads" % (FJ, nj)}
+            finally:
+                shutil.rmtree(jdir, ignore_errors=True)
+        except Exception as e:      # the leg is optional
+            e2e_jpeg = {"value": None, "unit": UNIT, "error": str(e)[:200]}
+
     # The same stack in PAGEABLE host memory (what a JNI shim holding Java arrays hands over): the copy engine
     # cannot gather from it, so reader threads pack the rows of the search regions into pinned staging.
     e2e_pageable = None
@@ -698,7 +738,7 @@ def main():
                         "parallelism": f"frames sharded over {world} GPU(s), no collective" + (f"; {lanes} lanes per GPU" if lanes > 1 else ""),
                         "lanes_per_gpu": lanes, "host_cores_of_this_rank": len(my_cores),
                         "accepted_frames_last_step": ok_frames},
-            "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "e2e_pageable": e2e_pageable, "gpu_launches": int(s_dev.kernel_launches),
+            "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "e2e_jpeg": e2e_jpeg, "e2e_pageable": e2e_pageable, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline, "extra": extra,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
                          "chunks_retracked": sh_dev.retracked, "chunks_retracked_late": getattr(sh_dev, "retracked_late", 0),

@@ -472,12 +472,14 @@ struct TcIssue {
 // .. b_hi = min(nbe-1, j); its band starts (nd-1-(j-b_lo)) blocks into the table row.  In the first template row column
 // block j gets its first contribution from K step j and must be overwritten, the blocks left of it accumulate.
 // ND, NBE > 0: the band shape is a compile-time constant, so the column ranges, band offsets and instruction descriptors
-// of the K steps are immediates and an MMA costs two adds; ND = 0: any shape.  Returns the cycles spent waiting for the ring.
-template <int ND, int NBE>
+// of the K steps are immediates and an MMA costs two adds; ND = 0: any shape.  NK < ND + NBE - 1: the last K steps would only
+// feed result columns beyond the map (a 113-column map in four 32-column blocks: window columns 160.. reach columns >= 113
+// only) and are not issued.  Returns the cycles spent waiting for the ring.
+template <int ND, int NBE, int NK = ND + NBE - 1>
 __device__ __forceinline__ long long tc_issue_item(const TcIssue &q)
 {
-    const int nd = ND > 0 ? ND : q.nd, nbe = ND > 0 ? NBE : q.nbe, nk = ND > 0 ? ND + NBE - 1 : q.nk;
-    constexpr int KMAX = ND > 0 ? ND + NBE - 1 : TC_MAXK;
+    const int nd = ND > 0 ? ND : q.nd, nbe = ND > 0 ? NBE : q.nbe, nk = ND > 0 ? NK : q.nk;
+    constexpr int KMAX = ND > 0 ? NK : TC_MAXK;
     const uint32_t a_hi32 = (uint32_t)(q.a_desc0 >> 32);
     long long waited = 0;
     int v = 0, gg = q.g;
@@ -690,8 +692,10 @@ lst_ncc_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUt
                     q.issue = !(tp.mode & 2);
                     // the loops are specialised for the band shapes of the named configurations (compile-time column ranges)
                     long long wr;
-                    if (nd == 3 && nbe == 4) wr = tc_issue_item<3, 4>(q);          // templates of 33..64 columns, four column blocks (config B)
-                    else if (nd == 2 && nbe == 3) wr = tc_issue_item<2, 3>(q);     // templates up to 32 columns, three blocks (config A)
+                    if (nd == 3 && nbe == 4 && nk == 5) wr = tc_issue_item<3, 4, 5>(q);      // 48-column templates, 113-column maps (config B)
+                    else if (nd == 3 && nbe == 4) wr = tc_issue_item<3, 4>(q);     // templates of 33..64 columns, four column blocks
+                    else if (nd == 2 && nbe == 3 && nk == 3) wr = tc_issue_item<2, 3, 3>(q);   // 32-column templates, 65-column maps (config A)
+                    else if (nd == 2 && nbe == 3) wr = tc_issue_item<2, 3>(q);     // templates up to 32 columns, three blocks
                     else if (nd == 3 && nbe == 2) wr = tc_issue_item<3, 2>(q);     // 64-column templates, two blocks (config C tiles)
                     else if (nd == 5 && nbe == 2) wr = tc_issue_item<5, 2>(q);     // 128-column templates, two blocks (config D tiles)
                     else wr = tc_issue_item<0, 0>(q);
