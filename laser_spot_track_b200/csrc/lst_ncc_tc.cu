@@ -36,6 +36,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "../../include/lst_b200.h"
@@ -1162,7 +1163,8 @@ static size_t tc_plan(int max_rw, int max_rh, int tw, int th, TcParams *tp)
         if (env_nbc > 0 && nbc > env_nbc) continue;
         for (int nab = 2; nab >= 1; nab--) {
             if (env_abuf > 0 && nab > env_abuf) continue;
-            const int nk = nbc + nd - 1;
+            // K steps (32 window columns each) a tile can need: the band of the widest template over the tile's valid columns
+            const int nk = std::min(nbc + nd - 1, ((std::min(TC_NB * nbc, max_rw) + tw - 2) >> 5) + 1);
             tp->nbc = nbc;
             tp->kc_a = 2 * nk;
             tp->n_abuf = nab;
