@@ -444,7 +444,10 @@ def main():
                "passes_per_step": s_e2e.passes / K, "tasks_per_step": s_e2e.tasks / K,
                "pcie": {"achieved_gbs_per_gpu": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9,
                         "peak_gbs_per_gpu": pcie, "frac": s_e2e.h2d_bytes / K / (ms_e2e / K * 1e-3) / 1e9 / pcie,
-                        "how": "peak = 256 MB pinned cudaMemcpyAsync H2D, every rank at the same time, slowest rank"},
+                        "how": "peak = 256 MB pinned cudaMemcpyAsync H2D, every rank at the same time, slowest rank",
+                        "ceiling_fps": world * pcie * 1e9 / max(1.0, s_e2e.h2d_bytes / K / F),
+                        "ceiling": "what this box's host side can deliver: all ranks' concurrent pinned-copy rate divided by the bytes "
+                                   "a slice sends (search regions + margin); the leg cannot scale past it whatever the GPUs do"},
                "ingest": "pinned host ring of whole slices; only the five search regions (+8 px margin, 32-byte aligned) of "
                          "each slice cross PCIe, as strided 3-D DMA copies on a copy stream while the previous batch computes"}
 
