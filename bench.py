@@ -761,4 +761,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries the JSON line and nothing else: whatever libraries write to file descriptor 1 meanwhile (NCCL's version
+    # banner, for one) goes to stderr
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, "w", buffering=1)
     main()
