@@ -1025,60 +1025,81 @@ int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, 
 // ------------------------------------------------------------------------------------------------
 // 3-channel match (RGB stacks, matchIntensity = false: LST4:2525-2535 case 24 hands OpenCV a CV_8UC3 image)
 // ------------------------------------------------------------------------------------------------
-// matchTemplate sums the correlation over the channels and normalises with per-channel window sums.  A rarely used mode:
-// a plain direct kernel -- a CTA owns a band of RGB_BAND result rows of one window, keeps the window rows of the three
-// planes it needs and the three template planes in shared memory, every thread walks the template for its positions
-// (integer arithmetic, exact), scores them with match_score3 and the CTA reduces the first maximum.
+// matchTemplate sums the correlation over the channels and normalises with per-channel window sums.  A rarely used mode, so
+// one direct kernel: a CTA owns RGB_BAND result rows x RGB_TILE result columns of one window, keeps the window rows of the
+// three planes it needs (as 32-bit words) and the three template planes (rows padded with zeros to whole words) in shared
+// memory; a thread walks the template for its positions four pixels at a time -- the window word realigned with a funnel
+// shift, then IDP.4A for the correlation, the window sum (against 0x01 bytes) and the sum of squares (the word against its
+// masked self), all exact integers -- scores them with match_score3 and the CTA reduces the first maximum.
 #define RGB_BAND 4
+#define RGB_TILE 128
 #define RGB_THREADS 256
 
 __global__ void __launch_bounds__(RGB_THREADS)
 lst_ncc_rgb(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ tpls, const uint8_t *__restrict__ win8,
-            unsigned long long plane_bytes, unsigned long long *__restrict__ best, int smem_pitch, int max_th)
+            unsigned long long plane_bytes, unsigned long long *__restrict__ best, int ww_pitch, int max_th, int max_kw, int ntiles)
 {
-    extern __shared__ __align__(16) uint8_t smem_rgb[];
+    extern __shared__ __align__(16) uint32_t smem_rgb[];
     __shared__ unsigned long long s_best[RGB_THREADS / 32];
     const DevTask t = tasks[blockIdx.y];
     const TplConst tc = tpls->c[t.tpl];
-    const int tw = tc.tw, th = tc.th;
-    const int y0 = blockIdx.x * RGB_BAND;
-    if (y0 >= t.rh) return;
-    const int nrows = min(RGB_BAND, t.rh - y0);
+    const int tw = tc.tw, th = tc.th, kw = (tw + 3) >> 2;
+    const int band = blockIdx.x / ntiles, tile = blockIdx.x - band * ntiles;
+    const int y0 = band * RGB_BAND, x0 = tile * RGB_TILE;
+    if (y0 >= t.rh || x0 >= t.rw) return;
+    const int nrows = min(RGB_BAND, t.rh - y0), ncols = min(RGB_TILE, t.rw - x0);
     const int wrows = nrows + th - 1;
-    uint8_t *s_win = smem_rgb;                                        // [3][RGB_BAND + max_th - 1][smem_pitch]
-    const size_t plane_smem = (size_t)(RGB_BAND + max_th - 1) * smem_pitch;
-    uint8_t *s_tpl = smem_rgb + 3 * plane_smem;                       // [3][th][tw]
+    const int wwords = (ncols + tw - 1 + 3) / 4 + 1;                  // window words per row (+1: the funnel shift reads one ahead)
+    uint32_t *s_win = smem_rgb;                                       // [3][RGB_BAND + max_th - 1][ww_pitch] words
+    const size_t plane_smem = (size_t)(RGB_BAND + max_th - 1) * ww_pitch;
+    uint32_t *s_tpl = s_win + 3 * plane_smem;                         // [3][th][kw] words, zero padded
+    uint32_t *s_ones = s_tpl + 3 * (size_t)max_th * max_kw;           // [kw]: 0x01 in the bytes of a template row
     for (int c = 0; c < 3; c++) {
-        const uint8_t *src = win8 + (size_t)c * plane_bytes + t.win_off;
-        const int vec = smem_pitch / 16;
-        for (int i = threadIdx.x; i < wrows * vec; i += blockDim.x) {
-            const int r = i / vec, cc = (i - r * vec) * 16;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (cc < t.pitch) v = *(const uint4 *)(src + (size_t)(y0 + r) * t.pitch + cc);
-            *(uint4 *)(s_win + c * plane_smem + (size_t)r * smem_pitch + cc) = v;
+        const uint8_t *src = win8 + (size_t)c * plane_bytes + t.win_off + x0;      // x0 is a multiple of 4, rows 16-byte aligned
+        for (int i = threadIdx.x; i < wrows * wwords; i += blockDim.x) {
+            const int r = i / wwords, k = i - r * wwords;
+            const int col = x0 + 4 * k;
+            uint32_t v = 0;
+            if (col < t.pitch) v = *(const uint32_t *)(src + (size_t)(y0 + r) * t.pitch + 4 * k);    // pitch padding is zero
+            s_win[c * plane_smem + (size_t)r * ww_pitch + k] = v;
         }
         const uint8_t *tp = tpls->raw[t.tpl] + (size_t)c * tw * th;
-        for (int i = threadIdx.x; i < tw * th; i += blockDim.x) s_tpl[(size_t)c * tw * th + i] = tp[i];
+        for (int i = threadIdx.x; i < th * kw; i += blockDim.x) {
+            const int v = i / kw, k = i - v * kw;
+            uint32_t word = 0;
+            for (int b = 0; b < 4; b++)
+                if (4 * k + b < tw) word |= (uint32_t)tp[v * tw + 4 * k + b] << (8 * b);
+            s_tpl[((size_t)c * th + v) * kw + k] = word;
+        }
+    }
+    for (int k = threadIdx.x; k < kw; k += blockDim.x) {
+        uint32_t m = 0;
+        for (int b = 0; b < 4; b++)
+            if (4 * k + b < tw) m |= 1u << (8 * b);
+        s_ones[k] = m;
     }
     __syncthreads();
     unsigned long long mybest = 0ull;
     const bool want_min = method_wants_min(tc.method);
-    for (int pos = threadIdx.x; pos < nrows * t.rw; pos += blockDim.x) {
-        const int r = pos / t.rw, x = pos - r * t.rw;
+    for (int pos = threadIdx.x; pos < nrows * ncols; pos += blockDim.x) {
+        const int r = pos / ncols, x = pos - r * ncols;
+        const uint32_t sh = 8u * (uint32_t)(x & 3);
         unsigned long long corr = 0, q = 0;      // a channel's sums fit 32 bits (tw * th <= 66000), the three together may not
         uint32_t s3[3];
         for (int c = 0; c < 3; c++) {
-            const uint8_t *w = s_win + c * plane_smem + (size_t)r * smem_pitch + x;
-            const uint8_t *tp = s_tpl + (size_t)c * tw * th;
+            const uint32_t *wrow = s_win + c * plane_smem + (size_t)r * ww_pitch + (x >> 2);
+            const uint32_t *trow = s_tpl + (size_t)c * th * kw;
             uint32_t sc = 0, cc = 0, qc = 0;
-            for (int v = 0; v < th; v++) {
-                const uint8_t *wr = w + (size_t)v * smem_pitch, *tr = tp + v * tw;
-#pragma unroll 4
-                for (int u = 0; u < tw; u++) {
-                    const uint32_t px = wr[u];
-                    cc += px * tr[u];
-                    sc += px;
-                    qc += px * px;
+            for (int v = 0; v < th; v++, wrow += ww_pitch, trow += kw) {
+                uint32_t lo = wrow[0];
+                for (int k = 0; k < kw; k++) {
+                    const uint32_t hi = wrow[k + 1];
+                    const uint32_t px = __funnelshift_r(lo, hi, sh);          // window bytes x + 4k .. x + 4k + 3 of this row
+                    const uint32_t ones = s_ones[k];
+                    cc = __dp4a(px, trow[k], cc);
+                    sc = __dp4a(px, ones, sc);
+                    qc = __dp4a(px, px & (ones * 255u), qc);
+                    lo = hi;
                 }
             }
             s3[c] = sc;
@@ -1087,7 +1108,7 @@ lst_ncc_rgb(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ 
         }
         const double ws[3] = {(double)s3[0], (double)s3[1], (double)s3[2]};
         const float score = match_score3(tc, (double)corr, ws, (double)q);
-        const unsigned long long key = pack_key(score, (uint32_t)((y0 + r) * t.rw + x), want_min);
+        const unsigned long long key = pack_key(score, (uint32_t)((y0 + r) * t.rw + x0 + x), want_min);
         mybest = key > mybest ? key : mybest;
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1105,15 +1126,20 @@ lst_ncc_rgb(const DevTask *__restrict__ tasks, const DevTemplates *__restrict__ 
 int launch_ncc_rgb(const DevTask *tasks, int n_tasks, int max_rh, int max_w, int max_tw, int max_th, const DevTemplates *tpls,
                    const uint8_t *win8, size_t plane_bytes, unsigned long long *best, cudaStream_t stream)
 {
-    const int pitch = (max_w + 15) & ~15;
-    const size_t smem = 3 * (size_t)(RGB_BAND + max_th - 1) * pitch + 3 * (size_t)max_tw * max_th + 16;
+    const int max_rw = max_w - 1 + 1;                                  // an upper bound of the map width (templates are >= 1 wide)
+    const int tile_cols = max_rw < RGB_TILE ? max_rw : RGB_TILE;
+    const int ww_pitch = ((tile_cols + max_tw - 1 + 3) / 4 + 1) | 1;   // odd pitch in words: the rows of a band fall into different banks
+    const int max_kw = (max_tw + 3) / 4;
+    const size_t smem = 4 * (3 * (size_t)(RGB_BAND + max_th - 1) * ww_pitch + 3 * (size_t)max_th * max_kw + max_kw) + 16;
     if (smem > 200 * 1024 || (long)max_tw * max_th > 66000) return -1;
     if (cudaFuncSetAttribute(lst_ncc_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
     const int bands = (max_rh + RGB_BAND - 1) / RGB_BAND;
+    const int ntiles = (max_rw + RGB_TILE - 1) / RGB_TILE;
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
         const int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
-        lst_ncc_rgb<<<dim3(bands, n), RGB_THREADS, smem, stream>>>(tasks + base, tpls, win8, plane_bytes, best + base, pitch, max_th);
+        lst_ncc_rgb<<<dim3(bands * ntiles, n), RGB_THREADS, smem, stream>>>(tasks + base, tpls, win8, plane_bytes, best + base, ww_pitch, max_th,
+                                                                            max_kw, ntiles);
         launches++;
     }
     return cudaPeekAtLastError() == cudaSuccess ? launches : -1;

@@ -586,6 +586,23 @@ def test_rgb_stack_three_channel_match(built_lib, oracle_clib, method):
                         assert abs(a.x - e.x) <= SUBPIX_TOL_CV2 and abs(a.y - e.y) <= SUBPIX_TOL_CV2, f"frame {i} tpl {k}"
 
 
+def test_rgb_three_channel_match_wide_maps_and_whole_slice(built_lib, oracle_clib):
+    """The 3-channel match with result maps wider than one column tile of lst_ncc_rgb (search area 70: 141 x 141 maps) and
+    as a whole-slice search (sArea = 0: the five templates share the three blurred planes of the slice)."""
+    for s_area, (wd, ht), n in ((70, (480, 360), 6), (0, (320, 240), 4)):
+        cfg = StackConfig(wd, ht, "u8", 24, s_area, n)
+        st, frames = _rgb3_stack(cfg, n)
+        op = util.oracle_params(cfg, match_intensity=False)
+        otr = O.OracleTracker(op)
+        otr.set_reference(frames[0], st.ref_xy)
+        want = otr.run(frames[1:])
+        with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area, matchIntensity=False,
+                             max_batch=4) as t:
+            info = t.set_reference(frames[0], st.ref_xy)
+            assert list(info.mideal) == otr.mideal
+            util.compare_records(t.track(np.stack(frames[1:])), want, label=f"RGB 3-channel sArea {s_area}")
+
+
 def test_lanes_on_one_device_with_device_resident_slices(stack_a):
     """Several lanes on one GPU (the device listed more than once in lst_multi_create) over slices that
     already lie in device memory: records identical to the sequential oracle, stats summed over lanes."""
