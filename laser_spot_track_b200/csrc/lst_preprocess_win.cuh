@@ -320,21 +320,18 @@ lst_preprocess_win(const DevTask *__restrict__ tasks, const Surface *__restrict_
             }
             // (int)((v - lo) * scale + 0.5) clamped to 0..255 as Java casts do (NaN -> 0, saturating); a negative argument
             // converts to 0 like the reference's max(v - lo, 0) would.  cvt.pack saturates two integers to bytes and packs them.
+            // the last quads: columns right of the window are pitch padding, written as 0 (one mask per quad)
+            const uint32_t keep = c0 + 3 < w ? 0xffffffffu : (c0 < w ? 0xffffffffu >> (8 * (c0 + 4 - w)) : 0u);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (i0 + j < yend) {
                     int b[4];
 #pragma unroll
                     for (int e = 0; e < 4; e++) b[e] = __float2int_rz((o[e][j] - lo) * scale + qadd);
-                    if (c0 + 3 >= w) {          // the last quads: columns right of the window are pitch padding, written as 0
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                            if (c0 + e >= w) b[e] = 0;
-                    }
                     uint32_t hi16, word;
                     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(b[3]), "r"(b[2]), "r"(0));
                     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(word) : "r"(b[1]), "r"(b[0]), "r"(hi16));
-                    *(uint32_t *)(dst + (size_t)(i0 + j) * pitch + c0) = word;
+                    *(uint32_t *)(dst + (size_t)(i0 + j) * pitch + c0) = word & keep;
                 }
             }
             q += ydq;
