@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <vector>
 
 #include "../../include/lst_b200.h"
@@ -116,6 +117,7 @@ int parse_header(const uint8_t *d, uint64_t n, Header *H, std::string *err)
             H->ncomp = s[5];
             if (H->ncomp != 1 && H->ncomp != 3) return fail(err, LST_ERR_UNSUPPORTED, "JPEG: only 1- and 3-component images are supported");
             if (sl < 6 + 3 * H->ncomp || H->width <= 0 || H->height <= 0) return fail(err, LST_ERR_INVALID, "JPEG: bad frame header");
+            if ((int64_t)H->width * H->height > ((int64_t)1 << 28)) return fail(err, LST_ERR_UNSUPPORTED, "JPEG: image larger than 2^28 pixels");
             for (int c = 0; c < H->ncomp; c++) {
                 H->comp[c].id = s[6 + 3 * c];
                 H->comp[c].h = s[7 + 3 * c] >> 4;
@@ -446,12 +448,16 @@ int jpeg_copy_rects(const uint8_t *data, uint64_t size, const TiffRect *rects, i
     int rc = parse_header(data, size, &H, err);
     if (rc != LST_OK) return rc;
     static thread_local Scratch S;
-    for (int c = 0; c < H.ncomp; c++) {
-        const size_t need = (size_t)H.comp[c].stride * H.comp[c].rows;
-        if (S.plane[c].size() < need) S.plane[c].resize(need);
+    try {
+        for (int c = 0; c < H.ncomp; c++) {
+            const size_t need = (size_t)H.comp[c].stride * H.comp[c].rows;
+            if (S.plane[c].size() < need) S.plane[c].resize(need);
+        }
+        S.need.assign((size_t)H.mcus_x * H.mcus_y, 0);
+    } catch (const std::bad_alloc &) {
+        return fail(err, LST_ERR_INVALID, "JPEG: out of memory for the sample planes");
     }
     // the MCUs whose samples the rectangles need: two pixels of margin cover the chroma context of the upsampling filters
-    S.need.assign((size_t)H.mcus_x * H.mcus_y, 0);
     int last_row = -1;
     for (int i = 0; i < n; i++) {
         const TiffRect &r = rects[i];
