@@ -258,7 +258,8 @@ int64_t lst_multi_retracked(const lst_multi *m);
  * LST4:1199-1223: baseline / extended-sequential Huffman, 8-bit, grey (an 8-bit slice) or YCbCr 4:4:4 /
  * 4:2:2 / 4:2:0 (a ColorProcessor slice, LST_PIX_RGB), restart intervals; reconstructed with the IJG
  * library's default integer IDCT, triangle-filter upsampling and colour tables -- what the JDK decoder
- * behind ImageJ's opener computes -- for the MCUs under the search regions only.  Other files (progressive
+ * behind ImageJ's opener computes -- for the MCUs under the search regions only: the reader threads do
+ * the entropy decoding, the reconstruction runs on the device (LST_JPEG_DEVICE=0: on the reader threads).  Other files (progressive
  * or arithmetic-coded JPEG, tiled or RGB TIFF / PNG ...): LST_ERR_UNSUPPORTED -- decode them and use
  * lst_track_ptrs. */
 typedef struct lst_tiff_info {

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblst_b200.so")
 SOURCES = ["lst_kernels.cu", "lst_ncc_tc.cu", "lst_runtime.cu", "lst_host.cpp", "lst_tiff.cpp", "lst_jpeg.cpp"]
-HEADERS = ["lst_math.h", "lst_host.h", "lst_tiff.h", "lst_jpeg.h", "lst_device.h", "lst_preprocess_win.cuh", os.path.join("..", "..", "include", "lst_b200.h")]
+HEADERS = ["lst_math.h", "lst_host.h", "lst_tiff.h", "lst_jpeg.h", "lst_jpeg_math.h", "lst_device.h", "lst_preprocess_win.cuh", os.path.join("..", "..", "include", "lst_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

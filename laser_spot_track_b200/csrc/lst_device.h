@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "lst_math.h"
+#include "lst_jpeg_math.h"
 
 namespace lst {
 
@@ -108,6 +109,22 @@ int launch_ncc_match(const DevTask *tasks, int n_tasks, int max_rw, int max_rh, 
 // window sums, common_matchTemplate's cn = 3 normalisation, first-maximum argmax.  The planes of a window lie plane_bytes apart.
 int launch_ncc_rgb(const DevTask *tasks, int n_tasks, int max_rh, int max_w, int max_tw, int max_th, const DevTemplates *tpls,
                    const uint8_t *win8, size_t plane_bytes, unsigned long long *best, cudaStream_t stream);
+// JPEG slice files: the reconstruction stage of the decoder on the device (lst_jpeg.h).  For every (region, slice) of a batch
+// the quantised coefficients the reader threads staged become pixels of the ROI ring: dequantisation + integer inverse DCT into
+// shared-memory sample planes, then fancy chroma upsampling + YCbCr -> RGB (or the luma samples of a grey file).
+struct JpegDevRegion {
+    int x, y, w, h;                          // output rectangle in slice pixels (w == 0: nothing)
+    JpegRegion m;                            // the MCUs staged for it
+    unsigned long long coef_off, coef_slice; // int16 elements: the region's blocks of slice 0, distance between slices
+    unsigned long long out_off, out_slice;   // bytes: the region in the ROI ring, distance between slices
+};
+struct JpegDevBatch {
+    JpegGeom g;
+    JpegDevRegion r[5];
+};
+size_t jpeg_reconstruct_smem(const JpegGeom &g, const JpegRegion &m);
+int launch_jpeg_reconstruct(const int16_t *coef, const uint16_t *qt, const JpegDevBatch &batch, int n_slices, uint8_t *roi_out,
+                            cudaStream_t stream);
 int launch_epilogue(const DevTask *tasks, int n_tasks, const DevTemplates *tpls, const uint8_t *win8,
                     const unsigned long long *best, const float *nbhd, DevResult *results, const MatchParams &mp,
                     cudaStream_t stream);

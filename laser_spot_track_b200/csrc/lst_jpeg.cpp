@@ -34,6 +34,8 @@ struct Huff {
     int32_t valoff[17];
     uint16_t look[512];   // 9-bit lookahead: (code length << 8) | symbol, 0 = longer code
     int16_t fast[512];    // AC tables: code and magnitude bits together within 9 bits: (value << 8) | (run << 4) | total bits
+    uint16_t skip[2048];  // AC tables, blocks that are only parsed: 11-bit lookahead -> bits 0-4 code + magnitude bits to drop,
+                          // bits 5-8 run, bit 9 end of block, bit 15 entry valid (code no longer than 11 bits)
 
     bool build()
     {
@@ -62,6 +64,20 @@ struct Huff {
             int v = (i >> (9 - len - ss)) & ((1 << ss) - 1);       // the magnitude bits that follow the code
             if (v < (1 << (ss - 1))) v += -(1 << ss) + 1;
             if (v >= -128 && v <= 127) fast[i] = (int16_t)(v * 256 + run * 16 + len + ss);
+        }
+        {
+            memset(skip, 0, sizeof(skip));
+            int32_t c2 = 0;
+            int k2 = 0;
+            for (int l = 1; l <= 11; l++) {
+                for (int i = 0; i < bits[l]; i++, k2++, c2++) {
+                    const int rs = vals[k2], run = rs >> 4, ss = rs & 15;
+                    const uint16_t e = (uint16_t)(0x8000u | (uint16_t)(l + ss) | (uint16_t)(run << 5) | (uint16_t)((rs == 0) << 9));
+                    const int first = c2 << (11 - l), cnt = 1 << (11 - l);
+                    for (int j = 0; j < cnt; j++) skip[first + j] = e;
+                }
+                c2 <<= 1;
+            }
         }
         ok = true;
         return true;
@@ -291,124 +307,60 @@ struct BitReader {
     }
 };
 
-// ---- jidctint.c: the accurate integer inverse DCT, dequantisation folded in ------------------------
-constexpr int CONST_BITS = 13, PASS1_BITS = 2;
-constexpr int64_t F_0_298631336 = 2446, F_0_390180644 = 3196, F_0_541196100 = 4433, F_0_765366865 = 6270, F_0_899976223 = 7373,
-                  F_1_175875602 = 9633, F_1_501321110 = 12299, F_1_847759065 = 15137, F_1_961570560 = 16069, F_2_053119869 = 16819,
-                  F_2_562915447 = 20995, F_3_072711026 = 25172;
-
-inline int64_t descale(int64_t x, int n) { return (x + ((int64_t)1 << (n - 1))) >> n; }
-// range_limit[x & RANGE_MASK] of the IDCT: x is taken modulo 1024 as a signed value, recentred by 128 and clamped
-inline uint8_t idct_limit(int64_t x)
+// One block of the scan: the DC difference feeds the prediction; STORE: the coefficients go to coef[64] in natural order,
+// else the AC symbols are only dropped, code and magnitude bits at once.
+template <bool STORE>
+inline void decode_block(BitReader &br, const Huff &DC, const Huff &AC, int &pred, int16_t *coef)
 {
-    int v = (int)(x & 1023);
-    if (v >= 512) v -= 1024;
-    v += 128;
-    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
-}
-
-inline void idct_1d(const int64_t in[8], int64_t out[8], int64_t &t10, int64_t &t11, int64_t &t12, int64_t &t13, int64_t &o0, int64_t &o1,
-                    int64_t &o2, int64_t &o3)
-{
-    (void)out;
-    int64_t z2 = in[2], z3 = in[6];
-    int64_t z1 = (z2 + z3) * F_0_541196100;
-    const int64_t tmp2 = z1 + z3 * (-F_1_847759065);
-    const int64_t tmp3 = z1 + z2 * F_0_765366865;
-    z2 = in[0], z3 = in[4];
-    const int64_t tmp0 = (z2 + z3) << CONST_BITS;
-    const int64_t tmp1 = (z2 - z3) << CONST_BITS;
-    t10 = tmp0 + tmp3, t13 = tmp0 - tmp3, t11 = tmp1 + tmp2, t12 = tmp1 - tmp2;
-    int64_t a0 = in[7], a1 = in[5], a2 = in[3], a3 = in[1];
-    z1 = a0 + a3;
-    z2 = a1 + a2;
-    z3 = a0 + a2;
-    int64_t z4 = a1 + a3;
-    const int64_t z5 = (z3 + z4) * F_1_175875602;
-    a0 *= F_0_298631336;
-    a1 *= F_2_053119869;
-    a2 *= F_3_072711026;
-    a3 *= F_1_501321110;
-    z1 *= -F_0_899976223;
-    z2 *= -F_2_562915447;
-    z3 *= -F_1_961570560;
-    z4 *= -F_0_390180644;
-    z3 += z5;
-    z4 += z5;
-    o0 = a0 + z1 + z3;
-    o1 = a1 + z2 + z4;
-    o2 = a2 + z2 + z3;
-    o3 = a3 + z1 + z4;
-}
-
-void idct_islow(const int16_t coef[64], const uint16_t q[64], uint8_t *out, int stride)
-{
-    int64_t ws[64];
-    for (int c = 0; c < 8; c++) {
-        int64_t in[8];
-        for (int r = 0; r < 8; r++) in[r] = (int64_t)coef[8 * r + c] * (int64_t)q[8 * r + c];
-        int64_t t10, t11, t12, t13, o0, o1, o2, o3;
-        idct_1d(in, nullptr, t10, t11, t12, t13, o0, o1, o2, o3);
-        const int sh = CONST_BITS - PASS1_BITS;
-        ws[8 * 0 + c] = descale(t10 + o3, sh);
-        ws[8 * 7 + c] = descale(t10 - o3, sh);
-        ws[8 * 1 + c] = descale(t11 + o2, sh);
-        ws[8 * 6 + c] = descale(t11 - o2, sh);
-        ws[8 * 2 + c] = descale(t12 + o1, sh);
-        ws[8 * 5 + c] = descale(t12 - o1, sh);
-        ws[8 * 3 + c] = descale(t13 + o0, sh);
-        ws[8 * 4 + c] = descale(t13 - o0, sh);
+    br.need32();
+    int s = br.decode(DC);
+    if (s) {
+        if (s > 15) s = 15;
+        pred += br.receive_extend(s);
     }
-    for (int r = 0; r < 8; r++) {
-        int64_t t10, t11, t12, t13, o0, o1, o2, o3;
-        idct_1d(ws + 8 * r, nullptr, t10, t11, t12, t13, o0, o1, o2, o3);
-        const int sh = CONST_BITS + PASS1_BITS + 3;
-        uint8_t *p = out + (size_t)r * stride;
-        p[0] = idct_limit(descale(t10 + o3, sh));
-        p[7] = idct_limit(descale(t10 - o3, sh));
-        p[1] = idct_limit(descale(t11 + o2, sh));
-        p[6] = idct_limit(descale(t11 - o2, sh));
-        p[2] = idct_limit(descale(t12 + o1, sh));
-        p[5] = idct_limit(descale(t12 - o1, sh));
-        p[3] = idct_limit(descale(t13 + o0, sh));
-        p[4] = idct_limit(descale(t13 - o0, sh));
+    if (!STORE) {
+        for (int k = 1; k < 64; k++) {
+            br.need32();
+            const uint32_t e = AC.skip[br.peek(11)];
+            if (e & 0x8000u) {
+                br.skip((int)(e & 31u));
+                if (e & 0x200u) break;
+                k += (int)((e >> 5) & 15u);
+                continue;
+            }
+            const int rs = br.decode(AC);
+            if (rs & 15) {
+                k += rs >> 4;
+                br.skip(rs & 15);
+            } else {
+                if ((rs >> 4) != 15) break;
+                k += 15;
+            }
+        }
+        return;
     }
-}
-
-// ---- jdcolor.c: YCbCr -> RGB with 16-bit fixed-point tables -----------------------------------------
-struct ColorTabs {
-    int cr_r[256], cb_b[256];
-    int64_t cr_g[256], cb_g[256];
-    ColorTabs()
-    {
-        for (int i = 0; i < 256; i++) {
-            const int64_t x = i - 128;
-            cr_r[i] = (int)((91881 * x + 32768) >> 16);      // FIX(1.40200)
-            cb_b[i] = (int)((116130 * x + 32768) >> 16);     // FIX(1.77200)
-            cr_g[i] = -46802 * x;                            // FIX(0.71414)
-            cb_g[i] = -22554 * x + 32768;                    // FIX(0.34414), + ONE_HALF
+    memset(coef, 0, sizeof(int16_t) * 64);
+    coef[0] = (int16_t)pred;
+    for (int k = 1; k < 64; k++) {
+        br.need32();
+        const int f = AC.fast[br.peek(9)];
+        if (f) {                     // code and value in one look-up
+            k += (f >> 4) & 15;
+            br.skip(f & 15);
+            if (k < 64) coef[kNatural[k]] = (int16_t)(f >> 8);
+            continue;
+        }
+        const int rs = br.decode(AC);
+        const int rr = rs >> 4, ss = rs & 15;
+        if (ss) {
+            k += rr;
+            const int v = br.receive_extend(ss);
+            if (k < 64) coef[kNatural[k]] = (int16_t)v;
+        } else {
+            if (rr != 15) break;
+            k += 15;
         }
     }
-};
-const ColorTabs kTabs;
-inline int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
-
-// ---- jdsample.c: "fancy" (triangle filter) upsampling, one output sample ---------------------------
-// h2v1: out[2i] = (3 in[i] + in[i-1] + 1) >> 2, out[2i+1] = (3 in[i] + in[i+1] + 2) >> 2; the first and the last output
-// sample of a row are copies of the first / last input sample.
-inline int up_h2v1(const uint8_t *row, int ds_w, int X)
-{
-    const int cx = X >> 1;
-    if (X & 1) return cx == ds_w - 1 ? row[cx] : (3 * row[cx] + row[cx + 1] + 2) >> 2;
-    return cx == 0 ? row[0] : (3 * row[cx] + row[cx - 1] + 1) >> 2;
-}
-// h2v2: column sums 3 * nearer row + further row, then the same horizontal filter on the sums with rounding 8 / 7
-inline int up_h2v2(const uint8_t *near_row, const uint8_t *far_row, int ds_w, int X)
-{
-    const int cx = X >> 1;
-    const int cur = 3 * near_row[cx] + far_row[cx];
-    if (X & 1) return cx == ds_w - 1 ? (cur * 4 + 7) >> 4 : (cur * 3 + 3 * near_row[cx + 1] + far_row[cx + 1] + 7) >> 4;
-    return cx == 0 ? (cur * 4 + 8) >> 4 : (cur * 3 + 3 * near_row[cx - 1] + far_row[cx - 1] + 8) >> 4;
 }
 
 struct Scratch {
@@ -490,36 +442,10 @@ int jpeg_copy_rects(const uint8_t *data, uint64_t size, const TiffRect *rects, i
                 const Huff &DC = H.dc[C.td], &AC = H.ac[C.ta];
                 for (int by = 0; by < C.v; by++)
                     for (int bx = 0; bx < C.h; bx++) {
-                        if (need) memset(coef, 0, sizeof(coef));
-                        br.need32();
-                        int s = br.decode(DC);
-                        if (s) {
-                            if (s > 15) s = 15;
-                            C.pred += br.receive_extend(s);
-                        }
-                        coef[0] = (int16_t)C.pred;
-                        for (int k = 1; k < 64; k++) {
-                            br.need32();
-                            const int f = AC.fast[br.peek(9)];
-                            if (f) {                     // code and value in one look-up
-                                k += (f >> 4) & 15;
-                                br.skip(f & 15);
-                                if (need && k < 64) coef[kNatural[k]] = (int16_t)(f >> 8);
-                                continue;
-                            }
-                            const int rs = br.decode(AC);
-                            const int rr = rs >> 4, ss = rs & 15;
-                            if (ss) {
-                                k += rr;
-                                const int v = br.receive_extend(ss);
-                                if (need && k < 64) coef[kNatural[k]] = (int16_t)v;
-                            } else {
-                                if (rr != 15) break;
-                                k += 15;
-                            }
-                        }
+                        if (need) decode_block<true>(br, DC, AC, C.pred, coef);
+                        else decode_block<false>(br, DC, AC, C.pred, nullptr);
                         if (need)
-                            idct_islow(coef, H.qt[C.tq],
+                            jpeg_idct_islow(coef, H.qt[C.tq],
                                        S.plane[c].data() + (size_t)((my * C.v + by) * 8) * C.stride + (size_t)(mx * C.h + bx) * 8, C.stride);
                     }
             }
@@ -540,34 +466,85 @@ int jpeg_copy_rects(const uint8_t *data, uint64_t size, const TiffRect *rects, i
         for (int y = 0; y < r.h; y++) {
             const int Y = r.y + y;
             const uint8_t *yrow = S.plane[0].data() + (size_t)Y * H.comp[0].stride;
-            const uint8_t *bn, *bf, *rn, *rf;
-            if (v2) {
-                const int cy = Y >> 1;
-                int fy = (Y & 1) ? cy + 1 : cy - 1;       // the row above the first / below the last is that row again
-                fy = fy < 0 ? 0 : (fy > Cb.ds_h - 1 ? Cb.ds_h - 1 : fy);
-                bn = S.plane[1].data() + (size_t)cy * Cb.stride, bf = S.plane[1].data() + (size_t)fy * Cb.stride;
-                rn = S.plane[2].data() + (size_t)cy * Cr.stride, rf = S.plane[2].data() + (size_t)fy * Cr.stride;
-            } else {
-                bn = bf = S.plane[1].data() + (size_t)Y * Cb.stride;
-                rn = rf = S.plane[2].data() + (size_t)Y * Cr.stride;
-            }
-            uint8_t *o = r.dst + (size_t)y * r.w * 4;
-            for (int x = 0; x < r.w; x++, o += 4) {
+            const int cy = v2 ? Y >> 1 : Y, fy = v2 ? jpeg_far_row(Y, Cb.ds_h) : Y;
+            const uint8_t *bn = S.plane[1].data() + (size_t)cy * Cb.stride, *bf = S.plane[1].data() + (size_t)fy * Cb.stride;
+            const uint8_t *rn = S.plane[2].data() + (size_t)cy * Cr.stride, *rf = S.plane[2].data() + (size_t)fy * Cr.stride;
+            uint32_t *o = (uint32_t *)(r.dst + (size_t)y * r.w * 4);
+            for (int x = 0; x < r.w; x++) {
                 const int X = r.x + x;
                 int c0 = yrow[X], c1, c2;
                 if (!h2) c1 = bn[X], c2 = rn[X];
-                else if (!v2) c1 = up_h2v1(bn, Cb.ds_w, X), c2 = up_h2v1(rn, Cr.ds_w, X);
-                else c1 = up_h2v2(bn, bf, Cb.ds_w, X), c2 = up_h2v2(rn, rf, Cr.ds_w, X);
-                int R, G, B;
-                if (H.ycc) {
-                    R = clamp255(c0 + kTabs.cr_r[c2]);
-                    G = clamp255(c0 + (int)((kTabs.cb_g[c1] + kTabs.cr_g[c2]) >> 16));
-                    B = clamp255(c0 + kTabs.cb_b[c1]);
-                } else {
-                    R = c0, G = c1, B = c2;
-                }
-                o[0] = (uint8_t)B, o[1] = (uint8_t)G, o[2] = (uint8_t)R, o[3] = 0;     // int32 0x00RRGGBB, little-endian
+                else if (!v2) c1 = jpeg_up_h2v1(bn, 0, Cb.ds_w, X), c2 = jpeg_up_h2v1(rn, 0, Cr.ds_w, X);
+                else c1 = jpeg_up_h2v2(bn, bf, 0, Cb.ds_w, X), c2 = jpeg_up_h2v2(rn, rf, 0, Cr.ds_w, X);
+                o[x] = H.ycc ? jpeg_ycc_to_rgb(c0, c1, c2) : ((uint32_t)c0 << 16) | ((uint32_t)c1 << 8) | (uint32_t)c2;   // int32 0x00RRGGBB
             }
+        }
+    }
+    return LST_OK;
+}
+
+int jpeg_geometry(const uint8_t *data, uint64_t size, JpegGeom *g, std::string *err)
+{
+    Header H;
+    int rc = parse_header(data, size, &H, err);
+    if (rc != LST_OK) return rc;
+    g->width = H.width, g->height = H.height, g->ncomp = H.ncomp, g->hmax = H.hmax, g->vmax = H.vmax, g->ycc = H.ycc ? 1 : 0;
+    return LST_OK;
+}
+
+int jpeg_decode_coeffs(const uint8_t *data, uint64_t size, const JpegGeom &g, const JpegRegion *regs, int16_t *const *coef, int n,
+                       uint16_t *qt_out, std::string *err)
+{
+    Header H;
+    int rc = parse_header(data, size, &H, err);
+    if (rc != LST_OK) return rc;
+    JpegGeom mine;
+    mine.width = H.width, mine.height = H.height, mine.ncomp = H.ncomp, mine.hmax = H.hmax, mine.vmax = H.vmax, mine.ycc = H.ycc ? 1 : 0;
+    if (!(mine == g)) return fail(err, LST_ERR_INVALID, "JPEG slice differs from the stack's size, components or chroma sampling");
+    if (n > 8) return fail(err, LST_ERR_INVALID, "too many regions");
+    for (int c = 0; c < 3; c++)
+        for (int i = 0; i < 64; i++) qt_out[64 * c + i] = c < H.ncomp ? H.qt[H.comp[c].tq][i] : (uint16_t)0;
+    static thread_local std::vector<uint8_t> mask;        // per MCU: the regions it belongs to
+    mask.assign((size_t)H.mcus_x * H.mcus_y, 0);
+    int last_row = -1;
+    for (int k = 0; k < n; k++) {
+        const JpegRegion &r = regs[k];
+        if (r.nmx <= 0 || r.nmy <= 0) continue;
+        if (r.mx0 < 0 || r.my0 < 0 || r.mx0 + r.nmx > H.mcus_x || r.my0 + r.nmy > H.mcus_y) return fail(err, LST_ERR_INVALID, "region outside the image");
+        for (int my = r.my0; my < r.my0 + r.nmy; my++)
+            for (int mx = r.mx0; mx < r.mx0 + r.nmx; mx++) mask[(size_t)my * H.mcus_x + mx] |= (uint8_t)(1u << k);
+        last_row = std::max(last_row, r.my0 + r.nmy - 1);
+    }
+    const int bpm = jpeg_blocks_per_mcu(g);
+    int16_t mcu[6 * 64];
+    BitReader br{data, size, H.scan_pos};
+    for (int c = 0; c < H.ncomp; c++) H.comp[c].pred = 0;
+    int to_restart = H.restart_interval;
+    for (int my = 0; my <= last_row; my++) {
+        for (int mx = 0; mx < H.mcus_x; mx++) {
+            if (H.restart_interval) {
+                if (to_restart == 0) {
+                    br.restart();
+                    for (int c = 0; c < H.ncomp; c++) H.comp[c].pred = 0;
+                    to_restart = H.restart_interval;
+                }
+                to_restart--;
+            }
+            const uint8_t m = mask[(size_t)my * H.mcus_x + mx];
+            int blk = 0;
+            for (int c = 0; c < H.ncomp; c++) {
+                Comp &C = H.comp[c];
+                const Huff &DC = H.dc[C.td], &AC = H.ac[C.ta];
+                for (int b = 0; b < C.v * C.h; b++, blk++) {
+                    if (m) decode_block<true>(br, DC, AC, C.pred, mcu + 64 * blk);
+                    else decode_block<false>(br, DC, AC, C.pred, nullptr);
+                }
+            }
+            for (int k = 0; m && k < n; k++)
+                if (m & (1u << k)) {
+                    const JpegRegion &r = regs[k];
+                    memcpy(coef[k] + ((size_t)(my - r.my0) * r.nmx + (mx - r.mx0)) * bpm * 64, mcu, sizeof(int16_t) * 64 * bpm);
+                }
         }
     }
     return LST_OK;

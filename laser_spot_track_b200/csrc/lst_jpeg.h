@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <string>
 
+#include "lst_jpeg_math.h"
 #include "lst_tiff.h"
 
 namespace lst {
@@ -31,5 +32,16 @@ int jpeg_parse(const uint8_t *data, uint64_t size, int page, TiffLayout *out, st
 
 // The rectangles of the decoded image: 8-bit samples, or little-endian int32 0x00RRGGBB pixels (row pitch w * 4).
 int jpeg_copy_rects(const uint8_t *data, uint64_t size, const TiffRect *rects, int n, std::string *err);
+
+// ---- the device path: entropy decoding here, reconstruction on the GPU (lst_jpeg_reconstruct) ---------------------------
+// Entropy decoding is a bit-serial dependency chain through the whole scan and stays on host threads (one file per thread);
+// what follows it -- dequantisation, inverse DCT, chroma upsampling, colour conversion -- is independent per block / pixel
+// and runs on the device for the MCUs of the search regions: the reader threads stage quantised coefficients instead of pixels.
+int jpeg_geometry(const uint8_t *data, uint64_t size, JpegGeom *g, std::string *err);
+// The quantised coefficients (64 int16 per block, natural order) of the MCUs of region k go to coef[k]: MCU-major
+// ((my - my0) * nmx + (mx - mx0)), within an MCU the luma blocks row-major, then Cb, Cr.  qt_out: 3 x 64 quantisation
+// values (component order, natural order).  The file must have the geometry g (LST_ERR_INVALID otherwise).
+int jpeg_decode_coeffs(const uint8_t *data, uint64_t size, const JpegGeom &g, const JpegRegion *regs, int16_t *const *coef, int n,
+                       uint16_t *qt_out, std::string *err);
 
 }  // namespace lst

@@ -1146,6 +1146,95 @@ int launch_ncc_rgb(const DevTask *tasks, int n_tasks, int max_rh, int max_w, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// JPEG slice files: reconstruction of the search regions on the device (SURVEY 8f-N2 "frame decode -> device")
+// ------------------------------------------------------------------------------------------------
+// One CTA per (region, slice).  Phase 1: a thread takes a block -- 64 quantised coefficients of the staging buffer, the
+// slice's quantisation table -- and runs jpeg_idct_islow (the IJG integer IDCT, the same code the host decoder uses) into the
+// region's sample planes in shared memory.  Phase 2: a thread takes an output pixel: luma sample, chroma through the fancy
+// upsampling filters (the staged MCUs include the two pixels of context around the rectangle; the edge rules use the image's
+// own downsampled size), YCbCr -> RGB, and writes the ColorProcessor pixel (or the grey sample) into the ROI ring.
+__global__ void __launch_bounds__(256)
+lst_jpeg_reconstruct(const int16_t *__restrict__ coef, const uint16_t *__restrict__ qt, const JpegDevBatch B, uint8_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t jp_smem[];
+    const JpegDevRegion R = B.r[blockIdx.x];
+    if (R.w <= 0 || R.h <= 0) return;
+    const JpegGeom g = B.g;
+    const int slice = blockIdx.y;
+    const int mw = 8 * g.hmax, mh = 8 * g.vmax, bpm = jpeg_blocks_per_mcu(g), nluma = g.ncomp == 1 ? 1 : g.hmax * g.vmax;
+    const int ys = R.m.nmx * mw, cs = R.m.nmx * 8;                          // row strides of the luma / chroma planes
+    uint8_t *Yp = jp_smem;
+    uint8_t *Cbp = Yp + (size_t)R.m.nmy * mh * ys;
+    uint8_t *Crp = Cbp + (size_t)R.m.nmy * 8 * cs;
+    const int16_t *cf = coef + R.coef_off + (size_t)slice * R.coef_slice;
+    const uint16_t *q = qt + (size_t)slice * 192;
+    const int nblocks = R.m.nmx * R.m.nmy * bpm;
+    for (int blk = threadIdx.x; blk < nblocks; blk += blockDim.x) {
+        const int mcu = blk / bpm, b = blk - mcu * bpm;
+        const int mcy = mcu / R.m.nmx, mcx = mcu - mcy * R.m.nmx;
+        if (b < nluma) {
+            const int by = b / g.hmax, bx = b - by * g.hmax;
+            jpeg_idct_islow(cf + (size_t)blk * 64, q, Yp + (size_t)((mcy * g.vmax + by) * 8) * ys + (mcx * g.hmax + bx) * 8, ys);
+        } else {
+            const int c = b - nluma + 1;
+            jpeg_idct_islow(cf + (size_t)blk * 64, q + 64 * c, (c == 1 ? Cbp : Crp) + (size_t)(mcy * 8) * cs + mcx * 8, cs);
+        }
+    }
+    __syncthreads();
+    const int y_org = R.m.my0 * mh, x_org = R.m.mx0 * mw;                   // slice pixel of the planes' first sample
+    const int cy_org = R.m.my0 * 8, cx_org = R.m.mx0 * 8;                   // chroma sample of the chroma planes' first sample
+    const bool h2 = g.hmax == 2, v2 = g.vmax == 2;
+    const int ds_w = jpeg_ds_w(g), ds_h = jpeg_ds_h(g);
+    uint8_t *o = out + R.out_off + (size_t)slice * R.out_slice;
+    for (int p = threadIdx.x; p < R.w * R.h; p += blockDim.x) {
+        const int y = p / R.w, x = p - y * R.w;
+        const int X = R.x + x, Y = R.y + y;
+        const int c0 = Yp[(size_t)(Y - y_org) * ys + (X - x_org)];
+        if (g.ncomp == 1) {
+            o[p] = (uint8_t)c0;
+            continue;
+        }
+        const int cy = v2 ? Y >> 1 : Y, fy = v2 ? jpeg_far_row(Y, ds_h) : Y;
+        const uint8_t *bn = Cbp + (size_t)(cy - cy_org) * cs, *bf = Cbp + (size_t)(fy - cy_org) * cs;
+        const uint8_t *rn = Crp + (size_t)(cy - cy_org) * cs, *rf = Crp + (size_t)(fy - cy_org) * cs;
+        int c1, c2;
+        if (!h2) c1 = bn[X - cx_org], c2 = rn[X - cx_org];
+        else if (!v2) c1 = jpeg_up_h2v1(bn, cx_org, ds_w, X), c2 = jpeg_up_h2v1(rn, cx_org, ds_w, X);
+        else c1 = jpeg_up_h2v2(bn, bf, cx_org, ds_w, X), c2 = jpeg_up_h2v2(rn, rf, cx_org, ds_w, X);
+        ((uint32_t *)o)[p] = g.ycc ? jpeg_ycc_to_rgb(c0, c1, c2) : ((uint32_t)c0 << 16) | ((uint32_t)c1 << 8) | (uint32_t)c2;
+    }
+}
+
+size_t jpeg_reconstruct_smem(const JpegGeom &g, const JpegRegion &m)
+{
+    const size_t luma = (size_t)m.nmy * 8 * g.vmax * m.nmx * 8 * g.hmax;
+    return luma + (g.ncomp == 3 ? 2 * (size_t)m.nmy * 8 * m.nmx * 8 : 0) + 16;
+}
+
+int launch_jpeg_reconstruct(const int16_t *coef, const uint16_t *qt, const JpegDevBatch &batch, int n_slices, uint8_t *roi_out,
+                            cudaStream_t stream)
+{
+    size_t smem = 0;
+    for (int k = 0; k < 5; k++)
+        if (batch.r[k].w > 0 && batch.r[k].h > 0) smem = std::max(smem, jpeg_reconstruct_smem(batch.g, batch.r[k].m));
+    if (smem == 0 || n_slices <= 0) return 0;
+    if (smem > 200 * 1024) return -1;
+    if (cudaFuncSetAttribute(lst_jpeg_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
+    int launches = 0;
+    for (int base = 0; base < n_slices; base += 65535) {
+        const int n = n_slices - base < 65535 ? n_slices - base : 65535;
+        JpegDevBatch b = batch;
+        for (int k = 0; k < 5; k++) {
+            b.r[k].coef_off += (unsigned long long)base * b.r[k].coef_slice;
+            b.r[k].out_off += (unsigned long long)base * b.r[k].out_slice;
+        }
+        lst_jpeg_reconstruct<<<dim3(5, n), 256, smem, stream>>>(coef, qt + (size_t)base * 192, b, roi_out);
+        launches++;
+    }
+    return cudaPeekAtLastError() == cudaSuccess ? launches : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-window epilogue: 3x3 neighbourhood, sub-pixel fit, accept test
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(288)

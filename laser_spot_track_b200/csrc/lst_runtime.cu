@@ -24,6 +24,7 @@
 #include "../../include/lst_b200.h"
 #include "lst_device.h"
 #include "lst_host.h"
+#include "lst_jpeg.h"
 #include "lst_tiff.h"
 
 using namespace lst;
@@ -104,6 +105,13 @@ struct lst_ctx : public Executor {
     // slices read from files (lst_track_files): pinned staging with the layout of the ROI ring
     uint8_t *h_fstage[2] = {nullptr, nullptr};
     size_t fstage_cap = 0;
+    // JPEG slice files: quantised coefficients of the MCUs under the search regions (+ the slices' quantisation tables), staged by
+    // the reader threads and reconstructed on the device (lst_jpeg_reconstruct); LST_JPEG_DEVICE=0 keeps the host reconstruction
+    int16_t *h_jcoef[2] = {nullptr, nullptr}, *d_jcoef[2] = {nullptr, nullptr};
+    uint16_t *h_jqt[2] = {nullptr, nullptr}, *d_jqt[2] = {nullptr, nullptr};
+    size_t jcoef_cap = 0;          // int16 elements per half
+    int jqt_cap = 0;               // slices per half
+    bool jpeg_device = true;
     uint8_t *h_fwhole = nullptr;   // whole slices of a sub-batch (fallback / whole-slice search)
     size_t fwhole_cap = 0;
     bool file_mode = false;        // the batch being resolved has no whole slice in memory to fall back to
@@ -833,6 +841,10 @@ void lst_destroy(lst_ctx *c)
         cudaFree(c->d_roi[i]);
         cudaFree(c->d_gptr[i]);
         cudaFreeHost(c->h_gptr[i]);
+        cudaFree(c->d_jcoef[i]);
+        cudaFree(c->d_jqt[i]);
+        if (c->h_jcoef[i]) cudaFreeHost(c->h_jcoef[i]);
+        if (c->h_jqt[i]) cudaFreeHost(c->h_jqt[i]);
     }
     cudaFree(c->d_ring[0]);
     cudaFree(c->d_ring[1]);
@@ -1052,8 +1064,16 @@ struct FileSource {
 
 // Reads the regions `roi` of the slices [f0, f0 + nb) of a file source into `stage` (layout of the ROI
 // ring), several files at a time.  whole: the entire slice i goes to stage + i * frame_bytes instead.
+// JPEG slices reconstructed on the device: what the reader threads stage for a batch
+struct JpegBatchPlan {
+    JpegDevBatch dev;            // geometry, regions, offsets (coefficients in int16 elements, pixels in bytes)
+    size_t coef_elems = 0;       // int16 elements of the whole batch
+    int16_t *h_coef = nullptr;   // pinned staging of this half
+    uint16_t *h_qt = nullptr;
+};
+
 static int read_slices(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, const RoiDesc roi[5], bool whole, uint8_t *stage,
-                       std::string *err)
+                       std::string *err, const JpegBatchPlan *jp = nullptr)
 {
     const int nthreads = std::max(1, std::min(c->file_threads, nb));
     std::vector<std::string> errs(nthreads);
@@ -1081,6 +1101,37 @@ static int read_slices(lst_ctx *c, const FileSource &fs, int64_t f0, int nb, con
             FileMap fm;
             TiffLayout L;
             int rc = fm.open(fs.paths[f0 + i], &errs[ti]);
+            if (rc == LST_OK && jp) {
+                // entropy decoding only: the quantised coefficients of the MCUs under the regions go to the staging buffer
+                static thread_local std::vector<uint8_t> file;
+                if (file.size() < fm.size) file.resize(fm.size);
+                uint64_t got = 0;
+                while (got < fm.size) {
+                    const ssize_t k = pread(fm.fd, file.data() + got, fm.size - got, (off_t)got);
+                    if (k <= 0) break;
+                    got += (uint64_t)k;
+                }
+                if (got < fm.size) {
+                    errs[ti] = std::string("short read of ") + fs.paths[f0 + i];
+                    rc = LST_ERR_INVALID;
+                } else {
+                    JpegRegion regs[5];
+                    int16_t *dst[5];
+                    for (int k = 0; k < 5; k++) {
+                        const JpegDevRegion &r = jp->dev.r[k];
+                        regs[k] = r.m;
+                        if (r.w <= 0 || r.h <= 0) regs[k].nmx = regs[k].nmy = 0;
+                        dst[k] = jp->h_coef + r.coef_off + (size_t)i * r.coef_slice;
+                    }
+                    rc = jpeg_decode_coeffs(file.data(), fm.size, jp->dev.g, regs, dst, 5, jp->h_qt + (size_t)i * 192, &errs[ti]);
+                    if (rc != LST_OK) errs[ti] = std::string(fs.paths[f0 + i]) + ": " + errs[ti];
+                }
+                if (rc != LST_OK) {
+                    rcs[ti] = rc;
+                    return;
+                }
+                continue;
+            }
             if (rc == LST_OK) rc = tiff_parse(fm.data, fm.size, fs.pages ? fs.pages[f0 + i] : 0, &L, &errs[ti]);
             if (rc == LST_OK && (L.width != c->p.width || L.height != c->p.height || L.bits != want_bits ||
                                  L.rgb != (c->p.pixel_type == LST_PIX_RGB) || (L.bits > 8 && L.big_endian != fs.big_endian))) {
@@ -1233,6 +1284,9 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
     std::vector<const void *> mapped;
     std::string file_err[2];          // declared first: the reader threads of file_job write them and are joined first
     std::future<int> file_job[2];
+    JpegGeom jgeom;
+    memset(&jgeom, 0, sizeof(jgeom));
+    bool jpeg_stack = false;          // the slices are JPEG files reconstructed on the device
     if (use_roi && !fs) {
         mapped.resize(n_frames);
         for (int64_t i = 0; i < n_frames && use_roi; i++) {
@@ -1256,7 +1310,49 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
         }
         rc = ensure_roi(c, (roi_block_max + 256) * (size_t)std::min<int64_t>(B, n_frames), B);
         if (rc != LST_OK) return rc;
-        if (fs && c->fstage_cap < c->roi_cap) {
+        // JPEG files: the reader threads do the entropy decoding, the device the reconstruction of the regions.  The
+        // coefficient staging is sized once per call from the same upper bound as the ROI ring.
+        if (fs && !fs->is_mem() && c->jpeg_device) {
+            FileMap fm;
+            std::string e;
+            if (fm.open(fs->paths[0], &e) == LST_OK && jpeg_signature(fm.data, fm.size) && jpeg_geometry(fm.data, fm.size, &jgeom, &e) == LST_OK &&
+                jgeom.width == c->p.width && jgeom.height == c->p.height && (jgeom.ncomp == 3) == (c->p.pixel_type == LST_PIX_RGB))
+                jpeg_stack = true;
+        }
+        if (jpeg_stack) {
+            const int ax = c->roi_align_bytes / (int)c->bpp(), mw = 8 * jgeom.hmax, mh = 8 * jgeom.vmax;
+            size_t elems = 0;
+            for (int k = 0; k < 5; k++) {
+                const int mg = std::max(c->roi_margin[k], kRoiMarginMax);
+                size_t w = std::min<size_t>((size_t)c->rect[k].w + 2 * c->p.s_area + 2 * mg + 2 * ax, (size_t)c->p.width + ax);
+                size_t h = std::min<size_t>((size_t)c->rect[k].h + 2 * c->p.s_area + 2 * mg, (size_t)c->p.height);
+                JpegRegion bound;
+                bound.mx0 = bound.my0 = 0, bound.nmx = (int)(w / mw + 3), bound.nmy = (int)(h / mh + 3);
+                if (jpeg_reconstruct_smem(jgeom, bound) > 200 * 1024) jpeg_stack = false;   // a region may outgrow one CTA: host path
+                elems += (size_t)bound.nmx * bound.nmy * (size_t)jpeg_blocks_per_mcu(jgeom) * 64;
+            }
+            const int nbmax = (int)std::min<int64_t>(B, n_frames);
+            elems *= (size_t)nbmax;
+            if (jpeg_stack && (elems > c->jcoef_cap || nbmax > c->jqt_cap)) {
+                CUC(c, cudaStreamSynchronize(c->s_copy));
+                CUC(c, cudaStreamSynchronize(c->s_compute));
+                const size_t cap = std::max(elems, c->jcoef_cap);
+                const int qcap = std::max(nbmax, c->jqt_cap);
+                for (int i = 0; i < 2; i++) {
+                    if (c->h_jcoef[i]) cudaFreeHost(c->h_jcoef[i]);
+                    if (c->h_jqt[i]) cudaFreeHost(c->h_jqt[i]);
+                    c->h_jcoef[i] = nullptr, c->h_jqt[i] = nullptr;
+                    c->jcoef_cap = 0, c->jqt_cap = 0;
+                    CUC(c, cudaHostAlloc((void **)&c->h_jcoef[i], cap * sizeof(int16_t), cudaHostAllocDefault));
+                    CUC(c, cudaHostAlloc((void **)&c->h_jqt[i], (size_t)qcap * 192 * sizeof(uint16_t), cudaHostAllocDefault));
+                    CUC(c, regrow(&c->d_jcoef[i], cap));
+                    CUC(c, regrow(&c->d_jqt[i], (size_t)qcap * 192));
+                }
+                c->jcoef_cap = cap;
+                c->jqt_cap = qcap;
+            }
+        }
+        if (fs && !jpeg_stack && c->fstage_cap < c->roi_cap) {
             for (int i = 0; i < 2; i++) {
                 if (c->h_fstage[i]) cudaFreeHost(c->h_fstage[i]);
                 c->h_fstage[i] = nullptr;
@@ -1290,6 +1386,47 @@ static int track_impl(lst_ctx *c, const void *base, size_t stride, const void *c
                 lst_ctx *cc = c;
                 const FileSource src = *fs;
                 std::string *errp = &file_err[half];
+                // JPEG files: the reader threads do the entropy decoding, the device the reconstruction of the regions
+                JpegBatchPlan jp;
+                bool jpeg_dev = jpeg_stack;
+                if (jpeg_dev) {
+                    jp.dev.g = jgeom;
+                    const int bpm = jpeg_blocks_per_mcu(jgeom);
+                    size_t off = 0;
+                    for (int k = 0; k < 5; k++) {
+                        JpegDevRegion &r = jp.dev.r[k];
+                        memset(&r, 0, sizeof(r));
+                        if (rois[k].w <= 0 || rois[k].h <= 0) continue;
+                        r.x = rois[k].x, r.y = rois[k].y, r.w = rois[k].w, r.h = rois[k].h;
+                        r.m = jpeg_region(jgeom, r.x, r.y, r.w, r.h);
+                        r.coef_slice = (unsigned long long)r.m.nmx * r.m.nmy * bpm * 64;
+                        r.coef_off = off;
+                        off += (size_t)r.coef_slice * nb;
+                        r.out_off = rois[k].off;
+                        r.out_slice = rois[k].slice_bytes;
+                        if (jpeg_reconstruct_smem(jgeom, r.m) > 200 * 1024) return c->fail(LST_ERR_STATE, "internal: JPEG region larger than planned");
+                    }
+                    jp.coef_elems = off;
+                    if (off > c->jcoef_cap || nb > c->jqt_cap) return c->fail(LST_ERR_STATE, "internal: JPEG coefficient staging smaller than planned");
+                }
+                if (jpeg_dev) {
+                    jp.h_coef = c->h_jcoef[half];
+                    jp.h_qt = c->h_jqt[half];
+                    c->stats.h2d_bytes += (int64_t)(jp.coef_elems * sizeof(int16_t) + (size_t)nb * 192 * sizeof(uint16_t));
+                    for (int k = 0; k < 5; k++) c->stats.h2d_bytes -= (int64_t)(rois[k].slice_bytes * nb);   // no pixels travel
+                    c->stats.kernel_launches += 1;
+                    file_job[half] = std::async(std::launch::async, [cc, src, f0, nb, half, rois, errp, jp]() -> int {
+                        int r = read_slices(cc, src, f0, nb, rois, false, nullptr, errp, &jp);
+                        if (r != LST_OK) return r;
+                        if (cudaSetDevice(cc->device) != cudaSuccess) return LST_ERR_CUDA;
+                        if (cudaMemcpyAsync(cc->d_jcoef[half], jp.h_coef, jp.coef_elems * sizeof(int16_t), cudaMemcpyHostToDevice, cc->s_copy) != cudaSuccess ||
+                            cudaMemcpyAsync(cc->d_jqt[half], jp.h_qt, (size_t)nb * 192 * sizeof(uint16_t), cudaMemcpyHostToDevice, cc->s_copy) != cudaSuccess)
+                            return LST_ERR_CUDA;
+                        if (launch_jpeg_reconstruct(cc->d_jcoef[half], cc->d_jqt[half], jp.dev, nb, cc->d_roi[half], cc->s_copy) < 0) return LST_ERR_CUDA;
+                        return cudaEventRecord(cc->ev_copy[half], cc->s_copy) == cudaSuccess ? LST_OK : LST_ERR_CUDA;
+                    });
+                    return LST_OK;
+                }
                 file_job[half] = std::async(std::launch::async, [cc, src, f0, nb, half, rois, errp]() -> int {
                     int r = read_slices(cc, src, f0, nb, rois, false, cc->h_fstage[half], errp);
                     if (r != LST_OK) return r;
@@ -1630,6 +1767,7 @@ int lst_track_files(lst_ctx *c, const char *const *paths, const int32_t *pages, 
         unsigned hc = std::thread::hardware_concurrency();
         c->file_threads = (int)std::min(16u, std::max(1u, hc));   // pread scales with the cores; the copy engine does the rest
         if (const char *e = getenv("LST_FILE_THREADS")) c->file_threads = std::max(1, atoi(e));
+        if (const char *e = getenv("LST_JPEG_DEVICE")) c->jpeg_device = atoi(e) != 0;   // 0: JPEG slices are reconstructed by the reader threads
     }
     c->swap_bytes = fs.big_endian && c->p.pixel_type != LST_PIX_U8;
     int rc = track_impl(c, nullptr, 0, nullptr, false, first_frame_index, n_frames, out, &fs);

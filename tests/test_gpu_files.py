@@ -147,13 +147,16 @@ def test_track_png_slice_files(built_lib, oracle_clib, tmp_path):
         util.compare_records(t.track_files(paths[1:]), want, label="png files")
 
 
+@pytest.mark.parametrize("device_stage", ["1", "0"])
 @pytest.mark.parametrize("sampling,intensity", [("420", True), ("444", True), ("422", False)])
-def test_track_jpeg_slices(built_lib, oracle_clib, tmp_path, sampling, intensity):
+def test_track_jpeg_slices(built_lib, oracle_clib, tmp_path, monkeypatch, sampling, intensity, device_stage):
     """a time-lapse of JPEG files (the virtual stack of LST4:808-831).  A 3-component JPEG is a ColorProcessor
     slice; the oracle runs on the frames cv2.imread decodes (libjpeg-turbo, bit-compatible with the JDK's IJG decoder), the
-    library reads the files itself -- only the MCUs under the search regions are reconstructed.  matchIntensity true
-    (convertToGray32) and false (3-channel match)."""
+    library reads the files itself -- only the MCUs under the search regions are reconstructed: on the device from the
+    quantised coefficients the reader threads stage (default), or by the reader threads (LST_JPEG_DEVICE=0).  matchIntensity
+    true (convertToGray32) and false (3-channel match)."""
     import cv2
+    monkeypatch.setenv("LST_JPEG_DEVICE", device_stage)
     samp = {"420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444,
             "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422}[sampling]
     cfg = StackConfig(400, 300, "u8", 32, 24, 16)
@@ -179,9 +182,11 @@ def test_track_jpeg_slices(built_lib, oracle_clib, tmp_path, sampling, intensity
         assert t.stats().roi_fallback_tasks == 0
 
 
-def test_track_grey_jpeg_slices(built_lib, oracle_clib, tmp_path):
+@pytest.mark.parametrize("device_stage", ["1", "0"])
+def test_track_grey_jpeg_slices(built_lib, oracle_clib, tmp_path, monkeypatch, device_stage):
     """1-component JPEG files are 8-bit slices (ImageJ converts grey JPEGs to 8 bits)."""
     import cv2
+    monkeypatch.setenv("LST_JPEG_DEVICE", device_stage)
     cfg = StackConfig(400, 300, "u8", 32, 24, 12)
     st = SyntheticStack(cfg)
     paths, frames = [], []
@@ -197,3 +202,29 @@ def test_track_grey_jpeg_slices(built_lib, oracle_clib, tmp_path):
     with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area) as t:
         with pytest.raises(LstError):
             t.set_reference_file(paths[0], st.ref_xy)       # an 8-bit file in an RGB context
+
+
+@pytest.mark.parametrize("sampling", ["420", "422", "444"])
+def test_jpeg_regions_at_the_image_border(built_lib, oracle_clib, tmp_path, sampling):
+    """Search windows that reach the border of a 250 x 187 image (partial MCUs on the right and at the bottom): the device
+    reconstruction has to apply the upsampling filters' edge rules at the image's own first / last chroma sample, not at the
+    border of the staged MCUs.  Any wrong pixel changes a blurred window and with it a score: records bit-exact."""
+    import cv2
+    samp = {"420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, "444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444,
+            "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422}[sampling]
+    cfg = StackConfig(250, 187, "u8", 24, 60, 8)
+    st = SyntheticStack(cfg)
+    paths, frames = [], []
+    for i in range(8):
+        g = st.frame(i).astype(np.uint8)
+        bgr = np.stack([255 - g // 2, g, (g.astype(np.uint16) * 3 // 4 + 17).astype(np.uint8)], axis=-1)
+        p = str(tmp_path / f"b{i:04d}.jpg")
+        assert cv2.imwrite(p, bgr, [cv2.IMWRITE_JPEG_QUALITY, 93, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, samp, cv2.IMWRITE_JPEG_RST_INTERVAL, 3])
+        dec = cv2.imread(p, cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        frames.append((dec[:, :, 2].astype(np.uint32) << 16) | (dec[:, :, 1].astype(np.uint32) << 8) | dec[:, :, 0])
+        paths.append(p)
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    assert any(t.wy == 0 for t in want[0].tm) and any(t.wy + t.wh == cfg.height for t in want[0].tm)
+    with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area, max_batch=4) as t:
+        t.set_reference_file(paths[0], st.ref_xy)
+        util.compare_records(t.track_files(paths[1:]), want, label=f"JPEG border {sampling}")
