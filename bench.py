@@ -63,6 +63,12 @@ def parse():
                     help="tracking lanes per GPU (lst_multi_create with the device listed this many times): the host-side "
                          "chain walk of one lane overlaps the kernels of the others; 0 = up to %d, fewer when the host has "
                          "less than one core per lane thread" % LANES_DEFAULT)
+    ap.add_argument("--continuous", action="store_true",
+                    help="device leg: the steps are consecutive pieces of ONE endless stack (slice numbers run on across ranks and "
+                         "steps), so with --frames not a multiple of the ring the chunk boundaries fall at different phases of the "
+                         "motion, the speculated boundary states are often wrong and chunks are re-tracked (resolver.chunks_retracked)")
+    ap.add_argument("--lead-in", type=int, default=0,
+                    help="--continuous: slices of the previous chunk a rank tracks first to refine its speculated start state")
     ap.add_argument("--no-files", action="store_true", help="skip the slices-from-TIFF-files leg (e2e_files)")
     ap.add_argument("--ingest", type=int, default=0, choices=[0, 1, 2], help="0 ROI DMA (default), 1 whole slices, 2 ROI gather kernel")
     ap.add_argument("--engine", default="auto", choices=["auto", "dp4a", "tc"], help="match kernel: tensor cores (default when the template fits) or IDP.4A")
@@ -348,11 +354,26 @@ def main():
         sh_dev = ShardedTracker(_AdapterAlt(runner.track_device_ptrs), comm)
         sh_e2e = ShardedTracker(_AdapterAlt(runner.track_host_ptrs), comm)
 
+    cont = {"t": 0, "ptrs": [], "lead": []}
+    LEAD = max(0, args.lead_in)
+    if args.continuous:      # pointer arrays of the steps of the device leg, built before the timed region
+        for t in range(args.steps + max(args.warmup, 0) + 2):
+            g0 = 1 + (t * world + rank) * F
+            cont["ptrs"].append((C.c_void_p * F)(*[dev_ring + ((g0 + j) % ring) * fb for j in range(F)]))
+            # the last slices of the previous chunk: tracked first from the speculated state, they pull it onto the true one
+            cont["lead"].append((C.c_void_p * LEAD)(*[dev_ring + ((g0 - LEAD + j) % ring) * fb for j in range(LEAD)]) if LEAD else None)
+
     def step_device():
+        ptrs, first, lead = dev_ptrs, 1 + rank * F, None
+        if args.continuous:
+            t = cont["t"]
+            cont["t"] = t + 1
+            ptrs, first = cont["ptrs"][t % len(cont["ptrs"])], 1 + (t * world + rank) * F
+            lead = cont["lead"][t % len(cont["ptrs"])]
         if pipelined:
-            sh_dev.track_chunk_pipelined(dev_ptrs, 1 + rank * F, runner.get_state())
+            sh_dev.track_chunk_pipelined(ptrs, first, runner.get_state(), lead)
         else:
-            sh_dev.track_chunk(dev_ptrs, 1 + rank * F, runner.get_state())
+            sh_dev.track_chunk(ptrs, first, runner.get_state(), lead)
 
     def step_e2e():
         if pipelined:
@@ -399,6 +420,12 @@ def main():
     if rank == 0:
         sampler.start()
     ms_dev, wall_dev, s_dev = timed(step_device, K, W)
+    # chunks tracked a second time because their speculated start state placed a window differently (warm-up steps
+    # included): between ranks and between the lanes of a rank, summed over the ranks
+    retr_t = torch.tensor([float(sh_dev.retracked), float(runner.retracked) if lanes > 1 else 0.0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(retr_t, op=dist.ReduceOp.SUM)
+    retr_all = [int(v) for v in retr_t.tolist()]
     clocks = sampler.stop() if rank == 0 else None
     ok_frames = sum(1 for r in out if r.status == 0)
     trk.set_kernel_timing(False)
@@ -744,7 +771,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "e2e_files": e2e_files, "e2e_jpeg": e2e_jpeg, "e2e_pageable": e2e_pageable, "gpu_launches": int(s_dev.kernel_launches),
             "roofline": roofline, "roofline_idp4a_engine": roofline_alt, "cpu_baseline": cpu_baseline, "extra": extra,
             "resolver": {"passes": int(s_dev.passes), "tasks": int(s_dev.tasks), "respeculated": int(s_dev.respeculated),
-                         "chunks_retracked": sh_dev.retracked, "chunks_retracked_late": getattr(sh_dev, "retracked_late", 0),
+                         "chunks_retracked": retr_all[0], "chunks_retracked_late": getattr(sh_dev, "retracked_late", 0),
+                         "lane_chunks_retracked": retr_all[1], "continuous_stack": bool(args.continuous), "lead_in": LEAD,
                          "boundary_exchange": ("pipelined: overlaps the next step" if pipelined else "synchronous") +
                                               (", " + os.environ.get("LST_BENCH_EXCHANGE", "nccl") if world > 1 else ""), "host_ms_per_step": s_dev.host_ms / K,
                          "device_wait_ms_per_step": s_dev.device_wait_ms / K},

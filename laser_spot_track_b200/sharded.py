@@ -149,10 +149,21 @@ class ShardedTracker:
         (rank 0: the true one).  ``lead_in``: optionally the last few frames of the previous chunk,
         tracked first from ``start_state`` to refine the speculation.  Returns (records, end_state);
         both are final after the boundary verification."""
+        import os, time
+        dbg = os.environ.get("LST_SHARD_DEBUG")
+        t0 = time.perf_counter()
         recs, end, guess, vals = self._track(frames, first_frame_index, start_state, lead_in)
+        t1 = time.perf_counter()
         gathered = self.comm.all_gather(vals)
+        t2 = time.perf_counter()
+        before = self.retracked
         recs, end = self._verify(gathered, frames, first_frame_index, recs, end, guess)
+        t3 = time.perf_counter()
         self.tracker.set_state(end)
+        if dbg:
+            import sys
+            print(f"[shard rank {self.rank}] track {1e3 * (t1 - t0):.1f} ms, gather {1e3 * (t2 - t1):.1f} ms, verify {1e3 * (t3 - t2):.1f} ms"
+                  f"{' (re-tracked)' if self.retracked != before else ''}", file=sys.stderr, flush=True)
         return recs, end
 
     # ---- the same with the boundary exchange off the critical path --------------------------------
