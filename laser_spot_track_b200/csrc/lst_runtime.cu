@@ -1047,8 +1047,9 @@ static size_t plan_rois(const lst_ctx *c, const double dis[10], int nb, RoiDesc 
 
 // The tracking loop body over n_frames slices given as one strided block (base) or as pointers
 // (ptrs); host memory unless on_device.  Host slices in pinned memory use the ROI ingest (only the
-// search regions cross PCIe, gathered by a kernel on the copy stream while the previous batch
-// computes); pageable slices and ingest_mode == 1 use whole-slice cudaMemcpyAsync into a ring.
+// search regions cross PCIe, as strided 3-D DMA copies on the copy stream while the previous batch
+// computes; a gather kernel reading mapped host memory when the slices are irregularly placed or
+// ingest_mode == 2); ingest_mode == 1 uses whole-slice cudaMemcpyAsync into a ring.
 // Slices that are not handed to the copy engine directly: files, or host memory whose search regions the
 // reader threads pack into pinned staging (pageable memory, e.g. Java arrays held through JNI; ingest_mode 3).
 struct FileSource {
