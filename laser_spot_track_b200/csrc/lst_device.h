@@ -71,6 +71,7 @@ struct PreprocParams {
     int minmax_in_kernel;  // the blur kernel finds the crop min/max itself (single column block)
     int swap_bytes;        // the slices hold big-endian samples (files read by lst_track_files)
     const uint32_t *frame_mm;   // LST_RANGE_FRAME: {min key, max key} per slice of the batch (px_key order)
+    int band_rows;         // lst_preprocess: output rows per CTA (0 = the whole window height); tall windows (whole-slice search) are split
     int rgb_shift;         // RGB slices: -1 = grey value of the pixel (matchIntensity), 16 / 8 / 0 = that channel alone (3-channel match)
 };
 

@@ -135,6 +135,11 @@ int launch_init_pass(int n_tasks, uint32_t *mm_keys, unsigned long long *best, f
 // min / max of the raw crop
 // ------------------------------------------------------------------------------------------------
 template <int PIX>
+__device__ __forceinline__ void mm_word(uint32_t wlo, uint32_t whi, uint32_t &lo, uint32_t &hi);
+template <int PIX>
+__device__ __forceinline__ void mm_finish(uint32_t &lo, uint32_t &hi);
+
+template <int PIX>
 __global__ void lst_minmax(const DevTask *__restrict__ tasks, const Surface *__restrict__ surfaces,
                            uint32_t *__restrict__ mm_keys, int swap_bytes)
 {
@@ -143,9 +148,32 @@ __global__ void lst_minmax(const DevTask *__restrict__ tasks, const Surface *__r
     const Surface sf = surfaces[t.frame];
     const void *fr = sf.ptr;
     uint32_t lo = 0xffffffffu, hi = 0u;
+    constexpr int ES = PIX == LST_PIX_U8 ? 1 : (PIX == LST_PIX_U16 ? 2 : 4);
     for (int r = blockIdx.x; r < t.h; r += gridDim.x) {
         size_t row = (size_t)(t.y0 - sf.org_y + r) * sf.pitch_px + (t.x0 - sf.org_x);
-        for (int c = threadIdx.x; c < t.w; c += blockDim.x) {
+        int c_first = 0;
+        if (PIX == LST_PIX_U8 || PIX == LST_PIX_U16) {
+            // whole 16-byte vectors of the row with packed min / max (whole slices: the rows start aligned); the rest pixel by pixel
+            const uint8_t *rp = (const uint8_t *)fr + row * ES;
+            if (((uintptr_t)rp & 15u) == 0) {
+                const int nvec = (t.w * ES) >> 4;
+                uint32_t plo = 0xffffffffu, phi = 0u;
+                for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+                    const uint4 q = __ldg((const uint4 *)rp + v);
+                    uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (PIX == LST_PIX_U16 && swap_bytes) w4[j] = __byte_perm(w4[j], 0, 0x2301);
+                        mm_word<PIX>(w4[j], w4[j], plo, phi);
+                    }
+                }
+                mm_finish<PIX>(plo, phi);
+                lo = min(lo, plo);
+                hi = max(hi, phi);
+                c_first = (nvec << 4) / ES;
+            }
+        }
+        for (int c = c_first + threadIdx.x; c < t.w; c += blockDim.x) {
             uint32_t k = swap_bytes ? px_key_swapped<PIX>(fr, row + c) : px_key<PIX>(fr, row + c);
             lo = min(lo, k);
             hi = max(hi, k);
@@ -511,9 +539,15 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
     const int ysg0 = threadIdx.x / ncw, ycc0 = threadIdx.x - ysg0 * ncw;
     const int ydsg = NT / ncw, ydcc = NT - ydsg * ncw;
 
-    int xdone = 0;   // x-pass rows [0, xdone) have been computed
-    for (int cy0 = 0; cy0 < t.h; cy0 += PRE_STRIP) {
-        const int cy1 = min(cy0 + PRE_STRIP, t.h);
+    // Tall windows (whole-slice search) are split into bands of band_rows output rows, one CTA (blockIdx.z) each; a band
+    // below the first starts KR-1 X-pass rows early, so its first strip is that much shorter (sraw holds PRE_STRIP + KR-1 rows).
+    const int y_begin = pp.band_rows > 0 ? (int)blockIdx.z * pp.band_rows : 0;
+    if (y_begin >= t.h) return;
+    const int y_end = pp.band_rows > 0 ? min(y_begin + pp.band_rows, t.h) : t.h;
+    int xdone = max(0, y_begin - (KR - 1));   // x-pass rows [.., xdone) have been computed
+    int prev_len = 0;
+    for (int cy0 = y_begin; cy0 < y_end; cy0 += prev_len) {
+        const int cy1 = min(cy0 + (cy0 == y_begin && y_begin > 0 ? PRE_STRIP - (KR - 1) : PRE_STRIP), y_end);
         const int need = min(cy1 + (KR - 1), t.h);          // x-pass rows needed up to here
         const int newr = need - xdone;                      // <= PRE_STRIP + KR - 1
         const int xrow0 = cy0 - (KR - 1);                   // crop row held by xp[0][.]
@@ -524,11 +558,11 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
                                          RWP, d0, d1, pp.swap_bytes != 0, PIX == LST_PIX_RGB ? pp.rgb_shift : -1);
         }
         // the X-pass rows this strip shares with the previous one move to the front
-        if (cy0 > 0) {
+        if (cy0 > y_begin) {
             const int n4 = XWP >> 2;
             for (int r = warp; r < 2 * (KR - 1); r += nwarps)
                 for (int c = lane; c < n4; c += 32)
-                    ((float4 *)(xp + (size_t)r * XWP))[c] = ((const float4 *)(xp + (size_t)(PRE_STRIP + r) * XWP))[c];
+                    ((float4 *)(xp + (size_t)r * XWP))[c] = ((const float4 *)(xp + (size_t)(prev_len + r) * XWP))[c];
         }
         __syncthreads();
         // X pass of the new rows
@@ -606,6 +640,7 @@ lst_preprocess(const DevTask *__restrict__ tasks, const Surface *__restrict__ su
             }
         }
         __syncthreads();   // the next strip overwrites sraw and moves the ring
+        prev_len = cy1 - cy0;
     }
 }
 
@@ -626,21 +661,24 @@ int launch_preprocess(const DevTask *tasks, int n_tasks, int max_w, int max_h, c
 {
     int tiles = (max_w + pp.tile_w - 1) / pp.tile_w;
     size_t smem = preprocess_smem(pp);
-    (void)max_h;
     const int nt = preprocess_threads(pp, max_w);
+    // whole slices: bands of 256 rows, so that a pass of a few tall windows still fills the GPU (12 extra X-pass rows per band)
+    PreprocParams pb = pp;
+    pb.band_rows = max_h > 512 ? 256 : 0;
+    const int bands = pb.band_rows > 0 ? (max_h + pb.band_rows - 1) / pb.band_rows : 1;
     int launches = 0;
     for (int base = 0; base < n_tasks; base += 65535) {
         int n = n_tasks - base < 65535 ? n_tasks - base : 65535;
-        dim3 grid(tiles, n);
+        dim3 grid(tiles, n, bands);
         const uint32_t *mm = mm_keys + 2 * base;
         if (pp.pixel_type == LST_PIX_U8)
-            lst_preprocess<LST_PIX_U8><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+            lst_preprocess<LST_PIX_U8><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pb, mm, win8);
         else if (pp.pixel_type == LST_PIX_U16)
-            lst_preprocess<LST_PIX_U16><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+            lst_preprocess<LST_PIX_U16><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pb, mm, win8);
         else if (pp.pixel_type == LST_PIX_RGB)
-            lst_preprocess<LST_PIX_RGB><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+            lst_preprocess<LST_PIX_RGB><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pb, mm, win8);
         else
-            lst_preprocess<LST_PIX_F32><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pp, mm, win8);
+            lst_preprocess<LST_PIX_F32><<<grid, nt, smem, stream>>>(tasks + base, surfaces, pb, mm, win8);
         launches++;
     }
     return launches;
