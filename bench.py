@@ -744,6 +744,23 @@ def main():
                     "preprocess_tflops": (38.0 * xs.preprocess_px / (xs.preprocess_ms * 1e-3) / 1e12) if xs.preprocess_ms > 0 else None,
                     "preprocess_hbm_gbs": (xs.preprocess_px * ((xbits // 8) + 1) / (xs.preprocess_ms * 1e-3) / 1e9) if xs.preprocess_ms > 0 else None,
                 }
+                # several lanes where the step is long enough to give each of them full batches (config A): the host-side chain
+                # walk of one lane runs under the kernels of the others, as in the main leg
+                xlanes = max(1, min(LANES_DEFAULT, len(my_cores)))
+                if xcfg.s_area > 0 and xf // xmb >= 4 and xlanes > 1:
+                    xm = LaserSpotTrack4Multi(xcfg.width, xcfg.height, xbits, [local_rank] * xlanes, templSize=xcfg.templ_size,
+                                              sArea=xcfg.s_area, max_batch=xmb)
+                    xm.set_reference(xst.frame(0), xst.ref_xy)
+
+                    def xstep_multi():
+                        xm.track_device_ptrs(xptrs, 1, xout)
+
+                    xms2, _, _ = timed(xstep_multi, 3, 2, xm)
+                    e = extra["config_" + name]
+                    e["value_one_lane"], e["ms_per_step_one_lane"] = e["value"], e["ms_per_step"]
+                    e["value"], e["ms_per_step"], e["lanes"] = xf * 3 / (xms2 * 1e-3), xms2 / 3, xlanes
+                    e["accepted_frames_last_step"] = sum(1 for r in xout if r.status == 0)
+                    xm.close()
                 xt.device_free(xdev)
                 xt.close()
             except Exception as e:      # the extras never fail the run
