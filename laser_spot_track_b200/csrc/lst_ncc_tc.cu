@@ -199,9 +199,24 @@ __device__ __forceinline__ uint32_t elect_one()
 }
 // int64 -> float32 without I2F.S64 (a slow conversion-unit instruction): |v| as two 32-bit halves through the
 // pipelined 32-bit conversions; relative error <= 2^-23
+// Exact float32 (round to nearest, what I2F gives) of an unsigned integer below 2^46 WITHOUT a conversion instruction: the
+// two 23-bit halves go into the mantissa of 2^23 (LOP3), the magic number is subtracted (FADD, exact) and the halves are
+// combined by one FMA, whose single rounding is the rounding of the integer itself.  I2F.S64 runs on the conversion unit at a
+// fraction of the FP32 rate, and the filter pass needs two of them per position.
+__device__ __forceinline__ float u46_to_f32_alu(unsigned long long a)
+{
+    const uint32_t lo = (uint32_t)a & 0x7fffffu, hi = (uint32_t)(a >> 23);
+    const float fl = __uint_as_float(lo | 0x4B000000u) - 8388608.0f;
+    const float fh = __uint_as_float(hi | 0x4B000000u) - 8388608.0f;
+    return __fmaf_rn(fh, 8388608.0f, fl);
+}
 __device__ __forceinline__ float i64_to_f32(long long v)
 {
-#if TC_CVT == 0
+#if TC_CVT == 3
+    const long long sgn = v >> 63;
+    const float f = u46_to_f32_alu((unsigned long long)((v ^ sgn) - sgn));       // |v| < 2^46 for every supported template
+    return __uint_as_float(__float_as_uint(f) | ((uint32_t)sgn & 0x80000000u));
+#elif TC_CVT == 0
     return (float)v;
 #elif TC_CVT == 1
     const long long sgn = v >> 63;
@@ -214,7 +229,9 @@ __device__ __forceinline__ float i64_to_f32(long long v)
 }
 __device__ __forceinline__ float u64_to_f32(unsigned long long a)
 {
-#if TC_CVT == 0
+#if TC_CVT == 3
+    return u46_to_f32_alu(a);
+#elif TC_CVT == 0
     return (float)(long long)a;
 #else
     return (float)(uint32_t)(a >> 32) * 4294967296.0f + (float)(uint32_t)a;

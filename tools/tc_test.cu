@@ -216,6 +216,11 @@ int main(int argc, char **argv)
         run_case(Geo{160, 160, 48, 48, 4704, 5, 0}, 0, 20);
         return 0;
     }
+    if (argc > 1 && !strcmp(argv[1], "timeA")) {
+        tc_init_device();
+        run_case(Geo{96, 96, 32, 32, 5000, 5, 0}, 0, 20);
+        return 0;
+    }
     tc_init_device();
     int fails = 0;
     // w, h, tw, th, n, method, mixed
