@@ -228,3 +228,29 @@ def test_jpeg_regions_at_the_image_border(built_lib, oracle_clib, tmp_path, samp
     with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area, max_batch=4) as t:
         t.set_reference_file(paths[0], st.ref_xy)
         util.compare_records(t.track_files(paths[1:]), want, label=f"JPEG border {sampling}")
+
+
+def test_jpeg_windows_leave_the_regions(built_lib, oracle_clib, tmp_path):
+    """JPEG slices with a jump larger than the margin staged around the search regions: the coefficient staging of that batch
+    does not hold the MCUs the windows need, so the batch is decoded whole (host reconstruction) and tracked again."""
+    import cv2
+    cfg = StackConfig(400, 300, "u8", 32, 24, 20)
+    st = SyntheticStack(cfg)
+    paths, frames = [], []
+    for i in range(20):
+        g = st.frame(i).astype(np.uint8)
+        if i >= 9:
+            g = np.roll(g, (15, -17), axis=(0, 1))
+        bgr = np.stack([255 - g // 2, g, (g.astype(np.uint16) * 3 // 4 + 17).astype(np.uint8)], axis=-1)
+        p = str(tmp_path / f"w{i:04d}.jpg")
+        assert cv2.imwrite(p, bgr, [cv2.IMWRITE_JPEG_QUALITY, 93, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420])
+        dec = cv2.imread(p, cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        frames.append((dec[:, :, 2].astype(np.uint32) << 16) | (dec[:, :, 1].astype(np.uint32) << 8) | dec[:, :, 0])
+        paths.append(p)
+    op, otr, want = _oracle(cfg, st, frames, match_intensity=True)
+    assert sum(w.status == 0 for w in want) >= 15
+    with LaserSpotTrack4(cfg.width, cfg.height, 24, templSize=cfg.templ_size, sArea=cfg.s_area, max_batch=5) as t:
+        t.set_reference_file(paths[0], st.ref_xy)
+        got = t.track_files(paths[1:])
+        util.compare_records(got, want, label="JPEG files with a jump")
+        assert t.stats().roi_fallback_tasks > 0
