@@ -303,7 +303,7 @@ def main():
     idx = [(1 + j) % ring for j in range(F)]
     dev_ptrs = (C.c_void_p * F)(*[dev_ring + i * fb for i in idx])
     host_ptrs = (C.c_void_p * F)(*[host_ring.value + i * fb for i in idx])
-    out = (N.Record * F)()
+    out = (N.Record * (F + max(0, args.lead_in)))()      # --continuous --lead-in: the lead-in slices' records come first
 
     # Sharding: the step's stack is world*F slices; rank r owns the contiguous chunk r.  The state
     # at the chunk boundary is speculated (the ring is periodic, so "my own previous end state" is
@@ -340,7 +340,7 @@ def main():
     # stack -- is already being tracked (ShardedTracker.track_chunk_pipelined); the records of a step are final when its
     # exchange has completed, which for the last step happens inside the timed region (finish()).  The two record
     # buffers alternate so that a late re-track would find its records intact.
-    out_alt = (N.Record * F)() if world > 1 else out
+    out_alt = (N.Record * (F + max(0, args.lead_in)))() if world > 1 else out
     flip = [0]
 
     def _next_out():
@@ -356,26 +356,25 @@ def main():
         sh_dev = ShardedTracker(_AdapterAlt(runner.track_device_ptrs), comm)
         sh_e2e = ShardedTracker(_AdapterAlt(runner.track_host_ptrs), comm)
 
-    cont = {"t": 0, "ptrs": [], "lead": []}
+    cont = {"t": 0, "ptrs": []}
     LEAD = max(0, args.lead_in)
     if args.continuous:      # pointer arrays of the steps of the device leg, built before the timed region
         for t in range(args.steps + max(args.warmup, 0) + 2):
             g0 = 1 + (t * world + rank) * F
-            cont["ptrs"].append((C.c_void_p * F)(*[dev_ring + ((g0 + j) % ring) * fb for j in range(F)]))
-            # the last slices of the previous chunk: tracked first from the speculated state, they pull it onto the true one
-            cont["lead"].append((C.c_void_p * LEAD)(*[dev_ring + ((g0 - LEAD + j) % ring) * fb for j in range(LEAD)]) if LEAD else None)
+            # with a lead-in the array starts with the last LEAD slices of the previous chunk: tracked in the same call from the
+            # speculated state, they pull it onto the true one (ShardedTracker.track_chunk(..., lead_in_count=LEAD))
+            cont["ptrs"].append((C.c_void_p * (F + LEAD))(*[dev_ring + ((g0 - LEAD + j) % ring) * fb for j in range(F + LEAD)]))
 
     def step_device():
-        ptrs, first, lead = dev_ptrs, 1 + rank * F, None
+        ptrs, first, nlead = dev_ptrs, 1 + rank * F, 0
         if args.continuous:
             t = cont["t"]
             cont["t"] = t + 1
-            ptrs, first = cont["ptrs"][t % len(cont["ptrs"])], 1 + (t * world + rank) * F
-            lead = cont["lead"][t % len(cont["ptrs"])]
+            ptrs, first, nlead = cont["ptrs"][t % len(cont["ptrs"])], 1 + (t * world + rank) * F, LEAD
         if pipelined:
-            sh_dev.track_chunk_pipelined(ptrs, first, runner.get_state(), lead)
+            sh_dev.track_chunk_pipelined(ptrs, first, runner.get_state(), None, nlead)
         else:
-            sh_dev.track_chunk(ptrs, first, runner.get_state(), lead)
+            sh_dev.track_chunk(ptrs, first, runner.get_state(), None, nlead)
 
     def step_e2e():
         if pipelined:
@@ -429,7 +428,7 @@ def main():
         dist.all_reduce(retr_t, op=dist.ReduceOp.SUM)
     retr_all = [int(v) for v in retr_t.tolist()]
     clocks = sampler.stop() if rank == 0 else None
-    ok_frames = sum(1 for r in out if r.status == 0)
+    ok_frames = sum(1 for i in range(F) if out[i].status == 0)      # rank 0 reports: its records start the buffer
     trk.set_kernel_timing(False)
     # Per-launch kernel times need kernels that do not overlap: with several lanes the roofline numbers come
     # from a second timed region of the same K steps on one lane (same kernels, same launches).

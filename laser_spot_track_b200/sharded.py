@@ -51,6 +51,17 @@ def chunk_bounds(n_frames: int, world: int):
     return out
 
 
+def _tail(seq, k: int):
+    """seq[k:] -- for ctypes arrays (slice pointers, records) a view of the same memory, not a copy."""
+    import ctypes as C
+    if k <= 0:
+        return seq
+    if isinstance(seq, C.Array):
+        n = len(seq) - k
+        return (seq._type_ * n).from_buffer(seq, k * C.sizeof(seq._type_))
+    return seq[k:]
+
+
 class TorchComm:
     """Host-side exchange over a torch.distributed process group (gloo on CPU tensors; with an NCCL
     group the 10 doubles travel as a tiny device tensor).  Not on the data path."""
@@ -96,9 +107,26 @@ class ShardedTracker:
         params = getattr(tracker, "params", None)      # LaserSpotTrack4 keeps its lst_params; the CPU stand-ins of the tests may not
         self.doubling = bool(getattr(params, "doubling", 0)) or bool(getattr(tracker, "doubling", False))
 
-    def _track(self, frames, first_frame_index, start_state, lead_in):
+    def _track(self, frames, first_frame_index, start_state, lead_in, lead_in_count=0):
         tr = self.tracker
         guess = list(start_state)
+        if lead_in_count > 0:
+            # `frames` starts with the last lead_in_count slices of the previous chunk: ONE tracking call covers them and the
+            # chunk (no extra call with its own passes and synchronisations); the state after the lead-in -- the refined
+            # speculation -- is what the last lead-in record carries (a skipped slice carries the state it kept)
+            L = lead_in_count
+            chunk = _tail(frames, L)
+            if self.rank > 0:
+                tr.set_state(guess)
+                recs_all = tr.track(frames, first_frame_index - L)
+                guess = [float(v) for v in recs_all[L - 1].dis]
+                recs = _tail(recs_all, L)
+            else:
+                tr.set_state(guess)
+                recs = tr.track(chunk, first_frame_index)
+            end = list(tr.get_state())
+            accepted_any = any(r.status == 0 for r in recs)
+            return recs, end, guess, end + guess + [1.0 if accepted_any else 0.0], chunk
         if self.rank > 0 and lead_in is not None and len(lead_in) > 0:
             tr.set_state(guess)
             tr.track(lead_in, first_frame_index - len(lead_in))
@@ -107,7 +135,7 @@ class ShardedTracker:
         recs = tr.track(frames, first_frame_index)
         end = list(tr.get_state())
         accepted_any = any(r.status == 0 for r in recs)
-        return recs, end, guess, end + guess + [1.0 if accepted_any else 0.0]
+        return recs, end, guess, end + guess + [1.0 if accepted_any else 0.0], frames
 
     def _verify(self, gathered, frames, first_frame_index, recs, end, guess):
         """Boundary verification.  One all_gather of (end state, speculated start, any-accepted flag)
@@ -144,15 +172,17 @@ class ShardedTracker:
         return recs, end
 
     def track_chunk(self, frames, first_frame_index: int, start_state: Sequence[float],
-                    lead_in: Optional[Sequence] = None):
+                    lead_in: Optional[Sequence] = None, lead_in_count: int = 0):
         """Track this rank's chunk.  ``start_state``: speculated displacement state before the chunk
         (rank 0: the true one).  ``lead_in``: optionally the last few frames of the previous chunk,
-        tracked first from ``start_state`` to refine the speculation.  Returns (records, end_state);
+        tracked first from ``start_state`` to refine the speculation -- or ``lead_in_count`` > 0: ``frames``
+        itself starts with that many slices of the previous chunk and one tracking call covers both
+        (``first_frame_index`` is still the chunk's).  Returns (records of the chunk, end_state);
         both are final after the boundary verification."""
         import os, time
         dbg = os.environ.get("LST_SHARD_DEBUG")
         t0 = time.perf_counter()
-        recs, end, guess, vals = self._track(frames, first_frame_index, start_state, lead_in)
+        recs, end, guess, vals, frames = self._track(frames, first_frame_index, start_state, lead_in, lead_in_count)
         t1 = time.perf_counter()
         gathered = self.comm.all_gather(vals)
         t2 = time.perf_counter()
@@ -168,7 +198,7 @@ class ShardedTracker:
 
     # ---- the same with the boundary exchange off the critical path --------------------------------
     def track_chunk_pipelined(self, frames, first_frame_index: int, start_state: Sequence[float],
-                              lead_in: Optional[Sequence] = None):
+                              lead_in: Optional[Sequence] = None, lead_in_count: int = 0):
         """Like track_chunk, but the exchange of THIS chunk's boundary states travels (on a helper thread) while the
         caller goes on -- typically into the next independent stack -- and the PREVIOUS call's exchange is completed
         after this chunk has been tracked.  Returns (records, end_state, previous) where ``previous`` is the verified
@@ -176,7 +206,7 @@ class ShardedTracker:
         fails verification re-tracks that chunk as track_chunk does; its records must not have been overwritten, so
         callers alternate their record buffers.  ``retracked_late`` counts such late re-tracks: whatever was tracked
         in between started from that chunk's unverified end state and has to be looked at by the caller."""
-        recs, end, guess, vals = self._track(frames, first_frame_index, start_state, lead_in)
+        recs, end, guess, vals, frames = self._track(frames, first_frame_index, start_state, lead_in, lead_in_count)
         prev, self._pending = getattr(self, "_pending", None), None
         if not hasattr(self, "_pool"):
             from concurrent.futures import ThreadPoolExecutor

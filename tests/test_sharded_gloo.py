@@ -45,6 +45,8 @@ def _worker(rank, world, port, mode, q):
         lo, hi = chunk_bounds(len(frames) - 1, world)[rank]
         chunk = frames[1 + lo:1 + hi]
         lead = frames[1 + lo - 2:1 + lo] if (mode == "lead_in" and rank > 0) else None
+        if mode == "lead_in_folded":      # the chunk handed over WITH the two slices before it (rank 0: the last two of nothing -- its own first two twice, ignored)
+            chunk = (frames[1 + lo - 2:1 + lo] if rank > 0 else frames[1:3]) + chunk
         if mode == "pipelined":
             # two independent passes over the same stack: the exchange of the first travels while the second is tracked
             _, _, none = sh.track_chunk_pipelined(chunk, 1 + lo, [0.0] * 10)
@@ -56,7 +58,7 @@ def _worker(rank, world, port, mode, q):
             assert key(first[0]) == key(second[0]) and first[1] == second[1]
             recs, end = second
         else:
-            recs, end = sh.track_chunk(chunk, 1 + lo, [0.0] * 10, lead_in=lead)
+            recs, end = sh.track_chunk(chunk, 1 + lo, [0.0] * 10, lead_in=lead, lead_in_count=2 if mode == "lead_in_folded" else 0)
         rows = [(int(r.frame), r.status, [(t.ix, t.iy, t.wx, t.wy, t.score, t.x, t.y) for t in r.tm],
                  list(r.dis), (r.dX_pix, r.dY_pix, r.x_abs, r.y_abs, r.dL)) for r in recs]
         q.put((rank, rows, end, sh.retracked))
@@ -64,7 +66,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["zero_guess", "lead_in", "pipelined"])
+@pytest.mark.parametrize("mode", ["zero_guess", "lead_in", "lead_in_folded", "pipelined"])
 def test_two_ranks_reproduce_sequential_loop(built_lib, oracle_clib, mode):
     import torch.multiprocessing as mp
     import util
